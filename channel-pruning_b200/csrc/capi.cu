@@ -1,0 +1,61 @@
+// libcpb200: handle lifetime, version, error string.
+#include "common.cuh"
+
+thread_local char cp_err_buf[512] = "";
+
+extern "C" int cp_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char *cp_last_error(void) { return cp_err_buf; }
+
+extern "C" int cp_create(cp_handle_t *out, int device) {
+    CP_REQUIRE(out != nullptr, "cp_create: out is NULL");
+    int ndev = 0;
+    CP_CUDA(cudaGetDeviceCount(&ndev));
+    CP_REQUIRE(device >= 0 && device < ndev, "cp_create: device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        CP_FAIL(CP_ERR_CUDA, "cp_create: device %d is sm_%d%d; libcpb200 is built for sm_100a only", device,
+                prop.major, prop.minor);
+    cp_handle_s *h = new cp_handle_s();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    h->tmap_encode = nullptr;
+    *out = h;
+    return CP_OK;
+}
+
+extern "C" int cp_destroy(cp_handle_t h) {
+    if (!h) return CP_OK;
+    if (h->ws) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(h->device);
+        cudaFree(h->ws);
+        cudaSetDevice(cur);
+    }
+    delete h;
+    return CP_OK;
+}
+
+extern "C" int64_t cp_workspace_bytes(cp_handle_t h) { return h ? (int64_t)h->ws_bytes : 0; }
+
+int cp_ws_reserve(cp_handle_t h, size_t bytes, void **out) {
+    if (bytes > h->ws_bytes) {
+        // cudaFree synchronises the device, so no in-flight kernel can still be using the old block
+        if (h->ws) CP_CUDA(cudaFree(h->ws));
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+        size_t want = cp_align_up(bytes + bytes / 8, (size_t)1 << 20);
+        cudaError_t e = cudaMalloc(&h->ws, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            CP_FAIL(CP_ERR_WORKSPACE, "workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        h->ws_bytes = want;
+    }
+    *out = h->ws;
+    return CP_OK;
+}

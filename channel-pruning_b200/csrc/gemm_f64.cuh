@@ -1,0 +1,253 @@
+// fp64-accumulate tile GEMM used wherever the path needs products that are exact with
+// respect to the reference's float64 arithmetic (Gram of fp32 data widened to fp64,
+// Cholesky trailing updates, triangular solves through inverted diagonal blocks).
+//
+//   C[m, nn] (op)= sum_{r = r_begin}^{r_end-1}  a(m, r) * b(nn, r)
+//
+//   a(m, r) = A_MC ? A[rowidx(r) * lda + m] : A[m * lda + r]      (TA = float | double)
+//   b(nn,r) = B_NC ? B[rowidx(r) * ldb + nn] - bias[nn] : B[nn * ldb + r]
+//
+// CTA tile 128 x 128, 256 threads, 8 x 8 register micro-tile per thread (interleaved
+// 2-wide so that every shared-memory read is a conflict-free LDS.128), reduction
+// staged 16 deep through double-buffered shared memory with register prefetch of the
+// next stage.  Bound: FP64 FMA pipe (64 DFMA / clk / SM).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpgemm {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+constexpr int LDS_ = BM + 2;  // padded leading dimension of a staged tile (doubles)
+constexpr size_t SMEM_BYTES = 2ull /*buffers*/ * 2 /*A,B*/ * BK * LDS_ * sizeof(double);
+
+enum TileMode { TILES_ALL = 0, TILES_UPPER_SYM = 1, TILES_LOWER = 2 };
+
+struct Args {
+    const void *A;
+    int64_t lda;
+    const void *B;
+    int64_t ldb;
+    double *C;
+    int64_t ldc;
+    int64_t c_split_stride;  // elements between split partials (nsplit > 1)
+    int M, Nn;
+    int64_t R;
+    const int32_t *rowidx;  // optional gather on the reduction index (A_MC / B_NC operands only)
+    const float *b_bias;    // optional, B_NC only
+    int nsplit;
+    int64_t r_per_split;    // multiple of BK
+    double alpha, beta;     // nsplit == 1: C = alpha*acc + beta*C ; nsplit > 1: partial = acc
+    int tile_mode;
+    int mirror;             // TILES_UPPER_SYM && nsplit == 1: also write C[nn, m]
+    int a_vec, b_vec;       // 16-byte vector loads allowed (alignment checked by the host)
+};
+
+template <typename T>
+__device__ __forceinline__ double to_f64(T v) { return (double)v; }
+
+// Loads 8 consecutive elements (contiguous direction) starting at p[0], valid count `nvalid` (0..8).
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, int nvalid, bool vec, double out[8]) {
+    if (nvalid >= 8 && vec) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+            out[0] = v0.x; out[1] = v0.y; out[2] = v0.z; out[3] = v0.w;
+            out[4] = v1.x; out[5] = v1.y; out[6] = v1.z; out[7] = v1.w;
+        } else {
+            const double2 *q = reinterpret_cast<const double2 *>(p);
+            const double2 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+            out[0] = v0.x; out[1] = v0.y; out[2] = v1.x; out[3] = v1.y;
+            out[4] = v2.x; out[5] = v2.y; out[6] = v3.x; out[7] = v3.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = (i < nvalid) ? to_f64(__ldg(p + i)) : 0.0;
+    }
+}
+
+// Operand whose tile dimension (m or nn) is contiguous in memory: element (x, r) = P[rowidx(r)*ld + x].
+// thread t fetches r = t/16, x = (t%16)*8 .. +8
+template <typename T>
+__device__ __forceinline__ void fetch_xcontig(const T *P, int64_t ld, const int32_t *rowidx, int x0, int xlim,
+                                              int64_t r0, int64_t rlim, bool vec, const float *bias,
+                                              double out[8]) {
+    const int t = threadIdx.x;
+    const int64_t r = r0 + (t >> 4);
+    const int x = x0 + (t & 15) * 8;
+    int nvalid = xlim - x;
+    nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+    if (r >= rlim) nvalid = 0;
+    if (nvalid == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = 0.0;
+        return;
+    }
+    const int64_t row = rowidx ? (int64_t)__ldg(rowidx + r) : r;
+    load8(P + row * ld + x, nvalid, vec, out);
+    if (bias) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nvalid) out[i] -= (double)__ldg(bias + x + i);
+    }
+}
+__device__ __forceinline__ void stage_xcontig(double *S, const double v[8]) {
+    const int t = threadIdx.x;
+    double *d = S + (t >> 4) * LDS_ + (t & 15) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) *reinterpret_cast<double2 *>(d + i) = make_double2(v[i], v[i + 1]);
+}
+
+// Operand whose reduction dimension is contiguous: element (x, r) = P[x*ld + r].
+// thread t fetches x = t/2, r = (t%2)*8 .. +8
+template <typename T>
+__device__ __forceinline__ void fetch_rcontig(const T *P, int64_t ld, int x0, int xlim, int64_t r0, int64_t rlim,
+                                              bool vec, double out[8]) {
+    const int t = threadIdx.x;
+    const int x = x0 + (t >> 1);
+    const int64_t r = r0 + (t & 1) * 8;
+    int64_t nv = rlim - r;
+    int nvalid = nv < 0 ? 0 : (nv > 8 ? 8 : (int)nv);
+    if (x >= xlim) nvalid = 0;
+    if (nvalid == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = 0.0;
+        return;
+    }
+    load8(P + (int64_t)x * ld + r, nvalid, vec, out);
+}
+__device__ __forceinline__ void stage_rcontig(double *S, const double v[8]) {
+    const int t = threadIdx.x;
+    double *d = S + ((t & 1) * 8) * LDS_ + (t >> 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i * LDS_] = v[i];
+}
+
+template <typename TA, typename TB, bool A_MC, bool B_NC>
+__global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
+    extern __shared__ __align__(16) double smem[];
+    // stage buffer b: A tile at smem + b*2*BK*LDS_, B tile right after it
+    auto As = [&](int b) { return smem + (size_t)b * 2 * BK * LDS_; };
+    auto Bs = [&](int b) { return smem + (size_t)b * 2 * BK * LDS_ + BK * LDS_; };
+
+    // ---- tile decode
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.Nn + BN - 1) / BN;
+    int l = blockIdx.x, ti, tj;
+    if (g.tile_mode == TILES_UPPER_SYM) {
+        ti = 0;
+        while (l >= tiles_n - ti) { l -= tiles_n - ti; ++ti; }
+        tj = ti + l;
+    } else if (g.tile_mode == TILES_LOWER) {
+        // column-tile major: for tj, row tiles ti = tj .. tiles_m-1
+        tj = 0;
+        while (l >= tiles_m - tj) { l -= tiles_m - tj; ++tj; }
+        ti = tj + l;
+    } else {
+        ti = l / tiles_n;
+        tj = l - ti * tiles_n;
+    }
+    const int split = blockIdx.y;
+    const int m0 = ti * BM, n0 = tj * BN;
+    const int64_t r_begin = (int64_t)split * g.r_per_split;
+    int64_t r_end = r_begin + g.r_per_split;
+    if (r_end > g.R) r_end = g.R;
+
+    const TA *A = reinterpret_cast<const TA *>(g.A);
+    const TB *B = reinterpret_cast<const TB *>(g.B);
+
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double ra[8], rb[8];
+
+    auto fetch = [&](int64_t r0) {
+        if constexpr (A_MC) fetch_xcontig<TA>(A, g.lda, g.rowidx, m0, g.M, r0, r_end, g.a_vec, nullptr, ra);
+        else fetch_rcontig<TA>(A, g.lda, m0, g.M, r0, r_end, g.a_vec, ra);
+        if constexpr (B_NC) fetch_xcontig<TB>(B, g.ldb, g.rowidx, n0, g.Nn, r0, r_end, g.b_vec, g.b_bias, rb);
+        else fetch_rcontig<TB>(B, g.ldb, n0, g.Nn, r0, r_end, g.b_vec, rb);
+    };
+    auto stage = [&](int buf) {
+        if constexpr (A_MC) stage_xcontig(As(buf), ra); else stage_rcontig(As(buf), ra);
+        if constexpr (B_NC) stage_xcontig(Bs(buf), rb); else stage_rcontig(Bs(buf), rb);
+    };
+
+    int buf = 0;
+    if (r_begin < r_end) {
+        fetch(r_begin);
+        stage(0);
+    }
+    __syncthreads();
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
+        const bool has_next = r0 + BK < r_end;
+        if (has_next) fetch(r0 + BK);
+        const double *a_s = As(buf), *b_s = Bs(buf);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double a[8], b[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 av = *reinterpret_cast<const double2 *>(a_s + kk * LDS_ + q * 32 + ty * 2);
+                const double2 bv = *reinterpret_cast<const double2 *>(b_s + kk * LDS_ + q * 32 + tx * 2);
+                a[2 * q] = av.x; a[2 * q + 1] = av.y;
+                b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        if (has_next) stage(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // ---- epilogue
+    double *C = g.C + (g.nsplit > 1 ? (int64_t)split * g.c_split_stride : 0);
+    const bool partial = g.nsplit > 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int nn = n0 + (j >> 1) * 32 + tx * 2 + (j & 1);
+            if (nn >= g.Nn) continue;
+            double v = acc[i][j];
+            if (!partial) {
+                v *= g.alpha;
+                if (g.beta != 0.0) v = fma(g.beta, C[(int64_t)m * g.ldc + nn], v);
+            }
+            C[(int64_t)m * g.ldc + nn] = v;
+            if (g.mirror && !partial && ti != tj) C[(int64_t)nn * g.ldc + m] = v;
+        }
+    }
+}
+
+inline int num_tiles(int M, int Nn, int mode) {
+    const int tm = (M + BM - 1) / BM, tn = (Nn + BN - 1) / BN;
+    if (mode == TILES_UPPER_SYM) return tn * (tn + 1) / 2;          // requires M == Nn
+    if (mode == TILES_LOWER) return tn * tm - tn * (tn - 1) / 2;    // requires tm >= tn
+    return tm * tn;
+}
+
+template <typename TA, typename TB, bool A_MC, bool B_NC>
+inline cudaError_t launch(const Args &g, cudaStream_t stream) {
+    auto kern = gemm_kernel<TA, TB, A_MC, B_NC>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((unsigned)num_tiles(g.M, g.Nn, g.tile_mode), (unsigned)(g.nsplit > 1 ? g.nsplit : 1));
+    if (grid.x == 0) return cudaSuccess;
+    kern<<<grid, NT, SMEM_BYTES, stream>>>(g);
+    return cudaGetLastError();
+}
+
+}  // namespace cpgemm

@@ -1,0 +1,348 @@
+// Least-squares reconstruction of the surviving weights.
+//
+//   cp_ls_solve       <- fc_kernel / LinearRegression(fit_intercept=True).fit
+//                        (reference lib/decompose.py:622-623, 636-669): centred normal
+//                        equations on the principal sub-block of the Gram matrix.
+//   cp_ls_solve_dual  <- the same call when N-1 < K' (gelsd's minimum-norm answer),
+//                        through the dual (row) normal equations.
+//
+// Both reduce to one routine: blocked right-looking Cholesky (panel 64) of an SPD matrix
+// with the right-hand sides appended as extra ROWS of the same array, so that the forward
+// substitution happens for free inside the panel TRSM / trailing update; the diagonal
+// blocks are inverted once (64x64, one CTA) and every other operation is an fp64 tile
+// GEMM (cpgemm::gemm_kernel).  The backward substitution reuses the inverted blocks.
+// Bound: FP64 pipe for the trailing updates (K'^3/3 flop), latency for the 64x64 panels.
+#include "common.cuh"
+#include "gemm_f64.cuh"
+
+namespace {
+
+constexpr int NB = 64;
+
+// ---------------------------------------------------------------- assemble
+// M rows 0..Ks-1    : G[sel_i, sel_j] - sx_i sx_j / N           (Ks x Ks)
+// M rows Ks..Ks+n-1 : Bxy[sel_j, t]   - sx_j sy_t / N           (n  x Ks)   (right-hand sides, transposed)
+__global__ void __launch_bounds__(256)
+ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const double *__restrict__ sx,
+            const double *__restrict__ sy, double invN, int K, int n, const int32_t *__restrict__ sel, int Ks,
+            double *__restrict__ M, int64_t ld) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= Ks) return;
+    const int sj = sel[j];
+    if (i < Ks) {
+        const int si = sel[i];
+        M[(int64_t)i * ld + j] = G[(int64_t)si * K + sj] - sx[si] * sx[sj] * invN;
+    } else {
+        const int t = i - Ks;
+        M[(int64_t)i * ld + j] = Bxy[(int64_t)sj * n + t] - sx[sj] * sy[t] * invN;
+    }
+}
+
+// ---------------------------------------------------------------- 64x64 diagonal block: L and L^-1
+constexpr int PD = NB + 1;
+constexpr size_t POTRF_SMEM = (2 * NB * PD + NB) * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv, int32_t *__restrict__ info,
+           int j0) {
+    // S: working copy; its strict upper triangle receives the finished factor transposed
+    // (L[i][k] -> S[k][i], i > k), the diagonal of L goes to Ld.  X: the inverse.
+    extern __shared__ __align__(16) double psm[];
+    double *S = psm, *X = psm + NB * PD, *Ld = psm + 2 * NB * PD;
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        double v = 0.0;
+        if (i < nb && j < nb && j <= i) v = A[(int64_t)i * ld + j];
+        if (i >= nb && i == j) v = 1.0;  // identity padding keeps the arithmetic finite
+        S[i * PD + j] = v;
+        X[i * PD + j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int k = 0; k < NB; ++k) {
+        __syncthreads();
+        double d = S[k * PD + k];
+        if (!(d > 0.0)) {
+            if (tid == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
+            d = 1.0;
+        }
+        const double inv = 1.0 / d;
+        if (ty == 0) {
+            const double rs = 1.0 / sqrt(d);
+            if (tx == k) Ld[k] = sqrt(d);
+            else if (tx > k) S[k * PD + tx] = S[tx * PD + k] * rs;  // L[tx][k], stored transposed
+        }
+        for (int i = k + 1 + ty; i < NB; i += 4) {
+            const int j = tx;
+            if (j > k && j <= i) S[i * PD + j] = fma(-S[i * PD + k] * inv, S[j * PD + k], S[i * PD + j]);
+        }
+    }
+    __syncthreads();
+    // X = L^-1, column-parallel forward substitution (thread column tx, 4 row lanes)
+    for (int k = 0; k < NB; ++k) {
+        if (ty == 0) X[k * PD + tx] = X[k * PD + tx] / Ld[k];
+        __syncthreads();
+        const double xk = X[k * PD + tx];
+        for (int i = k + 1 + ty; i < NB; i += 4) X[i * PD + tx] = fma(-S[k * PD + i], xk, X[i * PD + tx]);
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = (i == j) ? Ld[i] : S[j * PD + i];
+        Linv[e] = (j <= i) ? X[i * PD + j] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ sx, const double *__restrict__ sy,
+          const int32_t *__restrict__ sel, int Ks, double invN, double *__restrict__ W_out,
+          double *__restrict__ b_out) {
+    __shared__ double red[256];
+    const int t = blockIdx.x;
+    const double *src = Wt + (int64_t)t * ld;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < Ks; i += 256) {
+        const double w = src[i];
+        W_out[(int64_t)t * Ks + i] = w;
+        s = fma(sx[sel[i]], w, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) b_out[t] = (sy[t] - red[0]) * invN;
+}
+
+inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+template <bool B_NC>
+int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
+          int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
+    using namespace cpgemm;
+    Args g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.M = M; g.Nn = Nn; g.R = R;
+    g.nsplit = 1; g.r_per_split = R;
+    g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode;
+    g.a_vec = al16(A) && (lda % 2 == 0);
+    g.b_vec = al16(B) && (ldb % 2 == 0);
+    if (M <= 0 || Nn <= 0) return CP_OK;
+    CP_CUDA((launch<double, double, false, B_NC>(g, stream)));
+    return CP_OK;
+}
+
+}  // namespace
+
+// In-place: M is (Kd + n) x Kd (leading dimension ld), rows 0..Kd-1 an SPD matrix (lower part
+// used), rows Kd.. the transposed right-hand sides.  On return rows Kd.. hold the transposed
+// solution  (SPD^-1 Rhs)'.  Linv: scratch of ceil(Kd/64) * 64*64 doubles.
+static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv, int32_t *info,
+                              cudaStream_t stream) {
+    using namespace cpgemm;
+    const int Ktot = Kd + n;
+    const int npanel = (Kd + NB - 1) / NB;
+    static bool configured = false;
+    if (!configured) {
+        CP_CUDA(cudaFuncSetAttribute(potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+        configured = true;
+    }
+    for (int p = 0; p < npanel; ++p) {
+        const int j0 = p * NB;
+        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
+        const int j1 = j0 + nb;
+        double *Lp = Linv + (size_t)p * NB * NB;
+        potrf_diag<<<1, 256, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0);
+        CP_CHECK_LAUNCH();
+        const int below = Ktot - j1;
+        if (below > 0) {
+            // panel <- panel * L_d^-T   (C[m, nn] = sum_r P[m, r] * Linv[nn, r]), in place (single column tile)
+            double *Pn = M + (int64_t)j1 * ld + j0;
+            int rc = dgemm<false>(Pn, ld, Lp, NB, Pn, ld, below, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+            if (rc) return rc;
+            // trailing (lower) -= panel * panel'
+            const int ncols = Kd - j1;
+            if (ncols > 0) {
+                rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, below, ncols, nb, -1.0, 1.0,
+                                  TILES_LOWER, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    // backward: Wt * L = Zt, block columns last to first
+    double *Zt = M + (int64_t)Kd * ld;
+    for (int p = npanel - 1; p >= 0; --p) {
+        const int j0 = p * NB;
+        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
+        double *Lp = Linv + (size_t)p * NB * NB;
+        // Wt_p = Zt_p * Linv_p   (C[t, i] = sum_r Zt[t, j0 + r] * Linv[r, i]), in place
+        int rc = dgemm<true>(Zt + j0, ld, Lp, NB, Zt + j0, ld, n, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+        if (rc) return rc;
+        if (j0 > 0) {
+            // Zt[:, 0:j0] -= Wt_p * L[j0:j0+nb, 0:j0]
+            rc = dgemm<true>(Zt + j0, ld, M + (int64_t)j0 * ld, ld, Zt, ld, n, j0, nb, -1.0, 1.0, TILES_ALL, stream);
+            if (rc) return rc;
+        }
+    }
+    return CP_OK;
+}
+
+extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
+                           int64_t N, int K, int n, const int32_t *sel_cols, int Ksel, double *W_out, double *b_out,
+                           int32_t *info_out, cp_stream_t stream_) {
+    CP_REQUIRE(h && G && Bxy && sx && sy && sel_cols && W_out && b_out && info_out, "cp_ls_solve: NULL argument");
+    CP_REQUIRE(K > 0 && n > 0 && Ksel > 0 && Ksel <= K && N > 0, "cp_ls_solve: bad shape");
+    CP_REQUIRE(N - 1 >= Ksel, "cp_ls_solve: N-1=%lld < K'=%d: centred Gram is singular, use cp_ls_solve_dual",
+               (long long)(N - 1), Ksel);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t ld = (Ksel + 7) / 8 * 8;
+    const int npanel = (Ksel + NB - 1) / NB;
+    const size_t need = cp_carver::need((size_t)(Ksel + n) * ld, 8) + cp_carver::need((size_t)npanel * NB * NB, 8);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, need, &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    double *M = cv.take<double>((size_t)(Ksel + n) * ld);
+    double *Linv = cv.take<double>((size_t)npanel * NB * NB);
+    CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
+    const double invN = 1.0 / (double)N;
+    dim3 grid(cp_cdiv(Ksel, 256), Ksel + n);
+    ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld);
+    CP_CHECK_LAUNCH();
+    rc = chol_solve_inplace(M, ld, Ksel, n, Linv, info_out, stream);
+    if (rc) return rc;
+    ls_output<<<n, 256, 0, stream>>>(M + (int64_t)Ksel * ld, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// ---------------------------------------------------------------- dual (minimum-norm) path
+namespace {
+
+// column means of the selected columns of X (fp64, fixed order) and of Y - bias
+template <typename T>
+__global__ void __launch_bounds__(256)
+colmean_sel(const T *__restrict__ X, int64_t ld, const int32_t *__restrict__ sel, int ncols, int64_t N,
+            const float *__restrict__ bias, double *__restrict__ mean_out) {
+    __shared__ double s1[8][33];
+    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + cx;
+    double a = 0.0;
+    if (j < ncols) {
+        const int col = sel ? sel[j] : j;
+        const double b = bias ? (double)bias[col] : 0.0;
+        for (int64_t r = rg; r < N; r += 8) a += (double)__ldg(X + r * ld + col) - b;
+    }
+    s1[rg][cx] = a;
+    __syncthreads();
+    if (rg == 0 && j < ncols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s1[k][cx];
+        mean_out[j] = t / (double)N;
+    }
+}
+
+// Xc[r, j] = X[r, sel_j] - mean_j    (N x Ks fp64, ld)
+__global__ void __launch_bounds__(256)
+center_sel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ sel, int Ks,
+           const double *__restrict__ mean, double *__restrict__ Xc, int64_t ld) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (j < Ks) Xc[r * ld + j] = (double)__ldg(X + r * ldx + sel[j]) - mean[j];
+}
+
+// rows N..N+n-1 of the augmented matrix: Yc' (n x N):  M[N + t, r] = Y[r, t] - bias_t - ymean_t
+template <typename T>
+__global__ void __launch_bounds__(256)
+dual_rhs(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, const double *__restrict__ ymean,
+         int64_t N, int n, double *__restrict__ M, int64_t ld) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int t = blockIdx.y;
+    if (r < N) M[(N + t) * ld + r] = (double)__ldg(Y + r * ldy + t) - (bias ? (double)bias[t] : 0.0) - ymean[t];
+}
+
+__global__ void add_const_lower(double *__restrict__ M, int64_t ld, int N, double v) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j < N && j <= i) M[(int64_t)i * ld + j] += v;
+}
+
+__global__ void __launch_bounds__(256)
+dual_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ xmean,
+            const double *__restrict__ ymean, int Ks, double *__restrict__ W_out, double *__restrict__ b_out) {
+    __shared__ double red[256];
+    const int t = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < Ks; i += 256) {
+        const double w = Wt[(int64_t)t * ld + i];
+        W_out[(int64_t)t * Ks + i] = w;
+        s = fma(xmean[i], w, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) b_out[t] = ymean[t] - red[0];
+}
+
+}  // namespace
+
+extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw,
+                                int y_dtype, int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel,
+                                double *W_out, double *b_out, int32_t *info_out, cp_stream_t stream_) {
+    using namespace cpgemm;
+    CP_REQUIRE(h && X && Yraw && sel_cols && W_out && b_out && info_out, "cp_ls_solve_dual: NULL argument");
+    CP_REQUIRE(N > 1 && N < (1 << 15) && K > 0 && n > 0 && Ksel > 0 && Ksel <= K && ldx >= K && ldy >= n,
+               "cp_ls_solve_dual: bad shape (N must be < 32768)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int Ni = (int)N;
+    const int64_t ldc = (Ksel + 7) / 8 * 8;  // Xc
+    const int64_t ldm = (Ni + 7) / 8 * 8;    // dual system
+    const int npanel = (Ni + NB - 1) / NB;
+    const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + cp_carver::need((size_t)(Ni + n) * ldm, 8) +
+                        cp_carver::need((size_t)npanel * NB * NB, 8) + cp_carver::need((size_t)n * ldc, 8) +
+                        cp_carver::need(Ksel, 8) + cp_carver::need(n, 8);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, need, &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    double *Xc = cv.take<double>((size_t)Ni * ldc);
+    double *M = cv.take<double>((size_t)(Ni + n) * ldm);
+    double *Linv = cv.take<double>((size_t)npanel * NB * NB);
+    double *Wt = cv.take<double>((size_t)n * ldc);
+    double *xmean = cv.take<double>(Ksel);
+    double *ymean = cv.take<double>(n);
+    CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
+    CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_solve_dual: unknown y_dtype %d", y_dtype);
+    colmean_sel<float><<<cp_cdiv(Ksel, 32), 256, 0, stream>>>(X, ldx, sel_cols, Ksel, N, nullptr, xmean);
+    CP_CHECK_LAUNCH();
+    if (y_dtype == CP_F32)
+        colmean_sel<float><<<cp_cdiv(n, 32), 256, 0, stream>>>((const float *)Yraw, ldy, nullptr, n, N, y_bias, ymean);
+    else
+        colmean_sel<double><<<cp_cdiv(n, 32), 256, 0, stream>>>((const double *)Yraw, ldy, nullptr, n, N, y_bias, ymean);
+    CP_CHECK_LAUNCH();
+    center_sel<<<dim3(cp_cdiv(Ksel, 256), Ni), 256, 0, stream>>>(X, ldx, sel_cols, Ksel, xmean, Xc, ldc);
+    CP_CHECK_LAUNCH();
+    // H = Xc Xc' (lower tiles) + 1/N
+    rc = dgemm<false>(Xc, ldc, Xc, ldc, M, ldm, Ni, Ni, Ksel, 1.0, 0.0, TILES_LOWER, stream);
+    if (rc) return rc;
+    add_const_lower<<<dim3(cp_cdiv(Ni, 256), Ni), 256, 0, stream>>>(M, ldm, Ni, 1.0 / (double)N);
+    CP_CHECK_LAUNCH();
+    if (y_dtype == CP_F32)
+        dual_rhs<float><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
+    else
+        dual_rhs<double><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
+    CP_CHECK_LAUNCH();
+    rc = chol_solve_inplace(M, ldm, Ni, n, Linv, info_out, stream);
+    if (rc) return rc;
+    // Wt = At * Xc   (C[t, i] = sum_r At[t, r] * Xc[r, i])
+    rc = dgemm<true>(M + (int64_t)Ni * ldm, ldm, Xc, ldc, Wt, ldc, n, Ksel, Ni, 1.0, 0.0, TILES_ALL, stream);
+    if (rc) return rc;
+    dual_output<<<n, 256, 0, stream>>>(Wt, ldc, xmean, ymean, Ksel, W_out, b_out);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}

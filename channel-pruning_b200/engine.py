@@ -1,0 +1,275 @@
+"""Device-side engine: torch tensors as device buffers, libcpb200 kernels as the compute.
+
+One ``Engine`` per process/GPU.  It owns ``nstreams`` CUDA streams, each with its own
+libcpb200 handle (scratch workspace is per handle), so that independent layer problems
+can overlap: the LASSO search is a single-CTA latency-bound kernel and the Cholesky
+panels are small, while the Gram/trailing-update kernels fill the chip -- running
+several layers concurrently on separate streams keeps the SMs busy.
+
+Every method enqueues work on the *current* torch stream unless stated; nothing here
+touches the CPU oracle, and there is no fallback: without a CUDA device or without
+libcpb200.so construction fails.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+RAND_R_MAX = 2147483647
+MAX_PROBES = 64
+
+_LAYOUTS = {"nchw": 0, "nhwc": 1}
+GRAM_FP64, GRAM_3XTF32 = 0, 1
+
+
+class LassoResult:
+    """Device-resident outputs of one channel selection (cp_lasso_select)."""
+
+    __slots__ = ("idxs", "coef", "scalars", "probe_log", "seeds")
+
+    def __init__(self, idxs, coef, scalars, probe_log, seeds):
+        self.idxs, self.coef, self.scalars, self.probe_log, self.seeds = idxs, coef, scalars, probe_log, seeds
+
+
+class Engine:
+    def __init__(self, device=None, nstreams: int = 1, gram_mode: int = GRAM_FP64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cpb200: no CUDA device visible; the solver has no CPU path")
+        self.ffi, self.lib = _cabi.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.gram_mode = gram_mode
+        self._handles = []
+        self.streams = []
+        with torch.cuda.device(self.device):
+            for i in range(max(1, nstreams)):
+                hp = self.ffi.new("cp_handle_t*")
+                _cabi.check(self.lib.cp_create(hp, self.device.index))
+                self._handles.append(hp[0])
+                self.streams.append(torch.cuda.Stream(self.device) if nstreams > 1 else None)
+        self._cur = 0
+        self.launches = 0  # libcpb200 calls issued (each launches >= 1 kernel)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        for h in self._handles:
+            self.lib.cp_destroy(h)
+        self._handles = []
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_slot(self, i: int):
+        """Select which (handle, stream) pair subsequent calls use."""
+        self._cur = i % len(self._handles)
+        return self.streams[self._cur]
+
+    @property
+    def h(self):
+        return self._handles[self._cur]
+
+    def _s(self):
+        return self.ffi.cast("void*", torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _p(self, t, ctype):
+        if t is None:
+            return self.ffi.NULL
+        assert t.is_cuda and t.device == self.device, "tensor must live on %s" % self.device
+        return self.ffi.cast(ctype, t.data_ptr())
+
+    def _call(self, rc):
+        self.launches += 1
+        _cabi.check(rc)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ kernels
+    def patch_gather(self, fmap, randx, randy, B, P, k, pad, stride, relu=True, layout="nchw", out=None):
+        """fmap: (nbatch*B, c, H, W) [nchw] or (nbatch*B, H, W, c) [nhwc] fp32 on device;
+        randx/randy: (nbatch, P) int32 on device.  Returns X (nbatch*P*B, c*k*k) fp32."""
+        assert fmap.dtype == torch.float32 and fmap.is_contiguous()
+        nimg = fmap.shape[0]
+        assert nimg % B == 0
+        nbatch = nimg // B
+        if layout == "nchw":
+            c, H, W = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        else:
+            H, W, c = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        assert randx.dtype == torch.int32 and randx.numel() == nbatch * P and randx.is_contiguous()
+        assert randy.dtype == torch.int32 and randy.numel() == nbatch * P and randy.is_contiguous()
+        rows, K = nbatch * P * B, c * k * k
+        if out is None:
+            out = self.empty(rows, K, dtype=torch.float32)
+        assert out.shape == (rows, K) and out.dtype == torch.float32 and out.stride(1) == 1
+        self._call(self.lib.cp_patch_gather(self.h, self._p(fmap, "const float*"), nbatch, B, c, H, W,
+                                            _LAYOUTS[layout], self._p(randx, "const int32_t*"),
+                                            self._p(randy, "const int32_t*"), P, k, pad, stride, int(bool(relu)),
+                                            self._p(out, "float*"), out.stride(0), self._s()))
+        return out
+
+    def point_gather(self, fmap, randx, randy, B, P, layout="nchw", out=None):
+        assert fmap.dtype == torch.float32 and fmap.is_contiguous()
+        nimg = fmap.shape[0]
+        nbatch = nimg // B
+        if layout == "nchw":
+            n, H, W = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        else:
+            H, W, n = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        rows = nbatch * P * B
+        if out is None:
+            out = self.empty(rows, n, dtype=torch.float32)
+        self._call(self.lib.cp_point_gather(self.h, self._p(fmap, "const float*"), nbatch, B, n, H, W,
+                                            _LAYOUTS[layout], self._p(randx, "const int32_t*"),
+                                            self._p(randy, "const int32_t*"), P, self._p(out, "float*"),
+                                            out.stride(0), self._s()))
+        return out
+
+    def gram(self, X, Y=None, y_bias=None, rows=None, want_G=True, want_B=True, want_sums=True, want_yy=False,
+             mode=None):
+        """Sufficient statistics of (X, Y) (optionally over gathered rows).
+        Returns dict with G (K,K), B (K,n), sx (K), sy (n), yy (1) as fp64 device tensors."""
+        assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+        N, K = X.shape
+        out = {}
+        n = 0
+        y_dt = 0
+        if Y is not None:
+            assert Y.dim() == 2 and Y.shape[0] == N and Y.stride(1) == 1
+            assert Y.dtype in (torch.float32, torch.float64)
+            y_dt = 0 if Y.dtype == torch.float32 else 1
+            n = Y.shape[1]
+        if rows is not None:
+            assert rows.dtype == torch.int32 and rows.is_contiguous()
+        G = self.empty(K, K) if want_G else None
+        Bxy = self.empty(K, n) if (want_B and Y is not None) else None
+        sx = self.empty(K) if want_sums else None
+        sy = self.empty(n) if (want_sums and Y is not None) else None
+        yy = self.empty(1) if (want_yy and Y is not None) else None
+        self._call(self.lib.cp_gram(self.h, self._p(X, "const float*"), N, K, X.stride(0),
+                                    self._p(Y, "const void*"), y_dt, n, Y.stride(0) if Y is not None else 0,
+                                    self._p(y_bias, "const float*"), self._p(rows, "const int32_t*"),
+                                    rows.numel() if rows is not None else 0, self._p(G, "double*"),
+                                    self._p(Bxy, "double*"), self._p(sx, "double*"), self._p(sy, "double*"),
+                                    self._p(yy, "double*"), self.gram_mode if mode is None else mode, self._s()))
+        out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n)
+        return out
+
+    def lasso_build(self, gs, gw, W2m, c, k2, S):
+        """gs: gram over sampled rows (with yy); gw: gram of W2 viewed (n, K); W2m: (n, K) fp32."""
+        n = W2m.shape[0]
+        Q = self.empty(c, c)
+        qv = self.empty(c)
+        yn2 = self.empty(1)
+        self._call(self.lib.cp_lasso_build(self.h, self._p(gs["G"], "const double*"), self._p(gs["B"], "const double*"),
+                                           self._p(gs["sx"], "const double*"), self._p(gs["sy"], "const double*"),
+                                           self._p(gs["yy"], "const double*"), self._p(gw["G"], "const double*"),
+                                           self._p(gw["sx"], "const double*"), self._p(W2m, "const float*"), c, k2, n,
+                                           S, self._p(Q, "double*"), self._p(qv, "double*"), self._p(yn2, "double*"),
+                                           self._s()))
+        return Q, qv, yn2
+
+    def lasso_select(self, Q, qv, yn2, m, rank, lbound, rbound, right0, seeds, tol=1e-4, max_iter=1000):
+        c = Q.shape[0]
+        seeds_d = torch.as_tensor(np.asarray(seeds, dtype=np.int64), device=self.device).to(torch.int32)
+        maxp = seeds_d.numel()
+        idxs = self.empty(c, dtype=torch.uint8)
+        coef = self.empty(c)
+        scalars = self.empty(4)
+        plog = torch.zeros(maxp, 4, dtype=torch.float64, device=self.device)
+        self._call(self.lib.cp_lasso_select(self.h, self._p(Q, "const double*"), self._p(qv, "const double*"),
+                                            self._p(yn2, "const double*"), c, float(m), int(rank), float(lbound),
+                                            float(rbound), float(right0), float(tol), int(max_iter),
+                                            self._p(seeds_d, "const uint32_t*"), maxp, self._p(idxs, "uint8_t*"),
+                                            self._p(coef, "double*"), self._p(scalars, "double*"),
+                                            self._p(plog, "double*"), self._s()))
+        return LassoResult(idxs, coef, scalars, plog, seeds_d)
+
+    def ls_solve(self, g, sel_cols):
+        """Centred normal-equation LS on columns ``sel_cols`` (int32 device tensor, ascending).
+        Returns (W (n, Ksel) fp64, b (n,) fp64, info (1,) int32) on device."""
+        Ks = sel_cols.numel()
+        n = g["n"]
+        W = self.empty(n, Ks)
+        b = self.empty(n)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._call(self.lib.cp_ls_solve(self.h, self._p(g["G"], "const double*"), self._p(g["B"], "const double*"),
+                                        self._p(g["sx"], "const double*"), self._p(g["sy"], "const double*"),
+                                        g["N"], g["K"], n, self._p(sel_cols, "const int32_t*"), Ks,
+                                        self._p(W, "double*"), self._p(b, "double*"), self._p(info, "int32_t*"),
+                                        self._s()))
+        return W, b, info
+
+    def ls_solve_dual(self, X, Y, y_bias, sel_cols):
+        N, K = X.shape
+        n = Y.shape[1]
+        Ks = sel_cols.numel()
+        W = self.empty(n, Ks)
+        b = self.empty(n)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._call(self.lib.cp_ls_solve_dual(self.h, self._p(X, "const float*"), N, K, X.stride(0),
+                                             self._p(Y, "const void*"), 0 if Y.dtype == torch.float32 else 1, n,
+                                             Y.stride(0), self._p(y_bias, "const float*"),
+                                             self._p(sel_cols, "const int32_t*"), Ks, self._p(W, "double*"),
+                                             self._p(b, "double*"), self._p(info, "int32_t*"), self._s()))
+        return W, b, info
+
+    # ------------------------------------------------------------------ composite: one layer problem
+    def select_channels_async(self, X, W2m, Y, y_bias, samples, c, k2, rank, rank_tol, right0, seeds):
+        """Everything of decompose.dictionary up to (and including) the alpha search, enqueued
+        without host synchronisation.  Returns (g_full, LassoResult)."""
+        n = W2m.shape[0]
+        S = samples.numel()
+        g_full = self.gram(X, Y, y_bias=y_bias)
+        g_s = self.gram(X, Y, y_bias=y_bias, rows=samples, want_yy=True, mode=GRAM_FP64)
+        g_w = self.gram(W2m, None, want_B=False, mode=GRAM_FP64)
+        Q, qv, yn2 = self.lasso_build(g_s, g_w, W2m, c, k2, S)
+        lbound, rbound = window(rank, rank_tol)
+        res = self.lasso_select(Q, qv, yn2, float(S) * n, rank, lbound, rbound, right0, seeds)
+        return g_full, res
+
+    def reconstruct_async(self, g_full, X, Y, y_bias, idxs_host, k2):
+        """LS on the surviving channels (device outputs; no host sync)."""
+        sel = np.flatnonzero(idxs_host)
+        cols = (sel[:, None] * k2 + np.arange(k2)[None, :]).reshape(-1).astype(np.int32)
+        cols_d = torch.as_tensor(cols, device=self.device)
+        if g_full["N"] - 1 >= cols.size:
+            return self.ls_solve(g_full, cols_d)
+        return self.ls_solve_dual(X, Y, y_bias, cols_d)
+
+
+def window(rank, rank_tol):
+    """Acceptance window of the alpha search, reference lib/decompose.py:492-501."""
+    lbound = rank
+    if rank_tol >= 1:
+        rbound = rank + rank_tol
+    else:
+        rbound = rank + rank_tol * rank
+        if rank_tol == .2:
+            lbound = rank + 0.1 * rank
+            rbound = rank + 0.2 * rank
+    return lbound, rbound
+
+
+_ENGINE = None
+
+
+def get_engine(**kw) -> Engine:
+    """Process-wide engine on the current CUDA device."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(**kw)
+    return _ENGINE
+
+
+def reset_engine():
+    global _ENGINE
+    if _ENGINE is not None:
+        _ENGINE.close()
+    _ENGINE = None

@@ -1,0 +1,185 @@
+"""Layer-problem driver: one network's independent pruning problems on one or more B200s.
+
+Within a GPU, problems are pipelined over the engine's streams in two phases (the only host
+synchronisation points): phase 1 enqueues gather -> Gram statistics -> LASSO search for every
+problem; phase 2, once the kept-channel masks are known on the host, enqueues the
+least-squares reconstructions.  Across GPUs (one process per GPU, torch.distributed/NCCL) the
+problems are assigned by longest-processing-time-first on an analytic cost and the packed
+results are re-assembled on every rank with ONE all_gather (static upper-bound payload size, so
+no size exchange is needed).  There is no data-path collective: layer problems are independent
+ -- in the reference's *sequential* R3 mode (lib/net.py:1386,1698) they are
+coupled and this sharding does not apply (use lib.net.Net.R3 on one GPU).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import Engine, window
+
+
+# ---------------------------------------------------------------------------- assignment
+def assign_layers(costs, world_size):
+    """LPT: returns owner[i] for each problem; deterministic (ties by index)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world_size
+    owner = [0] * len(costs)
+    for i in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
+# ---------------------------------------------------------------------------- packing
+def slot_size(c, n, k2, rank, rank_tol):
+    """Upper bound (in float64 words) of one packed layer result."""
+    _, rbound = window(rank, rank_tol)
+    cmax = c if rank == c else min(c, int(np.floor(rbound)))
+    return 4 + c + n + n * cmax * k2
+
+
+def pack_result(buf, offset, idxs, W, b, alpha, nprobe, c, n, k2):
+    """buf: 1-D float64 tensor (any device).  Layout: [c', alpha, nprobe, 0, idxs(c), b(n), W(n*c'*k2)]."""
+    cp = int(idxs.sum())
+    head = torch.tensor([cp, alpha, nprobe, 0.0], dtype=torch.float64)
+    buf[offset:offset + 4] = head.to(buf.device)
+    buf[offset + 4:offset + 4 + c] = torch.as_tensor(idxs.astype(np.float64)).to(buf.device)
+    buf[offset + 4 + c:offset + 4 + c + n] = b.reshape(-1).to(buf.device, torch.float64)
+    buf[offset + 4 + c + n:offset + 4 + c + n + n * cp * k2] = W.reshape(-1).to(buf.device, torch.float64)
+
+
+def unpack_result(buf, offset, c, n, k2):
+    head = buf[offset:offset + 4].cpu().numpy()
+    cp = int(head[0])
+    idxs = buf[offset + 4:offset + 4 + c].cpu().numpy() != 0
+    b = buf[offset + 4 + c:offset + 4 + c + n].cpu().numpy()
+    k = int(round(np.sqrt(k2)))
+    W = buf[offset + 4 + c + n:offset + 4 + c + n + n * cp * k2].cpu().numpy().reshape(n, cp, k, k)
+    return dict(idxs=idxs, W=W, b=b, alpha=float(head[1]), nprobe=int(head[2]))
+
+
+def allgather_results(local_buf, world_size, group=None):
+    """ONE collective: every rank contributes a buffer of identical (upper-bound) length."""
+    import torch.distributed as dist
+
+    out = torch.empty(world_size * local_buf.numel(), dtype=local_buf.dtype, device=local_buf.device)
+    dist.all_gather_into_tensor(out, local_buf, group=group)
+    return out.view(world_size, -1)
+
+
+# ---------------------------------------------------------------------------- single-GPU pipeline
+class LayerResult:
+    __slots__ = ("idxs", "W", "b", "alpha", "nprobe", "probes", "info")
+
+
+def prune_layers(eng: Engine, shapes, datas, right0=1e-3, rank_tol=.1, from_host=False, to_host=False):
+    """Runs the layer problems ``shapes[i]`` / ``datas[i]`` (see synth.make_problem_device) on
+    ``eng``.  from_host: feature maps are taken from pinned host memory (datas[i]['fmap_host'])
+    and copied in the pipeline; to_host: results are copied back to pinned host memory.
+    Returns a list of LayerResult (W, b as device fp64 tensors unless to_host)."""
+    nslots = len(eng.streams)
+    main = torch.cuda.current_stream(eng.device)
+    phase1 = []
+    for i, (s, d) in enumerate(zip(shapes, datas)):
+        stream = eng.use_slot(i)
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctx:
+            if stream is not None:
+                stream.wait_stream(main)
+            if from_host:
+                fmap = torch.empty(d["fmap_host"].shape, dtype=torch.float32, device=eng.device)
+                fmap.copy_(d["fmap_host"], non_blocking=True)
+            else:
+                fmap = d["fmap"]
+            X = eng.patch_gather(fmap, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+            W2m = d["W2"].reshape(s.n, s.K)
+            if s.rank == s.c:
+                g_full = eng.gram(X, d["feats"], y_bias=d["b2"])
+                res = None
+                host = None
+            else:
+                g_full, res = eng.select_channels_async(X, W2m, d["feats"], d["b2"], d["samples"], s.c, s.k * s.k,
+                                                        s.rank, rank_tol, right0, d["seeds"])
+                host = (torch.empty(4, dtype=torch.float64, pin_memory=True),
+                        torch.empty(s.c, dtype=torch.uint8, pin_memory=True))
+                host[0].copy_(res.scalars, non_blocking=True)
+                host[1].copy_(res.idxs, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        phase1.append((X, g_full, res, host, ev))
+    out = []
+    for i, (s, d) in enumerate(zip(shapes, datas)):
+        X, g_full, res, host, ev = phase1[i]
+        stream = eng.use_slot(i)
+        r = LayerResult()
+        if res is None:
+            r.idxs = np.ones(s.c, dtype=bool)
+            r.alpha, r.nprobe = 1e-4, 0  # lib/decompose.py:386 argument default survives (:627)
+        else:
+            ev.synchronize()
+            scal = host[0].numpy()
+            if int(scal[2]) != 0:
+                raise RuntimeError("layer %s: alpha search hit the probe cap" % s.name)
+            r.idxs = host[1].numpy().astype(bool)
+            r.alpha, r.nprobe = float(scal[0]), int(scal[1])
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctx:
+            W, b, info = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], r.idxs, s.k * s.k)
+            if to_host:
+                Wh = torch.empty(W.shape, dtype=torch.float64, pin_memory=True)
+                bh = torch.empty(b.shape, dtype=torch.float64, pin_memory=True)
+                Wh.copy_(W, non_blocking=True)
+                bh.copy_(b, non_blocking=True)
+                r.W, r.b = Wh, bh
+            else:
+                r.W, r.b = W, b
+            r.info = info
+        r.probes = res
+        out.append(r)
+    for st in eng.streams:
+        if st is not None:
+            main.wait_stream(st)
+    return out
+
+
+class _null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+# ---------------------------------------------------------------------------- multi-GPU
+def prune_network_sharded(eng: Engine, shapes, make_data, rank, world_size, right0=1e-3, rank_tol=.1, group=None):
+    """Each rank solves its LPT share and all ranks end with every layer's result.
+    make_data(i) -> data dict for problem i (only called for owned problems)."""
+    owner = assign_layers([s.cost() for s in shapes], world_size)
+    mine = [i for i, o in enumerate(owner) if o == rank]
+    datas = [make_data(i) for i in mine]
+    res = prune_layers(eng, [shapes[i] for i in mine], datas, right0=right0, rank_tol=rank_tol)
+    sizes = [slot_size(s.c, s.n, s.k * s.k, s.rank, rank_tol) for s in shapes]
+    # static layout: rank r's buffer holds its problems in index order; pad to the largest rank buffer
+    per_rank = [sum(sizes[i] for i in range(len(shapes)) if owner[i] == r) for r in range(world_size)]
+    buf = torch.zeros(max(per_rank), dtype=torch.float64, device=eng.device)
+    off = 0
+    for j, i in enumerate(mine):
+        s = shapes[i]
+        pack_result(buf, off, res[j].idxs, res[j].W, res[j].b, res[j].alpha, res[j].nprobe, s.c, s.n, s.k * s.k)
+        off += sizes[i]
+    if world_size > 1:
+        allbuf = allgather_results(buf, world_size, group)
+    else:
+        allbuf = buf.view(1, -1)
+    return owner, sizes, allbuf
+
+
+def unpack_network(shapes, owner, sizes, allbuf):
+    offs = [0] * allbuf.shape[0]
+    out = [None] * len(shapes)
+    for i, s in enumerate(shapes):
+        r = owner[i]
+        out[i] = unpack_result(allbuf[r], offs[r], s.c, s.n, s.k * s.k)
+        offs[r] += sizes[i]
+    return out

@@ -1,0 +1,172 @@
+/*
+ * cpb200 -- C ABI of the B200-native channel-pruning solver (libcpb200.so).
+ *
+ * The reference (ethanhe42/channel-pruning) has no FFI of its own for this path:
+ * the hot path is Python calling numpy / scikit-learn / scipy.  Each
+ * entry point below replaces one piece of that Python/third-party arithmetic; the
+ * reference location it stands in for is cited per function.  The host side that
+ * mirrors the reference's Python interface (lib/decompose.py, lib/net.py) lives in
+ * channel-pruning_b200/lib/ and binds these symbols with cffi (ABI mode).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *   - every call is asynchronous and stream-ordered on `stream`; nothing
+ *     synchronises unless stated.  Outputs live in caller-owned device memory.
+ *   - the handle owns only scratch workspace (grown on demand) and is bound to one
+ *     device; one handle per process/GPU; a handle must not be used from two
+ *     streams concurrently (use one handle per stream).
+ *   - return value: CP_OK (0), <0 invalid argument, >0 CUDA / numerical failure;
+ *     cp_last_error() returns a thread-local message for the last failure.
+ *   - column order of a patch matrix X (N x K, K = c*k*k) is the reference's
+ *     (c, kh, kw): column = a*k*k + p  (lib/net.py:1702 rollaxis -> (N,c,k,k)).
+ *   - row order of gathered matrices is the reference's (batch, point, image):
+ *     row = (batch*P + point)*B + image  (lib/net.py:509-513, 640).
+ */
+#ifndef CPB200_H
+#define CPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cp_handle_s *cp_handle_t;
+typedef void *cp_stream_t; /* cudaStream_t */
+
+enum {
+    CP_OK = 0,
+    CP_ERR_INVALID = -1,
+    CP_ERR_CUDA = 1,
+    CP_ERR_NOT_SPD = 2,
+    CP_ERR_WORKSPACE = 3
+};
+
+/* feature-map layouts accepted by the gather kernels */
+enum { CP_LAYOUT_NCHW = 0, CP_LAYOUT_NHWC = 1 };
+
+/* element type of the Y operand (feature maps are fp32; a caller of the Python-level
+ * decompose.dictionary may hand over float64 targets, which are then used exactly) */
+enum { CP_F32 = 0, CP_F64 = 1 };
+
+/* arithmetic of cp_gram */
+enum {
+    CP_GRAM_FP64 = 0,  /* fp32 inputs widened to fp64, DFMA accumulate (exact products) */
+    CP_GRAM_3XTF32 = 1 /* tcgen05 kind::tf32, hi/lo split, fp32 TMEM accumulate per row chunk,
+                          fp64 reduction over chunks */
+};
+
+int cp_version(void);
+const char *cp_last_error(void);
+
+int cp_create(cp_handle_t *out, int device);
+int cp_destroy(cp_handle_t h);
+/* bytes of scratch currently owned by the handle (diagnostics) */
+int64_t cp_workspace_bytes(cp_handle_t h);
+
+/*
+ * Sparse-point im2col -- replaces Net.extract_XY (lib/net.py:534-684, w1=None
+ * branch) plus the relu of Net.dictionary_kernel (lib/net.py:1720) when relu != 0.
+ *
+ *   fmap   : nbatch*B images, layout NCHW (B,c,H,W) or NHWC (B,H,W,c), fp32.
+ *   randx  : nbatch*P sampled output rows   (points_dict[(batch, Y, "randx")])
+ *   randy  : nbatch*P sampled output cols
+ *   window : rows [stride*x - pad, +k), cols [stride*y - pad, +k) of the bottom
+ *            blob, zero outside (net.py:564-589, 631-632).
+ *   X_out  : (nbatch*P*B) x (c*k*k) fp32, leading dimension ldx (elements),
+ *            column = a*k*k + py*k + px.
+ */
+int cp_patch_gather(cp_handle_t h, const float *fmap, int nbatch, int B, int c, int H, int W, int layout,
+                    const int32_t *randx, const int32_t *randy, int P, int k, int pad, int stride, int relu,
+                    float *X_out, int64_t ldx, cp_stream_t stream);
+
+/*
+ * Point gather -- replaces the gather of Net.extract_features (lib/net.py:509-519):
+ *   Y_out[(batch*P+point)*B + image, j] = fmap[batch*B+image, j, randx, randy].
+ * fp32 out (the reference widens to fp64; the bias of lib/net.py:1707 is applied
+ * exactly, in fp64, inside cp_gram via y_bias).
+ */
+int cp_point_gather(cp_handle_t h, const float *fmap, int nbatch, int B, int n, int H, int W, int layout,
+                    const int32_t *randx, const int32_t *randy, int P, float *Y_out, int64_t ldy,
+                    cp_stream_t stream);
+
+/*
+ * Tall-skinny Gram / cross products -- replaces the O(N K^2) arithmetic inside
+ * LinearRegression.fit (lib/decompose.py:665-666) and the Z / Lasso.fit data passes
+ * (lib/decompose.py:428-434,457) by sufficient statistics:
+ *
+ *   G   = X' X  (K x K, full symmetric, row-major fp64)          [may be NULL]
+ *   Bxy = X' Y  (K x n, row-major fp64), Y = fp64(Yraw) - y_bias [may be NULL]
+ *   sx  = 1' X  (K),  sy = 1' Y (n),  yy = sum(Y**2) (1 double)  [each may be NULL]
+ *
+ *   X : N x K fp32, leading dimension ldx.   Yraw : N x n (y_dtype CP_F32 | CP_F64), leading dimension ldy.
+ *   y_bias : n fp32 or NULL.
+ *   rows : nrows int32 row indices (repetitions allowed -- the reference samples
+ *          with replacement, lib/decompose.py:425) or NULL for all N rows.
+ */
+int cp_gram(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
+            int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy,
+            double *sx, double *sy, double *yy, int mode, cp_stream_t stream);
+
+/*
+ * LASSO sufficient statistics in channel space -- replaces the construction of
+ * Z (lib/decompose.py:428-434) and sklearn's centring of (Z, reY):
+ *   Q[a,b] = sum_{p,q} Gs[(a,p),(b,q)] * WW[(a,p),(b,q)] - m zbar_a zbar_b
+ *   qv[a]  = sum_{p,j} W2[j,(a,p)] * Bs[(a,p),j]          - m zbar_a ybar
+ *   yn2    = yy_s - m ybar^2,       m = S*n
+ * Gs/Bs/sxs/sys/yys : cp_gram over the S sampled rows;  WW/sw : cp_gram of W2
+ * viewed as an (n x c*k2) matrix.  Outputs: Q (c x c), qv (c), yn2 (1), fp64.
+ */
+int cp_lasso_build(cp_handle_t h, const double *Gs, const double *Bs, const double *sxs, const double *sys,
+                   const double *yys, const double *WW, const double *sw, const float *W2, int c, int k2,
+                   int n, int S, double *Q, double *qv, double *yn2, cp_stream_t stream);
+
+/*
+ * Channel selection -- replaces the alpha search of decompose.dictionary
+ * (lib/decompose.py:489-525) including every Lasso.fit it performs
+ * (sklearn _cd_fast.enet_coordinate_descent: random coordinate order from a 32-bit
+ * xorshift seeded per fit, warm start, tol / duality-gap stopping rule, gap-safe
+ * screening), evaluated in Gram arithmetic, fp64, in ONE launch.
+ *
+ *   right0        : cfgs.alpha on entry (lib/decompose.py:491)
+ *   rank, lbound, rbound : target count and acceptance window (:492-501)
+ *   seeds         : max_probes uint32, the values rng.randint(0, 2**31-1) would
+ *                   return for successive fits (host draws them)
+ *   out_idxs      : c bytes (coef != 0)          out_coef : c doubles
+ *   out_scalars   : [alpha, n_probes, status, nnz]  (status 0 ok, 1 probe cap hit)
+ *   out_probe_log : max_probes x 4 doubles (alpha, nnz, n_iter, gap)
+ */
+int cp_lasso_select(cp_handle_t h, const double *Q, const double *qv, const double *yn2, int c, double m,
+                    int rank, double lbound, double rbound, double right0, double tol, int max_iter,
+                    const uint32_t *seeds, int max_probes, uint8_t *out_idxs, double *out_coef,
+                    double *out_scalars, double *out_probe_log, cp_stream_t stream);
+
+/*
+ * Least-squares reconstruction on the surviving channels -- replaces fc_kernel /
+ * LinearRegression(fit_intercept=True).fit (lib/decompose.py:622-623, 665-669) by
+ * the centred normal equations on the principal sub-block of G:
+ *   Gc = G[sel,sel] - sx sx'/N,  Bc = Bxy[sel,:] - sx sy'/N,  Gc W = Bc  (Cholesky)
+ *   b  = (sy - sx' W)/N
+ * sel_cols : Ksel int32 column indices (device), ascending.
+ * W_out : n x Ksel fp64 row-major (== coef_, i.e. newW2.reshape(n, c', k, k));
+ * b_out : n fp64.  info_out : 1 int32 (0 ok, j>0: pivot j not positive).
+ * Requires N - 1 >= Ksel (otherwise use cp_ls_solve_dual).
+ */
+int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
+                int64_t N, int K, int n, const int32_t *sel_cols, int Ksel, double *W_out, double *b_out,
+                int32_t *info_out, cp_stream_t stream);
+
+/*
+ * Minimum-norm least squares for N - 1 < Ksel (what gelsd returns for the
+ * rank-deficient case, lib/decompose.py:665-666 at small N): dual normal
+ * equations  (Xc Xc' + (1/N) 1 1') A = Yc,  W = Xc' A.
+ * X : N x K fp32 (ldx);  Yraw/y_bias as in cp_gram.
+ */
+int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                     int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, double *W_out,
+                     double *b_out, int32_t *info_out, cp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPB200_H */

@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE: generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/lib/decompose.py and lib/net.py, imported through oracle/ref_shims.py) on
+small seeded inputs.  Runs only in the build container (the reference is Python and cannot
+travel to the GPU box); the fixtures it writes are committed.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+What is pinned
+  dictionary_*.npz   outputs of reference ``dictionary`` (mask, weights, bias, final cfgs.alpha)
+                     for inputs regenerated from a seed by tests/cases.py
+  net_*.npz          outputs of reference ``Net.extract_features`` / ``Net.extract_XY`` /
+                     ``Net.dictionary_kernel`` driven through a duck-typed Net (no Caffe): a tiny
+                     two-conv network whose forward pass is computed with numpy.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ref_shims  # noqa: E402
+import cases  # noqa: E402  (tests/cases.py)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def run_dictionary_cases(D, CF):
+    for name, spec in cases.DICTIONARY_CASES.items():
+        X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+        CF.alpha = spec["alpha0"]
+        CF.c.dic.rank_tol = spec.get("rank_tol", .1)
+        np.random.seed(spec["np_seed"])
+        idxs, W, B = D.dictionary(X.astype(np.float64), W2, Y, rank=spec["rank"], B2=np.zeros(W2.shape[0]))
+        after = np.random.randint(0, 1 << 30)  # pins how many global draws the reference consumed
+        np.savez_compressed(os.path.join(OUT, "dictionary_%s.npz" % name), idxs=idxs, W=W, B=B,
+                            alpha_final=CF.alpha, rng_after=after,
+                            checksum=np.array([X.sum(dtype=np.float64), W2.sum(dtype=np.float64), Y.sum()]))
+        print(name, "kept", int(idxs.sum()), "of", len(idxs), "alpha", CF.alpha)
+    CF.c.dic.rank_tol = .1
+
+
+def conv2d_numpy(x, w, b, pad, stride):
+    """fp32 direct convolution (what Caffe's forward would give up to rounding)."""
+    B, c, H, W = x.shape
+    n, _, k, _ = w.shape
+    xp = np.zeros((B, c, H + 2 * pad, W + 2 * pad), dtype=np.float32)
+    xp[:, :, pad:H + pad, pad:W + pad] = x
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = np.zeros((B, n, Ho, Wo), dtype=np.float32)
+    for i in range(Ho):
+        for j in range(Wo):
+            patch = xp[:, :, i * stride:i * stride + k, j * stride:j * stride + k].reshape(B, -1)
+            out[:, :, i, j] = patch @ w.reshape(n, -1).T + b
+    return out
+
+
+def make_fake_net(NET, CF, images, specs, weights, biases):
+    """A reference ``Net`` whose Caffe accessors are replaced by numpy state."""
+
+    class _Inner:  # stands in for pycaffe's net object
+        def __init__(self, outer):
+            self.outer = outer
+
+        def set_input_arrays(self, data, label):
+            self.outer._cur = (data, label)
+
+    class FakeNet(NET.Net):
+        def __init__(self):
+            self._mem = True
+            self.net = _Inner(self)
+            self._batch_iter = 0
+            self._cur = None
+            self._blobs = {}
+            self.convs = [s["name"] for s in specs]
+            self.innerproduct, self.sums, self.bns = [], [], []
+            self._bottom_names = {s["name"]: [s["bottom"]] for s in specs}  # backs the bottom_names property
+            self.num = images[0].shape[0]
+            self.acc = []
+            self.forward()  # dry pass: Caffe knows blob shapes statically
+            self._shapes = {k: v.shape for k, v in self._blobs.items()}
+            self._batch_iter = 0
+
+        def forward(self):
+            if self._cur is None:  # first (non-frozen) pass draws the next batch itself
+                data = images[self._batch_iter % len(images)]
+                label = np.zeros((data.shape[0], 1, 1, 1), dtype=np.float32)
+                self._batch_iter += 1
+            else:
+                data, label = self._cur
+            self._data, self._label = data, label
+            blobs = {"data": data}
+            for s in specs:
+                y = conv2d_numpy(blobs[s["bottom"]], weights[s["name"]], biases[s["name"]], s["pad"], s["stride"])
+                blobs[s["name"]] = y
+                blobs[s["name"] + "_relu"] = np.maximum(y, 0)
+            self._blobs = blobs
+            self._cur = None
+            return {}
+
+        def data(self):
+            return self._data
+
+        def label(self):
+            return self._label
+
+        def clr_acc(self):
+            pass
+
+        def blobs_data(self, name): return self._blobs[name]
+        def blobs_shape(self, name): return self._shape(name)
+        def blobs_num(self, name): return self._shape(name)[0]
+        def blobs_channels(self, name): return self._shape(name)[1]
+        def blobs_height(self, name): return self._shape(name)[2]
+        def blobs_width(self, name): return self._shape(name)[3]
+        def blobs_type(self, name): return np.float32
+
+        def _shape(self, name):
+            return self._shapes[name]
+
+        def _sp(self, name): return [s for s in specs if s["name"] == name][0]
+        def conv_param_pad(self, name): return self._sp(name)["pad"]
+        def conv_param_kernel_size(self, name): return self._sp(name)["k"]
+        def conv_param_stride(self, name): return self._sp(name)["stride"]
+        def param_shape(self, name): return weights[name].shape
+        def param_data(self, name): return weights[name]
+        def param_b_data(self, name): return biases[name]
+        def appresb(self, name): return 0  # dcfgs.res.short == 0 (net.py:1648)
+
+    return FakeNet()
+
+
+def run_net_cases(NET, CF, D):
+    for name, spec in cases.NET_CASES.items():
+        images, specs, weights, biases = cases.net_inputs(**spec["gen"])
+        CF.c.nBatches = spec["nBatches"]
+        CF.c.nPointsPerLayer = spec["P"]
+        CF.c.dic.option = 0
+        CF.c.dic.fitfc = 0
+        CF.c.model = ''
+        CF.alpha = 1e-3
+        net = make_fake_net(NET, CF, images, specs, weights, biases)
+        np.random.seed(spec["np_seed"])
+        names = [s["name"] for s in specs]
+        feats_dict, points_dict = net.extract_features(names, save=1)
+        net.load_frozen(feats_dict=feats_dict, points_dict=points_dict)
+        x_name, y_name = spec["xy"]
+        XY = net.extract_XY(x_name, y_name)
+        out = dict(XY=XY)
+        for nm in names:
+            out["feats_" + nm] = feats_dict[nm]
+            for b in range(spec["nBatches"]):
+                out["randx_%s_%d" % (nm, b)] = points_dict[(b, nm, "randx")]
+                out["randy_%s_%d" % (nm, b)] = points_dict[(b, nm, "randy")]
+        if spec.get("dictionary_kernel"):
+            c_out = weights[x_name].shape[0]
+            d_prime = int(c_out / 1.15)
+            np.random.seed(spec["np_seed"] + 1)
+            idxs, W2n, B2n = net.dictionary_kernel(x_name, None, d_prime, y_name, None)
+            out.update(dk_idxs=idxs, dk_W=W2n, dk_B=B2n, dk_alpha=CF.alpha, dk_dprime=d_prime)
+            print(name, "dictionary_kernel kept", int(idxs.sum()), "of", len(idxs))
+        np.savez_compressed(os.path.join(OUT, "net_%s.npz" % name), **out)
+        print(name, "XY", XY.shape, {k: v.shape for k, v in feats_dict.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    D, NET, CF = ref_shims.load_reference()
+    assert NET is not None, ref_shims._loaded.get("net_error")
+    run_dictionary_cases(D, CF)
+    run_net_cases(NET, CF, D)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+"""CPU: the oracle (oracle/cp_oracle.py + cd_oracle.c) against (a) golden vectors produced by the
+reference's own code (oracle/make_golden.py) and (b) scikit-learn itself."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import cp_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", list(cases.DICTIONARY_CASES))
+@pytest.mark.parametrize("form", ["dense", "gram"])
+def test_dictionary_matches_reference_golden(golden_dir, name, form):
+    spec = cases.DICTIONARY_CASES[name]
+    g = _load(golden_dir, "dictionary_%s.npz" % name)
+    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    np.testing.assert_array_equal(g["checksum"], [X.sum(dtype=np.float64), W2.sum(dtype=np.float64), Y.sum()])
+    st = O.DictState(alpha=spec["alpha0"], rank_tol=spec.get("rank_tol", .1))
+    np.random.seed(spec["np_seed"])
+    idxs, W, B = O.dictionary(X.astype(np.float64), W2, Y, rank=spec["rank"], B2=np.zeros(W2.shape[0]), state=st,
+                              form=form)
+    after = np.random.randint(0, 1 << 30)
+    assert np.array_equal(idxs, g["idxs"])  # selected-channel set: exact
+    assert after == int(g["rng_after"])  # same number of global RNG draws as the reference
+    assert st.alpha == float(g["alpha_final"])
+    assert W.shape == g["W"].shape
+    # same LAPACK driver as the reference -> identical up to threading order
+    assert np.linalg.norm(W - g["W"]) <= 1e-9 * np.linalg.norm(g["W"])
+    assert np.abs(B - g["B"]).max() <= 1e-9 * max(1.0, np.abs(g["B"]).max())
+
+
+def test_lasso_cd_matches_sklearn():
+    from sklearn.linear_model import Lasso
+
+    X, W2, Y = cases.dictionary_inputs(c=48, n=24, N=800, k=3, seed=3)
+    N, c = X.shape[0], X.shape[1]
+    samples = np.random.RandomState(0).randint(0, N, 40)
+    reX = np.rollaxis(X.reshape((N, c, -1))[samples], 1, 0).astype(np.float64)
+    reW2 = np.transpose(W2.reshape((24, c, -1)), [1, 2, 0])
+    Z = np.matmul(reX, reW2).reshape((c, -1)).T
+    y = Y[samples].reshape(-1)
+    sk = Lasso(alpha=1e-3, warm_start=True, selection='random')
+    for form in ("dense", "gram"):
+        mine = O.LassoCD(alpha=1e-3, form=form)
+        sk = Lasso(alpha=1e-3, warm_start=True, selection='random')
+        for a in (1e-3, 4e-3, 1.6e-2, 8e-3):
+            np.random.seed(17)
+            sk.alpha = a
+            sk.fit(Z, y)
+            np.random.seed(17)
+            mine.alpha = a
+            mine.fit(Z, y)
+            assert mine.n_iter_ == sk.n_iter_
+            assert np.array_equal(mine.coef_ != 0, sk.coef_ != 0)
+            np.testing.assert_allclose(mine.coef_, sk.coef_, rtol=0, atol=1e-11 * np.abs(sk.coef_).max())
+            assert abs(mine.intercept_ - sk.intercept_) < 1e-10
+
+
+def test_rand_r_sequence():
+    import ctypes
+
+    lib = O._clib()
+    s = ctypes.c_uint32(12345)
+    got = [lib.cp_our_rand_r(ctypes.byref(s)) for _ in range(5)]
+
+    def ref(seed):
+        out = []
+        for _ in range(5):
+            seed ^= (seed << 13) & 0xFFFFFFFF
+            seed ^= seed >> 17
+            seed ^= (seed << 5) & 0xFFFFFFFF
+            out.append(seed % (2147483647 + 1))
+        return out
+
+    assert got == ref(12345)
+
+
+def test_linear_regression_matches_sklearn():
+    from sklearn.linear_model import LinearRegression
+
+    r = np.random.RandomState(2)
+    for (N, K, n) in [(300, 40, 7), (50, 90, 5)]:  # over- and under-determined
+        X = r.standard_normal((N, K))
+        Y = r.standard_normal((N, n))
+        reg = LinearRegression().fit(X, Y)
+        coef, b = O.fc_kernel(X, Y)
+        np.testing.assert_allclose(coef, reg.coef_, atol=1e-10)
+        np.testing.assert_allclose(b, reg.intercept_, atol=1e-10)
+
+
+def _forward_from(images, specs, weights, biases):
+    from make_golden import conv2d_numpy
+
+    cache = {}
+
+    def forward(batch):
+        if batch not in cache:
+            blobs = {"data": images[batch % len(images)]}
+            for s in specs:
+                y = conv2d_numpy(blobs[s["bottom"]], weights[s["name"]], biases[s["name"]], s["pad"], s["stride"])
+                blobs[s["name"]] = y
+                blobs[s["name"] + "_relu"] = np.maximum(y, 0)
+            cache[batch] = blobs
+        return cache[batch]
+
+    return forward
+
+
+@pytest.mark.parametrize("name", list(cases.NET_CASES))
+def test_gathers_match_reference_golden(golden_dir, name):
+    spec = cases.NET_CASES[name]
+    g = _load(golden_dir, "net_%s.npz" % name)
+    images, specs, weights, biases = cases.net_inputs(**spec["gen"])
+    forward = _forward_from(images, specs, weights, biases)
+    names = [s["name"] for s in specs]
+    np.random.seed(spec["np_seed"])
+    feats, points = O.extract_features(forward, names, spec["nBatches"], spec["P"])
+    for nm in names:
+        assert feats[nm].dtype == np.float64
+        np.testing.assert_array_equal(feats[nm], g["feats_" + nm])  # bit exact
+        for b in range(spec["nBatches"]):
+            np.testing.assert_array_equal(points[(b, nm, "randx")], g["randx_%s_%d" % (nm, b)])
+            np.testing.assert_array_equal(points[(b, nm, "randy")], g["randy_%s_%d" % (nm, b)])
+    s2 = specs[1]
+    yspec = O.ConvSpec(s2["name"], s2["bottom"], s2["k"], s2["pad"], s2["stride"])
+    XY = O.extract_XY(forward, spec["xy"][0], yspec, points)
+    np.testing.assert_array_equal(XY, g["XY"])  # bit exact
+    if spec.get("dictionary_kernel"):
+        st = O.DictState(alpha=1e-3)
+        np.random.seed(spec["np_seed"] + 1)
+        idxs, W, B = O.dictionary_kernel(forward, spec["xy"][0], yspec, weights["conv2"], biases["conv2"],
+                                         feats["conv2"], points, int(g["dk_dprime"]), state=st)
+        assert np.array_equal(idxs, g["dk_idxs"])
+        assert st.alpha == float(g["dk_alpha"])
+        assert np.linalg.norm(W - g["dk_W"]) <= 1e-9 * np.linalg.norm(g["dk_W"])
+        assert np.abs(B - g["dk_B"]).max() <= 1e-9
+
+
+def test_patch_invariant():
+    """The reference's own debug check (lib/net.py:659-679): relu(patch) . W2 + b2 == conv output."""
+    spec = cases.NET_CASES["k3s2"]
+    images, specs, weights, biases = cases.net_inputs(**spec["gen"])
+    forward = _forward_from(images, specs, weights, biases)
+    np.random.seed(1)
+    feats, points = O.extract_features(forward, ["conv2"], spec["nBatches"], spec["P"])
+    s2 = specs[1]
+    XY = O.extract_XY(forward, "conv1", O.ConvSpec("conv2", "conv1_relu", s2["k"], s2["pad"], s2["stride"]), points)
+    k = s2["k"]
+    X = np.rollaxis(XY.reshape((-1, k, k, XY.shape[1])), 3, 1)
+    fake = O.relu(X).reshape(X.shape[0], -1) @ weights["conv2"].reshape(weights["conv2"].shape[0], -1).T + biases["conv2"]
+    assert np.abs(fake - feats["conv2"]).max() < 1e-4  # CHECK_EQ tolerance, lib/utils.py:75-82
