@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: conv layers pruned per second on synthetic VGG-16 conv stacks
+(BASELINE.json configs[1]: 13 layers, N=5000 sampled 3x3 patches per layer, random-init weights).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference, same metric
+
+One "step" = the whole hot path (sparse-point im2col -> Gram statistics -> LASSO channel
+selection -> least-squares reconstruction) over one pool of layer problems.  At N GPUs the pool
+holds N networks (13*N independent layer problems, weak scaling), assigned to ranks by LPT, and
+every step ends with the single all_gather that re-assembles the pruned weight dict on all ranks.
+
+value : layers/s with the feature maps already resident in HBM (device timed, max over ranks)
+e2e   : the same metric with feature maps in pinned HOST memory (H2D inside the timed region) and
+        the results copied back to the host
+Inputs per step (~18 GB of feature maps per network) are far larger than the 126 MB L2, so no L2
+flush is needed between timed iterations of the step; the stand-alone kernel timing for the
+roofline flushes L2 explicitly.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "conv_layers_pruned_per_sec"
+UNIT = "layers/s"
+WORKLOAD = "vgg16_conv_stack_13_layers_N5000"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cpb200", choices=["cpb200", "reference"])
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layers", default="", help="comma list of VGG layer names (debug); default all 13")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle)
+def shape_classes(shapes):
+    """One representative per distinct (c, n, k) -- CPU cost does not depend on the map size."""
+    classes = {}
+    for s in shapes:
+        classes.setdefault((s.c, s.n, s.k), []).append(s)
+    return classes
+
+
+def cpu_layer_seconds(shape, seed):
+    """Times the oracle (restated reference: numpy patch gather + sklearn-faithful LASSO search +
+    gelsd least squares, float64) on one layer problem.  Returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import cp_oracle as O
+    import cpb200
+
+    d = cpb200.synth.make_problem_numpy(shape, seed)
+    pd = {"nPointsPerLayer": shape.P, "nBatches": shape.nbatch}
+    for b in range(shape.nbatch):
+        pd[(b, "y", "randx")] = d["randx"][b]
+        pd[(b, "y", "randy")] = d["randy"][b]
+    fm = d["fmap"]
+    forward = lambda b: {"x": fm[b * shape.B:(b + 1) * shape.B]}  # noqa: E731
+    spec = O.ConvSpec("y", "x", shape.k, shape.pad, shape.stride)
+    feats = d["feats"].astype(np.float64)
+    st = O.DictState(alpha=1e-3)
+    t0 = time.perf_counter()
+    O.dictionary_kernel(forward, "x", spec, d["W2"], d["b2"], feats, pd, shape.rank, state=st, samples=d["samples"])
+    return time.perf_counter() - t0
+
+
+def cpu_pass(shapes):
+    """One CPU 'step' = one problem per shape class, extrapolated to the 13-layer stack by class
+    multiplicity.  Returns (layers_per_sec, seconds_measured, description)."""
+    import cpb200
+
+    classes = shape_classes(shapes)
+    total, measured = 0.0, 0.0
+    for i, (key, members) in enumerate(sorted(classes.items())):
+        # use the smallest map of the class: identical solver work, less host memory for the maps
+        rep = min(members, key=lambda s: s.H)
+        small = cpb200.synth.LayerShape(rep.name, rep.c, rep.n, min(rep.H, 28), k=rep.k, pad=rep.pad, stride=rep.stride,
+                                        N=rep.N, B=rep.B, P=rep.P)
+        t = cpu_layer_seconds(small, 900 + i)
+        measured += t
+        total += t * len(members)
+    desc = "one layer problem per distinct (c,n,k) class (%d classes, feature maps capped at 28x28), " \
+           "times class multiplicity = full %d-layer stack" % (len(classes), len(shapes))
+    return len(shapes) / total, measured, desc
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cpb200
+
+    shapes = select_shapes(cpb200.synth.vgg16_layers(), args.layers)
+    for _ in range(args.warmup):
+        cpu_pass(shapes)
+    vals, secs = [], []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        v, m, desc = cpu_pass(shapes)
+        secs.append(time.perf_counter() - t0)
+        vals.append(v)
+    v = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * len(shapes) / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU restatement of lib/net.py + lib/decompose.py (oracle port); "
+                   "the Python reference itself cannot travel to the GPU box"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ helpers
+def select_shapes(shapes, layers):
+    if not layers:
+        return shapes
+    want = set(layers.split(","))
+    return [s for s in shapes if s.name in want]
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cpb200
+    from cpb200 import pruner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = cpb200.Engine(device=local, nstreams=args.streams)
+    lib = cpb200._cabi.load()[1]
+    dev = eng.device
+
+    base = select_shapes(cpb200.synth.vgg16_layers(), args.layers)
+    shapes = [s for _ in range(world) for s in base]  # one network per GPU in the pool (weak scaling)
+    owner = pruner.assign_layers([s.cost() for s in shapes], world)
+    mine = [i for i, o in enumerate(owner) if o == rank]
+    my_shapes = [shapes[i] for i in mine]
+    want_e2e = not args.no_e2e
+    datas = [cpb200.synth.make_problem_device(shapes[i], 1000 + i, eng, pinned_host=want_e2e) for i in mine]
+    sizes = [pruner.slot_size(s.c, s.n, s.k * s.k, s.rank, .1) for s in shapes]
+    per_rank = [sum(sizes[i] for i in range(len(shapes)) if owner[i] == r) for r in range(world)]
+    gbuf = torch.zeros(max(per_rank), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step(from_host):
+        res = pruner.prune_layers(eng, my_shapes, datas, right0=1e-3, rank_tol=.1, from_host=from_host,
+                                  to_host=from_host)
+        if world > 1:
+            off = 0
+            for j, i in enumerate(mine):
+                s = shapes[i]
+                pruner.pack_result(gbuf, off, res[j].idxs, res[j].W.to(dev, non_blocking=True) if from_host else res[j].W,
+                                   res[j].b.to(dev, non_blocking=True) if from_host else res[j].b, res[j].alpha,
+                                   res[j].nprobe, s.c, s.n, s.k * s.k)
+                off += sizes[i]
+            pruner.allgather_results(gbuf, world)
+        return res
+
+    def timed(nsteps, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.cp_launch_count()
+        e0.record()
+        res = None
+        for _ in range(nsteps):
+            res = step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = lib.cp_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, launches, res
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, res = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+    total_layers = len(shapes) * args.steps
+    value = total_layers / (ms / 1e3)
+
+    e2e = None
+    if want_e2e:
+        for _ in range(min(args.warmup, 3)):
+            step(True)
+        ms_e, _, res_e = timed(args.steps, True)
+        h2d = sum(int(d["fmap_host"].numel()) * 4 for d in datas)
+        d2h = sum(int(r.W.numel() + r.b.numel()) * 8 + s.c + 32 for r, s in zip(res_e, my_shapes))
+        if world > 1:
+            t = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        e2e = {"value": total_layers / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / args.steps}
+
+    # ---- roofline of the dominant kernel: Gram statistics of the widest layer, timed alone
+    roof = None
+    if rank == 0:
+        peaks, which = measured_peaks()
+        s = max(base, key=lambda q: q.K)
+        d = datas[[shapes[i].name for i in mine].index(s.name)] if s.name in [shapes[i].name for i in mine] else \
+            cpb200.synth.make_problem_device(s, 5, eng)
+        X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        times = []
+        for it in range(6):
+            flush.fill_(it)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False)
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                times.append(a.elapsed_time(b))
+        t_ms = statistics.mean(times)
+        flops = float(s.N) * s.K * (s.K + 1) + 2.0 * s.N * s.K * s.n  # symmetric half + X'Y
+        achieved = flops / (t_ms / 1e3) / 1e12
+        if eng.gram_mode == cpb200.engine.GRAM_FP64:
+            peak, peak_note = 40.0, "nominal B200 FP64 (no measured FP64 figure in MEASURED_PEAKS.json)"
+        else:
+            peak, peak_note = peaks["bf16_tflops"] / 2.0, "tf32 = half of the %s bf16 cuBLAS peak" % which
+        roof = {"kernel": "cp_gram (X'X upper tiles + X'Y) on %s: N=%d K=%d n=%d" % (s.name, s.N, s.K, s.n),
+                "bound": "tensor" if eng.gram_mode != cpb200.engine.GRAM_FP64 else "fp64-pipe",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "ms": t_ms, "algorithmic_flops": flops, "peak_source": peak_note,
+                "mode": "fp64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "3xtf32"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, m, desc = cpu_pass(base)
+        cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc, "seconds": m}
+
+    if rank == 0:
+        kept = [int(r.idxs.sum()) for r in res]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "tf32x3+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "layers_per_network": len(base), "networks": world,
+                       "N_patches": base[0].N, "l2": "inputs (feature maps, ~%.1f GB per network) exceed L2; no flush needed"
+                       % (sum(4.0 * s.N // (s.B * s.P) * s.B * s.c * s.H * s.W for s in base) / 1e9),
+                       "streams": args.streams, "kept_channels_rank0": kept},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches // max(1, args.steps)),
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

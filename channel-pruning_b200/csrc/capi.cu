@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 thread_local char cp_err_buf[512] = "";
+unsigned long long cp_launch_counter = 0;
+
+extern "C" int64_t cp_launch_count(void) { return (int64_t)cp_launch_counter; }
 
 extern "C" int cp_version(void) { return 100; }  // 0.1.0
 

@@ -30,7 +30,18 @@ extern thread_local char cp_err_buf[512];
             CP_FAIL(CP_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
     } while (0)
 
-#define CP_CHECK_LAUNCH() CP_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through one of these two, so the counter is exact
+extern unsigned long long cp_launch_counter;
+#define CP_CHECK_LAUNCH()              \
+    do {                               \
+        ++cp_launch_counter;           \
+        CP_CUDA(cudaGetLastError());   \
+    } while (0)
+#define CP_GEMM_LAUNCH(call)           \
+    do {                               \
+        ++cp_launch_counter;           \
+        CP_CUDA((call));               \
+    } while (0)
 
 #define CP_REQUIRE(cond, ...)                         \
     do {                                              \

@@ -110,14 +110,14 @@ static int gram_product(cp_handle_t h, const float *A, int64_t lda, int M, const
         g.C = C; g.ldc = Nn; g.c_split_stride = 0;
         g.mirror = sym ? 1 : 0;
         g.r_per_split = R > 0 ? R : 1;
-        CP_CUDA((launch<float, TB, true, true>(g, stream)));
+        CP_GEMM_LAUNCH((launch<float, TB, true, true>(g, stream)));
     } else {
         void *ws = nullptr;
         int rc = cp_ws_reserve(h, (size_t)nsplit * M * Nn * sizeof(double), &ws);
         if (rc) return rc;
         g.C = (double *)ws; g.ldc = Nn; g.c_split_stride = (int64_t)M * Nn;
         g.mirror = 0;
-        CP_CUDA((launch<float, TB, true, true>(g, stream)));
+        CP_GEMM_LAUNCH((launch<float, TB, true, true>(g, stream)));
         const int64_t total = (int64_t)M * Nn;
         reduce_partials<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const double *)ws, g.c_split_stride,
                                                                            nsplit, C, M, Nn, Nn, sym ? 1 : 0);
@@ -139,6 +139,14 @@ extern "C" int cp_gram(cp_handle_t h, const float *X, int64_t N, int K, int64_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t R = rows ? (int64_t)nrows : N;
 
+    if (R == 0) {  // empty input: all statistics are zero
+        if (G) CP_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)K * K, stream));
+        if (Bxy) CP_CUDA(cudaMemsetAsync(Bxy, 0, sizeof(double) * (size_t)K * n, stream));
+        if (sx) CP_CUDA(cudaMemsetAsync(sx, 0, sizeof(double) * (size_t)K, stream));
+        if (sy) CP_CUDA(cudaMemsetAsync(sy, 0, sizeof(double) * (size_t)n, stream));
+        if (yy) CP_CUDA(cudaMemsetAsync(yy, 0, sizeof(double), stream));
+        return CP_OK;
+    }
     if (mode == CP_GRAM_3XTF32)
         return cp_gram_tc(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
 

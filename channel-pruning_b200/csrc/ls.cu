@@ -25,14 +25,16 @@ constexpr int NB = 64;
 __global__ void __launch_bounds__(256)
 ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const double *__restrict__ sx,
             const double *__restrict__ sy, double invN, int K, int n, const int32_t *__restrict__ sel, int Ks,
-            double *__restrict__ M, int64_t ld) {
+            double *__restrict__ M, int64_t ld, double *__restrict__ diag0) {
     const int j = blockIdx.x * 256 + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= Ks) return;
     const int sj = sel[j];
     if (i < Ks) {
         const int si = sel[i];
-        M[(int64_t)i * ld + j] = G[(int64_t)si * K + sj] - sx[si] * sx[sj] * invN;
+        const double v = G[(int64_t)si * K + sj] - sx[si] * sx[sj] * invN;
+        M[(int64_t)i * ld + j] = v;
+        if (i == j) diag0[i] = v;
     } else {
         const int t = i - Ks;
         M[(int64_t)i * ld + j] = Bxy[(int64_t)sj * n + t] - sx[sj] * sy[t] * invN;
@@ -45,7 +47,7 @@ constexpr size_t POTRF_SMEM = (2 * NB * PD + NB) * sizeof(double);
 
 __global__ void __launch_bounds__(256)
 potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv, int32_t *__restrict__ info,
-           int j0) {
+           int j0, const double *__restrict__ diag0) {
     // S: working copy; its strict upper triangle receives the finished factor transposed
     // (L[i][k] -> S[k][i], i > k), the diagonal of L goes to Ld.  X: the inverse.
     extern __shared__ __align__(16) double psm[];
@@ -62,7 +64,9 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
     for (int k = 0; k < NB; ++k) {
         __syncthreads();
         double d = S[k * PD + k];
-        if (!(d > 0.0)) {
+        // pivot must stay above 1e-12 of the original diagonal entry: the squared form of the
+        // sigma < 1e-6 sigma_max cut-off LinearRegression applies (sklearn _base.py:752-753)
+        if (!(d > (k < nb ? 1e-12 * diag0[j0 + k] : 0.0))) {
             if (tid == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
             d = 1.0;
         }
@@ -129,7 +133,7 @@ int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
     g.a_vec = al16(A) && (lda % 2 == 0);
     g.b_vec = al16(B) && (ldb % 2 == 0);
     if (M <= 0 || Nn <= 0) return CP_OK;
-    CP_CUDA((launch<double, double, false, B_NC>(g, stream)));
+    CP_GEMM_LAUNCH((launch<double, double, false, B_NC>(g, stream)));
     return CP_OK;
 }
 
@@ -138,8 +142,8 @@ int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
 // In-place: M is (Kd + n) x Kd (leading dimension ld), rows 0..Kd-1 an SPD matrix (lower part
 // used), rows Kd.. the transposed right-hand sides.  On return rows Kd.. hold the transposed
 // solution  (SPD^-1 Rhs)'.  Linv: scratch of ceil(Kd/64) * 64*64 doubles.
-static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv, int32_t *info,
-                              cudaStream_t stream) {
+static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv, const double *diag0,
+                              int32_t *info, cudaStream_t stream) {
     using namespace cpgemm;
     const int Ktot = Kd + n;
     const int npanel = (Kd + NB - 1) / NB;
@@ -153,7 +157,7 @@ static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv
         const int nb = Kd - j0 < NB ? Kd - j0 : NB;
         const int j1 = j0 + nb;
         double *Lp = Linv + (size_t)p * NB * NB;
-        potrf_diag<<<1, 256, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0);
+        potrf_diag<<<1, 256, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0, diag0);
         CP_CHECK_LAUNCH();
         const int below = Ktot - j1;
         if (below > 0) {
@@ -198,19 +202,21 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t ld = (Ksel + 7) / 8 * 8;
     const int npanel = (Ksel + NB - 1) / NB;
-    const size_t need = cp_carver::need((size_t)(Ksel + n) * ld, 8) + cp_carver::need((size_t)npanel * NB * NB, 8);
+    const size_t need = cp_carver::need((size_t)(Ksel + n) * ld, 8) + cp_carver::need((size_t)npanel * NB * NB, 8) +
+                        cp_carver::need(Ksel, 8);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     double *M = cv.take<double>((size_t)(Ksel + n) * ld);
     double *Linv = cv.take<double>((size_t)npanel * NB * NB);
+    double *diag0 = cv.take<double>(Ksel);
     CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
     const double invN = 1.0 / (double)N;
     dim3 grid(cp_cdiv(Ksel, 256), Ksel + n);
-    ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld);
+    ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld, diag0);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(M, ld, Ksel, n, Linv, info_out, stream);
+    rc = chol_solve_inplace(M, ld, Ksel, n, Linv, diag0, info_out, stream);
     if (rc) return rc;
     ls_output<<<n, 256, 0, stream>>>(M + (int64_t)Ksel * ld, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
     CP_CHECK_LAUNCH();
@@ -263,10 +269,14 @@ dual_rhs(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ bias, c
     if (r < N) M[(N + t) * ld + r] = (double)__ldg(Y + r * ldy + t) - (bias ? (double)bias[t] : 0.0) - ymean[t];
 }
 
-__global__ void add_const_lower(double *__restrict__ M, int64_t ld, int N, double v) {
+__global__ void add_const_lower(double *__restrict__ M, int64_t ld, int N, double v, double *__restrict__ diag0) {
     const int j = blockIdx.x * 256 + threadIdx.x;
     const int i = blockIdx.y;
-    if (j < N && j <= i) M[(int64_t)i * ld + j] += v;
+    if (j < N && j <= i) {
+        const double x = M[(int64_t)i * ld + j] + v;
+        M[(int64_t)i * ld + j] = x;
+        if (i == j) diag0[i] = x;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -305,7 +315,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     const int npanel = (Ni + NB - 1) / NB;
     const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + cp_carver::need((size_t)(Ni + n) * ldm, 8) +
                         cp_carver::need((size_t)npanel * NB * NB, 8) + cp_carver::need((size_t)n * ldc, 8) +
-                        cp_carver::need(Ksel, 8) + cp_carver::need(n, 8);
+                        cp_carver::need(Ksel, 8) + cp_carver::need(n, 8) + cp_carver::need(Ni, 8);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
@@ -316,6 +326,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     double *Wt = cv.take<double>((size_t)n * ldc);
     double *xmean = cv.take<double>(Ksel);
     double *ymean = cv.take<double>(n);
+    double *diag0 = cv.take<double>(Ni);
     CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
     CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_solve_dual: unknown y_dtype %d", y_dtype);
     colmean_sel<float><<<cp_cdiv(Ksel, 32), 256, 0, stream>>>(X, ldx, sel_cols, Ksel, N, nullptr, xmean);
@@ -330,14 +341,14 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     // H = Xc Xc' (lower tiles) + 1/N
     rc = dgemm<false>(Xc, ldc, Xc, ldc, M, ldm, Ni, Ni, Ksel, 1.0, 0.0, TILES_LOWER, stream);
     if (rc) return rc;
-    add_const_lower<<<dim3(cp_cdiv(Ni, 256), Ni), 256, 0, stream>>>(M, ldm, Ni, 1.0 / (double)N);
+    add_const_lower<<<dim3(cp_cdiv(Ni, 256), Ni), 256, 0, stream>>>(M, ldm, Ni, 1.0 / (double)N, diag0);
     CP_CHECK_LAUNCH();
     if (y_dtype == CP_F32)
         dual_rhs<float><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
     else
         dual_rhs<double><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(M, ldm, Ni, n, Linv, info_out, stream);
+    rc = chol_solve_inplace(M, ldm, Ni, n, Linv, diag0, info_out, stream);
     if (rc) return rc;
     // Wt = At * Xc   (C[t, i] = sum_r At[t, r] * Xc[r, i])
     rc = dgemm<true>(M + (int64_t)Ni * ldm, ldm, Xc, ldc, Wt, ldc, n, Ksel, Ni, 1.0, 0.0, TILES_ALL, stream);

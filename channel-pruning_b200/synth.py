@@ -76,7 +76,7 @@ def make_problem_numpy(shape: LayerShape, seed: int, noise=0.01):
 def gather_patches_numpy(fmap, randx, randy, B, k, pad, stride, relu):
     """Plain numpy statement of the patch layout (rows (batch, point, image); columns (c,kh,kw))
     used to build synthetic targets.  (The *checked* restatement of the reference's
-    extract_XY lives in oracle/cp_oracle.py; tests compare the two.)"""
+    extract_XY lives in the oracle directory; tests compare the two.)"""
     nimg, c, H, W = fmap.shape
     nbatch, P = randx.shape
     fp = np.zeros((nimg, c, H + 2 * pad, W + 2 * pad), dtype=fmap.dtype)

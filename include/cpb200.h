@@ -61,6 +61,9 @@ const char *cp_last_error(void);
 
 int cp_create(cp_handle_t *out, int device);
 int cp_destroy(cp_handle_t h);
+/* number of CUDA kernels this library has launched in the process so far (diagnostics; bench.py
+ * reports the per-step difference as gpu_launches) */
+int64_t cp_launch_count(void);
 /* bytes of scratch currently owned by the handle (diagnostics) */
 int64_t cp_workspace_bytes(cp_handle_t h);
 

@@ -1,0 +1,192 @@
+"""GPU: the drop-in entry points (cpb200.lib.decompose / cpb200.lib.net) against
+ (a) golden outputs of the reference's own code (tests/golden, oracle/make_golden.py),
+ (b) the oracle on BASELINE-config-sized inputs,
+ (c) size-independent properties at full size (KKT of the LASSO, normal equations of the LS).
+Gates (BASELINE.json north_star): selected-channel set identical; reconstructed weights within
+1e-4 relative Frobenius error (in practice ~1e-9 with the fp64 Gram mode)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import cp_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+W_TOL = 1e-4  # north_star tolerance on reconstructed weights (relative Frobenius)
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", list(cases.DICTIONARY_CASES))
+def test_dictionary_matches_reference_golden(engine, golden_dir, name):
+    import cpb200
+    from cpb200.lib import cfgs, decompose
+
+    spec = cases.DICTIONARY_CASES[name]
+    g = np.load(os.path.join(golden_dir, "dictionary_%s.npz" % name))
+    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    cfgs.alpha = spec["alpha0"]
+    cfgs.c.dic.rank_tol = spec.get("rank_tol", .1)
+    try:
+        np.random.seed(spec["np_seed"])
+        idxs, W, B = decompose.dictionary(X.astype(np.float64), W2, Y, rank=spec["rank"], B2=np.zeros(W2.shape[0]))
+        after = np.random.randint(0, 1 << 30)
+    finally:
+        cfgs.c.dic.rank_tol = .1
+    assert idxs.dtype == np.bool_ and np.array_equal(idxs, g["idxs"])  # exact channel set
+    assert after == int(g["rng_after"])  # consumed the same global RNG draws as the reference
+    assert cfgs.alpha == float(g["alpha_final"])
+    assert W.dtype == np.float64 and W.shape == g["W"].shape
+    assert _rel(W, g["W"]) <= W_TOL
+    assert _rel(W, g["W"]) <= 1e-7  # what the fp64 path actually delivers
+    assert np.abs(B - g["B"]).max() <= 1e-7 * max(1.0, np.abs(g["B"]).max())
+
+
+def test_dictionary_accepts_cuda_tensors(engine, golden_dir):
+    from cpb200.lib import cfgs, decompose
+
+    spec = cases.DICTIONARY_CASES["c32"]
+    g = np.load(os.path.join(golden_dir, "dictionary_c32.npz"))
+    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    cfgs.alpha = spec["alpha0"]
+    np.random.seed(spec["np_seed"])
+    idxs, W, B = decompose.dictionary(torch.as_tensor(X, device=engine.device), torch.as_tensor(W2, device=engine.device),
+                                      torch.as_tensor(Y, device=engine.device), rank=spec["rank"])
+    assert np.array_equal(idxs, g["idxs"]) and _rel(W, g["W"]) <= 1e-7
+
+
+def test_fc_kernel_matches_oracle(engine):
+    from cpb200.lib import decompose
+
+    r = np.random.RandomState(8)
+    X = np.maximum(r.standard_normal((900, 250)), 0).astype(np.float32)
+    Y = (X @ r.standard_normal((250, 20)) + 0.1 * r.standard_normal((900, 20)))
+    coef, icpt = decompose.fc_kernel(X.astype(np.float64), Y)
+    rc, ri = O.fc_kernel(X.astype(np.float64), Y)
+    assert _rel(coef, rc) <= 1e-8 and np.abs(icpt - ri).max() <= 1e-8
+    with pytest.raises(AssertionError):
+        decompose.fc_kernel(X[None], Y)  # reference asserts 2-D input (decompose.py:641)
+
+
+def _forward_np(images, specs, weights, biases):
+    from make_golden import conv2d_numpy
+
+    cache = {}
+
+    def forward(batch):
+        if batch not in cache:
+            blobs = {"data": images[batch % len(images)]}
+            for s in specs:
+                y = conv2d_numpy(blobs[s["bottom"]], weights[s["name"]], biases[s["name"]], s["pad"], s["stride"])
+                blobs[s["name"]] = y
+                blobs[s["name"] + "_relu"] = np.maximum(y, 0)
+            cache[batch] = blobs
+        return cache[batch]
+
+    return forward
+
+
+@pytest.mark.parametrize("name", list(cases.NET_CASES))
+def test_net_methods_match_reference_golden(engine, golden_dir, name):
+    from cpb200.lib import cfgs, net as cpnet
+
+    spec = cases.NET_CASES[name]
+    g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
+    images, specs, weights, biases = cases.net_inputs(**spec["gen"])
+    fnp = _forward_np(images, specs, weights, biases)
+
+    def forward(net, batch):  # feature provider: the same blobs the reference saw, on the device
+        return {k: torch.as_tensor(v, device=engine.device) for k, v in fnp(batch).items()}
+
+    cs = [cpnet.ConvSpec(s["name"], s["bottom"], weights[s["name"]].shape[0], s["k"], s["pad"], s["stride"])
+          for s in specs]
+    net = cpnet.Net(cs, weights, biases, forward)
+    cfgs.c.nBatches, cfgs.c.nPointsPerLayer = spec["nBatches"], spec["P"]
+    cfgs.alpha = 1e-3
+    names = [s["name"] for s in specs]
+    np.random.seed(spec["np_seed"])
+    feats, points = net.extract_features(names, save=1)
+    for nm in names:
+        assert feats[nm].dtype == np.float64
+        np.testing.assert_array_equal(feats[nm], g["feats_" + nm])
+        for b in range(spec["nBatches"]):
+            np.testing.assert_array_equal(points[(b, nm, "randx")], g["randx_%s_%d" % (nm, b)])
+    net.load_frozen(feats_dict=feats, points_dict=points)
+    XY = net.extract_XY(spec["xy"][0], spec["xy"][1])
+    assert XY.dtype == np.float64
+    np.testing.assert_array_equal(XY, g["XY"])
+    if spec.get("dictionary_kernel"):
+        np.random.seed(spec["np_seed"] + 1)
+        idxs, W, B = net.dictionary_kernel(spec["xy"][0], None, int(g["dk_dprime"]), spec["xy"][1], None)
+        assert np.array_equal(idxs, g["dk_idxs"])
+        assert cfgs.alpha == float(g["dk_alpha"])
+        assert _rel(W, g["dk_W"]) <= 1e-7 and np.abs(B - g["dk_B"]).max() <= 1e-7
+
+
+def test_baseline_config1_mask_bit_compare(engine):
+    """BASELINE.json configs[0]: single 256->256 3x3 layer, N=1000 patches; oracle = the reference's
+    algorithm (sklearn-faithful CD + gelsd) on the CPU; N-1 < K' so the LS is the minimum-norm one."""
+    from cpb200.lib import cfgs, decompose
+
+    X, W2, Y = cases.dictionary_inputs(c=256, n=256, N=1000, k=3, seed=101)
+    rank = int(256 / 1.15)
+    st = O.DictState(alpha=1e-3)
+    np.random.seed(77)
+    info = {}
+    oi, oW, oB = O.dictionary(X.astype(np.float64), W2, Y, rank=rank, state=st, info=info)
+    cfgs.alpha = 1e-3
+    np.random.seed(77)
+    idxs, W, B = decompose.dictionary(X.astype(np.float64), W2, Y, rank=rank)
+    assert np.array_equal(idxs, oi)
+    assert decompose.DictionaryInfo.last["probes"] == info["probes"]  # same alpha probes and counts
+    assert cfgs.alpha == st.alpha
+    assert _rel(W, oW) <= W_TOL and np.abs(B - oB).max() <= W_TOL
+
+
+def test_full_size_properties_conv4_shape(engine):
+    """c=n=512, k=3, N=5000 (VGG conv4_x; too slow for the CPU oracle in a unit test): check what
+    must hold for ANY correct solution -- LASSO KKT conditions on the device-built statistics and
+    the normal equations of the reconstruction -- plus agreement of the Gram-form statistics with
+    a torch fp64 evaluation."""
+    import cpb200
+
+    s = cpb200.synth.LayerShape("conv4_x", 512, 512, 28, N=5000)
+    d = cpb200.synth.make_problem_device(s, 123, engine)
+    X = engine.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+    assert X.shape == (5000, 4608) and float(X.min()) >= 0
+    W2m = d["W2"].reshape(s.n, s.K)
+    g_full, res = engine.select_channels_async(X, W2m, d["feats"], d["b2"], d["samples"], s.c, 9, s.rank, .1, 1e-3,
+                                               d["seeds"])
+    scal = res.scalars.cpu().numpy()
+    assert int(scal[2]) == 0
+    nnz = int(scal[3])
+    assert s.rank <= nnz <= s.rank * 1.1
+    # Gram statistics vs torch fp64 on a sub-block
+    X64 = X[:, :300].double()
+    Yc = d["feats"].double() - d["b2"].double()
+    assert torch.allclose(g_full["G"][:300, :300], X64.T @ X64, rtol=1e-11, atol=1e-8)
+    assert torch.allclose(g_full["B"][:300], X64.T @ Yc, rtol=1e-10, atol=1e-8)
+    # KKT of the final LASSO fit (duality gap criterion => subgradient condition up to the gap)
+    gs = engine.gram(X, d["feats"], y_bias=d["b2"], rows=d["samples"], want_yy=True, mode=0)
+    gw = engine.gram(W2m, None, want_B=False, mode=0)
+    Q, qv, yn2 = engine.lasso_build(gs, gw, W2m, s.c, 9, s.S)
+    w = res.coef
+    grad = qv - Q @ w
+    l1 = float(scal[0]) * s.S * s.n
+    active = w != 0
+    assert float((grad[~active].abs()).max()) <= l1 * 1.05
+    assert float((grad[active] - l1 * torch.sign(w[active])).abs().max()) <= 5e-2 * l1
+    # reconstruction: centred normal equations  Xc'(Yc - Xc W - b) = 0
+    idxs = res.idxs.cpu().numpy().astype(bool)
+    Wd, bd, info = engine.reconstruct_async(g_full, X, d["feats"], d["b2"], idxs, 9)
+    assert int(info.cpu()[0]) == 0
+    cols = torch.as_tensor((np.flatnonzero(idxs)[:, None] * 9 + np.arange(9)).reshape(-1), device=engine.device)
+    Xs = X[:, cols].double()
+    R = Yc - Xs @ Wd.T - bd
+    assert float(R.mean(0).abs().max()) <= 1e-9
+    assert float((Xs.T @ R).abs().max()) <= 1e-6 * float((Xs.T @ Yc).abs().max())

@@ -1,0 +1,169 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import cp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import cpb200
+
+    syms = cpb200._cabi.declared_symbols()
+    assert len(syms) >= 12
+    lib = ctypes.CDLL(cpb200._cabi.LIBRARY)  # fails loudly if the .so is missing
+    for s in syms:
+        assert hasattr(lib, s), "libcpb200.so does not export %s declared in include/cpb200.h" % s
+    ffi, l2 = cpb200._cabi.load()
+    assert l2.cp_version() >= 100
+    assert isinstance(ffi.string(l2.cp_last_error()), bytes)
+
+
+def test_header_cites_reference_for_every_entry_point():
+    src = open(os.path.join(ROOT, "include", "cpb200.h")).read()
+    for fn in ("cp_patch_gather", "cp_point_gather", "cp_gram", "cp_lasso_build", "cp_lasso_select", "cp_ls_solve",
+               "cp_ls_solve_dual"):
+        head = src[:src.index("int " + fn + "(")]
+        comment = head[head.rindex("/*"):]
+        assert "lib/" in comment and ".py:" in comment, "no reference file:line cited for " + fn
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "channel-pruning_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            txt = open(os.path.join(dp, f), errors="ignore").read() if f.endswith((".py", ".cu", ".cuh", ".h")) else ""
+            if f.endswith(".py"):
+                assert "cp_oracle" not in txt and "cd_oracle" not in txt and "ref_shims" not in txt, f
+                import re
+
+                assert not re.search(r"^\s*(import|from)\s+\S*oracle", txt, flags=re.M), f
+                assert not re.search(r"""["']oracle["'/]""", txt), f  # no path into oracle/ either
+                assert "import sklearn" not in txt and "from sklearn" not in txt and "import scipy" not in txt, f
+            elif txt:
+                for line in txt.splitlines():  # C/CUDA sources may cite the oracle in comments only
+                    if "#include" in line:
+                        assert "oracle" not in line, f
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+
+    import cpb200
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        cpb200.Engine()
+
+
+def test_window_matches_reference_quirks():
+    from cpb200.engine import window
+
+    assert window(27, .1) == (27, 27 + 2.7)
+    assert window(30, .2) == (30 + 3.0, 30 + 6.0)  # lib/decompose.py:498-501
+    assert window(10, 2) == (10, 12)  # rank_tol >= 1 is absolute (:493-494)
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    import cpb200
+
+    shapes = cpb200.synth.vgg16_layers()
+    costs = [s.cost() for s in shapes]
+    for world in (1, 2, 4, 8):
+        owner = cpb200.pruner.assign_layers(costs, world)
+        assert owner == cpb200.pruner.assign_layers(costs, world)
+        loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(world)]
+        assert max(loads) <= max(sum(costs) / world * 1.6, max(costs) * 1.0001)
+        assert set(owner) <= set(range(world))
+
+
+def test_pack_unpack_roundtrip():
+    import torch
+
+    import cpb200
+
+    pr = cpb200.pruner
+    c, n, k2, rank = 40, 12, 9, 34
+    size = pr.slot_size(c, n, k2, rank, .1)
+    r = np.random.RandomState(0)
+    idxs = np.zeros(c, bool)
+    idxs[r.choice(c, 36, replace=False)] = True
+    W = torch.as_tensor(r.standard_normal((n, 36 * k2)))
+    b = torch.as_tensor(r.standard_normal(n))
+    buf = torch.zeros(size + 5, dtype=torch.float64)
+    pr.pack_result(buf, 5, idxs, W, b, 0.004, 7, c, n, k2)
+    out = pr.unpack_result(buf, 5, c, n, k2)
+    assert np.array_equal(out["idxs"], idxs) and out["alpha"] == 0.004 and out["nprobe"] == 7
+    np.testing.assert_array_equal(out["W"].reshape(n, -1), W.numpy())
+    np.testing.assert_array_equal(out["b"], b.numpy())
+
+
+def test_synth_patch_layout_equals_oracle_extract_XY():
+    import cpb200
+
+    s = cpb200.synth.LayerShape("t", 6, 4, 9, k=3, pad=1, stride=1, N=60, B=3, P=5)
+    d = cpb200.synth.make_problem_numpy(s, 4)
+    pd = {"nPointsPerLayer": s.P, "nBatches": s.nbatch}
+    for b in range(s.nbatch):
+        pd[(b, "y", "randx")] = d["randx"][b]
+        pd[(b, "y", "randy")] = d["randy"][b]
+    forward = lambda b: {"x": d["fmap"][b * s.B:(b + 1) * s.B]}  # noqa: E731
+    XY = O.extract_XY(forward, "x", O.ConvSpec("y", "x", 3, 1, 1), pd)
+    Xo = np.rollaxis(XY.reshape((-1, 3, 3, XY.shape[1])), 3, 1)
+    np.testing.assert_array_equal(np.maximum(Xo, 0), d["X"].astype(np.float64))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import cpb200
+pr = cpb200.pruner
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+shapes = [cpb200.synth.LayerShape("L%%d" %% i, c, n, 8, N=200, B=2, P=5) for i, (c, n) in enumerate([(8, 4), (16, 8), (12, 6), (10, 5), (20, 4)])]
+owner = pr.assign_layers([s.cost() for s in shapes], world)
+sizes = [pr.slot_size(s.c, s.n, 9, s.rank, .1) for s in shapes]
+per_rank = [sum(sizes[i] for i in range(len(shapes)) if owner[i] == r) for r in range(world)]
+buf = torch.zeros(max(per_rank), dtype=torch.float64)
+off = 0
+def fake(i):  # deterministic stand-in for a solved layer
+    s = shapes[i]; r = np.random.RandomState(100 + i)
+    idxs = np.zeros(s.c, bool); idxs[r.choice(s.c, s.rank, replace=False)] = True
+    return idxs, torch.as_tensor(r.standard_normal((s.n, s.rank * 9))), torch.as_tensor(r.standard_normal(s.n))
+for i in range(len(shapes)):
+    if owner[i] == rank:
+        idxs, W, b = fake(i)
+        pr.pack_result(buf, off, idxs, W, b, 0.001 * (i + 1), i, shapes[i].c, shapes[i].n, 9)
+        off += sizes[i]
+allbuf = pr.allgather_results(buf, world)
+res = pr.unpack_network(shapes, owner, sizes, allbuf)
+for i in range(len(shapes)):
+    idxs, W, b = fake(i)
+    assert np.array_equal(res[i]["idxs"], idxs) and res[i]["nprobe"] == i
+    assert np.array_equal(res[i]["W"].reshape(shapes[i].n, -1), W.numpy())
+    assert np.array_equal(res[i]["b"], b.numpy())
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_allgather_reassembles_every_layer(tmp_path):
+    """world_size-2 gloo run of the sharding protocol (assignment, static packing, ONE all_gather)."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
