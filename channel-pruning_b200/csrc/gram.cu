@@ -129,7 +129,7 @@ static int gram_product(cp_handle_t h, const float *A, int64_t lda, int M, const
 extern "C" int cp_gram(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
                        int n, int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy,
                        double *sx, double *sy, double *yy, int mode, cp_stream_t stream_) {
-    CP_REQUIRE(h && X, "cp_gram: NULL handle or X");
+    CP_REQUIRE(h && (X || N == 0), "cp_gram: NULL handle or X");
     CP_REQUIRE(N >= 0 && K > 0 && ldx >= K, "cp_gram: bad X shape (N=%lld K=%d ldx=%lld)", (long long)N, K, (long long)ldx);
     CP_REQUIRE((Bxy == nullptr && sy == nullptr && yy == nullptr) || (Yraw != nullptr && n > 0 && ldy >= n),
                "cp_gram: Y outputs requested without a valid Y");
