@@ -9,32 +9,42 @@
 //
 // The executable specification of cp_lasso_select is oracle/cd_oracle.c:cp_enet_cd_gram
 // (same control flow as sklearn's data-form solver, evaluated on Q = Zc'Zc, q = Zc'yc,
-// |yc|^2).  The kernel reproduces that model BIT FOR BIT: every floating-point
-// operation that the model rounds separately is issued with an explicit *_rn intrinsic
-// (no FMA contraction), reductions run in the model's serial order, and the random
-// coordinate order comes from the same 32-bit xorshift.
+// |yc|^2).  The kernel reproduces that model BIT FOR BIT: every floating-point operation
+// the model rounds separately is issued with an explicit *_rn intrinsic (no FMA
+// contraction), the gap reductions run in the model's "warp order", the division is
+// correctly rounded, and the random coordinate order comes from the same 32-bit xorshift.
 //
-// Coordinate descent is a serial chain (one coordinate update needs the previous one),
-// so the search runs in ONE persistent CTA: it is latency bound, not HBM/tensor bound.
-// Per coordinate step: the owner thread of coordinate j forms the soft-threshold update
-// and publishes delta; after one CTA barrier all threads apply  Qw += delta * Q[j,:]  to the
-// elements they own.  Rows of Q are streamed from L2 through an 8-deep cp.async ring that
-// runs ahead along the (data-independent) random coordinate sequence.
+// Coordinate descent is one long serial dependency chain (each coordinate update needs the
+// previous one), so the whole search is latency bound; it runs in ONE WARP per problem:
+//   * Qw (= Q w) lives in shared memory, each lane owning interleaved pairs of elements;
+//     a step applies  Qw += delta * Q[j,:]  with LDS.128 / DMUL / DADD / STS.128 per pair;
+//   * the pair that holds the NEXT coordinate is updated first and its value is broadcast
+//     with a shuffle, so the serial chain (update -> soft threshold -> divide -> delta) of
+//     step f+1 is issued in the shadow of step f's remaining pair updates;
+//   * rows of Q stream from L2 through an 8-deep cp.async ring that runs ahead along the
+//     (data-independent) random coordinate sequence; every lane copies exactly the pairs it
+//     will read back, so no barrier is needed for the ring;
+//   * the division  num / Q_jj  uses a pre-computed correctly rounded reciprocal and one
+//     Markstein correction step (DMUL + 2 DFMA) -- IEEE-exact, 3 dependent ops instead of ~10.
+// No CTA barrier anywhere; __syncwarp() only orders the lane-0 scalar stores.
 #include "common.cuh"
 
 namespace {
 
-constexpr int LT = 256;     // threads of the persistent CTA
 constexpr int RING = 8;     // prefetch depth (rows of Q in flight)
 constexpr int MAXC = 2048;  // largest channel count (shared-memory bound)
 
 // ------------------------------------------------------------------ build
 __global__ void __launch_bounds__(256)
 lasso_build_Q(const double *__restrict__ Gs, const double *__restrict__ WW, const double *__restrict__ sxs,
-              const double *__restrict__ sw, int c, int k2, double m, double *__restrict__ Q) {
+              const double *__restrict__ sw, int c, int k2, double m, double *__restrict__ Q, int ldq) {
     const int b = blockIdx.x * 16 + (threadIdx.x & 15);
     const int a = blockIdx.y * 16 + (threadIdx.x >> 4);
-    if (a >= c || b >= c) return;
+    if (a >= c || b >= ldq) return;
+    if (b >= c) {  // padding column (keeps rows 16-byte aligned for the selection kernel)
+        Q[(int64_t)a * ldq + b] = 0.0;
+        return;
+    }
     const int64_t K = (int64_t)c * k2;
     double s = 0.0, za = 0.0, zb = 0.0;
     for (int p = 0; p < k2; ++p) {
@@ -44,7 +54,7 @@ lasso_build_Q(const double *__restrict__ Gs, const double *__restrict__ WW, cons
         za = fma(sxs[a * k2 + p], sw[a * k2 + p], za);
         zb = fma(sxs[b * k2 + p], sw[b * k2 + p], zb);
     }
-    Q[(int64_t)a * c + b] = s - za * zb / m;  // - m * zbar_a * zbar_b
+    Q[(int64_t)a * ldq + b] = s - za * zb / m;  // - m * zbar_a * zbar_b
 }
 
 // qv[a] = sum_{p,j} W2[j,(a,p)] * Bs[(a,p), j] - m zbar_a ybar ;  block per channel, fixed-shape tree.
@@ -78,7 +88,9 @@ lasso_build_q(const float *__restrict__ W2, const double *__restrict__ Bs, const
 
 // ------------------------------------------------------------------ select
 struct SelectParams {
-    const double *Q, *qv, *yn2;
+    const double *Q;
+    int ldq;
+    const double *qv, *yn2;
     int c;
     double m;
     int rank;
@@ -90,231 +102,298 @@ struct SelectParams {
     double *out_coef, *out_scalars, *out_probe_log;
 };
 
-__device__ __forceinline__ uint32_t our_rand_r(uint32_t &s) {  // sklearn/utils/_random.pxd:20-34
+__device__ __forceinline__ uint32_t xorshift(uint32_t &s) {  // sklearn/utils/_random.pxd:20-34
     if (s == 0) s = 1;
     s ^= s << 13;
     s ^= s >> 17;
     s ^= s << 5;
     return s & 0x7fffffffu;  // % (RAND_R_MAX + 1)
 }
-__device__ __forceinline__ uint32_t rand_int(uint32_t end, uint32_t &s) { return our_rand_r(s) % end; }
+// a % d for 32-bit a through a pre-computed M = floor(2^64 / d) + 1 (Lemire's fastmod; exact)
+__device__ __forceinline__ uint32_t fastmod(uint32_t a, uint64_t M, uint32_t d) {
+    return (uint32_t)__umul64hi(M * (uint64_t)a, (uint64_t)d);
+}
 
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-struct Ctl {        // CTA-wide scalars published by thread 0
-    double gap, dual_norm;
-    double bc[2][2];  // per-step broadcast: {delta, |w_new|}
-    int n_active, nnz, n_zero;
-};
+__device__ __forceinline__ double warp_sum_butterfly(double v) {  // model: p[l] + p[l ^ off], off = 16..1
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
 
-__global__ void __launch_bounds__(LT, 1) lasso_select_kernel(const SelectParams P) {
+// correctly rounded num / d given rc = RN(1/d):  q0 = RN(num*rc), r = num - q0*d (exact), q = RN(q0 + r*rc)
+__device__ __forceinline__ double div_markstein(double num, double d, double rc) {
+    const double q0 = __dmul_rn(num, rc);
+    const double r = __fma_rn(-q0, d, num);
+    return __fma_rn(r, rc, q0);
+}
+
+template <int NP>  // pairs per lane; padded channel count CP = 64 * NP
+__global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams P) {
+    constexpr int CP = 64 * NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = P.c, tid = threadIdx.x;
-    double *w = reinterpret_cast<double *>(smem_raw);
-    double *Qw = w + c;
-    double *qv = Qw + c;
-    double *dg = qv + c;
-    double *XtA = dg + c;
-    double *ring = XtA + c;                                       // RING * c
-    uint32_t *active = reinterpret_cast<uint32_t *>(ring + (size_t)RING * c);
-    uint32_t *zlist = active + c;                                  // features zeroed by screening
-    uint8_t *excluded = reinterpret_cast<uint8_t *>(zlist + c);
-    __shared__ Ctl ctl;
+    const int c = P.c, lane = threadIdx.x;
+    double *w = reinterpret_cast<double *>(smem_raw);  // [CP]
+    double *Qw = w + CP;
+    double *qv = Qw + CP;
+    double *dg = qv + CP;
+    double *rc = dg + CP;
+    double *ring = rc + CP;  // [RING][CP]
+    uint32_t *active = reinterpret_cast<uint32_t *>(ring + (size_t)RING * CP);
+    uint32_t *zlist = active + CP;
+    uint32_t *jq = zlist + CP;  // [RING] upcoming coordinates
+    uint8_t *excluded = reinterpret_cast<uint8_t *>(jq + RING);
 
     const double *__restrict__ Q = P.Q;
+    const int ldq = P.ldq;
     const double yn2 = *P.yn2;
-    for (int e = tid; e < c; e += LT) {
+    for (int e = lane; e < CP; e += 32) {
         w[e] = 0.0;
-        qv[e] = P.qv[e];
-        dg[e] = Q[(int64_t)e * c + e];
+        Qw[e] = 0.0;
+        const bool in = e < c;
+        const double d = in ? Q[(int64_t)e * ldq + e] : 0.0;
+        qv[e] = in ? P.qv[e] : 0.0;
+        dg[e] = d;
+        rc[e] = d != 0.0 ? __drcp_rn(d) : 0.0;
+        active[e] = e;
+        excluded[e] = 0;
     }
-    __syncthreads();
+    for (int e = lane; e < RING * CP; e += 32) ring[e] = 0.0;  // padding pairs stay zero
+    __syncwarp();
 
     const double tolS = __dmul_rn(P.tol, yn2);
-    int probe = 0;
-    int status = 0;
+    int probe = 0, status = 0;
 
-    // ---- one Lasso.fit (warm start) at l1 = alpha*m; returns nnz (uniform across threads)
+    // this lane's pair `s` lives at element 64*s + 2*lane
+    auto prefetch_row = [&](uint32_t j, int slot) {
+        const double *src = Q + (int64_t)j * ldq;
+        double *dst = ring + (size_t)slot * CP;
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+            const int e = 64 * s + 2 * lane;
+            if (e < c) cp_async16(dst + e, src + e);
+        }
+    };
+
+    // Qw += a * Q[j,:], row fetched directly (rare paths: screening evictions)
+    auto axpy_row_direct = [&](uint32_t j, double a) {
+        const double *src = Q + (int64_t)j * ldq;
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+            const int e = 64 * s + 2 * lane;
+            if (e < c) {
+                const double2 r = *reinterpret_cast<const double2 *>(src + e);
+                double2 v = *reinterpret_cast<double2 *>(Qw + e);
+                v.x = __dadd_rn(v.x, __dmul_rn(a, r.x));
+                v.y = __dadd_rn(v.y, __dmul_rn(a, r.y));
+                *reinterpret_cast<double2 *>(Qw + e) = v;
+            }
+        }
+    };
+
+    // ---- one Lasso.fit (warm start) at l1 = alpha*m; returns nnz (uniform across lanes)
     auto solve = [&](double alpha_user) -> int {
         const double l1 = __dmul_rn(alpha_user, P.m);
-        uint32_t state = P.seeds[probe];
+        uint32_t la = P.seeds[probe];  // coordinate-order RNG, runs RING draws ahead of the update
         int n_active = c;
         int n_iter_ret = 0;
-        double gap = 0.0;
+        double gap = 0.0, dual_norm = 0.0;
 
-        // Qw = sum_j w[j] * Q[j,:]  (model: serial daxpy per nonzero j)
-        for (int e = tid; e < c; e += LT) Qw[e] = 0.0;
-        for (int j = 0; j < c; ++j) {
-            const double wj = w[j];
-            if (wj != 0.0)
-                for (int e = tid; e < c; e += LT) Qw[e] = __dadd_rn(Qw[e], __dmul_rn(wj, Q[(int64_t)j * c + e]));
-        }
-        __syncthreads();
-
-        // gap_enet_gram + dual_gap_formulation_A (beta = 0), serial like the model
+        // gap_enet_gram + dual_gap_formulation_A (beta = 0) in warp order
         auto gap_check = [&]() {
-            if (tid == 0) {
-                double q_dot_w = 0.0, wQw = 0.0, dn = 0.0, l1n = 0.0;
-                for (int j = 0; j < c; ++j) q_dot_w = __dadd_rn(q_dot_w, __dmul_rn(w[j], qv[j]));
-                for (int j = 0; j < c; ++j) wQw = __dadd_rn(wQw, __dmul_rn(w[j], Qw[j]));
-                const double R_norm2 = __dadd_rn(__dadd_rn(yn2, wQw), -__dmul_rn(2.0, q_dot_w));
-                const double Ry = __dadd_rn(yn2, -q_dot_w);
-                for (int j = 0; j < c; ++j) {
-                    const double x = __dadd_rn(qv[j], -Qw[j]);
-                    XtA[j] = x;
-                    const double ax = fabs(x);
-                    if (j == 0 || ax > dn) dn = ax;
-                    l1n = __dadd_rn(l1n, fabs(w[j]));
-                }
-                const double primal = __dadd_rn(__dmul_rn(0.5, R_norm2), __dmul_rn(l1, l1n));
-                const double scale = dn > l1 ? __ddiv_rn(l1, dn) : 1.0;
-                const double dual = __dadd_rn(__dmul_rn(__dmul_rn(-0.5, __dmul_rn(scale, scale)), R_norm2),
-                                              __dmul_rn(scale, Ry));
-                ctl.gap = __dadd_rn(primal, -dual);
-                ctl.dual_norm = dn;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0, dn = 0.0;
+            for (int i = lane; i < c; i += 32) {
+                const double wi = w[i];
+                a1 = __dadd_rn(a1, __dmul_rn(wi, qv[i]));
+                a2 = __dadd_rn(a2, __dmul_rn(wi, Qw[i]));
+                a3 = __dadd_rn(a3, fabs(wi));
+                dn = fmax(dn, fabs(__dadd_rn(qv[i], -Qw[i])));
             }
-            __syncthreads();
+            const double q_dot_w = warp_sum_butterfly(a1);
+            const double wQw = warp_sum_butterfly(a2);
+            const double l1n = warp_sum_butterfly(a3);
+            dn = warp_max(dn);
+            const double R_norm2 = __dadd_rn(__dadd_rn(yn2, wQw), -__dmul_rn(2.0, q_dot_w));
+            const double Ry = __dadd_rn(yn2, -q_dot_w);
+            const double primal = __dadd_rn(__dmul_rn(0.5, R_norm2), __dmul_rn(l1, l1n));
+            const double scale = dn > l1 ? __ddiv_rn(l1, dn) : 1.0;
+            const double dual = __dadd_rn(__dmul_rn(__dmul_rn(-0.5, __dmul_rn(scale, scale)), R_norm2),
+                                          __dmul_rn(scale, Ry));
+            gap = __dadd_rn(primal, -dual);
+            dual_norm = dn;
         };
-        // gap-safe screening (model: radius = sqrt(2|gap|)/alpha; d_j = (1-|XtA_j/max(alpha,dn)|)/sqrt(Q_jj))
+        // gap-safe screening: keep j iff (1 - |XtA_j / max(l1, dn)|) / sqrt(Q_jj) <= sqrt(2|gap|) / l1
         auto screen = [&](bool first) {
-            const double radius = __ddiv_rn(sqrt(__dmul_rn(2.0, fabs(ctl.gap))), l1);
-            const double den = l1 > ctl.dual_norm ? l1 : ctl.dual_norm;
-            for (int j = tid; j < c; j += LT) {
-                uint8_t ex;
-                if (first) {
-                    if (dg[j] == 0.0) ex = 2;  // zero column: w[j] = 0, excluded (no Qw change needed)
-                    else {
-                        const double th = __ddiv_rn(XtA[j], den);
-                        const double d_j = __ddiv_rn(__dadd_rn(1.0, -fabs(th)), sqrt(dg[j]));
-                        ex = d_j <= radius ? 0 : 1;
-                    }
-                } else if (excluded[j]) ex = 3;  // stays excluded
-                else {
-                    const double th = __ddiv_rn(XtA[j], den);
-                    const double d_j = __ddiv_rn(__dadd_rn(1.0, -fabs(th)), sqrt(dg[j]));
-                    ex = d_j <= radius ? 0 : 1;
-                }
-                excluded[j] = ex;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int na = 0, nz = 0;
-                for (int j = 0; j < c; ++j) {
-                    const uint8_t ex = excluded[j];
-                    if (ex == 0) active[na++] = j;
-                    else {
-                        if (ex == 1 && w[j] != 0.0) zlist[nz++] = j;
-                        if (ex == 2) w[j] = 0.0;
+            const double radius = __ddiv_rn(sqrt(__dmul_rn(2.0, fabs(gap))), l1);
+            const double den = l1 > dual_norm ? l1 : dual_norm;
+            int na = 0, nz = 0;
+            for (int base = 0; base < c; base += 32) {
+                const int j = base + lane;
+                bool keep = false, evict_nonzero = false;
+                if (j < c) {
+                    if (first && dg[j] == 0.0) {
+                        w[j] = 0.0;  // zero column
                         excluded[j] = 1;
+                    } else if (!first && excluded[j]) {
+                        // stays excluded
+                    } else {
+                        const double th = __ddiv_rn(__dadd_rn(qv[j], -Qw[j]), den);
+                        const double d_j = __ddiv_rn(__dadd_rn(1.0, -fabs(th)), sqrt(dg[j]));
+                        keep = d_j <= radius;
+                        if (!keep) {
+                            evict_nonzero = w[j] != 0.0;
+                            excluded[j] = 1;
+                        } else excluded[j] = 0;
                     }
                 }
-                ctl.n_active = na;
-                ctl.n_zero = nz;
+                const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+                const uint32_t mz = __ballot_sync(0xffffffffu, evict_nonzero);
+                const uint32_t lt = (1u << lane) - 1u;
+                if (keep) active[na + __popc(mk & lt)] = j;
+                if (evict_nonzero) zlist[nz + __popc(mz & lt)] = j;
+                na += __popc(mk);
+                nz += __popc(mz);
             }
-            __syncthreads();
-            const int nz = ctl.n_zero;
-            for (int z = 0; z < nz; ++z) {  // Qw -= w[j] * Q[j,:], in ascending j like the model
-                const int j = zlist[z];
-                const double a = -w[j];
-                for (int e = tid; e < c; e += LT) Qw[e] = __dadd_rn(Qw[e], __dmul_rn(a, Q[(int64_t)j * c + e]));
+            __syncwarp();
+            for (int z = 0; z < nz; ++z) {  // Qw -= w[j] * Q[j,:], ascending j like the model
+                const uint32_t j = zlist[z];
+                axpy_row_direct(j, -w[j]);
             }
-            __syncthreads();
-            if (tid == 0)
-                for (int z = 0; z < nz; ++z) w[zlist[z]] = 0.0;
-            __syncthreads();
-            n_active = ctl.n_active;
+            __syncwarp();
+            for (int z = lane; z < nz; z += 32) w[zlist[z]] = 0.0;
+            __syncwarp();
+            n_active = na;
         };
 
         gap_check();
-        gap = ctl.gap;
-        bool converged0 = gap <= tolS;
-        if (!converged0) {
-            for (int j = tid; j < c; j += LT) excluded[j] = 0;
-            __syncthreads();
+        if (!(gap <= tolS)) {
             screen(true);
             bool broke = false;
             int n_iter = 0;
             for (n_iter = 0; n_iter < P.max_iter; ++n_iter) {
                 double w_max = 0.0, d_w_max = 0.0;
-                // prime the ring along the coordinate sequence of this sweep
-                uint32_t la = state;
-                const int nprime = n_active < RING ? n_active : RING;
-                for (int d = 0; d < RING; ++d) {
-                    if (d < nprime) {
-                        const uint32_t jd = active[rand_int((uint32_t)n_active, la)];
-                        const double *src = Q + (int64_t)jd * c;
-                        double *dst = ring + (size_t)d * c;
-                        for (int e = tid; e < c; e += LT) cp_async8(dst + e, src + e);
+                if (n_active > 0) {
+                    const uint64_t M = ~0ull / (uint32_t)n_active + 1ull;
+                    // prime the ring and the coordinate queue
+#pragma unroll
+                    for (int d = 0; d < RING; ++d) {
+                        if (d < n_active) {
+                            const uint32_t jd = active[fastmod(xorshift(la), M, (uint32_t)n_active)];
+                            if (lane == 0) jq[d] = jd;
+                            prefetch_row(jd, d);
+                        }
+                        cp_async_commit();
                     }
-                    cp_async_commit();
-                }
-                for (int f = 0; f < n_active; ++f) {
-                    const uint32_t j = active[rand_int((uint32_t)n_active, state)];
-                    const int slot = f % RING;
-                    if ((int)(j % LT) == tid) {  // owner of coordinate j
+                    __syncwarp();
+                    // soft-threshold update of coordinate j given the current Qw[j]; all lanes redundantly
+                    auto cd_update = [&](uint32_t j, double x, double w_j, double &delta, double &aw, double &w_new) {
                         const double Qjj = dg[j];
-                        double delta = 0.0, aw = -1.0;  // aw < 0 flags the "Qjj == 0: continue" case
+                        delta = 0.0;
+                        aw = -1.0;  // aw < 0 flags "Qjj == 0: continue"
+                        w_new = w_j;
                         if (Qjj != 0.0) {
-                            const double w_j = w[j];
-                            const double tmp = __dadd_rn(__dadd_rn(qv[j], -Qw[j]), __dmul_rn(w_j, Qjj));
-                            const double sgn = tmp == 0.0 ? 0.0 : (tmp > 0.0 ? 1.0 : -1.0);
+                            const double tmp = __dadd_rn(__dadd_rn(qv[j], -x), __dmul_rn(w_j, Qjj));
                             const double mag = __dadd_rn(fabs(tmp), -l1);
-                            const double w_new = __ddiv_rn(__dmul_rn(sgn, mag > 0.0 ? mag : 0.0), Qjj);
-                            w[j] = w_new;
+                            // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
+                            w_new = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rc[j])
+                                              : (tmp < 0.0 ? -0.0 : 0.0);
                             delta = __dadd_rn(w_new, -w_j);
                             aw = fabs(w_new);
                         }
-                        ctl.bc[f & 1][0] = delta;
-                        ctl.bc[f & 1][1] = aw;
-                    }
-                    cp_async_wait<RING - 1>();  // this thread's copies of the row for step f have landed
-                    __syncthreads();
-                    const double delta = ctl.bc[f & 1][0], aw = ctl.bc[f & 1][1];
-                    if (aw >= 0.0) {
-                        if (delta != 0.0) {
-                            const double *row = ring + (size_t)slot * c;
-                            for (int e = tid; e < c; e += LT) Qw[e] = __dadd_rn(Qw[e], __dmul_rn(delta, row[e]));
+                    };
+                    // w[] is read and written by lane 0 only during a sweep (broadcast by shuffle): no races
+                    uint32_t j = jq[0];
+                    double delta, aw, w_new;
+                    cd_update(j, Qw[j], __shfl_sync(0xffffffffu, lane == 0 ? w[j] : 0.0, 0), delta, aw, w_new);
+                    if (lane == 0) w[j] = w_new;
+                    for (int f = 0; f < n_active; ++f) {
+                        const int slot = f & (RING - 1);
+                        const bool has_next = f + 1 < n_active;
+                        const uint32_t jn = has_next ? jq[(f + 1) & (RING - 1)] : j;
+                        cp_async_wait<RING - 1>();  // this lane's pairs of row f have landed
+                        const double *row = ring + (size_t)slot * CP;
+                        const bool apply = (aw >= 0.0) && (delta != 0.0);
+                        // pair holding the next coordinate first, broadcast its updated value
+                        const int sn = (int)(jn >> 6);
+                        const int ln = (int)((jn >> 1) & 31);
+                        double2 vn = *reinterpret_cast<double2 *>(Qw + 64 * sn + 2 * lane);
+                        if (apply) {
+                            const double2 r = *reinterpret_cast<const double2 *>(row + 64 * sn + 2 * lane);
+                            vn.x = __dadd_rn(vn.x, __dmul_rn(delta, r.x));
+                            vn.y = __dadd_rn(vn.y, __dmul_rn(delta, r.y));
+                            *reinterpret_cast<double2 *>(Qw + 64 * sn + 2 * lane) = vn;
                         }
-                        const double d = fabs(delta);
-                        if (d > d_w_max) d_w_max = d;
-                        if (aw > w_max) w_max = aw;
+                        const double xn = __shfl_sync(0xffffffffu, (jn & 1) ? vn.y : vn.x, ln);
+                        const double w_jn = __shfl_sync(0xffffffffu, lane == 0 ? w[jn] : 0.0, 0);
+                        // bookkeeping of step f
+                        if (aw >= 0.0) {
+                            const double d = fabs(delta);
+                            if (d > d_w_max) d_w_max = d;
+                            if (aw > w_max) w_max = aw;
+                        }
+                        // serial chain of step f+1 (issued in the shadow of the remaining pair updates)
+                        double delta_n = 0.0, aw_n = -1.0, w_new_n = 0.0;
+                        if (has_next) cd_update(jn, xn, w_jn, delta_n, aw_n, w_new_n);
+                        // remaining pairs of step f
+                        if (apply) {
+#pragma unroll
+                            for (int s = 0; s < NP; ++s) {
+                                if (s != sn) {
+                                    const int e = 64 * s + 2 * lane;
+                                    const double2 r = *reinterpret_cast<const double2 *>(row + e);
+                                    double2 v = *reinterpret_cast<double2 *>(Qw + e);
+                                    v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
+                                    v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
+                                    *reinterpret_cast<double2 *>(Qw + e) = v;
+                                }
+                            }
+                        }
+                        // refill the slot just consumed with the row of step f + RING
+                        if (f + RING < n_active) {
+                            const uint32_t jf = active[fastmod(xorshift(la), M, (uint32_t)n_active)];
+                            if (lane == 0) jq[slot] = jf;
+                            prefetch_row(jf, slot);
+                        }
+                        cp_async_commit();
+                        if (has_next && lane == 0) w[jn] = w_new_n;
+                        __syncwarp();
+                        j = jn;
+                        delta = delta_n;
+                        aw = aw_n;
+                        w_new = w_new_n;
                     }
-                    if (f + RING < n_active) {
-                        const uint32_t jn = active[rand_int((uint32_t)n_active, la)];
-                        const double *src = Q + (int64_t)jn * c;
-                        double *dst = ring + (size_t)slot * c;
-                        for (int e = tid; e < c; e += LT) cp_async8(dst + e, src + e);
-                    }
-                    cp_async_commit();
+                    cp_async_wait<0>();
                 }
-                cp_async_wait<0>();
-                __syncthreads();
                 if (w_max == 0.0 || __ddiv_rn(d_w_max, w_max) <= P.tol || n_iter == P.max_iter - 1) {
                     gap_check();
-                    gap = ctl.gap;
                     if (gap <= tolS) { broke = true; break; }
                     screen(false);
                 }
             }
             n_iter_ret = broke ? n_iter + 1 : P.max_iter;
         }
-        // nnz
-        if (tid == 0) {
-            int nnz = 0;
-            for (int j = 0; j < c; ++j) nnz += (w[j] != 0.0);
-            ctl.nnz = nnz;
+        int cnt = 0;
+        for (int i = lane; i < c; i += 32) cnt += (w[i] != 0.0);
+#pragma unroll
+        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) {
             double *lg = P.out_probe_log + (size_t)probe * 4;
-            lg[0] = alpha_user; lg[1] = (double)nnz; lg[2] = (double)n_iter_ret; lg[3] = gap;
+            lg[0] = alpha_user; lg[1] = (double)cnt; lg[2] = (double)n_iter_ret; lg[3] = gap;
         }
-        __syncthreads();
         ++probe;
-        return ctl.nnz;
+        return cnt;
     };
 
     // ---- alpha search, reference lib/decompose.py:489-525
@@ -336,11 +415,11 @@ __global__ void __launch_bounds__(LT, 1) lasso_select_kernel(const SelectParams 
         else if ((double)nnz < P.lbound) right = alpha;
         else break;
     }
-    for (int e = tid; e < c; e += LT) {
+    for (int e = lane; e < c; e += 32) {
         P.out_idxs[e] = w[e] != 0.0 ? 1 : 0;
         P.out_coef[e] = w[e];
     }
-    if (tid == 0) {
+    if (lane == 0) {
         P.out_scalars[0] = alpha;
         P.out_scalars[1] = (double)probe;
         P.out_scalars[2] = (double)status;
@@ -348,42 +427,57 @@ __global__ void __launch_bounds__(LT, 1) lasso_select_kernel(const SelectParams 
     }
 }
 
+template <int NP>
+int launch_select(const SelectParams &P, cudaStream_t stream) {
+    constexpr int CP = 64 * NP;
+    const size_t smem = (size_t)CP * (5 + RING) * sizeof(double) + (size_t)CP * (2 * sizeof(uint32_t) + 1) +
+                        RING * sizeof(uint32_t) + 16;
+    static bool configured = false;
+    if (!configured) {
+        CP_CUDA(cudaFuncSetAttribute(lasso_select_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    lasso_select_kernel<NP><<<1, 32, smem, stream>>>(P);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
 }  // namespace
 
 extern "C" int cp_lasso_build(cp_handle_t h, const double *Gs, const double *Bs, const double *sxs,
                               const double *sys, const double *yys, const double *WW, const double *sw,
-                              const float *W2, int c, int k2, int n, int S, double *Q, double *qv, double *yn2,
-                              cp_stream_t stream_) {
+                              const float *W2, int c, int k2, int n, int S, double *Q, int ldq, double *qv,
+                              double *yn2, cp_stream_t stream_) {
     CP_REQUIRE(h && Gs && Bs && sxs && sys && yys && WW && sw && W2 && Q && qv && yn2, "cp_lasso_build: NULL argument");
     CP_REQUIRE(c > 0 && k2 > 0 && n > 0 && S > 0, "cp_lasso_build: bad shape");
+    CP_REQUIRE(ldq >= c && (ldq % 2) == 0, "cp_lasso_build: ldq must be even and >= c (got %d)", ldq);
     cudaStream_t stream = (cudaStream_t)stream_;
     const double m = (double)S * (double)n;
-    dim3 grid(cp_cdiv(c, 16), cp_cdiv(c, 16));
-    lasso_build_Q<<<grid, 256, 0, stream>>>(Gs, WW, sxs, sw, c, k2, m, Q);
+    dim3 grid(cp_cdiv(ldq, 16), cp_cdiv(c, 16));
+    lasso_build_Q<<<grid, 256, 0, stream>>>(Gs, WW, sxs, sw, c, k2, m, Q, ldq);
     CP_CHECK_LAUNCH();
     lasso_build_q<<<c, 128, 0, stream>>>(W2, Bs, sxs, sw, sys, yys, c, k2, n, m, qv, yn2);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
 
-extern "C" int cp_lasso_select(cp_handle_t h, const double *Q, const double *qv, const double *yn2, int c, double m,
-                               int rank, double lbound, double rbound, double right0, double tol, int max_iter,
-                               const uint32_t *seeds, int max_probes, uint8_t *out_idxs, double *out_coef,
-                               double *out_scalars, double *out_probe_log, cp_stream_t stream_) {
+extern "C" int cp_lasso_select(cp_handle_t h, const double *Q, int ldq, const double *qv, const double *yn2, int c,
+                               double m, int rank, double lbound, double rbound, double right0, double tol,
+                               int max_iter, const uint32_t *seeds, int max_probes, uint8_t *out_idxs,
+                               double *out_coef, double *out_scalars, double *out_probe_log, cp_stream_t stream_) {
     CP_REQUIRE(h && Q && qv && yn2 && seeds && out_idxs && out_coef && out_scalars && out_probe_log,
                "cp_lasso_select: NULL argument");
     CP_REQUIRE(c > 0 && c <= MAXC, "cp_lasso_select: c=%d outside 1..%d", c, MAXC);
+    CP_REQUIRE(ldq >= c && (ldq % 2) == 0 && (((uintptr_t)Q) & 15) == 0,
+               "cp_lasso_select: Q rows must be 16-byte aligned (even ldq >= c, aligned base)");
     CP_REQUIRE(max_probes > 0 && max_iter > 0 && right0 > 0 && m > 0, "cp_lasso_select: bad parameters");
-    SelectParams P{Q, qv, yn2, c, m, rank, lbound, rbound, right0, tol, max_iter, seeds, max_probes,
+    SelectParams P{Q, ldq, qv, yn2, c, m, rank, lbound, rbound, right0, tol, max_iter, seeds, max_probes,
                    out_idxs, out_coef, out_scalars, out_probe_log};
-    const size_t smem = (size_t)c * (5 + RING) * sizeof(double) + (size_t)c * (2 * sizeof(uint32_t) + 1) + 16;
-    static bool configured = false;
-    if (!configured) {
-        CP_CUDA(cudaFuncSetAttribute(lasso_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-        configured = true;
-    }
-    CP_REQUIRE(smem <= 227 * 1024 - 256, "cp_lasso_select: c=%d needs %zu bytes of shared memory", c, smem);
-    lasso_select_kernel<<<1, LT, smem, (cudaStream_t)stream_>>>(P);
-    CP_CHECK_LAUNCH();
-    return CP_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (c <= 64) return launch_select<1>(P, stream);
+    if (c <= 128) return launch_select<2>(P, stream);
+    if (c <= 256) return launch_select<4>(P, stream);
+    if (c <= 512) return launch_select<8>(P, stream);
+    if (c <= 1024) return launch_select<16>(P, stream);
+    return launch_select<32>(P, stream);
 }

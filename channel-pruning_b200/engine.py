@@ -164,26 +164,32 @@ class Engine:
     def lasso_build(self, gs, gw, W2m, c, k2, S):
         """gs: gram over sampled rows (with yy); gw: gram of W2 viewed (n, K); W2m: (n, K) fp32."""
         n = W2m.shape[0]
-        Q = self.empty(c, c)
+        ldq = c + (c & 1)  # even leading dimension: 16-byte aligned rows for the selection kernel
+        Q = self.empty(c, ldq)
         qv = self.empty(c)
         yn2 = self.empty(1)
         self._call(self.lib.cp_lasso_build(self.h, self._p(gs["G"], "const double*"), self._p(gs["B"], "const double*"),
                                            self._p(gs["sx"], "const double*"), self._p(gs["sy"], "const double*"),
                                            self._p(gs["yy"], "const double*"), self._p(gw["G"], "const double*"),
                                            self._p(gw["sx"], "const double*"), self._p(W2m, "const float*"), c, k2, n,
-                                           S, self._p(Q, "double*"), self._p(qv, "double*"), self._p(yn2, "double*"),
-                                           self._s()))
-        return Q, qv, yn2
+                                           S, self._p(Q, "double*"), ldq, self._p(qv, "double*"),
+                                           self._p(yn2, "double*"), self._s()))
+        return Q[:, :c], qv, yn2
 
     def lasso_select(self, Q, qv, yn2, m, rank, lbound, rbound, right0, seeds, tol=1e-4, max_iter=1000):
         c = Q.shape[0]
+        if Q.stride(1) != 1 or Q.stride(0) % 2 or Q.data_ptr() % 16:
+            Qp = torch.zeros(c, c + (c & 1), dtype=torch.float64, device=self.device)
+            Qp[:, :c] = Q
+            Q = Qp[:, :c]
         seeds_d = torch.as_tensor(np.asarray(seeds, dtype=np.int64), device=self.device).to(torch.int32)
         maxp = seeds_d.numel()
         idxs = self.empty(c, dtype=torch.uint8)
         coef = self.empty(c)
         scalars = self.empty(4)
         plog = torch.zeros(maxp, 4, dtype=torch.float64, device=self.device)
-        self._call(self.lib.cp_lasso_select(self.h, self._p(Q, "const double*"), self._p(qv, "const double*"),
+        self._call(self.lib.cp_lasso_select(self.h, self._p(Q, "const double*"), Q.stride(0),
+                                            self._p(qv, "const double*"),
                                             self._p(yn2, "const double*"), c, float(m), int(rank), float(lbound),
                                             float(rbound), float(right0), float(tol), int(max_iter),
                                             self._p(seeds_d, "const uint32_t*"), maxp, self._p(idxs, "uint8_t*"),

@@ -118,18 +118,21 @@ int cp_gram(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const 
  *   qv[a]  = sum_{p,j} W2[j,(a,p)] * Bs[(a,p),j]          - m zbar_a ybar
  *   yn2    = yy_s - m ybar^2,       m = S*n
  * Gs/Bs/sxs/sys/yys : cp_gram over the S sampled rows;  WW/sw : cp_gram of W2
- * viewed as an (n x c*k2) matrix.  Outputs: Q (c x c), qv (c), yn2 (1), fp64.
+ * viewed as an (n x c*k2) matrix.  Outputs: Q (c x ldq, ldq even >= c, padding column
+ * zeroed so that rows are 16-byte aligned for cp_lasso_select), qv (c), yn2 (1), fp64.
  */
 int cp_lasso_build(cp_handle_t h, const double *Gs, const double *Bs, const double *sxs, const double *sys,
                    const double *yys, const double *WW, const double *sw, const float *W2, int c, int k2,
-                   int n, int S, double *Q, double *qv, double *yn2, cp_stream_t stream);
+                   int n, int S, double *Q, int ldq, double *qv, double *yn2, cp_stream_t stream);
 
 /*
  * Channel selection -- replaces the alpha search of decompose.dictionary
  * (lib/decompose.py:489-525) including every Lasso.fit it performs
  * (sklearn _cd_fast.enet_coordinate_descent: random coordinate order from a 32-bit
  * xorshift seeded per fit, warm start, tol / duality-gap stopping rule, gap-safe
- * screening), evaluated in Gram arithmetic, fp64, in ONE launch.
+ * screening), evaluated in Gram arithmetic, fp64, in ONE launch (one warp: the search is a
+ * serial dependency chain).  Q: c x ldq row-major, ldq even, base 16-byte aligned, any
+ * padding column zero.
  *
  *   right0        : cfgs.alpha on entry (lib/decompose.py:491)
  *   rank, lbound, rbound : target count and acceptance window (:492-501)
@@ -139,7 +142,7 @@ int cp_lasso_build(cp_handle_t h, const double *Gs, const double *Bs, const doub
  *   out_scalars   : [alpha, n_probes, status, nnz]  (status 0 ok, 1 probe cap hit)
  *   out_probe_log : max_probes x 4 doubles (alpha, nnz, n_iter, gap)
  */
-int cp_lasso_select(cp_handle_t h, const double *Q, const double *qv, const double *yn2, int c, double m,
+int cp_lasso_select(cp_handle_t h, const double *Q, int ldq, const double *qv, const double *yn2, int c, double m,
                     int rank, double lbound, double rbound, double right0, double tol, int max_iter,
                     const uint32_t *seeds, int max_probes, uint8_t *out_idxs, double *out_coef,
                     double *out_scalars, double *out_probe_log, cp_stream_t stream);

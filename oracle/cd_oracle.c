@@ -13,8 +13,8 @@
  * cp_enet_cd_dense  follows enet_coordinate_descent statement by statement
  *                   (including the gap-safe screening rule of 1.9.0).
  * cp_enet_cd_gram   is the same control flow evaluated in Gram arithmetic
- *                   (Q = X'X, q = X'y, |y|^2): the executable specification of
- *                   the CUDA kernel cp_lasso_select (csrc/lasso.cu).
+ *                   (Q = X'X, q = X'y, |y|^2): the executable, bit-exact specification
+ *                   of the CUDA kernel cp_lasso_select (csrc/lasso.cu).
  *
  * Parity is pinned in tests/test_oracle.py against sklearn itself and against
  * golden vectors produced by the reference's own lib/decompose.py.
@@ -158,31 +158,63 @@ done:
 }
 
 /*
- * Same control flow, Gram arithmetic.  Q (nf x nf, row-major, symmetric) = X'X, q = X'y, y_norm2 = y'y
- * (all of centred data).  This is what csrc/lasso.cu implements on the device.
- * Qw is caller-provided scratch of nf doubles (in/out not required).
+ * Same control flow, Gram arithmetic.  Q (nf x nf, row-major, leading dimension ldq, symmetric)
+ * = X'X, q = X'y, y_norm2 = y'y (all of centred data).  This is, operation for operation, what
+ * the CUDA kernel cp_lasso_select (csrc/lasso.cu) executes:
+ *   - Qw = Q w is CARRIED between fits (in/out argument; all zeros with w = 0 before the first
+ *     fit) instead of being recomputed from w at every fit start as sklearn recomputes R = y - Xw
+ *     (a 1e-16-level rounding difference, not an algorithmic one);
+ *   - the reductions of the duality-gap check run in "warp order": 32 strided partial sums
+ *     combined by a 5-level butterfly, which is how 32 lanes evaluate them;
+ *   - every product/sum is rounded separately (no FMA), division is IEEE.
  */
+static double wdot(int n, const double *a, const double *b) {
+    double p[32], t[32];
+    for (int l = 0; l < 32; ++l) {
+        double s = 0.0;
+        for (int i = l; i < n; i += 32) s += a[i] * b[i];
+        p[l] = s;
+    }
+    for (int off = 16; off; off >>= 1) {
+        for (int l = 0; l < 32; ++l) t[l] = p[l] + p[l ^ off];
+        memcpy(p, t, sizeof(p));
+    }
+    return p[0];
+}
+static double wasum(int n, const double *a) {
+    double p[32], t[32];
+    for (int l = 0; l < 32; ++l) {
+        double s = 0.0;
+        for (int i = l; i < n; i += 32) s += fabs(a[i]);
+        p[l] = s;
+    }
+    for (int off = 16; off; off >>= 1) {
+        for (int l = 0; l < 32; ++l) t[l] = p[l] + p[l ^ off];
+        memcpy(p, t, sizeof(p));
+    }
+    return p[0];
+}
+
 static double gap_enet_gram(int nf, const double *w, double alpha, const double *Qw, const double *q,
                             double y_norm2, double *XtA, double *dual_norm_out) {
-    double q_dot_w = ddot(nf, w, q);
-    double wQw = ddot(nf, w, Qw);
+    double q_dot_w = wdot(nf, w, q);
+    double wQw = wdot(nf, w, Qw);
     double R_norm2 = y_norm2 + wQw - 2.0 * q_dot_w;
     double Ry = y_norm2 - q_dot_w;
-    double dn = 0.0, l1 = 0.0;
+    double dn = 0.0;
     for (int j = 0; j < nf; ++j) {
         XtA[j] = q[j] - Qw[j];
         double a = fabs(XtA[j]);
-        if (j == 0 || a > dn) dn = a;
-        l1 += fabs(w[j]);
+        if (a > dn) dn = a;
     }
+    double l1 = wasum(nf, w);
     *dual_norm_out = dn;
     return gap_formulation_A(alpha, 0.0, l1, 0.0, R_norm2, Ry, dn);
 }
 
-int cp_enet_cd_gram(double *w, double alpha, const double *Q, const double *q, double y_norm2, int nf,
-                    int max_iter, double tol, uint32_t seed, int random, int do_screening, double *gap_out,
+int cp_enet_cd_gram(double *w, double *Qw, double alpha, const double *Q, int ldq, const double *q, double y_norm2,
+                    int nf, int max_iter, double tol, uint32_t seed, int random, int do_screening, double *gap_out,
                     double *tol_out) {
-    double *Qw = (double *)calloc(nf, sizeof(double));
     double *XtA = (double *)malloc(sizeof(double) * nf);
     uint32_t *active = (uint32_t *)malloc(sizeof(uint32_t) * nf);
     uint8_t *excluded = (uint8_t *)malloc(nf);
@@ -191,8 +223,6 @@ int cp_enet_cd_gram(double *w, double alpha, const double *Q, const double *q, d
     unsigned n_active = nf;
     int n_iter = 0, ret_iter = 0;
     if (alpha == 0) do_screening = 0;
-    for (int j = 0; j < nf; ++j)
-        if (w[j] != 0) daxpy(nf, w[j], Q + (size_t)j * nf, Qw);
     tol *= y_norm2;
     gap = gap_enet_gram(nf, w, alpha, Qw, q, y_norm2, XtA, &dual_norm);
     if (gap <= tol) { ret_iter = 0; goto done; }
@@ -200,29 +230,31 @@ int cp_enet_cd_gram(double *w, double alpha, const double *Q, const double *q, d
         double radius = sqrt(2 * fabs(gap)) / alpha;
         n_active = 0;
         for (int j = 0; j < nf; ++j) {
-            double Qjj = Q[(size_t)j * nf + j];
+            double Qjj = Q[(size_t)j * ldq + j];
             if (Qjj == 0) { w[j] = 0; excluded[j] = 1; continue; }
             double Xj_theta = XtA[j] / dmax(alpha, dual_norm);
             double d_j = (1 - fabs(Xj_theta)) / sqrt(Qjj);
             if (d_j <= radius) { active[n_active++] = j; excluded[j] = 0; }
             else {
-                if (w[j] != 0) { daxpy(nf, -w[j], Q + (size_t)j * nf, Qw); w[j] = 0; }
+                if (w[j] != 0) { daxpy(nf, -w[j], Q + (size_t)j * ldq, Qw); w[j] = 0; }
                 excluded[j] = 1;
             }
         }
+    } else {
+        for (int j = 0; j < nf; ++j) active[j] = j;
     }
     int broke = 0;
     for (n_iter = 0; n_iter < max_iter; ++n_iter) {
         double w_max = 0.0, d_w_max = 0.0;
         for (unsigned f = 0; f < n_active; ++f) {
             unsigned j = random ? rand_int(n_active, &state) : f;
-            if (do_screening) j = active[j];
-            double Qjj = Q[(size_t)j * nf + j];
+            j = active[j];
+            double Qjj = Q[(size_t)j * ldq + j];
             if (Qjj == 0.0) continue;
             double w_j = w[j];
             double tmp = q[j] - Qw[j] + w_j * Qjj;
             w[j] = fsign(tmp) * dmax(fabs(tmp) - alpha, 0) / Qjj;
-            if (w[j] != w_j) daxpy(nf, w[j] - w_j, Q + (size_t)j * nf, Qw);
+            if (w[j] != w_j) daxpy(nf, w[j] - w_j, Q + (size_t)j * ldq, Qw);
             double d = fabs(w[j] - w_j);
             d_w_max = dmax(d_w_max, d);
             w_max = dmax(w_max, fabs(w[j]));
@@ -235,12 +267,12 @@ int cp_enet_cd_gram(double *w, double alpha, const double *Q, const double *q, d
                 n_active = 0;
                 for (int j = 0; j < nf; ++j) {
                     if (excluded[j]) continue;
-                    double Qjj = Q[(size_t)j * nf + j];
+                    double Qjj = Q[(size_t)j * ldq + j];
                     double Xj_theta = XtA[j] / dmax(alpha, dual_norm);
                     double d_j = (1 - fabs(Xj_theta)) / sqrt(Qjj);
                     if (d_j <= radius) { active[n_active++] = j; excluded[j] = 0; }
                     else {
-                        if (w[j] != 0) { daxpy(nf, -w[j], Q + (size_t)j * nf, Qw); w[j] = 0; }
+                        if (w[j] != 0) { daxpy(nf, -w[j], Q + (size_t)j * ldq, Qw); w[j] = 0; }
                         excluded[j] = 1;
                     }
                 }
@@ -251,6 +283,6 @@ int cp_enet_cd_gram(double *w, double alpha, const double *Q, const double *q, d
 done:
     *gap_out = gap;
     *tol_out = tol;
-    free(Qw); free(XtA); free(active); free(excluded);
+    free(XtA); free(active); free(excluded);
     return ret_iter;
 }

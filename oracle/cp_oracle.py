@@ -74,9 +74,9 @@ def _clib():
                                          ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_uint32,
                                          ctypes.c_int, ctypes.c_int, dp, dp]
         lib.cp_enet_cd_gram.restype = ctypes.c_int
-        lib.cp_enet_cd_gram.argtypes = [dp, ctypes.c_double, dp, dp, ctypes.c_double, ctypes.c_int,
-                                        ctypes.c_int, ctypes.c_double, ctypes.c_uint32, ctypes.c_int,
-                                        ctypes.c_int, dp, dp]
+        lib.cp_enet_cd_gram.argtypes = [dp, dp, ctypes.c_double, dp, ctypes.c_int, dp, ctypes.c_double,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_uint32,
+                                        ctypes.c_int, ctypes.c_int, dp, dp]
         lib.cp_our_rand_r.restype = ctypes.c_uint32
         lib.cp_our_rand_r.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
         _LIB = lib
@@ -120,6 +120,7 @@ class LassoCD:
         self.rng = rng if rng is not None else np.random.mtrand._rand
         self.do_screening = do_screening
         self.coef_ = None
+        self._Qw = None  # Gram form: Q @ coef_, carried between fits like the device kernel does
         self._prep = None
         self.history = []  # (alpha, seed, n_iter, gap, nnz)
 
@@ -157,8 +158,10 @@ class LassoCD:
                                               ctypes.byref(gap), ctypes.byref(tol_s))
         else:
             Q, q, yn2 = extra
-            n_iter = _clib().cp_enet_cd_gram(_dp(w), l1_reg, _dp(Q), _dp(q), yn2, nf, self.max_iter,
-                                             self.tol, seed, 1, int(self.do_screening),
+            if self._Qw is None:
+                self._Qw = np.ascontiguousarray(Q @ w)  # zeros on a cold start
+            n_iter = _clib().cp_enet_cd_gram(_dp(w), _dp(self._Qw), l1_reg, _dp(Q), nf, _dp(q), yn2, nf,
+                                             self.max_iter, self.tol, seed, 1, int(self.do_screening),
                                              ctypes.byref(gap), ctypes.byref(tol_s))
         self.coef_ = w
         self.intercept_ = ymean - zmean @ w

@@ -153,7 +153,8 @@ def test_lasso_build_matches_centred_design(engine, c, n, N, k):
     np.testing.assert_allclose(yn2.cpu().numpy()[0], yc @ yc, rtol=1e-11)
 
 
-@pytest.mark.parametrize("c,n,N,k,rank", [(32, 16, 600, 3, 27), (96, 32, 800, 1, 83), (300, 24, 1000, 3, 260)])
+@pytest.mark.parametrize("c,n,N,k,rank", [(32, 16, 600, 3, 27), (96, 32, 800, 1, 83), (131, 24, 1000, 3, 113),
+                                           (300, 24, 1000, 3, 260), (600, 8, 2000, 1, 520)])
 def test_lasso_select_bit_exact_vs_gram_model(engine, c, n, N, k, rank):
     """Device alpha search == oracle/cd_oracle.c:cp_enet_cd_gram driven by the same search loop,
     fed the device-built (Q, q, |y|^2): identical probes, iteration counts, coefficients (bitwise)."""
@@ -174,12 +175,13 @@ def test_lasso_select_bit_exact_vs_gram_model(engine, c, n, N, k, rank):
     # model: same search, C Gram-form CD
     lib = O._clib()
     w = np.zeros(c)
+    Qw = np.zeros(c)  # carried between fits, like the kernel
     gap, tol_s = ctypes.c_double(), ctypes.c_double()
     probes = []
 
     def solve(a):
-        it = lib.cp_enet_cd_gram(O._dp(w), a * m, O._dp(Q), O._dp(q), yn2, c, 1000, 1e-4, int(seeds[len(probes)]), 1,
-                                 1, ctypes.byref(gap), ctypes.byref(tol_s))
+        it = lib.cp_enet_cd_gram(O._dp(w), O._dp(Qw), a * m, O._dp(Q), c, O._dp(q), yn2, c, 1000, 1e-4,
+                                 int(seeds[len(probes)]), 1, 1, ctypes.byref(gap), ctypes.byref(tol_s))
         nnz = int(np.count_nonzero(w))
         probes.append((a, nnz, it, gap.value))
         return nnz
