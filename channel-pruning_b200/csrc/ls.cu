@@ -42,58 +42,87 @@ ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const 
 }
 
 // ---------------------------------------------------------------- 64x64 diagonal block: L and L^-1
-constexpr int PD = NB + 1;
-constexpr size_t POTRF_SMEM = (2 * NB * PD + NB) * sizeof(double);
+// One CTA of 1024 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 16 m (m = 0..3) of
+// column j in registers.  Right-looking factorisation: at step k the 16 threads of column k publish the
+// raw column (pivot included) to shared memory, ONE barrier, then every thread applies the rank-1 update
+// to its 4 registers.  The inverse is a forward substitution with the same ownership (one barrier per
+// row).  ~2 x 64 barriers of ~130 cycles instead of the earlier 4 x 64 x (division + 16-trip loops).
+constexpr int PT = 1024;
+constexpr size_t POTRF_SMEM = (size_t)(NB * (NB + 1) + 5 * NB) * sizeof(double);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PT, 1)
 potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv, int32_t *__restrict__ info,
            int j0, const double *__restrict__ diag0) {
-    // S: working copy; its strict upper triangle receives the finished factor transposed
-    // (L[i][k] -> S[k][i], i > k), the diagonal of L goes to Ld.  X: the inverse.
     extern __shared__ __align__(16) double psm[];
-    double *S = psm, *X = psm + NB * PD, *Ld = psm + 2 * NB * PD;
-    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 6, j = e & 63;
+    double *Ls = psm;                      // [64][65] finished factor (row-major)
+    double *col = psm + NB * (NB + 1);     // [2][64] raw column k (double buffered)
+    double *xrow = col + 2 * NB;           // [2][64] finished row k of the inverse
+    double *rsd = xrow + 2 * NB;           // [64] 1 / L[k][k]
+    const int tid = threadIdx.x, j = tid & 63, ig = tid >> 6;
+    double a[4], x[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int i = ig + 16 * m;
         double v = 0.0;
         if (i < nb && j < nb && j <= i) v = A[(int64_t)i * ld + j];
         if (i >= nb && i == j) v = 1.0;  // identity padding keeps the arithmetic finite
-        S[i * PD + j] = v;
-        X[i * PD + j] = (i == j) ? 1.0 : 0.0;
+        a[m] = v;
+        x[m] = (i == j) ? 1.0 : 0.0;
     }
     for (int k = 0; k < NB; ++k) {
+        double *ck = col + (k & 1) * NB;
+        if (j == k) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ck[ig + 16 * m] = a[m];
+        }
         __syncthreads();
-        double d = S[k * PD + k];
+        double d = ck[k];
         // pivot must stay above 1e-12 of the original diagonal entry: the squared form of the
         // sigma < 1e-6 sigma_max cut-off LinearRegression applies (sklearn _base.py:752-753)
         if (!(d > (k < nb ? 1e-12 * diag0[j0 + k] : 0.0))) {
             if (tid == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
             d = 1.0;
         }
-        const double inv = 1.0 / d;
-        if (ty == 0) {
-            const double rs = 1.0 / sqrt(d);
-            if (tx == k) Ld[k] = sqrt(d);
-            else if (tx > k) S[k * PD + tx] = S[tx * PD + k] * rs;  // L[tx][k], stored transposed
+        const double rs = rsqrt(d);
+        const double ljk = ck[j] * rs;
+        if (j == k) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int i = ig + 16 * m;
+                Ls[i * (NB + 1) + k] = (i > k) ? ck[i] * rs : (i == k ? d * rs : 0.0);
+            }
+            if (ig == 0) rsd[k] = rs;
         }
-        for (int i = k + 1 + ty; i < NB; i += 4) {
-            const int j = tx;
-            if (j > k && j <= i) S[i * PD + j] = fma(-S[i * PD + k] * inv, S[j * PD + k], S[i * PD + j]);
+        if (j > k) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int i = ig + 16 * m;
+                if (i >= j) a[m] = fma(-ck[i] * rs, ljk, a[m]);
+            }
         }
     }
     __syncthreads();
-    // X = L^-1, column-parallel forward substitution (thread column tx, 4 row lanes)
+    // X = L^-1: row k of X is final once rows < k have been eliminated
     for (int k = 0; k < NB; ++k) {
-        if (ty == 0) X[k * PD + tx] = X[k * PD + tx] / Ld[k];
+        double *xr = xrow + (k & 1) * NB;
+        if (ig == (k & 15)) {
+            const int mk = k >> 4;
+            const double xv = (mk == 0 ? x[0] : mk == 1 ? x[1] : mk == 2 ? x[2] : x[3]) * rsd[k];
+            xr[j] = xv;
+            Linv[k * NB + j] = (j <= k) ? xv : 0.0;
+        }
         __syncthreads();
-        const double xk = X[k * PD + tx];
-        for (int i = k + 1 + ty; i < NB; i += 4) X[i * PD + tx] = fma(-S[k * PD + i], xk, X[i * PD + tx]);
-        __syncthreads();
+        const double xk = xr[j];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int i = ig + 16 * m;
+            if (i > k) x[m] = fma(-Ls[i * (NB + 1) + k], xk, x[m]);
+        }
     }
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 6, j = e & 63;
-        if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = (i == j) ? Ld[i] : S[j * PD + i];
-        Linv[e] = (j <= i) ? X[i * PD + j] : 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int i = ig + 16 * m;
+        if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = Ls[i * (NB + 1) + j];
     }
 }
 
@@ -157,7 +186,7 @@ static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv
         const int nb = Kd - j0 < NB ? Kd - j0 : NB;
         const int j1 = j0 + nb;
         double *Lp = Linv + (size_t)p * NB * NB;
-        potrf_diag<<<1, 256, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0, diag0);
+        potrf_diag<<<1, PT, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0, diag0);
         CP_CHECK_LAUNCH();
         const int below = Ktot - j1;
         if (below > 0) {
