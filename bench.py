@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cpb200", choices=["cpb200", "reference"])
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=13)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--layers", default="", help="comma list of VGG layer names (debug); default all 13")

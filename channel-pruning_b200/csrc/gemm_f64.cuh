@@ -39,7 +39,6 @@ struct Args {
     int64_t r_per_split;    // multiple of BK
     double alpha, beta;     // nsplit == 1: C = alpha*acc + beta*C ; nsplit > 1: partial = acc
     int tile_mode;
-    int mirror;             // TILES_UPPER_SYM && nsplit == 1: also write C[nn, m]
     int a_vec, b_vec;       // 16-byte vector loads allowed (alignment checked by the host)
 };
 
@@ -223,7 +222,6 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
                 if (g.beta != 0.0) v = fma(g.beta, C[(int64_t)m * g.ldc + nn], v);
             }
             C[(int64_t)m * g.ldc + nn] = v;
-            if (g.mirror && !partial && ti != tj) C[(int64_t)nn * g.ldc + m] = v;
         }
     }
 }

@@ -28,7 +28,25 @@ __global__ void reduce_partials(const double *__restrict__ part, int64_t split_s
     double s = 0.0;
     for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * split_stride + (int64_t)i * ldc + j];
     C[(int64_t)i * ldc + j] = s;
-    if (sym && (i / cpgemm::BM) != (j / cpgemm::BN)) C[(int64_t)j * ldc + i] = s;
+}
+
+// C[j, i] = C[i, j] for every element of the strictly-upper 128x128 tiles, through a padded
+// shared-memory tile so that both the reads and the writes are coalesced.
+__global__ void __launch_bounds__(256)
+mirror_upper_tiles(double *__restrict__ C, int M, int64_t ldc) {
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;  // 32x32 sub-tile (row block by, column block bx)
+    if ((by * 32) / cpgemm::BM >= (bx * 32) / cpgemm::BN) return;  // only strictly-upper 128-tiles
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = by * 32 + r, j = bx * 32 + tx;
+        if (i < M && j < M) t[r][tx] = C[(int64_t)i * ldc + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bx * 32 + r, i = by * 32 + tx;
+        if (i < M && j < M) C[(int64_t)j * ldc + i] = t[tx][r];
+    }
 }
 
 // column sums (and optionally sums of squares) of an fp32 matrix, fp64 accumulation,
@@ -108,7 +126,6 @@ static int gram_product(cp_handle_t h, const float *A, int64_t lda, int M, const
     g.r_per_split = rps;
     if (nsplit == 1) {
         g.C = C; g.ldc = Nn; g.c_split_stride = 0;
-        g.mirror = sym ? 1 : 0;
         g.r_per_split = R > 0 ? R : 1;
         CP_GEMM_LAUNCH((launch<float, TB, true, true>(g, stream)));
     } else {
@@ -116,11 +133,15 @@ static int gram_product(cp_handle_t h, const float *A, int64_t lda, int M, const
         int rc = cp_ws_reserve(h, (size_t)nsplit * M * Nn * sizeof(double), &ws);
         if (rc) return rc;
         g.C = (double *)ws; g.ldc = Nn; g.c_split_stride = (int64_t)M * Nn;
-        g.mirror = 0;
         CP_GEMM_LAUNCH((launch<float, TB, true, true>(g, stream)));
         const int64_t total = (int64_t)M * Nn;
         reduce_partials<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const double *)ws, g.c_split_stride,
                                                                            nsplit, C, M, Nn, Nn, sym ? 1 : 0);
+        CP_CHECK_LAUNCH();
+    }
+    if (sym && M > BM) {
+        const int nb32 = (M + 31) / 32;
+        mirror_upper_tiles<<<dim3(nb32, nb32), 256, 0, stream>>>(C, M, Nn);
         CP_CHECK_LAUNCH();
     }
     return CP_OK;

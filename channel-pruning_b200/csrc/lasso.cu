@@ -31,7 +31,8 @@
 
 namespace {
 
-constexpr int RING = 8;     // prefetch depth (rows of Q in flight)
+// prefetch depth (rows of Q in flight): 16 while the ring fits next to the state, 8 for c > 1024
+template <int NP> struct RingDepth { static constexpr int value = NP <= 16 ? 16 : 8; };
 constexpr int MAXC = 2048;  // largest channel count (shared-memory bound)
 
 // ------------------------------------------------------------------ build
@@ -143,6 +144,7 @@ __device__ __forceinline__ double div_markstein(double num, double d, double rc)
 template <int NP>  // pairs per lane; padded channel count CP = 64 * NP
 __global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams P) {
     constexpr int CP = 64 * NP;
+    constexpr int RING = RingDepth<NP>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = P.c, lane = threadIdx.x;
     double *w = reinterpret_cast<double *>(smem_raw);  // [CP]
@@ -297,82 +299,81 @@ __global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams 
                         cp_async_commit();
                     }
                     __syncwarp();
-                    // soft-threshold update of coordinate j given the current Qw[j]; all lanes redundantly
-                    auto cd_update = [&](uint32_t j, double x, double w_j, double &delta, double &aw, double &w_new) {
-                        const double Qjj = dg[j];
-                        delta = 0.0;
-                        aw = -1.0;  // aw < 0 flags "Qjj == 0: continue"
-                        w_new = w_j;
-                        if (Qjj != 0.0) {
-                            const double tmp = __dadd_rn(__dadd_rn(qv[j], -x), __dmul_rn(w_j, Qjj));
-                            const double mag = __dadd_rn(fabs(tmp), -l1);
-                            // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
-                            w_new = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rc[j])
-                                              : (tmp < 0.0 ? -0.0 : 0.0);
-                            delta = __dadd_rn(w_new, -w_j);
-                            aw = fabs(w_new);
-                        }
+                    // soft-threshold update of one coordinate from the current x = Qw[j]; all lanes redundantly
+                    auto cd_update = [&](double qj, double Qjj, double rj, double x, double w_j, double &delta,
+                                         double &aw, double &w_new) {
+                        const double tmp = __dadd_rn(__dadd_rn(qj, -x), __dmul_rn(w_j, Qjj));
+                        const double mag = __dadd_rn(fabs(tmp), -l1);
+                        // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
+                        const double wn = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rj) : (tmp < 0.0 ? -0.0 : 0.0);
+                        const bool live = Qjj != 0.0;  // model: "if Qjj == 0: continue"
+                        w_new = live ? wn : w_j;
+                        delta = live ? __dadd_rn(wn, -w_j) : 0.0;
+                        aw = live ? fabs(wn) : -1.0;
                     };
-                    // w[] is read and written by lane 0 only during a sweep (broadcast by shuffle): no races
+                    // value of this lane's pair in slot(jx) that corresponds to column jx (garbage unless owner)
+                    auto own_elem = [&](const double *base, uint32_t jx) -> double {
+                        const double2 v = *reinterpret_cast<const double2 *>(base + 64 * (jx >> 6) + 2 * lane);
+                        return (jx & 1) ? v.y : v.x;
+                    };
+                    // ---- software pipeline: the serial chain of step f+1 runs in the shadow of step f's pair updates.
+                    // w[] is read and written by lane 0 only during a sweep (broadcast by shuffle): no races.
+                    cp_async_wait<RING - 1>();  // row 0 (own pairs)
                     uint32_t j = jq[0];
                     double delta, aw, w_new;
-                    cd_update(j, Qw[j], __shfl_sync(0xffffffffu, lane == 0 ? w[j] : 0.0, 0), delta, aw, w_new);
+                    cd_update(qv[j], dg[j], rc[j], Qw[j], __shfl_sync(0xffffffffu, lane == 0 ? w[j] : 0.0, 0), delta, aw,
+                              w_new);
                     if (lane == 0) w[j] = w_new;
+                    // package of step 1
+                    bool valid_n = n_active > 1;
+                    uint32_t jn = valid_n ? jq[1] : j;
+                    double qn = qv[jn], dn_ = dg[jn], rn = rc[jn];
+                    double wn_ = __shfl_sync(0xffffffffu, lane == 0 ? w[jn] : 0.0, 0);
+                    double xo = __shfl_sync(0xffffffffu, own_elem(Qw, jn), (jn >> 1) & 31);
+                    double rr = __shfl_sync(0xffffffffu, own_elem(ring, jn), (jn >> 1) & 31);  // row 0 sits in slot 0
                     for (int f = 0; f < n_active; ++f) {
                         const int slot = f & (RING - 1);
-                        const bool has_next = f + 1 < n_active;
-                        const uint32_t jn = has_next ? jq[(f + 1) & (RING - 1)] : j;
-                        cp_async_wait<RING - 1>();  // this lane's pairs of row f have landed
+                        cp_async_wait<RING - 2>();  // rows <= f+1 have landed (own pairs)
+                        // (1) serial chain of step f+1
+                        const double xnew = __dadd_rn(xo, __dmul_rn(delta, rr));
+                        double delta_n, aw_n, w_new_n;
+                        cd_update(qn, dn_, rn, xnew, wn_, delta_n, aw_n, w_new_n);
+                        if (valid_n && lane == 0) w[jn] = w_new_n;
+                        // (2) pair updates of step f:  Qw += delta * Q[j_f, :]
                         const double *row = ring + (size_t)slot * CP;
-                        const bool apply = (aw >= 0.0) && (delta != 0.0);
-                        // pair holding the next coordinate first, broadcast its updated value
-                        const int sn = (int)(jn >> 6);
-                        const int ln = (int)((jn >> 1) & 31);
-                        double2 vn = *reinterpret_cast<double2 *>(Qw + 64 * sn + 2 * lane);
-                        if (apply) {
-                            const double2 r = *reinterpret_cast<const double2 *>(row + 64 * sn + 2 * lane);
-                            vn.x = __dadd_rn(vn.x, __dmul_rn(delta, r.x));
-                            vn.y = __dadd_rn(vn.y, __dmul_rn(delta, r.y));
-                            *reinterpret_cast<double2 *>(Qw + 64 * sn + 2 * lane) = vn;
-                        }
-                        const double xn = __shfl_sync(0xffffffffu, (jn & 1) ? vn.y : vn.x, ln);
-                        const double w_jn = __shfl_sync(0xffffffffu, lane == 0 ? w[jn] : 0.0, 0);
-                        // bookkeeping of step f
-                        if (aw >= 0.0) {
-                            const double d = fabs(delta);
-                            if (d > d_w_max) d_w_max = d;
-                            if (aw > w_max) w_max = aw;
-                        }
-                        // serial chain of step f+1 (issued in the shadow of the remaining pair updates)
-                        double delta_n = 0.0, aw_n = -1.0, w_new_n = 0.0;
-                        if (has_next) cd_update(jn, xn, w_jn, delta_n, aw_n, w_new_n);
-                        // remaining pairs of step f
-                        if (apply) {
 #pragma unroll
-                            for (int s = 0; s < NP; ++s) {
-                                if (s != sn) {
-                                    const int e = 64 * s + 2 * lane;
-                                    const double2 r = *reinterpret_cast<const double2 *>(row + e);
-                                    double2 v = *reinterpret_cast<double2 *>(Qw + e);
-                                    v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
-                                    v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
-                                    *reinterpret_cast<double2 *>(Qw + e) = v;
-                                }
-                            }
+                        for (int s = 0; s < NP; ++s) {
+                            const int e = 64 * s + 2 * lane;
+                            const double2 r = *reinterpret_cast<const double2 *>(row + e);
+                            double2 v = *reinterpret_cast<double2 *>(Qw + e);
+                            v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
+                            v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
+                            *reinterpret_cast<double2 *>(Qw + e) = v;
                         }
-                        // refill the slot just consumed with the row of step f + RING
+                        // (3) bookkeeping of step f
+                        {
+                            const double d = fabs(delta);
+                            d_w_max = (aw >= 0.0 && d > d_w_max) ? d : d_w_max;
+                            w_max = (aw > w_max) ? aw : w_max;
+                        }
+                        // (4) package of step f+2 (needs the pair updates above and row f+1)
+                        const bool valid_nn = f + 2 < n_active;
+                        const uint32_t jnn = valid_nn ? jq[(f + 2) & (RING - 1)] : jn;
+                        const double qnn = qv[jnn], dnn = dg[jnn], rnn = rc[jnn];
+                        const double wnn = __shfl_sync(0xffffffffu, lane == 0 ? w[jnn] : 0.0, 0);
+                        const double xo2 = __shfl_sync(0xffffffffu, own_elem(Qw, jnn), (jnn >> 1) & 31);
+                        const double rr2 = __shfl_sync(0xffffffffu, own_elem(ring + (size_t)((f + 1) & (RING - 1)) * CP, jnn),
+                                                       (jnn >> 1) & 31);
+                        // (5) refill the slot just consumed with the row of step f + RING
                         if (f + RING < n_active) {
                             const uint32_t jf = active[fastmod(xorshift(la), M, (uint32_t)n_active)];
                             if (lane == 0) jq[slot] = jf;
                             prefetch_row(jf, slot);
                         }
                         cp_async_commit();
-                        if (has_next && lane == 0) w[jn] = w_new_n;
                         __syncwarp();
-                        j = jn;
-                        delta = delta_n;
-                        aw = aw_n;
-                        w_new = w_new_n;
+                        j = jn; delta = delta_n; aw = aw_n;
+                        jn = jnn; valid_n = valid_nn; qn = qnn; dn_ = dnn; rn = rnn; wn_ = wnn; xo = xo2; rr = rr2;
                     }
                     cp_async_wait<0>();
                 }
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams 
 template <int NP>
 int launch_select(const SelectParams &P, cudaStream_t stream) {
     constexpr int CP = 64 * NP;
+    constexpr int RING = RingDepth<NP>::value;
     const size_t smem = (size_t)CP * (5 + RING) * sizeof(double) + (size_t)CP * (2 * sizeof(uint32_t) + 1) +
                         RING * sizeof(uint32_t) + 16;
     static bool configured = false;
