@@ -16,6 +16,10 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
                const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy, double *sx,
                double *sy, double *yy, cudaStream_t stream);
 
+int cp_gram_fp64_products(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                          int n, int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G,
+                          double *Bxy, double *sx, double *sy, double *yy, cudaStream_t stream);
+
 namespace {
 
 // sums partials over splits in order; symmetric mode mirrors the upper tile region.
@@ -168,9 +172,15 @@ extern "C" int cp_gram(cp_handle_t h, const float *X, int64_t N, int K, int64_t 
         if (yy) CP_CUDA(cudaMemsetAsync(yy, 0, sizeof(double), stream));
         return CP_OK;
     }
-    if (mode == CP_GRAM_3XTF32)
+    if (mode == CP_GRAM_3XTF32)  // falls back to the fp64 products when TMA alignment rules are not met
         return cp_gram_tc(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
+    return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
+}
 
+int cp_gram_fp64_products(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                          int n, int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G,
+                          double *Bxy, double *sx, double *sy, double *yy, cudaStream_t stream) {
+    const int64_t R = rows ? (int64_t)nrows : N;
     if (G) {
         int rc = gram_product<float>(h, X, ldx, K, X, ldx, K, nullptr, rows, R, G, true, stream);
         if (rc) return rc;

@@ -1,8 +1,507 @@
-// cp_gram, mode CP_GRAM_3XTF32: tcgen05 tensor-core path (under construction in this file).
+// cp_gram, mode CP_GRAM_3XTF32: the tall-skinny Gram / cross product on the 5th-gen tensor cores.
+//
+//   G = X'X (K x K),  Bxy = X'(Y - b) (K x n)      X: N x K fp32 row-major, N ~ 5e3..1e5, K = c*k*k
+//
+// The reference does this arithmetic in float64 on the CPU (numpy matmul / LAPACK inside
+// LinearRegression.fit, lib/decompose.py:665-666).  tcgen05 has no fp32/fp64 MMA, so the kernel
+// evaluates every product with the error-compensated 3xTF32 scheme on SHIFTED data:
+//
+//   xs = fl32(x - s_col)            s = fp32 column mean (one extra pass): removes the rank-one
+//                                   mean component that would otherwise dominate the fp32 sums
+//   xs = hi + lo                    hi = tf32_rn(xs), lo = tf32_rn(xs - hi)  (22 mantissa bits kept)
+//   P += hi'hi + hi'lo + lo'hi      three kind::tf32 MMAs per k-step, fp32 accumulation in TMEM
+//
+// and keeps each fp32 accumulation short: the N rows are cut into chunks, every (tile, chunk)
+// is one CTA writing an fp32 partial tile, and a second kernel sums the partials in fp64 and
+// undoes the shift exactly (G = P + s T' + T s' + N s s',  T = column sums of xs in fp64).
+//
+// CTA anatomy (192 threads, one 128x128 output tile, K-major SWIZZLE_128B operands):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D boxes of raw fp32 X (32 rows x 128 cols),
+//              two-stage ring, mbarrier complete_tx
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of 128x128x8 per
+//              32-row k-block), tcgen05.commit frees operand stages / signals the epilogue
+//   warps 2-5  converters: shift, split hi/lo, TRANSPOSE the row-major box into the K-major
+//              128B-swizzled operand layout (X is "MN-major" in memory; the transposition is
+//              free here because the data passes through registers for the split anyway),
+//              fence.proxy.async, then the epilogue: tcgen05.ld 32x32b -> fp32 partial tile.
+// Bound: tensor pipe (3 passes -> at most 1/3 of the dense TF32 rate in algorithmic flops).
+#include <cuda.h>
+
 #include "common.cuh"
 
-int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n, int64_t ldy,
-               const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy, double *sx,
+int cp_gram_fp64_products(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                          int n, int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G,
+                          double *Bxy, double *sx, double *sy, double *yy, cudaStream_t stream);
+
+namespace {
+
+constexpr int TM = 128, TN = 128, KB = 32;           // output tile, rows per k-block
+constexpr int RAW_TILE = KB * TM * 4;                // 16 KB raw fp32 box
+constexpr int OP_TILE = TM * 128;                    // 16 KB operand tile (128 rows x 128 B)
+constexpr int STAGES = 2;
+constexpr int NTHREADS = 192;
+constexpr int NCONV = 128;
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int OFF_OPS = 0;                                    // STAGES x {Ahi, Alo, Bhi, Blo}
+constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // STAGES x {rawA, rawB}
+constexpr int OFF_SHIFT = OFF_RAW + STAGES * 2 * RAW_TILE;    // shiftA[128], shiftB[128] fp32
+constexpr int OFF_BAR = OFF_SHIFT + 2 * TM * 4;               // mbarriers
+constexpr int NBAR = 4 * STAGES + 1;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
+
+struct TcParams {
+    const float *shiftA;  // K   fp32 column shifts of X
+    const float *shiftB;  // K or n: shifts of the B operand (X again, or Y)
+    float *partial;       // [nchunks][ntiles][128][128]
+    int K, nB;            // columns of A source, columns of B source
+    int64_t N;
+    int rows_per_chunk;
+    int tiles_sym;        // number of upper-triangular G tiles (0 when G is not requested)
+    int tk;               // ceil(K / 128)
+    int tnb;              // ceil(nB / 128) for the X'Y tiles
+    int ntiles;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    // cute::UMMA::SmemDescriptor: start[0,14) (>>4) | LBO[16,30) | SBO[32,46) | version[46,48) = 1 | layout[61,64) = 2
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------ main kernel
+__global__ void __launch_bounds__(NTHREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- work item
+    int l = blockIdx.x, ti, tj;
+    bool is_xy = false;
+    if (l < P.tiles_sym) {
+        ti = 0;
+        while (l >= P.tk - ti) { l -= P.tk - ti; ++ti; }
+        tj = ti + l;
+    } else {
+        l -= P.tiles_sym;
+        is_xy = true;
+        ti = l / P.tnb;
+        tj = l - ti * P.tnb;
+    }
+    const bool diag = !is_xy && ti == tj;  // A and B operands are the same tile
+    const int64_t r_begin = (int64_t)blockIdx.y * P.rows_per_chunk;
+    int64_t r_end = r_begin + P.rows_per_chunk;
+    if (r_end > P.N) r_end = P.N;
+    const int nkb = (int)((r_end - r_begin + KB - 1) / KB);
+
+    auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
+    // barrier indices: raw_full[s] = s, raw_empty[s] = STAGES+s, ops_full[s] = 2*STAGES+s, ops_empty[s] = 3*STAGES+s
+    const int ACC_FULL = 4 * STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(s), 1);
+            mbar_init(bar(STAGES + s), NCONV);
+            mbar_init(bar(2 * STAGES + s), NCONV);
+            mbar_init(bar(3 * STAGES + s), 1);
+        }
+        mbar_init(bar(ACC_FULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 128 fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // column shifts of the two operand tiles
+    float *shA = reinterpret_cast<float *>(smem + OFF_SHIFT), *shB = shA + TM;
+    if (threadIdx.x < TM) {
+        const int ca = ti * TM + threadIdx.x;
+        shA[threadIdx.x] = ca < P.K ? P.shiftA[ca] : 0.f;
+        const int cb = tj * TN + threadIdx.x;
+        shB[threadIdx.x] = cb < P.nB ? P.shiftB[cb] : 0.f;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(bar(STAGES + s), ph ^ 1);  // slot free (fresh barrier passes immediately)
+                mbar_arrive_expect_tx(bar(s), diag ? RAW_TILE : 2 * RAW_TILE);
+                const int row = (int)(r_begin + (int64_t)kb * KB);
+                tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, &mapA, bar(s), ti * TM, row);
+                if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, &mapB, bar(s), tj * TN, row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // InstrDescriptor: c_format F32 (1<<4) | a,b TF32 (2<<7, 2<<10) | K-major | N>>3 at 17 | M>>4 at 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(bar(2 * STAGES + s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ops = sbase + OFF_OPS + s * 4 * OP_TILE;
+                const uint32_t a_hi = ops, a_lo = ops + OP_TILE;
+                const uint32_t b_hi = diag ? a_hi : ops + 2 * OP_TILE, b_lo = diag ? a_lo : ops + 3 * OP_TILE;
+#pragma unroll
+                for (int ks = 0; ks < KB / 8; ++ks) {
+                    const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzled row
+                    const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
+                    umma_tf32(tmem_base, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
+                    umma_tf32(tmem_base, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
+                }
+                umma_commit(bar(3 * STAGES + s));  // operand stage free once these MMAs have read it
+            }
+            umma_commit(bar(ACC_FULL));  // accumulator complete
+        }
+    } else {
+        // ===================== converters (then epilogue) =====================
+        const int t = threadIdx.x - 64;  // 0..127 = column of the raw box = row of the K-major operand
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(bar(s), ph);                    // raw boxes landed
+            mbar_wait(bar(3 * STAGES + s), ph ^ 1);   // operand stage no longer read by the tensor core
+            const int64_t row0 = r_begin + (int64_t)kb * KB;
+            const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (which == 1 && diag) break;
+                const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (s * 2 + which) * RAW_TILE);
+                unsigned char *hi = smem + OFF_OPS + (s * 4 + which * 2) * OP_TILE;
+                unsigned char *lo = hi + OP_TILE;
+                const float sh = which == 0 ? shA[t] : shB[t];
+#pragma unroll
+                for (int q = 0; q < KB / 4; ++q) {
+                    float4 h, l4;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * q + e;
+                        const float x = raw[k * TM + t];
+                        v[e] = k < nvalid ? __fsub_rn(x, sh) : 0.f;
+                    }
+                    h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+                    l4.x = tf32_rn(__fsub_rn(v[0], h.x)); l4.y = tf32_rn(__fsub_rn(v[1], h.y));
+                    l4.z = tf32_rn(__fsub_rn(v[2], h.z)); l4.w = tf32_rn(__fsub_rn(v[3], h.w));
+                    const int off = t * 128 + ((q ^ (t & 7)) << 4);  // Swizzle<3,4,3>: 16B chunk ^= row & 7
+                    *reinterpret_cast<float4 *>(hi + off) = h;
+                    *reinterpret_cast<float4 *>(lo + off) = l4;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
+            mbar_arrive(bar(2 * STAGES + s));  // operands ready
+            mbar_arrive(bar(STAGES + s));      // raw stage free
+        }
+        // ---- epilogue: TMEM -> fp32 partial tile
+        mbar_wait(bar(ACC_FULL), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
+        const int m = quad * 32 + lane;     // row of the output tile
+        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)m * TN;
+#pragma unroll
+        for (int cb = 0; cb < TN; cb += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<uint4 *>(dst + cb + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    }
+}
+
+// ------------------------------------------------------------------ small kernels around it
+// shift32[j] = fl32(sum[j] / N)
+__global__ void make_shift(const double *__restrict__ sum, int ncols, double invN, float *__restrict__ shift) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncols) shift[j] = (float)(sum[j] * invN);
+}
+
+// raw column sums (mode 0) or sums of fl32(x - shift[col]) (mode 1), fp64, fixed order
+__global__ void __launch_bounds__(256)
+colsum_f32(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, const float *__restrict__ shift,
+           double *__restrict__ out) {
+    __shared__ double s1[8][33];
+    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    double a = 0.0;
+    if (col < ncols) {
+        const float sh = shift ? shift[col] : 0.f;
+        for (int64_t r = rg; r < nrows; r += 8) a += (double)__fsub_rn(__ldg(X + r * ld + col), sh);
+    }
+    s1[rg][cx] = a;
+    __syncthreads();
+    if (rg == 0 && col < ncols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s1[k][cx];
+        out[col] = t;
+    }
+}
+
+// Sums the fp32 partial tiles over the row chunks in fp64 and undoes the shift:
+//   C[i,j] = sum_c P_c[i,j] + uA_i TB_j + TA_i uB_j + N uA_i uB_j ,  u = (double)shift32 - bias
+__global__ void __launch_bounds__(256)
+reduce_tc(const float *__restrict__ partial, int nchunks, int ntiles, int tile0, int tiles_cols, int sym, int tk,
+          const float *__restrict__ shiftA, const double *__restrict__ TA, const float *__restrict__ shiftB,
+          const float *__restrict__ biasB, const double *__restrict__ TB, double Nd, int M, int Nn,
+          double *__restrict__ C, int64_t ldc) {
+    int l = blockIdx.x, ti, tj;
+    if (sym) {
+        ti = 0;
+        while (l >= tk - ti) { l -= tk - ti; ++ti; }
+        tj = ti + l;
+    } else {
+        ti = l / tiles_cols;
+        tj = l - ti * tiles_cols;
+    }
+    const size_t tile_elems = (size_t)TM * TN;
+    const float *p0 = partial + (size_t)(tile0 + blockIdx.x) * tile_elems;
+    for (int e = threadIdx.x; e < TM * TN; e += 256) {
+        const int i = ti * TM + e / TN, j = tj * TN + e % TN;
+        if (i >= M || j >= Nn) continue;
+        double s = 0.0;
+        for (int c = 0; c < nchunks; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
+        const double ua = (double)shiftA[i];
+        const double ub = (double)shiftB[j] - (biasB ? (double)biasB[j] : 0.0);
+        s += ua * TB[j] + TA[i] * ub + Nd * ua * ub;
+        C[(int64_t)i * ldc + j] = s;
+    }
+}
+
+// out[j] = T[j] + N * ((double)shift[j] - bias[j])
+__global__ void finish_sums(const double *__restrict__ T, const float *__restrict__ shift, const float *__restrict__ bias,
+                            double Nd, int ncols, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncols) out[j] = T[j] + Nd * ((double)shift[j] - (bias ? (double)bias[j] : 0.0));
+}
+
+__global__ void __launch_bounds__(256)
+mirror_upper_tiles_tc(double *__restrict__ C, int M, int64_t ldc) {
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if ((by * 32) / TM >= (bx * 32) / TN) return;  // strictly-upper 128-tiles only
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = by * 32 + r, j = bx * 32 + tx;
+        if (i < M && j < M) t[r][tx] = C[(int64_t)i * ldc + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bx * 32 + r, i = by * 32 + tx;
+        if (i < M && j < M) C[(int64_t)j * ldc + i] = t[tx][r];
+    }
+}
+
+typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(cp_handle_t h, CUtensorMap *map, const float *base, int64_t rows, int cols, int64_t ld) {
+    if (!h->tmap_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) CP_FAIL(CP_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        h->tmap_encode = fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TM, (cuuint32_t)KB};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((encode_fn_t)h->tmap_encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box,
+                                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CP_FAIL(CP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CP_OK;
+}
+
+}  // namespace
+
+bool cp_gram_tc_eligible(const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n, int64_t ldy,
+                         const int32_t *rows, bool wantB) {
+    if (rows != nullptr || N < 64 || K < 64) return false;
+    if ((((uintptr_t)X) & 15) || (ldx % 4)) return false;  // TMA: 16-byte aligned base and row pitch
+    if (wantB && (y_dtype != CP_F32 || (((uintptr_t)Yraw) & 15) || (ldy % 4) || n < 1)) return false;
+    return true;
+}
+
+int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
+               int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy, double *sx,
                double *sy, double *yy, cudaStream_t stream) {
-    CP_FAIL(CP_ERR_INVALID, "cp_gram: CP_GRAM_3XTF32 is not available in this build");
+    const bool wantB = Bxy != nullptr;
+    if (yy != nullptr || !cp_gram_tc_eligible(X, N, K, ldx, Yraw, y_dtype, n, ldy, rows, wantB || sy != nullptr))
+        return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
+    const float *Y = (const float *)Yraw;
+    const bool haveY = (Bxy != nullptr || sy != nullptr);
+    const int tk = cp_cdiv(K, TM);
+    const int tiles_sym = G ? tk * (tk + 1) / 2 : 0;
+    const int tnb = wantB ? cp_cdiv(n, TN) : 0;
+    const int ntiles = tiles_sym + tk * tnb;
+    // rows per chunk: enough CTAs for >= 2 waves, 128 <= rows <= 1024, multiple of 32
+    int nchunks = ntiles > 0 ? cp_cdiv(2 * h->num_sms, ntiles) : 1;
+    const int cmin = cp_cdiv(N, 1024), cmax = cp_cdiv(N, 128);
+    if (nchunks < cmin) nchunks = cmin;
+    if (nchunks > cmax) nchunks = cmax;
+    if (nchunks < 1) nchunks = 1;
+    int rpc = cp_cdiv(cp_cdiv(N, nchunks), KB) * KB;
+    nchunks = cp_cdiv(N, rpc);
+
+    const size_t part_bytes = (size_t)nchunks * ntiles * TM * TN * sizeof(float);
+    const size_t need = cp_carver::need(part_bytes, 1) + 2 * cp_carver::need(K, 8) + 2 * cp_carver::need(n > 0 ? n : 1, 8) +
+                        cp_carver::need(K, 4) + cp_carver::need(n > 0 ? n : 1, 4);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, need, &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    float *partial = cv.take<float>((size_t)nchunks * ntiles * TM * TN);
+    double *sumX = cv.take<double>(K), *TX = cv.take<double>(K);
+    double *sumY = cv.take<double>(n > 0 ? n : 1), *TY = cv.take<double>(n > 0 ? n : 1);
+    float *shX = cv.take<float>(K), *shY = cv.take<float>(n > 0 ? n : 1);
+    const double invN = 1.0 / (double)N, Nd = (double)N;
+
+    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, nullptr, sumX);
+    CP_CHECK_LAUNCH();
+    make_shift<<<cp_cdiv(K, 256), 256, 0, stream>>>(sumX, K, invN, shX);
+    CP_CHECK_LAUNCH();
+    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, shX, TX);
+    CP_CHECK_LAUNCH();
+    if (haveY) {
+        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, nullptr, sumY);
+        CP_CHECK_LAUNCH();
+        make_shift<<<cp_cdiv(n, 256), 256, 0, stream>>>(sumY, n, invN, shY);
+        CP_CHECK_LAUNCH();
+        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, shY, TY);
+        CP_CHECK_LAUNCH();
+    }
+    if (ntiles > 0) {
+        CUtensorMap mapA, mapB;
+        rc = make_map(h, &mapA, X, N, K, ldx);
+        if (rc) return rc;
+        TcParams P{};
+        P.shiftA = shX; P.partial = partial; P.K = K; P.N = N; P.rows_per_chunk = rpc;
+        P.tiles_sym = tiles_sym; P.tk = tk; P.ntiles = ntiles;
+        static bool configured = false;
+        if (!configured) {
+            CP_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            configured = true;
+        }
+        // X'X tiles and X'Y tiles need different B sources -> two launches over disjoint tile ranges of
+        // the same partial buffer (blockIdx.x offsets are folded into tiles_sym / tnb).
+        if (tiles_sym > 0) {
+            TcParams Pg = P;
+            Pg.shiftB = shX; Pg.nB = K; Pg.tnb = 0; Pg.ntiles = ntiles;
+            gram_tc_kernel<<<dim3(tiles_sym, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapA, Pg);
+            CP_CHECK_LAUNCH();
+        }
+        if (wantB) {
+            rc = make_map(h, &mapB, Y, N, n, ldy);
+            if (rc) return rc;
+            TcParams Pb = P;
+            Pb.shiftB = shY; Pb.nB = n; Pb.tnb = tnb; Pb.tiles_sym = 0; Pb.ntiles = ntiles;
+            Pb.partial = partial + (size_t)tiles_sym * TM * TN;  // tile slots after the symmetric ones
+            gram_tc_kernel<<<dim3(tk * tnb, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, Pb);
+            CP_CHECK_LAUNCH();
+        }
+        if (tiles_sym > 0) {
+            reduce_tc<<<tiles_sym, 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, Nd, K, K,
+                                                    G, K);
+            CP_CHECK_LAUNCH();
+            if (K > TM) {
+                const int nb32 = cp_cdiv(K, 32);
+                mirror_upper_tiles_tc<<<dim3(nb32, nb32), 256, 0, stream>>>(G, K, K);
+                CP_CHECK_LAUNCH();
+            }
+        }
+        if (wantB) {
+            reduce_tc<<<tk * tnb, 256, 0, stream>>>(partial, nchunks, ntiles, tiles_sym, tnb, 0, tk, shX, TX, shY, y_bias, TY,
+                                                   Nd, K, n, Bxy, n);
+            CP_CHECK_LAUNCH();
+        }
+    }
+    if (sx) {
+        finish_sums<<<cp_cdiv(K, 256), 256, 0, stream>>>(TX, shX, nullptr, Nd, K, sx);
+        CP_CHECK_LAUNCH();
+    }
+    if (sy) {
+        finish_sums<<<cp_cdiv(n, 256), 256, 0, stream>>>(TY, shY, y_bias, Nd, n, sy);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
 }
