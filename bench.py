@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cpb200", choices=["cpb200", "reference"])
     ap.add_argument("--streams", type=int, default=13)
+    ap.add_argument("--gram", default="tc", choices=["tc", "fp64"],
+                    help="arithmetic of the big Gram products: tc = tcgen05 3xTF32 (default), fp64 = DFMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--layers", default="", help="comma list of VGG layer names (debug); default all 13")
@@ -215,7 +217,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    eng = cpb200.Engine(device=local, nstreams=args.streams)
+    eng = cpb200.Engine(device=local, nstreams=args.streams,
+                        gram_mode=cpb200.engine.GRAM_3XTF32 if args.gram == "tc" else cpb200.engine.GRAM_FP64)
     lib = cpb200._cabi.load()[1]
     dev = eng.device
 

@@ -159,8 +159,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_init(bar(ACC_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 128 fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    if (warp == 1) {  // TMEM: all 512 columns = 4 fp32 accumulators of 128 columns, used round-robin by k-block
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // column shifts of the two operand tiles
@@ -205,10 +205,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int ks = 0; ks < KB / 8; ++ks) {
                     const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzled row
-                    const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                    umma_tf32(tmem_base, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
-                    umma_tf32(tmem_base, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
-                    umma_tf32(tmem_base, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
+                    // The tensor core truncates when it adds into the fp32 accumulator, so long positive sums
+                    // drift low in proportion to the number of additions: rotate over 4 accumulators.
+                    const uint32_t acc = tmem_base + (uint32_t)((kb & 3) * TN);
+                    const uint32_t first = (kb < 4 && ks == 0) ? 0u : 1u;
+                    umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
+                    umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
+                    umma_tf32(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
                 }
                 umma_commit(bar(3 * STAGES + s));  // operand stage free once these MMAs have read it
             }
@@ -259,30 +262,38 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
         const int m = quad * 32 + lane;     // row of the output tile
         float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)m * TN;
+        const int nacc = nkb < 4 ? nkb : 4;
 #pragma unroll
         for (int cb = 0; cb < TN; cb += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float accv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) accv[e] = 0.f;
+            for (int a = 0; a < nacc; ++a) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TN + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 32; ++e) accv[e] += __uint_as_float(r[e]);
+            }
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<uint4 *>(dst + cb + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+                *reinterpret_cast<float4 *>(dst + cb + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -296,22 +307,28 @@ __global__ void make_shift(const double *__restrict__ sum, int ncols, double inv
 // raw column sums (mode 0) or sums of fl32(x - shift[col]) (mode 1), fp64, fixed order
 __global__ void __launch_bounds__(256)
 colsum_f32(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, const float *__restrict__ shift,
-           double *__restrict__ out) {
-    __shared__ double s1[8][33];
+           double *__restrict__ out, double *__restrict__ out_sq) {
+    __shared__ double s1[8][33], s2[8][33];
     const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
-    double a = 0.0;
+    double a = 0.0, q = 0.0;
     if (col < ncols) {
         const float sh = shift ? shift[col] : 0.f;
-        for (int64_t r = rg; r < nrows; r += 8) a += (double)__fsub_rn(__ldg(X + r * ld + col), sh);
+        for (int64_t r = rg; r < nrows; r += 8) {
+            const double v = (double)__fsub_rn(__ldg(X + r * ld + col), sh);
+            a += v;
+            q = fma(v, v, q);
+        }
     }
     s1[rg][cx] = a;
+    s2[rg][cx] = q;
     __syncthreads();
     if (rg == 0 && col < ncols) {
-        double t = 0.0;
+        double t = 0.0, t2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += s1[k][cx];
+        for (int k = 0; k < 8; ++k) { t += s1[k][cx]; t2 += s2[k][cx]; }
         out[col] = t;
+        if (out_sq) out_sq[col] = t2;
     }
 }
 
@@ -320,8 +337,8 @@ colsum_f32(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, co
 __global__ void __launch_bounds__(256)
 reduce_tc(const float *__restrict__ partial, int nchunks, int ntiles, int tile0, int tiles_cols, int sym, int tk,
           const float *__restrict__ shiftA, const double *__restrict__ TA, const float *__restrict__ shiftB,
-          const float *__restrict__ biasB, const double *__restrict__ TB, double Nd, int M, int Nn,
-          double *__restrict__ C, int64_t ldc) {
+          const float *__restrict__ biasB, const double *__restrict__ TB, const double *__restrict__ diag_sq, double Nd,
+          int M, int Nn, double *__restrict__ C, int64_t ldc) {
     int l = blockIdx.x, ti, tj;
     if (sym) {
         ti = 0;
@@ -338,6 +355,9 @@ reduce_tc(const float *__restrict__ partial, int nchunks, int ntiles, int tile0,
         if (i >= M || j >= Nn) continue;
         double s = 0.0;
         for (int c = 0; c < nchunks; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
+        // the diagonal is a sum of squares (no cancellation: worst case for the truncating fp32
+        // accumulation) and costs one fused pass to get exactly -- use the fp64 value
+        if (sym && i == j) s = diag_sq[i];
         const double ua = (double)shiftA[i];
         const double ub = (double)shiftB[j] - (biasB ? (double)biasB[j] : 0.0);
         s += ua * TB[j] + TA[i] * ub + Nd * ua * ub;
@@ -414,9 +434,9 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
     const int tiles_sym = G ? tk * (tk + 1) / 2 : 0;
     const int tnb = wantB ? cp_cdiv(n, TN) : 0;
     const int ntiles = tiles_sym + tk * tnb;
-    // rows per chunk: enough CTAs for >= 2 waves, 128 <= rows <= 1024, multiple of 32
+    // rows per chunk: enough CTAs for >= 2 waves, 128 <= rows <= 512 (short fp32 accumulations), multiple of 32
     int nchunks = ntiles > 0 ? cp_cdiv(2 * h->num_sms, ntiles) : 1;
-    const int cmin = cp_cdiv(N, 1024), cmax = cp_cdiv(N, 128);
+    const int cmin = cp_cdiv(N, 512), cmax = cp_cdiv(N, 128);
     if (nchunks < cmin) nchunks = cmin;
     if (nchunks > cmax) nchunks = cmax;
     if (nchunks < 1) nchunks = 1;
@@ -424,30 +444,30 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
     nchunks = cp_cdiv(N, rpc);
 
     const size_t part_bytes = (size_t)nchunks * ntiles * TM * TN * sizeof(float);
-    const size_t need = cp_carver::need(part_bytes, 1) + 2 * cp_carver::need(K, 8) + 2 * cp_carver::need(n > 0 ? n : 1, 8) +
+    const size_t need = cp_carver::need(part_bytes, 1) + 3 * cp_carver::need(K, 8) + 2 * cp_carver::need(n > 0 ? n : 1, 8) +
                         cp_carver::need(K, 4) + cp_carver::need(n > 0 ? n : 1, 4);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     float *partial = cv.take<float>((size_t)nchunks * ntiles * TM * TN);
-    double *sumX = cv.take<double>(K), *TX = cv.take<double>(K);
+    double *sumX = cv.take<double>(K), *TX = cv.take<double>(K), *SQX = cv.take<double>(K);
     double *sumY = cv.take<double>(n > 0 ? n : 1), *TY = cv.take<double>(n > 0 ? n : 1);
     float *shX = cv.take<float>(K), *shY = cv.take<float>(n > 0 ? n : 1);
     const double invN = 1.0 / (double)N, Nd = (double)N;
 
-    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, nullptr, sumX);
+    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, nullptr, sumX, nullptr);
     CP_CHECK_LAUNCH();
     make_shift<<<cp_cdiv(K, 256), 256, 0, stream>>>(sumX, K, invN, shX);
     CP_CHECK_LAUNCH();
-    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, shX, TX);
+    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, shX, TX, SQX);
     CP_CHECK_LAUNCH();
     if (haveY) {
-        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, nullptr, sumY);
+        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, nullptr, sumY, nullptr);
         CP_CHECK_LAUNCH();
         make_shift<<<cp_cdiv(n, 256), 256, 0, stream>>>(sumY, n, invN, shY);
         CP_CHECK_LAUNCH();
-        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, shY, TY);
+        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, shY, TY, nullptr);
         CP_CHECK_LAUNCH();
     }
     if (ntiles > 0) {
@@ -480,8 +500,8 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
             CP_CHECK_LAUNCH();
         }
         if (tiles_sym > 0) {
-            reduce_tc<<<tiles_sym, 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, Nd, K, K,
-                                                    G, K);
+            reduce_tc<<<tiles_sym, 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, SQX, Nd,
+                                                    K, K, G, K);
             CP_CHECK_LAUNCH();
             if (K > TM) {
                 const int nb32 = cp_cdiv(K, 32);
@@ -491,7 +511,7 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
         }
         if (wantB) {
             reduce_tc<<<tk * tnb, 256, 0, stream>>>(partial, nchunks, ntiles, tiles_sym, tnb, 0, tk, shX, TX, shY, y_bias, TY,
-                                                   Nd, K, n, Bxy, n);
+                                                   nullptr, Nd, K, n, Bxy, n);
             CP_CHECK_LAUNCH();
         }
     }
