@@ -27,6 +27,8 @@
 // Bound: tensor pipe (3 passes -> at most 1/3 of the dense TF32 rate in algorithmic flops).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 int cp_gram_fp64_products(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
@@ -39,8 +41,8 @@ constexpr int TM = 128, TN = 128, KB = 32;           // output tile, rows per k-
 constexpr int RAW_TILE = KB * TM * 4;                // 16 KB raw fp32 box
 constexpr int OP_TILE = TM * 128;                    // 16 KB operand tile (128 rows x 128 B)
 constexpr int STAGES = 2;
-constexpr int NTHREADS = 192;
-constexpr int NCONV = 128;
+constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 converters/epilogue
+constexpr int NCONV = 256;
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_OPS = 0;                                    // STAGES x {Ahi, Alo, Bhi, Blo}
 constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // STAGES x {rawA, rawB}
@@ -111,10 +113,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa with two full-rate integer ops; identical to
+// cvt.rna.tf32.f32 for finite inputs, but not issued on the quarter-rate conversion pipe
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -219,7 +221,34 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         // ===================== converters (then epilogue) =====================
-        const int t = threadIdx.x - 64;  // 0..127 = column of the raw box = row of the K-major operand
+        const int t = threadIdx.x - 64;   // 0..255
+        const int m = t & 127;            // column of the raw box = row of the K-major operand
+        const int kh = t >> 7;            // which half of the 32-row k-block this thread converts
+        auto convert = [&](int s, int which, int nvalid, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (s * 2 + which) * RAW_TILE);
+            unsigned char *hi = smem + OFF_OPS + (s * 4 + which * 2) * OP_TILE + m * 128;
+            unsigned char *lo = hi + OP_TILE;
+            const float sh = which == 0 ? shA[m] : shB[m];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int q = kh * 4 + q4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * q + e;
+                    const float x = raw[k * TM + m];
+                    v[e] = (FULL || k < nvalid) ? __fsub_rn(x, sh) : 0.f;
+                }
+                float4 h, l4;
+                h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+                l4.x = tf32_rn(__fsub_rn(v[0], h.x)); l4.y = tf32_rn(__fsub_rn(v[1], h.y));
+                l4.z = tf32_rn(__fsub_rn(v[2], h.z)); l4.w = tf32_rn(__fsub_rn(v[3], h.w));
+                const int off = (q ^ (m & 7)) << 4;  // Swizzle<3,4,3>: 16B chunk ^= row & 7
+                *reinterpret_cast<float4 *>(hi + off) = h;
+                *reinterpret_cast<float4 *>(lo + off) = l4;
+            }
+        };
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
@@ -227,30 +256,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(bar(3 * STAGES + s), ph ^ 1);   // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                if (which == 1 && diag) break;
-                const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (s * 2 + which) * RAW_TILE);
-                unsigned char *hi = smem + OFF_OPS + (s * 4 + which * 2) * OP_TILE;
-                unsigned char *lo = hi + OP_TILE;
-                const float sh = which == 0 ? shA[t] : shB[t];
-#pragma unroll
-                for (int q = 0; q < KB / 4; ++q) {
-                    float4 h, l4;
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = 4 * q + e;
-                        const float x = raw[k * TM + t];
-                        v[e] = k < nvalid ? __fsub_rn(x, sh) : 0.f;
-                    }
-                    h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
-                    l4.x = tf32_rn(__fsub_rn(v[0], h.x)); l4.y = tf32_rn(__fsub_rn(v[1], h.y));
-                    l4.z = tf32_rn(__fsub_rn(v[2], h.z)); l4.w = tf32_rn(__fsub_rn(v[3], h.w));
-                    const int off = t * 128 + ((q ^ (t & 7)) << 4);  // Swizzle<3,4,3>: 16B chunk ^= row & 7
-                    *reinterpret_cast<float4 *>(hi + off) = h;
-                    *reinterpret_cast<float4 *>(lo + off) = l4;
-                }
+            if (nvalid == KB) {
+                convert(s, 0, KB, std::true_type{});
+                if (!diag) convert(s, 1, KB, std::true_type{});
+            } else {
+                convert(s, 0, nvalid, std::false_type{});
+                if (!diag) convert(s, 1, nvalid, std::false_type{});
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(bar(2 * STAGES + s));  // operands ready
@@ -260,11 +271,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(bar(ACC_FULL), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
-        const int m = quad * 32 + lane;     // row of the output tile
-        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)m * TN;
+        const int mrow = quad * 32 + lane;  // row of the output tile
+        const int chalf = (warp - 2) >> 2;  // two warps share a lane quadrant: each drains 64 of the 128 columns
+        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)mrow * TN;
         const int nacc = nkb < 4 ? nkb : 4;
 #pragma unroll
-        for (int cb = 0; cb < TN; cb += 32) {
+        for (int cb = chalf * 64; cb < chalf * 64 + 64; cb += 32) {
             float accv[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) accv[e] = 0.f;
@@ -298,23 +310,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------ small kernels around it
-// shift32[j] = fl32(sum[j] / N)
-__global__ void make_shift(const double *__restrict__ sum, int ncols, double invN, float *__restrict__ shift) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < ncols) shift[j] = (float)(sum[j] * invN);
-}
+constexpr int RS = 32;  // row splits of the column-sum passes (parallelism; partials combined in fixed order)
 
-// raw column sums (mode 0) or sums of fl32(x - shift[col]) (mode 1), fp64, fixed order
+// partial column sums over a slice of the rows: raw values (shift == nullptr) or fl32(x - shift[col]);
+// optionally sums of squares; fp64, fixed order
 __global__ void __launch_bounds__(256)
-colsum_f32(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, const float *__restrict__ shift,
-           double *__restrict__ out, double *__restrict__ out_sq) {
+colsum_part(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, const float *__restrict__ shift,
+            double *__restrict__ part, double *__restrict__ part_sq) {
     __shared__ double s1[8][33], s2[8][33];
     const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
+    const int64_t per = (nrows + RS - 1) / RS;
+    const int64_t r0 = (int64_t)blockIdx.y * per;
+    const int64_t r1 = r0 + per < nrows ? r0 + per : nrows;
     double a = 0.0, q = 0.0;
     if (col < ncols) {
         const float sh = shift ? shift[col] : 0.f;
-        for (int64_t r = rg; r < nrows; r += 8) {
+        for (int64_t r = r0 + rg; r < r1; r += 8) {
             const double v = (double)__fsub_rn(__ldg(X + r * ld + col), sh);
             a += v;
             q = fma(v, v, q);
@@ -327,9 +339,24 @@ colsum_f32(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, co
         double t = 0.0, t2 = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { t += s1[k][cx]; t2 += s2[k][cx]; }
-        out[col] = t;
-        if (out_sq) out_sq[col] = t2;
+        part[(size_t)blockIdx.y * ncols + col] = t;
+        if (part_sq) part_sq[(size_t)blockIdx.y * ncols + col] = t2;
     }
+}
+
+// out[j] = sum_rs part[rs][j]; optionally shift32[j] = fl32(out[j] / N)
+__global__ void colsum_finish(const double *__restrict__ part, const double *__restrict__ part_sq, int ncols, double invN,
+                              double *__restrict__ out, double *__restrict__ out_sq, float *__restrict__ shift_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    double t = 0.0, t2 = 0.0;
+    for (int r = 0; r < RS; ++r) {
+        t += part[(size_t)r * ncols + j];
+        if (part_sq) t2 += part_sq[(size_t)r * ncols + j];
+    }
+    if (out) out[j] = t;
+    if (out_sq) out_sq[j] = t2;
+    if (shift_out) shift_out[j] = (float)(t * invN);
 }
 
 // Sums the fp32 partial tiles over the row chunks in fp64 and undoes the shift:
@@ -350,7 +377,8 @@ reduce_tc(const float *__restrict__ partial, int nchunks, int ntiles, int tile0,
     }
     const size_t tile_elems = (size_t)TM * TN;
     const float *p0 = partial + (size_t)(tile0 + blockIdx.x) * tile_elems;
-    for (int e = threadIdx.x; e < TM * TN; e += 256) {
+    const int e0 = blockIdx.y * (TM * TN / 4);  // four CTAs per tile
+    for (int e = e0 + threadIdx.x; e < e0 + TM * TN / 4; e += 256) {
         const int i = ti * TM + e / TN, j = tj * TN + e % TN;
         if (i >= M || j >= Nn) continue;
         double s = 0.0;
@@ -444,30 +472,37 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
     nchunks = cp_cdiv(N, rpc);
 
     const size_t part_bytes = (size_t)nchunks * ntiles * TM * TN * sizeof(float);
-    const size_t need = cp_carver::need(part_bytes, 1) + 3 * cp_carver::need(K, 8) + 2 * cp_carver::need(n > 0 ? n : 1, 8) +
+    const size_t need = cp_carver::need(part_bytes, 1) + 2 * cp_carver::need(K, 8) + cp_carver::need(n > 0 ? n : 1, 8) +
+                        2 * cp_carver::need((size_t)RS * (K > n ? K : n), 8) +
                         cp_carver::need(K, 4) + cp_carver::need(n > 0 ? n : 1, 4);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     float *partial = cv.take<float>((size_t)nchunks * ntiles * TM * TN);
-    double *sumX = cv.take<double>(K), *TX = cv.take<double>(K), *SQX = cv.take<double>(K);
-    double *sumY = cv.take<double>(n > 0 ? n : 1), *TY = cv.take<double>(n > 0 ? n : 1);
+    double *TX = cv.take<double>(K), *SQX = cv.take<double>(K);
+    double *TY = cv.take<double>(n > 0 ? n : 1);
+    const int wmax = K > n ? K : n;
+    double *cpart = cv.take<double>((size_t)RS * wmax), *cpart_sq = cv.take<double>((size_t)RS * wmax);
     float *shX = cv.take<float>(K), *shY = cv.take<float>(n > 0 ? n : 1);
     const double invN = 1.0 / (double)N, Nd = (double)N;
 
-    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, nullptr, sumX, nullptr);
+    colsum_part<<<dim3(cp_cdiv(K, 32), RS), 256, 0, stream>>>(X, ldx, K, N, nullptr, cpart, nullptr);
     CP_CHECK_LAUNCH();
-    make_shift<<<cp_cdiv(K, 256), 256, 0, stream>>>(sumX, K, invN, shX);
+    colsum_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, nullptr, K, invN, nullptr, nullptr, shX);
     CP_CHECK_LAUNCH();
-    colsum_f32<<<cp_cdiv(K, 32), 256, 0, stream>>>(X, ldx, K, N, shX, TX, SQX);
+    colsum_part<<<dim3(cp_cdiv(K, 32), RS), 256, 0, stream>>>(X, ldx, K, N, shX, cpart, cpart_sq);
+    CP_CHECK_LAUNCH();
+    colsum_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, cpart_sq, K, invN, TX, SQX, nullptr);
     CP_CHECK_LAUNCH();
     if (haveY) {
-        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, nullptr, sumY, nullptr);
+        colsum_part<<<dim3(cp_cdiv(n, 32), RS), 256, 0, stream>>>(Y, ldy, n, N, nullptr, cpart, nullptr);
         CP_CHECK_LAUNCH();
-        make_shift<<<cp_cdiv(n, 256), 256, 0, stream>>>(sumY, n, invN, shY);
+        colsum_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, nullptr, n, invN, nullptr, nullptr, shY);
         CP_CHECK_LAUNCH();
-        colsum_f32<<<cp_cdiv(n, 32), 256, 0, stream>>>(Y, ldy, n, N, shY, TY, nullptr);
+        colsum_part<<<dim3(cp_cdiv(n, 32), RS), 256, 0, stream>>>(Y, ldy, n, N, shY, cpart, nullptr);
+        CP_CHECK_LAUNCH();
+        colsum_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, nullptr, n, invN, TY, nullptr, nullptr);
         CP_CHECK_LAUNCH();
     }
     if (ntiles > 0) {
@@ -500,7 +535,7 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
             CP_CHECK_LAUNCH();
         }
         if (tiles_sym > 0) {
-            reduce_tc<<<tiles_sym, 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, SQX, Nd,
+            reduce_tc<<<dim3(tiles_sym, 4), 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, SQX, Nd,
                                                     K, K, G, K);
             CP_CHECK_LAUNCH();
             if (K > TM) {
@@ -510,7 +545,7 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
             }
         }
         if (wantB) {
-            reduce_tc<<<tk * tnb, 256, 0, stream>>>(partial, nchunks, ntiles, tiles_sym, tnb, 0, tk, shX, TX, shY, y_bias, TY,
+            reduce_tc<<<dim3(tk * tnb, 4), 256, 0, stream>>>(partial, nchunks, ntiles, tiles_sym, tnb, 0, tk, shX, TX, shY, y_bias, TY,
                                                    nullptr, Nd, K, n, Bxy, n);
             CP_CHECK_LAUNCH();
         }

@@ -35,7 +35,8 @@ def test_gram_tc_close_to_fp64(engine, N, K, n):
     eb = np.abs(B - Br) / np.outer(dx, dy)
     print("max rel err G %.2e  B %.2e" % (eg.max(), eb.max()))
     assert eg.max() <= 1e-6 and eb.max() <= 1e-6
-    assert np.abs(np.diag(G) - np.diag(Gr)).max() <= 1e-11 * np.diag(Gr).max()  # diagonal: exact fp64 pass
+    # diagonal: separate fp64 pass over fl32(x - shift); what is left is the fp32 rounding of the shifted data
+    assert np.abs(np.diag(G) - np.diag(Gr)).max() <= 1e-7 * np.diag(Gr).max()
     np.testing.assert_array_equal(G, G.T)
     np.testing.assert_allclose(g["sx"].cpu().numpy(), X64.sum(0), rtol=1e-12)
     np.testing.assert_allclose(g["sy"].cpu().numpy(), Y64.sum(0), rtol=1e-10, atol=1e-9)
