@@ -382,7 +382,10 @@ reduce_tc(const float *__restrict__ partial, int nchunks, int ntiles, int tile0,
         const int i = ti * TM + e / TN, j = tj * TN + e % TN;
         if (i >= M || j >= Nn) continue;
         double s = 0.0;
-        for (int c = 0; c < nchunks; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
+        // inside a diagonal tile the tensor core produced both (i,j) and (j,i) with different rounding:
+        // read the upper one for both so that G is bitwise symmetric
+        const int er = (sym && ti == tj && (e / TN) > (e % TN)) ? (e % TN) * TN + (e / TN) : e;
+        for (int c = 0; c < nchunks; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + er];
         // the diagonal is a sum of squares (no cancellation: worst case for the truncating fp32
         // accumulation) and costs one fused pass to get exactly -- use the fp64 value
         if (sym && i == j) s = diag_sq[i];

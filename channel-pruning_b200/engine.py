@@ -80,7 +80,12 @@ class Engine:
     def _p(self, t, ctype):
         if t is None:
             return self.ffi.NULL
-        assert t.is_cuda and t.device == self.device, "tensor must live on %s" % self.device
+        if not t.is_cuda:
+            # pinned (page-locked) host memory is mapped into the device address space under UVA: kernels may
+            # read it in place over PCIe -- used by the sparse gathers, which touch a small part of each map
+            assert t.is_pinned(), "host tensors must be pinned to be read by a kernel"
+        else:
+            assert t.device == self.device, "tensor must live on %s" % self.device
         return self.ffi.cast(ctype, t.data_ptr())
 
     def _call(self, rc):
