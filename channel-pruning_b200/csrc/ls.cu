@@ -171,89 +171,54 @@ int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
 // In-place: M is (Kd + n) x Kd (leading dimension ld), rows 0..Kd-1 an SPD matrix (lower part
 // used), rows Kd.. the transposed right-hand sides.  On return rows Kd.. hold the transposed
 // solution  (SPD^-1 Rhs)'.  Linv: scratch of ceil(Kd/64) * 64*64 doubles.
-//
-// Recursive formulation (splits at multiples of 64): almost all flops land in tile GEMMs whose
-// inner dimension is a large fraction of Kd (efficient), only the leaves are 64-wide.
-//   potrf(A)        : potrf(A11); A21 <- A21 L11^-T; A22 -= A21 A21'; potrf(A22)
-//   trsm (X L^-T)   : X1 <- X1 L11^-T; X2 -= X1 L21'; X2 <- X2 L22^-T          (forward substitution)
-//   bsolve (X L^-1) : X2 <- X2 L22^-1; X1 -= X2 L21; X1 <- X1 L11^-1            (backward substitution)
-namespace {
-struct CholCtx {
-    double *M;
-    int64_t ld;
-    double *Linv;
-    const double *diag0;
-    int32_t *info;
-    cudaStream_t stream;
-};
-inline int split64(int m) {  // first part: multiple of 64, 0 < h < m
-    int h = ((m / 2 + NB - 1) / NB) * NB;
-    if (h >= m) h = ((m - 1) / NB) * NB;
-    return h;
-}
-int trsm_rec(const CholCtx &c, int r0, int nr, int c0, int m) {
-    using namespace cpgemm;
-    if (nr <= 0 || m <= 0) return CP_OK;
-    double *X = c.M + (int64_t)r0 * c.ld + c0;
-    if (m <= NB)  // X <- X * Linv'   (C[i, nn] = sum_r X[i, r] * Linv[nn, r]), in place (single column tile)
-        return dgemm<false>(X, c.ld, c.Linv + (size_t)(c0 / NB) * NB * NB, NB, X, c.ld, nr, m, m, 1.0, 0.0, TILES_ALL, c.stream);
-    const int m1 = split64(m), m2 = m - m1;
-    int rc = trsm_rec(c, r0, nr, c0, m1);
-    if (rc) return rc;
-    rc = dgemm<false>(X, c.ld, c.M + (int64_t)(c0 + m1) * c.ld + c0, c.ld, X + m1, c.ld, nr, m2, m1, -1.0, 1.0, TILES_ALL,
-                      c.stream);
-    if (rc) return rc;
-    return trsm_rec(c, r0, nr, c0 + m1, m2);
-}
-int potrf_rec(const CholCtx &c, int j0, int m) {
-    using namespace cpgemm;
-    if (m <= NB) {
-        potrf_diag<<<1, PT, POTRF_SMEM, c.stream>>>(c.M + (int64_t)j0 * c.ld + j0, c.ld, m,
-                                                    c.Linv + (size_t)(j0 / NB) * NB * NB, c.info, j0, c.diag0);
-        CP_CHECK_LAUNCH();
-        return CP_OK;
-    }
-    const int m1 = split64(m), m2 = m - m1;
-    int rc = potrf_rec(c, j0, m1);
-    if (rc) return rc;
-    rc = trsm_rec(c, j0 + m1, m2, j0, m1);
-    if (rc) return rc;
-    double *A21 = c.M + (int64_t)(j0 + m1) * c.ld + j0;
-    rc = dgemm<false>(A21, c.ld, A21, c.ld, c.M + (int64_t)(j0 + m1) * c.ld + j0 + m1, c.ld, m2, m2, m1, -1.0, 1.0,
-                      TILES_LOWER, c.stream);
-    if (rc) return rc;
-    return potrf_rec(c, j0 + m1, m2);
-}
-int bsolve_rec(const CholCtx &c, int r0, int nr, int c0, int m) {
-    using namespace cpgemm;
-    if (nr <= 0 || m <= 0) return CP_OK;
-    double *X = c.M + (int64_t)r0 * c.ld + c0;
-    if (m <= NB)  // X <- X * Linv    (C[t, i] = sum_r X[t, r] * Linv[r, i]), in place
-        return dgemm<true>(X, c.ld, c.Linv + (size_t)(c0 / NB) * NB * NB, NB, X, c.ld, nr, m, m, 1.0, 0.0, TILES_ALL, c.stream);
-    const int m1 = split64(m), m2 = m - m1;
-    int rc = bsolve_rec(c, r0, nr, c0 + m1, m2);
-    if (rc) return rc;
-    // X1 -= X2 * L21   (C[t, i] -= sum_r X2[t, r] * L[c0+m1+r, c0+i])
-    rc = dgemm<true>(X + m1, c.ld, c.M + (int64_t)(c0 + m1) * c.ld + c0, c.ld, X, c.ld, nr, m1, m2, -1.0, 1.0, TILES_ALL,
-                     c.stream);
-    if (rc) return rc;
-    return bsolve_rec(c, r0, nr, c0, m1);
-}
-}  // namespace
-
 static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv, const double *diag0,
                               int32_t *info, cudaStream_t stream) {
+    using namespace cpgemm;
+    const int Ktot = Kd + n;
+    const int npanel = (Kd + NB - 1) / NB;
     static bool configured = false;
     if (!configured) {
         CP_CUDA(cudaFuncSetAttribute(potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         configured = true;
     }
-    CholCtx c{M, ld, Linv, diag0, info, stream};
-    int rc = potrf_rec(c, 0, Kd);
-    if (rc) return rc;
-    rc = trsm_rec(c, Kd, n, 0, Kd);  // Zt = Rhs' L^-T
-    if (rc) return rc;
-    return bsolve_rec(c, Kd, n, 0, Kd);  // Wt = Zt L^-1
+    for (int p = 0; p < npanel; ++p) {
+        const int j0 = p * NB;
+        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
+        const int j1 = j0 + nb;
+        double *Lp = Linv + (size_t)p * NB * NB;
+        potrf_diag<<<1, PT, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0, diag0);
+        CP_CHECK_LAUNCH();
+        const int below = Ktot - j1;
+        if (below > 0) {
+            // panel <- panel * L_d^-T   (C[m, nn] = sum_r P[m, r] * Linv[nn, r]), in place (single column tile)
+            double *Pn = M + (int64_t)j1 * ld + j0;
+            int rc = dgemm<false>(Pn, ld, Lp, NB, Pn, ld, below, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+            if (rc) return rc;
+            // trailing (lower) -= panel * panel'
+            const int ncols = Kd - j1;
+            if (ncols > 0) {
+                rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, below, ncols, nb, -1.0, 1.0,
+                                  TILES_LOWER, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    // backward: Wt * L = Zt, block columns last to first
+    double *Zt = M + (int64_t)Kd * ld;
+    for (int p = npanel - 1; p >= 0; --p) {
+        const int j0 = p * NB;
+        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
+        double *Lp = Linv + (size_t)p * NB * NB;
+        // Wt_p = Zt_p * Linv_p   (C[t, i] = sum_r Zt[t, j0 + r] * Linv[r, i]), in place
+        int rc = dgemm<true>(Zt + j0, ld, Lp, NB, Zt + j0, ld, n, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+        if (rc) return rc;
+        if (j0 > 0) {
+            // Zt[:, 0:j0] -= Wt_p * L[j0:j0+nb, 0:j0]
+            rc = dgemm<true>(Zt + j0, ld, M + (int64_t)j0 * ld, ld, Zt, ld, n, j0, nb, -1.0, 1.0, TILES_ALL, stream);
+            if (rc) return rc;
+        }
+    }
+    return CP_OK;
 }
 
 extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
