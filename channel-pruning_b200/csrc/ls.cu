@@ -181,40 +181,64 @@ static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv
         CP_CUDA(cudaFuncSetAttribute(potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
         configured = true;
     }
-    for (int p = 0; p < npanel; ++p) {
-        const int j0 = p * NB;
-        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
-        const int j1 = j0 + nb;
-        double *Lp = Linv + (size_t)p * NB * NB;
-        potrf_diag<<<1, PT, POTRF_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, Lp, info, j0, diag0);
-        CP_CHECK_LAUNCH();
-        const int below = Ktot - j1;
-        if (below > 0) {
-            // panel <- panel * L_d^-T   (C[m, nn] = sum_r P[m, r] * Linv[nn, r]), in place (single column tile)
-            double *Pn = M + (int64_t)j1 * ld + j0;
-            int rc = dgemm<false>(Pn, ld, Lp, NB, Pn, ld, below, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+    // Two-level blocking: 256-wide outer panels are factored with 64-wide inner blocks whose updates
+    // stay inside the panel; the trailing matrix is then updated ONCE per outer panel with inner
+    // dimension 256 (4x fewer, 4x deeper tile GEMMs than a plain 64-wide right-looking sweep).
+    constexpr int NBO = 4 * NB;
+    (void)npanel;
+    for (int J0 = 0; J0 < Kd; J0 += NBO) {
+        const int w = Kd - J0 < NBO ? Kd - J0 : NBO;
+        const int J1 = J0 + w;
+        for (int jb = J0; jb < J1; jb += NB) {
+            const int nb = J1 - jb < NB ? J1 - jb : NB;
+            const int j1 = jb + nb;
+            double *Lp = Linv + (size_t)(jb / NB) * NB * NB;
+            potrf_diag<<<1, PT, POTRF_SMEM, stream>>>(M + (int64_t)jb * ld + jb, ld, nb, Lp, info, jb, diag0);
+            CP_CHECK_LAUNCH();
+            const int below = Ktot - j1;
+            if (below > 0) {
+                // block column <- block column * L_d^-T (all rows below, right-hand-side rows included), in place
+                double *Pn = M + (int64_t)j1 * ld + jb;
+                int rc = dgemm<false>(Pn, ld, Lp, NB, Pn, ld, below, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+                if (rc) return rc;
+                const int nin = J1 - j1;  // columns of this outer panel still to be factored
+                if (nin > 0) {
+                    rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, below, nin, nb, -1.0, 1.0, TILES_ALL,
+                                      stream);
+                    if (rc) return rc;
+                }
+            }
+        }
+        const int ncols = Kd - J1;
+        if (ncols > 0) {  // trailing (lower) -= panel * panel', inner dimension w
+            double *Pn = M + (int64_t)J1 * ld + J0;
+            int rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)J1 * ld + J1, ld, Ktot - J1, ncols, w, -1.0, 1.0, TILES_LOWER,
+                                  stream);
             if (rc) return rc;
-            // trailing (lower) -= panel * panel'
-            const int ncols = Kd - j1;
-            if (ncols > 0) {
-                rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, below, ncols, nb, -1.0, 1.0,
-                                  TILES_LOWER, stream);
+        }
+    }
+    // backward: Wt * L = Zt, outer panels last to first, inner blocks last to first
+    double *Zt = M + (int64_t)Kd * ld;
+    const int nouter = (Kd + NBO - 1) / NBO;
+    for (int P = nouter - 1; P >= 0; --P) {
+        const int J0 = P * NBO;
+        const int w = Kd - J0 < NBO ? Kd - J0 : NBO;
+        const int nin = (w + NB - 1) / NB;
+        for (int b = nin - 1; b >= 0; --b) {
+            const int jb = J0 + b * NB;
+            const int nb = J0 + w - jb < NB ? J0 + w - jb : NB;
+            double *Lp = Linv + (size_t)(jb / NB) * NB * NB;
+            // Wt_b = Zt_b * Linv_b   (C[t, i] = sum_r Zt[t, jb + r] * Linv[r, i]), in place
+            int rc = dgemm<true>(Zt + jb, ld, Lp, NB, Zt + jb, ld, n, nb, nb, 1.0, 0.0, TILES_ALL, stream);
+            if (rc) return rc;
+            if (jb > J0) {  // remaining columns of this outer panel
+                rc = dgemm<true>(Zt + jb, ld, M + (int64_t)jb * ld + J0, ld, Zt + J0, ld, n, jb - J0, nb, -1.0, 1.0, TILES_ALL,
+                                 stream);
                 if (rc) return rc;
             }
         }
-    }
-    // backward: Wt * L = Zt, block columns last to first
-    double *Zt = M + (int64_t)Kd * ld;
-    for (int p = npanel - 1; p >= 0; --p) {
-        const int j0 = p * NB;
-        const int nb = Kd - j0 < NB ? Kd - j0 : NB;
-        double *Lp = Linv + (size_t)p * NB * NB;
-        // Wt_p = Zt_p * Linv_p   (C[t, i] = sum_r Zt[t, j0 + r] * Linv[r, i]), in place
-        int rc = dgemm<true>(Zt + j0, ld, Lp, NB, Zt + j0, ld, n, nb, nb, 1.0, 0.0, TILES_ALL, stream);
-        if (rc) return rc;
-        if (j0 > 0) {
-            // Zt[:, 0:j0] -= Wt_p * L[j0:j0+nb, 0:j0]
-            rc = dgemm<true>(Zt + j0, ld, M + (int64_t)j0 * ld, ld, Zt, ld, n, j0, nb, -1.0, 1.0, TILES_ALL, stream);
+        if (J0 > 0) {  // Zt[:, 0:J0] -= Wt_P * L[J0:J0+w, 0:J0], inner dimension w
+            int rc = dgemm<true>(Zt + J0, ld, M + (int64_t)J0 * ld, ld, Zt, ld, n, J0, w, -1.0, 1.0, TILES_ALL, stream);
             if (rc) return rc;
         }
     }

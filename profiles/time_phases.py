@@ -32,6 +32,14 @@ for name, c, n, H in shapes:
     d = cpb200.synth.make_problem_device(s, 7, eng)
     W2m = d["W2"].reshape(s.n, s.K)
     tg, X = t(lambda: eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True))
+    fm_nhwc = d["fmap"].permute(0, 2, 3, 1).contiguous()
+    tg2, X2 = t(lambda: eng.patch_gather(fm_nhwc, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True,
+                                         layout="nhwc"))
+    assert torch.equal(X, X2)
+    del fm_nhwc, X2
+    gb = 8.0 * s.N * s.K / 1e9
+    print("   gather %s: NCHW %.3f ms = %.0f GB/s | NHWC %.3f ms = %.0f GB/s (algorithmic 8NK bytes)"
+          % (name, tg, gb / tg * 1e3, tg2, gb / tg2 * 1e3), flush=True)
     tgram, g_full = t(lambda: eng.gram(X, d["feats"], y_bias=d["b2"]))
     tgs, g_s = t(lambda: eng.gram(X, d["feats"], y_bias=d["b2"], rows=d["samples"], want_yy=True, mode=0))
     tgw, g_w = t(lambda: eng.gram(W2m, None, want_B=False, mode=0))
