@@ -42,13 +42,21 @@ ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const 
 }
 
 // ---------------------------------------------------------------- 64x64 diagonal block: L and L^-1
-// One CTA of 1024 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 16 m (m = 0..3) of
-// column j in registers.  Right-looking factorisation: at step k the 16 threads of column k publish the
-// raw column (pivot included) to shared memory, ONE barrier, then every thread applies the rank-1 update
-// to its 4 registers.  The inverse is a forward substitution with the same ownership (one barrier per
-// row).  ~2 x 64 barriers of ~130 cycles instead of the earlier 4 x 64 x (division + 16-trip loops).
-constexpr int PT = 1024;
+// One CTA of 256 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 4 m (m = 0..15) of
+// column j in registers.  Right-looking factorisation: at step k the 4 threads of column k publish the
+// raw column (pivot included) to shared memory, ONE barrier (8 warps), then every thread applies the
+// rank-1 update to its registers.  The inverse is a forward substitution with the same ownership (one
+// barrier per row).  1/sqrt(pivot) comes from the fp32 MUFU seed + two fp64 Newton steps.
+constexpr int PT = 256;
+constexpr int PR = 16;  // rows per thread
 constexpr size_t POTRF_SMEM = (size_t)(NB * (NB + 1) + 5 * NB) * sizeof(double);
+
+__device__ __forceinline__ double rsqrt_newton(double d) {
+    double y = (double)rsqrtf((float)d);
+    y = y * (1.5 - 0.5 * d * y * y);
+    y = y * (1.5 - 0.5 * d * y * y);
+    return y;
+}
 
 __global__ void __launch_bounds__(PT, 1)
 potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv, int32_t *__restrict__ info,
@@ -59,10 +67,10 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
     double *xrow = col + 2 * NB;           // [2][64] finished row k of the inverse
     double *rsd = xrow + 2 * NB;           // [64] 1 / L[k][k]
     const int tid = threadIdx.x, j = tid & 63, ig = tid >> 6;
-    double a[4], x[4];
+    double a[PR], x[PR];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int i = ig + 16 * m;
+    for (int m = 0; m < PR; ++m) {
+        const int i = ig + 4 * m;
         double v = 0.0;
         if (i < nb && j < nb && j <= i) v = A[(int64_t)i * ld + j];
         if (i >= nb && i == j) v = 1.0;  // identity padding keeps the arithmetic finite
@@ -73,7 +81,7 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
         double *ck = col + (k & 1) * NB;
         if (j == k) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) ck[ig + 16 * m] = a[m];
+            for (int m = 0; m < PR; ++m) ck[ig + 4 * m] = a[m];
         }
         __syncthreads();
         double d = ck[k];
@@ -83,21 +91,21 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
             if (tid == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
             d = 1.0;
         }
-        const double rs = rsqrt(d);
-        const double ljk = ck[j] * rs;
+        const double rs = rsqrt_newton(d);
         if (j == k) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int i = ig + 16 * m;
+            for (int m = 0; m < PR; ++m) {
+                const int i = ig + 4 * m;
                 Ls[i * (NB + 1) + k] = (i > k) ? ck[i] * rs : (i == k ? d * rs : 0.0);
             }
             if (ig == 0) rsd[k] = rs;
         }
         if (j > k) {
+            const double ljk = -ck[j] * rs * rs;  // -L[j][k] / sqrt(d)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int i = ig + 16 * m;
-                if (i >= j) a[m] = fma(-ck[i] * rs, ljk, a[m]);
+            for (int m = 0; m < PR; ++m) {
+                const int i = ig + 4 * m;
+                if (i >= j) a[m] = fma(ck[i], ljk, a[m]);
             }
         }
     }
@@ -105,23 +113,28 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
     // X = L^-1: row k of X is final once rows < k have been eliminated
     for (int k = 0; k < NB; ++k) {
         double *xr = xrow + (k & 1) * NB;
-        if (ig == (k & 15)) {
-            const int mk = k >> 4;
-            const double xv = (mk == 0 ? x[0] : mk == 1 ? x[1] : mk == 2 ? x[2] : x[3]) * rsd[k];
+        if (ig == (k & 3)) {
+            const int mk = k >> 2;
+            double xv = 0.0;
+#pragma unroll
+            for (int m = 0; m < PR; ++m) xv = (m == mk) ? x[m] : xv;
+            xv *= rsd[k];
             xr[j] = xv;
             Linv[k * NB + j] = (j <= k) ? xv : 0.0;
         }
         __syncthreads();
-        const double xk = xr[j];
+        if (j <= k) {  // columns right of the diagonal stay zero
+            const double xk = xr[j];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int i = ig + 16 * m;
-            if (i > k) x[m] = fma(-Ls[i * (NB + 1) + k], xk, x[m]);
+            for (int m = 0; m < PR; ++m) {
+                const int i = ig + 4 * m;
+                if (i > k) x[m] = fma(-Ls[i * (NB + 1) + k], xk, x[m]);
+            }
         }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int i = ig + 16 * m;
+    for (int m = 0; m < PR; ++m) {
+        const int i = ig + 4 * m;
         if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = Ls[i * (NB + 1) + j];
     }
 }
