@@ -15,25 +15,24 @@
 // correctly rounded, and the random coordinate order comes from the same 32-bit xorshift.
 //
 // Coordinate descent is one long serial dependency chain (each coordinate update needs the
-// previous one), so the whole search is latency bound; it runs in ONE WARP per problem:
-//   * Qw (= Q w) lives in shared memory, each lane owning interleaved pairs of elements;
-//     a step applies  Qw += delta * Q[j,:]  with LDS.128 / DMUL / DADD / STS.128 per pair;
-//   * the pair that holds the NEXT coordinate is updated first and its value is broadcast
-//     with a shuffle, so the serial chain (update -> soft threshold -> divide -> delta) of
-//     step f+1 is issued in the shadow of step f's remaining pair updates;
-//   * rows of Q stream from L2 through an 8-deep cp.async ring that runs ahead along the
-//     (data-independent) random coordinate sequence; every lane copies exactly the pairs it
-//     will read back, so no barrier is needed for the ring;
-//   * the division  num / Q_jj  uses a pre-computed correctly rounded reciprocal and one
-//     Markstein correction step (DMUL + 2 DFMA) -- IEEE-exact, 3 dependent ops instead of ~10.
-// No CTA barrier anywhere; __syncwarp() only orders the lane-0 scalar stores.
+// previous one), so the search is latency bound and is organised as ONE warp-specialised CTA
+// per problem (7 warps), every warp doing only what must be on its own critical path:
+//   chain warp     the serial recurrence only: x = Qw[j] (as published by the pair-update warps
+//                  LAG steps ago) + the last LAG deltas applied locally, soft threshold,
+//                  correctly rounded division (pre-computed reciprocal + one Markstein step),
+//                  publish delta
+//   4 update warps own interleaved pairs of Qw in shared memory, apply  Qw += delta * Q[j,:]
+//                  (LDS.128 / DMUL / DADD / STS.128), stream the rows of Q from L2 through a
+//                  cp.async ring (each lane copies exactly the pairs it reads back), and
+//                  publish the Qw entry the chain warp will need LAG+1 steps later
+//   packager warp  per-step operands of the chain (q_j, Q_jj, 1/Q_jj, the LAG entries
+//                  Q[j_s][j_{s-i}]) gathered 32 steps at a time, lane-parallel
+//   sequencer warp the xorshift stream of the NEXT sweep (it does not depend on the active set)
+// Hand-offs are release/acquire counters in shared memory (bounded spins: a protocol bug traps
+// instead of hanging); CTA barriers only at sweep boundaries.
 #include "common.cuh"
 
 namespace {
-
-// prefetch depth (rows of Q in flight): 16 while the ring fits next to the state, 8 for c > 1024
-template <int NP> struct RingDepth { static constexpr int value = NP <= 16 ? 16 : 8; };
-constexpr int MAXC = 2048;  // largest channel count (shared-memory bound)
 
 // ------------------------------------------------------------------ build
 __global__ void __launch_bounds__(256)
@@ -103,12 +102,20 @@ struct SelectParams {
     double *out_coef, *out_scalars, *out_probe_log;
 };
 
-__device__ __forceinline__ uint32_t xorshift(uint32_t &s) {  // sklearn/utils/_random.pxd:20-34
+constexpr int MAXC = 2048;   // largest channel count (shared-memory bound)
+constexpr int LAG = 3;       // deltas the chain warp applies itself (slack of the update warps)
+constexpr int NBULK = 4;     // pair-update warps
+constexpr int PK_WARP = 1 + NBULK, SEQ_WARP = 2 + NBULK;
+constexpr int WS_THREADS = 32 * (3 + NBULK);
+constexpr int QR = 64;       // rings of per-step scalars (steps in flight << QR)
+template <int NPB> struct RingDepth { static constexpr int value = NPB <= 4 ? 16 : 6; };
+
+__device__ __forceinline__ uint32_t xorshift_step(uint32_t s) {  // sklearn/utils/_random.pxd:20-34 (state update)
     if (s == 0) s = 1;
     s ^= s << 13;
     s ^= s >> 17;
     s ^= s << 5;
-    return s & 0x7fffffffu;  // % (RAND_R_MAX + 1)
+    return s;
 }
 // a % d for 32-bit a through a pre-computed M = floor(2^64 / d) + 1 (Lemire's fastmod; exact)
 __device__ __forceinline__ uint32_t fastmod(uint32_t a, uint64_t M, uint32_t d) {
@@ -122,6 +129,20 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+// bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void wait_ge(const int *p, int target) {
+    for (uint32_t spin = 0; ld_acquire(p) < target; ++spin)
+        if (spin > (1u << 26)) __trap();
+}
 
 __device__ __forceinline__ double warp_sum_butterfly(double v) {  // model: p[l] + p[l ^ off], off = 16..1
 #pragma unroll
@@ -141,260 +162,340 @@ __device__ __forceinline__ double div_markstein(double num, double d, double rc)
     return __fma_rn(r, rc, q0);
 }
 
-template <int NP>  // pairs per lane; padded channel count CP = 64 * NP
-__global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams P) {
-    constexpr int CP = 64 * NP;
-    constexpr int RING = RingDepth<NP>::value;
+struct Ctl {  // CTA-wide scalars
+    int chain_pos, bulk_pos[NBULK], pk_pos;
+    int n_active, nnz, pad;
+    double gap, dual_norm, w_max, d_w_max;
+};
+
+template <int NPB>  // pairs per update lane; padded channel count CP = 2 * 32 * NBULK * NPB
+__global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const SelectParams P) {
+    constexpr int BL = 32 * NBULK;  // update lanes
+    constexpr int CP = 2 * BL * NPB;
+    constexpr int RING = RingDepth<NPB>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = P.c, lane = threadIdx.x;
+    const int c = P.c, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double *w = reinterpret_cast<double *>(smem_raw);  // [CP]
     double *Qw = w + CP;
     double *qv = Qw + CP;
     double *dg = qv + CP;
-    double *rc = dg + CP;
-    double *ring = rc + CP;  // [RING][CP]
-    uint32_t *active = reinterpret_cast<uint32_t *>(ring + (size_t)RING * CP);
-    uint32_t *zlist = active + CP;
-    uint32_t *jq = zlist + CP;  // [RING] upcoming coordinates
-    uint8_t *excluded = reinterpret_cast<uint8_t *>(jq + RING);
+    double *ring = dg + CP;                 // [RING][CP]
+    double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1, r2, r3
+    double *dq = pk + QR * 8;               // [QR] published deltas
+    double *xq = dq + QR;                   // [QR] published Qw entries
+    uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR);
+    uint32_t *jz = active + CP;             // coordinate sequence of the sweep / eviction list of the screening
+    uint32_t *raw = jz + CP;                // [2][CP] xorshift states (this sweep / next sweep)
+    uint8_t *excluded = reinterpret_cast<uint8_t *>(raw + 2 * CP);
+    __shared__ Ctl ctl;
 
     const double *__restrict__ Q = P.Q;
     const int ldq = P.ldq;
     const double yn2 = *P.yn2;
-    for (int e = lane; e < CP; e += 32) {
+    for (int e = tid; e < CP; e += WS_THREADS) {
         w[e] = 0.0;
         Qw[e] = 0.0;
         const bool in = e < c;
-        const double d = in ? Q[(int64_t)e * ldq + e] : 0.0;
         qv[e] = in ? P.qv[e] : 0.0;
-        dg[e] = d;
-        rc[e] = d != 0.0 ? __drcp_rn(d) : 0.0;
+        dg[e] = in ? Q[(int64_t)e * ldq + e] : 0.0;
         active[e] = e;
         excluded[e] = 0;
     }
-    for (int e = lane; e < RING * CP; e += 32) ring[e] = 0.0;  // padding pairs stay zero
-    __syncwarp();
+    for (int e = tid; e < RING * CP; e += WS_THREADS) ring[e] = 0.0;  // padding pairs stay zero
+    __syncthreads();
 
     const double tolS = __dmul_rn(P.tol, yn2);
     int probe = 0, status = 0;
 
-    // this lane's pair `s` lives at element 64*s + 2*lane
-    auto prefetch_row = [&](uint32_t j, int slot) {
-        const double *src = Q + (int64_t)j * ldq;
-        double *dst = ring + (size_t)slot * CP;
-#pragma unroll
-        for (int s = 0; s < NP; ++s) {
-            const int e = 64 * s + 2 * lane;
-            if (e < c) cp_async16(dst + e, src + e);
-        }
-    };
-
-    // Qw += a * Q[j,:], row fetched directly (rare paths: screening evictions)
+    // ================= helpers that run on warp 0 alone (between sweeps) =================
+    // Qw += a * Q[j,:], row fetched directly (rare path: screening evictions)
     auto axpy_row_direct = [&](uint32_t j, double a) {
         const double *src = Q + (int64_t)j * ldq;
-#pragma unroll
-        for (int s = 0; s < NP; ++s) {
-            const int e = 64 * s + 2 * lane;
-            if (e < c) {
-                const double2 r = *reinterpret_cast<const double2 *>(src + e);
-                double2 v = *reinterpret_cast<double2 *>(Qw + e);
-                v.x = __dadd_rn(v.x, __dmul_rn(a, r.x));
-                v.y = __dadd_rn(v.y, __dmul_rn(a, r.y));
-                *reinterpret_cast<double2 *>(Qw + e) = v;
-            }
+        for (int e = 2 * lane; e < c; e += 64) {
+            const double2 r = *reinterpret_cast<const double2 *>(src + e);
+            double2 v = *reinterpret_cast<double2 *>(Qw + e);
+            v.x = __dadd_rn(v.x, __dmul_rn(a, r.x));
+            v.y = __dadd_rn(v.y, __dmul_rn(a, r.y));
+            *reinterpret_cast<double2 *>(Qw + e) = v;
         }
     };
-
-    // ---- one Lasso.fit (warm start) at l1 = alpha*m; returns nnz (uniform across lanes)
-    auto solve = [&](double alpha_user) -> int {
-        const double l1 = __dmul_rn(alpha_user, P.m);
-        uint32_t la = P.seeds[probe];  // coordinate-order RNG, runs RING draws ahead of the update
-        int n_active = c;
-        int n_iter_ret = 0;
-        double gap = 0.0, dual_norm = 0.0;
-
-        // gap_enet_gram + dual_gap_formulation_A (beta = 0) in warp order
-        auto gap_check = [&]() {
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0, dn = 0.0;
-            for (int i = lane; i < c; i += 32) {
-                const double wi = w[i];
-                a1 = __dadd_rn(a1, __dmul_rn(wi, qv[i]));
-                a2 = __dadd_rn(a2, __dmul_rn(wi, Qw[i]));
-                a3 = __dadd_rn(a3, fabs(wi));
-                dn = fmax(dn, fabs(__dadd_rn(qv[i], -Qw[i])));
-            }
-            const double q_dot_w = warp_sum_butterfly(a1);
-            const double wQw = warp_sum_butterfly(a2);
-            const double l1n = warp_sum_butterfly(a3);
-            dn = warp_max(dn);
-            const double R_norm2 = __dadd_rn(__dadd_rn(yn2, wQw), -__dmul_rn(2.0, q_dot_w));
-            const double Ry = __dadd_rn(yn2, -q_dot_w);
-            const double primal = __dadd_rn(__dmul_rn(0.5, R_norm2), __dmul_rn(l1, l1n));
-            const double scale = dn > l1 ? __ddiv_rn(l1, dn) : 1.0;
-            const double dual = __dadd_rn(__dmul_rn(__dmul_rn(-0.5, __dmul_rn(scale, scale)), R_norm2),
-                                          __dmul_rn(scale, Ry));
-            gap = __dadd_rn(primal, -dual);
-            dual_norm = dn;
-        };
-        // gap-safe screening: keep j iff (1 - |XtA_j / max(l1, dn)|) / sqrt(Q_jj) <= sqrt(2|gap|) / l1
-        auto screen = [&](bool first) {
-            const double radius = __ddiv_rn(sqrt(__dmul_rn(2.0, fabs(gap))), l1);
-            const double den = l1 > dual_norm ? l1 : dual_norm;
-            int na = 0, nz = 0;
-            for (int base = 0; base < c; base += 32) {
-                const int j = base + lane;
-                bool keep = false, evict_nonzero = false;
-                if (j < c) {
-                    if (first && dg[j] == 0.0) {
-                        w[j] = 0.0;  // zero column
+    // gap_enet_gram + dual_gap_formulation_A (beta = 0) in warp order
+    auto gap_check = [&](double l1) {
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0, dn = 0.0;
+        for (int i = lane; i < c; i += 32) {
+            const double wi = w[i];
+            a1 = __dadd_rn(a1, __dmul_rn(wi, qv[i]));
+            a2 = __dadd_rn(a2, __dmul_rn(wi, Qw[i]));
+            a3 = __dadd_rn(a3, fabs(wi));
+            dn = fmax(dn, fabs(__dadd_rn(qv[i], -Qw[i])));
+        }
+        const double q_dot_w = warp_sum_butterfly(a1);
+        const double wQw = warp_sum_butterfly(a2);
+        const double l1n = warp_sum_butterfly(a3);
+        dn = warp_max(dn);
+        const double R_norm2 = __dadd_rn(__dadd_rn(yn2, wQw), -__dmul_rn(2.0, q_dot_w));
+        const double Ry = __dadd_rn(yn2, -q_dot_w);
+        const double primal = __dadd_rn(__dmul_rn(0.5, R_norm2), __dmul_rn(l1, l1n));
+        const double scale = dn > l1 ? __ddiv_rn(l1, dn) : 1.0;
+        const double dual = __dadd_rn(__dmul_rn(__dmul_rn(-0.5, __dmul_rn(scale, scale)), R_norm2), __dmul_rn(scale, Ry));
+        if (lane == 0) {
+            ctl.gap = __dadd_rn(primal, -dual);
+            ctl.dual_norm = dn;
+        }
+        __syncwarp();
+    };
+    // gap-safe screening: keep j iff (1 - |XtA_j / max(l1, dn)|) / sqrt(Q_jj) <= sqrt(2|gap|) / l1
+    auto screen = [&](bool first, double l1, double gap, double dual_norm) {
+        const double radius = __ddiv_rn(sqrt(__dmul_rn(2.0, fabs(gap))), l1);
+        const double den = l1 > dual_norm ? l1 : dual_norm;
+        int na = 0, nz = 0;
+        for (int base = 0; base < c; base += 32) {
+            const int j = base + lane;
+            bool keep = false, evict_nonzero = false;
+            if (j < c) {
+                if (first && dg[j] == 0.0) {
+                    w[j] = 0.0;  // zero column
+                    excluded[j] = 1;
+                } else if (!first && excluded[j]) {
+                    // stays excluded
+                } else {
+                    const double th = __ddiv_rn(__dadd_rn(qv[j], -Qw[j]), den);
+                    const double d_j = __ddiv_rn(__dadd_rn(1.0, -fabs(th)), sqrt(dg[j]));
+                    keep = d_j <= radius;
+                    if (!keep) {
+                        evict_nonzero = w[j] != 0.0;
                         excluded[j] = 1;
-                    } else if (!first && excluded[j]) {
-                        // stays excluded
-                    } else {
-                        const double th = __ddiv_rn(__dadd_rn(qv[j], -Qw[j]), den);
-                        const double d_j = __ddiv_rn(__dadd_rn(1.0, -fabs(th)), sqrt(dg[j]));
-                        keep = d_j <= radius;
-                        if (!keep) {
-                            evict_nonzero = w[j] != 0.0;
-                            excluded[j] = 1;
-                        } else excluded[j] = 0;
+                    } else excluded[j] = 0;
+                }
+            }
+            const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+            const uint32_t mz = __ballot_sync(0xffffffffu, evict_nonzero);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (keep) active[na + __popc(mk & lt)] = j;
+            if (evict_nonzero) jz[nz + __popc(mz & lt)] = j;
+            na += __popc(mk);
+            nz += __popc(mz);
+        }
+        __syncwarp();
+        for (int z = 0; z < nz; ++z) {  // Qw -= w[j] * Q[j,:], ascending j like the model
+            const uint32_t j = jz[z];
+            axpy_row_direct(j, -w[j]);
+            __syncwarp();
+        }
+        for (int z = lane; z < nz; z += 32) w[jz[z]] = 0.0;
+        if (lane == 0) ctl.n_active = na;
+        __syncwarp();
+    };
+
+    // ================= one sweep over the active set, all warps =================
+    // soft-threshold update of one coordinate from the current x = Qw[j]
+    auto cd_update = [&](double qj, double Qjj, double rj, double x, double w_j, double l1, double &delta, double &aw,
+                         double &w_new) {
+        const double tmp = __dadd_rn(__dadd_rn(qj, -x), __dmul_rn(w_j, Qjj));
+        const double mag = __dadd_rn(fabs(tmp), -l1);
+        // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
+        const double wn = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rj) : (tmp < 0.0 ? -0.0 : 0.0);
+        const bool live = Qjj != 0.0;  // model: "if Qjj == 0: continue"
+        w_new = live ? wn : w_j;
+        delta = live ? __dadd_rn(wn, -w_j) : 0.0;
+        aw = live ? fabs(wn) : -1.0;
+    };
+    auto sweep = [&](int n_active, bool fresh, uint32_t seed, int cur, double l1) {
+        uint32_t *raw_cur = raw + cur * CP, *raw_nxt = raw + (cur ^ 1) * CP;
+        if (fresh) {  // first sweep of a fit: the stream restarts from this fit's seed
+            if (tid == SEQ_WARP * 32) {
+                uint32_t st = seed;
+                for (int f = 0; f < n_active; ++f) {
+                    st = xorshift_step(st);
+                    raw_cur[f] = st;
+                }
+            }
+            __syncthreads();
+        }
+        {
+            const uint64_t M = ~0ull / (uint32_t)n_active + 1ull;
+            for (int f = tid; f < n_active; f += WS_THREADS)
+                jz[f] = active[fastmod(raw_cur[f] & 0x7fffffffu, M, (uint32_t)n_active)];
+            if (tid == 0) {
+                ctl.chain_pos = 0;
+                ctl.pk_pos = 0;
+#pragma unroll
+                for (int b = 0; b < NBULK; ++b) ctl.bulk_pos[b] = 0;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // -------- chain warp: the serial recurrence and nothing else
+            double d1 = 0.0, d2 = 0.0, d3 = 0.0, w_max = 0.0, d_w_max = 0.0;
+            for (int s = 0; s < n_active; ++s) {
+                const uint32_t j = jz[s];
+                if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
+                if ((s & 15) == 0 && s >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
+#pragma unroll
+                    for (int b = 0; b < NBULK; ++b) wait_ge(&ctl.bulk_pos[b], s - 30);
+                }
+                const double2 p0 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8);
+                const double2 p1 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 2);
+                const double2 p2 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 4);
+                const double w_j = w[j];
+                const int ow = (int)((j >> 1) & (BL - 1)) >> 5;
+                wait_ge(&ctl.bulk_pos[ow], s - LAG + 1 > 1 ? s - LAG + 1 : 1);
+                double x = xq[s & (QR - 1)];
+                x = __dadd_rn(x, __dmul_rn(d3, p2.y));  // delta_{s-3} * Q[j_s][j_{s-3}]
+                x = __dadd_rn(x, __dmul_rn(d2, p2.x));
+                x = __dadd_rn(x, __dmul_rn(d1, p1.y));
+                double delta, aw, w_new;
+                cd_update(p0.x, p0.y, p1.x, x, w_j, l1, delta, aw, w_new);
+                w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
+                if (lane == 0) dq[s & (QR - 1)] = delta;
+                __syncwarp();
+                if (lane == 0) st_release(&ctl.chain_pos, s + 1);
+                const double d = fabs(delta);
+                d_w_max = (aw >= 0.0 && d > d_w_max) ? d : d_w_max;
+                w_max = (aw > w_max) ? aw : w_max;
+                d3 = d2; d2 = d1; d1 = delta;
+            }
+            if (lane == 0) {
+                ctl.w_max = w_max;
+                ctl.d_w_max = d_w_max;
+            }
+        } else if (warp <= NBULK) {
+            // -------- pair-update warps
+            const int b = warp - 1, bt = b * 32 + lane;
+            auto prefetch_row = [&](uint32_t j, int slot) {
+                const double *src = Q + (int64_t)j * ldq;
+                double *dst = ring + (size_t)slot * CP;
+#pragma unroll
+                for (int sp = 0; sp < NPB; ++sp) {
+                    const int e = 2 * BL * sp + 2 * bt;
+                    if (e < c) cp_async16(dst + e, src + e);
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < RING; ++d) {
+                if (d < n_active) prefetch_row(jz[d], d);
+                cp_async_commit();
+            }
+            for (int s = 0; s <= LAG && s < n_active; ++s) {  // entries the chain needs before any update
+                const uint32_t js = jz[s];
+                if ((int)((js >> 1) & (BL - 1)) == bt) xq[s] = Qw[js];
+            }
+            __syncwarp();
+            if (lane == 0) st_release(&ctl.bulk_pos[b], 1);
+            for (int t = 0; t < n_active; ++t) {
+                const int slot = t % RING;
+                wait_ge(&ctl.chain_pos, t + 1);
+                const double delta = dq[t & (QR - 1)];
+                cp_async_wait<RING - 1>();  // this lane's pairs of row t have landed
+                if (delta != 0.0) {
+                    const double *row = ring + (size_t)slot * CP;
+#pragma unroll
+                    for (int sp = 0; sp < NPB; ++sp) {
+                        const int e = 2 * BL * sp + 2 * bt;
+                        const double2 r = *reinterpret_cast<const double2 *>(row + e);
+                        double2 v = *reinterpret_cast<double2 *>(Qw + e);
+                        v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
+                        v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
+                        *reinterpret_cast<double2 *>(Qw + e) = v;
                     }
                 }
-                const uint32_t mk = __ballot_sync(0xffffffffu, keep);
-                const uint32_t mz = __ballot_sync(0xffffffffu, evict_nonzero);
-                const uint32_t lt = (1u << lane) - 1u;
-                if (keep) active[na + __popc(mk & lt)] = j;
-                if (evict_nonzero) zlist[nz + __popc(mz & lt)] = j;
-                na += __popc(mk);
-                nz += __popc(mz);
+                const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
+                if (sp1 < n_active) {
+                    const uint32_t js = jz[sp1];
+                    if ((int)((js >> 1) & (BL - 1)) == bt) xq[sp1 & (QR - 1)] = Qw[js];
+                }
+                if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
+                cp_async_commit();
+                __syncwarp();
+                if (lane == 0) st_release(&ctl.bulk_pos[b], t + 2);
             }
-            __syncwarp();
-            for (int z = 0; z < nz; ++z) {  // Qw -= w[j] * Q[j,:], ascending j like the model
-                const uint32_t j = zlist[z];
-                axpy_row_direct(j, -w[j]);
+            cp_async_wait<0>();
+        } else if (warp == PK_WARP) {
+            // -------- packager: operands of 32 chain steps at a time
+            for (int base = 0; base < n_active; base += 32) {
+                if (base >= QR) wait_ge(&ctl.chain_pos, base - 32);  // slots of batch base-64 are free
+                const int s = base + lane;
+                if (s < n_active) {
+                    const uint32_t j = jz[s];
+                    const double d = dg[j];
+                    const double *qrow = Q + (int64_t)j * ldq;
+                    const double r1 = s >= 1 ? __ldg(qrow + jz[s - 1]) : 0.0;
+                    const double r2 = s >= 2 ? __ldg(qrow + jz[s - 2]) : 0.0;
+                    const double r3 = s >= 3 ? __ldg(qrow + jz[s - 3]) : 0.0;
+                    double *o = pk + (s & (QR - 1)) * 8;
+                    *reinterpret_cast<double2 *>(o) = make_double2(qv[j], d);
+                    *reinterpret_cast<double2 *>(o + 2) = make_double2(d != 0.0 ? __drcp_rn(d) : 0.0, r1);
+                    *reinterpret_cast<double2 *>(o + 4) = make_double2(r2, r3);
+                }
+                __syncwarp();
+                if (lane == 0) st_release(&ctl.pk_pos, base + 32 < n_active ? base + 32 : n_active);
             }
-            __syncwarp();
-            for (int z = lane; z < nz; z += 32) w[zlist[z]] = 0.0;
-            __syncwarp();
-            n_active = na;
-        };
+        } else {
+            // -------- sequencer: xorshift states of the next sweep (independent of the active set)
+            if (lane == 0) {
+                uint32_t st = raw_cur[n_active - 1];
+                for (int f = 0; f < n_active; ++f) {
+                    st = xorshift_step(st);
+                    raw_nxt[f] = st;
+                }
+            }
+        }
+        __syncthreads();
+    };
 
-        gap_check();
+    // ---- one Lasso.fit (warm start) at l1 = alpha*m; returns nnz (uniform across the CTA)
+    auto solve = [&](double alpha_user) -> int {
+        const double l1 = __dmul_rn(alpha_user, P.m);
+        const uint32_t seed = P.seeds[probe];
+        int n_active = c, n_iter_ret = 0;
+        if (warp == 0) gap_check(l1);
+        __syncthreads();
+        double gap = ctl.gap, dual_norm = ctl.dual_norm;
         if (!(gap <= tolS)) {
-            screen(true);
-            bool broke = false;
-            int n_iter = 0;
+            if (warp == 0) screen(true, l1, gap, dual_norm);
+            __syncthreads();
+            n_active = ctl.n_active;
+            bool broke = false, fresh = true;
+            int cur = 0, n_iter = 0;
             for (n_iter = 0; n_iter < P.max_iter; ++n_iter) {
                 double w_max = 0.0, d_w_max = 0.0;
                 if (n_active > 0) {
-                    const uint64_t M = ~0ull / (uint32_t)n_active + 1ull;
-                    // prime the ring and the coordinate queue
-#pragma unroll
-                    for (int d = 0; d < RING; ++d) {
-                        if (d < n_active) {
-                            const uint32_t jd = active[fastmod(xorshift(la), M, (uint32_t)n_active)];
-                            if (lane == 0) jq[d] = jd;
-                            prefetch_row(jd, d);
-                        }
-                        cp_async_commit();
-                    }
-                    __syncwarp();
-                    // soft-threshold update of one coordinate from the current x = Qw[j]; all lanes redundantly
-                    auto cd_update = [&](double qj, double Qjj, double rj, double x, double w_j, double &delta,
-                                         double &aw, double &w_new) {
-                        const double tmp = __dadd_rn(__dadd_rn(qj, -x), __dmul_rn(w_j, Qjj));
-                        const double mag = __dadd_rn(fabs(tmp), -l1);
-                        // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
-                        const double wn = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rj) : (tmp < 0.0 ? -0.0 : 0.0);
-                        const bool live = Qjj != 0.0;  // model: "if Qjj == 0: continue"
-                        w_new = live ? wn : w_j;
-                        delta = live ? __dadd_rn(wn, -w_j) : 0.0;
-                        aw = live ? fabs(wn) : -1.0;
-                    };
-                    // value of this lane's pair in slot(jx) that corresponds to column jx (garbage unless owner)
-                    auto own_elem = [&](const double *base, uint32_t jx) -> double {
-                        const double2 v = *reinterpret_cast<const double2 *>(base + 64 * (jx >> 6) + 2 * lane);
-                        return (jx & 1) ? v.y : v.x;
-                    };
-                    // ---- software pipeline: the serial chain of step f+1 runs in the shadow of step f's pair updates.
-                    // w[] is read and written by lane 0 only during a sweep (broadcast by shuffle): no races.
-                    cp_async_wait<RING - 1>();  // row 0 (own pairs)
-                    uint32_t j = jq[0];
-                    double delta, aw, w_new;
-                    cd_update(qv[j], dg[j], rc[j], Qw[j], __shfl_sync(0xffffffffu, lane == 0 ? w[j] : 0.0, 0), delta, aw,
-                              w_new);
-                    if (lane == 0) w[j] = w_new;
-                    // package of step 1
-                    bool valid_n = n_active > 1;
-                    uint32_t jn = valid_n ? jq[1] : j;
-                    double qn = qv[jn], dn_ = dg[jn], rn = rc[jn];
-                    double wn_ = __shfl_sync(0xffffffffu, lane == 0 ? w[jn] : 0.0, 0);
-                    double xo = __shfl_sync(0xffffffffu, own_elem(Qw, jn), (jn >> 1) & 31);
-                    double rr = __shfl_sync(0xffffffffu, own_elem(ring, jn), (jn >> 1) & 31);  // row 0 sits in slot 0
-                    for (int f = 0; f < n_active; ++f) {
-                        const int slot = f & (RING - 1);
-                        cp_async_wait<RING - 2>();  // rows <= f+1 have landed (own pairs)
-                        // (1) serial chain of step f+1
-                        const double xnew = __dadd_rn(xo, __dmul_rn(delta, rr));
-                        double delta_n, aw_n, w_new_n;
-                        cd_update(qn, dn_, rn, xnew, wn_, delta_n, aw_n, w_new_n);
-                        if (valid_n && lane == 0) w[jn] = w_new_n;
-                        // (2) pair updates of step f:  Qw += delta * Q[j_f, :]
-                        const double *row = ring + (size_t)slot * CP;
-#pragma unroll
-                        for (int s = 0; s < NP; ++s) {
-                            const int e = 64 * s + 2 * lane;
-                            const double2 r = *reinterpret_cast<const double2 *>(row + e);
-                            double2 v = *reinterpret_cast<double2 *>(Qw + e);
-                            v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
-                            v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
-                            *reinterpret_cast<double2 *>(Qw + e) = v;
-                        }
-                        // (3) bookkeeping of step f
-                        {
-                            const double d = fabs(delta);
-                            d_w_max = (aw >= 0.0 && d > d_w_max) ? d : d_w_max;
-                            w_max = (aw > w_max) ? aw : w_max;
-                        }
-                        // (4) package of step f+2 (needs the pair updates above and row f+1)
-                        const bool valid_nn = f + 2 < n_active;
-                        const uint32_t jnn = valid_nn ? jq[(f + 2) & (RING - 1)] : jn;
-                        const double qnn = qv[jnn], dnn = dg[jnn], rnn = rc[jnn];
-                        const double wnn = __shfl_sync(0xffffffffu, lane == 0 ? w[jnn] : 0.0, 0);
-                        const double xo2 = __shfl_sync(0xffffffffu, own_elem(Qw, jnn), (jnn >> 1) & 31);
-                        const double rr2 = __shfl_sync(0xffffffffu, own_elem(ring + (size_t)((f + 1) & (RING - 1)) * CP, jnn),
-                                                       (jnn >> 1) & 31);
-                        // (5) refill the slot just consumed with the row of step f + RING
-                        if (f + RING < n_active) {
-                            const uint32_t jf = active[fastmod(xorshift(la), M, (uint32_t)n_active)];
-                            if (lane == 0) jq[slot] = jf;
-                            prefetch_row(jf, slot);
-                        }
-                        cp_async_commit();
-                        __syncwarp();
-                        j = jn; delta = delta_n; aw = aw_n;
-                        jn = jnn; valid_n = valid_nn; qn = qnn; dn_ = dnn; rn = rnn; wn_ = wnn; xo = xo2; rr = rr2;
-                    }
-                    cp_async_wait<0>();
+                    sweep(n_active, fresh, seed, cur, l1);
+                    fresh = false;
+                    cur ^= 1;
+                    w_max = ctl.w_max;
+                    d_w_max = ctl.d_w_max;
                 }
                 if (w_max == 0.0 || __ddiv_rn(d_w_max, w_max) <= P.tol || n_iter == P.max_iter - 1) {
-                    gap_check();
+                    __syncthreads();  // everyone has read ctl.w_max before warp 0 moves on
+                    if (warp == 0) gap_check(l1);
+                    __syncthreads();
+                    gap = ctl.gap;
+                    dual_norm = ctl.dual_norm;
                     if (gap <= tolS) { broke = true; break; }
-                    screen(false);
+                    if (warp == 0) screen(false, l1, gap, dual_norm);
+                    __syncthreads();
+                    n_active = ctl.n_active;
                 }
             }
             n_iter_ret = broke ? n_iter + 1 : P.max_iter;
         }
-        int cnt = 0;
-        for (int i = lane; i < c; i += 32) cnt += (w[i] != 0.0);
+        if (warp == 0) {
+            int cnt = 0;
+            for (int i = lane; i < c; i += 32) cnt += (w[i] != 0.0);
 #pragma unroll
-        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        if (lane == 0) {
-            double *lg = P.out_probe_log + (size_t)probe * 4;
-            lg[0] = alpha_user; lg[1] = (double)cnt; lg[2] = (double)n_iter_ret; lg[3] = gap;
+            for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            if (lane == 0) {
+                ctl.nnz = cnt;
+                double *lg = P.out_probe_log + (size_t)probe * 4;
+                lg[0] = alpha_user; lg[1] = (double)cnt; lg[2] = (double)n_iter_ret; lg[3] = gap;
+            }
         }
+        __syncthreads();
+        const int nnz = ctl.nnz;
+        __syncthreads();
         ++probe;
-        return cnt;
+        return nnz;
     };
 
     // ---- alpha search, reference lib/decompose.py:489-525
@@ -416,11 +517,11 @@ __global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams 
         else if ((double)nnz < P.lbound) right = alpha;
         else break;
     }
-    for (int e = lane; e < c; e += 32) {
+    for (int e = tid; e < c; e += WS_THREADS) {
         P.out_idxs[e] = w[e] != 0.0 ? 1 : 0;
         P.out_coef[e] = w[e];
     }
-    if (lane == 0) {
+    if (tid == 0) {
         P.out_scalars[0] = alpha;
         P.out_scalars[1] = (double)probe;
         P.out_scalars[2] = (double)status;
@@ -428,18 +529,18 @@ __global__ void __launch_bounds__(32, 1) lasso_select_kernel(const SelectParams 
     }
 }
 
-template <int NP>
+template <int NPB>
 int launch_select(const SelectParams &P, cudaStream_t stream) {
-    constexpr int CP = 64 * NP;
-    constexpr int RING = RingDepth<NP>::value;
-    const size_t smem = (size_t)CP * (5 + RING) * sizeof(double) + (size_t)CP * (2 * sizeof(uint32_t) + 1) +
-                        RING * sizeof(uint32_t) + 16;
+    constexpr int CP = 2 * 32 * NBULK * NPB;
+    constexpr int RING = RingDepth<NPB>::value;
+    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 10 * sizeof(double) +
+                        (size_t)CP * (4 * sizeof(uint32_t) + 1) + 16;
     static bool configured = false;
     if (!configured) {
-        CP_CUDA(cudaFuncSetAttribute(lasso_select_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CP_CUDA(cudaFuncSetAttribute(lasso_select_kernel<NPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    lasso_select_kernel<NP><<<1, 32, smem, stream>>>(P);
+    lasso_select_kernel<NPB><<<1, WS_THREADS, smem, stream>>>(P);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -476,10 +577,8 @@ extern "C" int cp_lasso_select(cp_handle_t h, const double *Q, int ldq, const do
     SelectParams P{Q, ldq, qv, yn2, c, m, rank, lbound, rbound, right0, tol, max_iter, seeds, max_probes,
                    out_idxs, out_coef, out_scalars, out_probe_log};
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (c <= 64) return launch_select<1>(P, stream);
-    if (c <= 128) return launch_select<2>(P, stream);
-    if (c <= 256) return launch_select<4>(P, stream);
-    if (c <= 512) return launch_select<8>(P, stream);
-    if (c <= 1024) return launch_select<16>(P, stream);
-    return launch_select<32>(P, stream);
+    if (c <= 256) return launch_select<1>(P, stream);
+    if (c <= 512) return launch_select<2>(P, stream);
+    if (c <= 1024) return launch_select<4>(P, stream);
+    return launch_select<8>(P, stream);
 }
