@@ -143,6 +143,27 @@ __device__ __forceinline__ void wait_ge(const int *p, int target) {
     for (uint32_t spin = 0; ld_acquire(p) < target; ++spin)
         if (spin > (1u << 26)) __trap();
 }
+// progress hints (ring-reuse slack only; a stale value merely delays the waiter)
+__device__ __forceinline__ void wait_ge_relaxed(const int *p, int target) {
+    for (uint32_t spin = 0; *reinterpret_cast<const volatile int *>(p) < target; ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+// Tagged 16-byte records {value, tag}: written with ONE st.shared.v2.f64 and read with ONE ld.shared.v2.f64, so
+// value and tag always travel together -- no separate flag, no fence on the serial chain.
+__device__ __forceinline__ void put_tagged(uint32_t slot_saddr, double v, unsigned long long tag) {
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot_saddr), "d"(v),
+                 "d"(__longlong_as_double((long long)tag))
+                 : "memory");
+}
+__device__ __forceinline__ double get_tagged(uint32_t slot_saddr, unsigned long long tag) {
+    double v, t;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(slot_saddr) : "memory");
+        if ((unsigned long long)__double_as_longlong(t) == tag) break;
+        if (spin > (1u << 26)) __trap();
+    }
+    return v;
+}
 
 __device__ __forceinline__ double warp_sum_butterfly(double v) {  // model: p[l] + p[l ^ off], off = 16..1
 #pragma unroll
@@ -181,9 +202,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
     double *dg = qv + CP;
     double *ring = dg + CP;                 // [RING][CP]
     double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1, r2, r3
-    double *dq = pk + QR * 8;               // [QR] published deltas
-    double *xq = dq + QR;                   // [QR] published Qw entries
-    uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR);
+    double *dq = pk + QR * 8;               // [QR][2] published {delta, tag}
+    double *xq = dq + QR * 2;               // [QR][2] published {Qw entry, tag}
+    uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR * 2);
     uint32_t *jz = active + CP;             // coordinate sequence of the sweep / eviction list of the screening
     uint32_t *raw = jz + CP;                // [2][CP] xorshift states (this sweep / next sweep)
     uint8_t *excluded = reinterpret_cast<uint8_t *>(raw + 2 * CP);
@@ -202,7 +223,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         excluded[e] = 0;
     }
     for (int e = tid; e < RING * CP; e += WS_THREADS) ring[e] = 0.0;  // padding pairs stay zero
+    for (int e = tid; e < QR * 4; e += WS_THREADS) dq[e] = 0.0;        // dq and xq: tag 0 never matches
     __syncthreads();
+    unsigned long long sweep_no = 0;  // tags are (sweep_no << 32) | (step + 1): unique over the whole launch
 
     const double tolS = __dmul_rn(P.tol, yn2);
     int probe = 0, status = 0;
@@ -324,32 +347,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             }
         }
         __syncthreads();
+        const unsigned long long tag0 = sweep_no << 32;
+        const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         if (warp == 0) {
             // -------- chain warp: the serial recurrence and nothing else
             double d1 = 0.0, d2 = 0.0, d3 = 0.0, w_max = 0.0, d_w_max = 0.0;
             for (int s = 0; s < n_active; ++s) {
                 const uint32_t j = jz[s];
                 if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
-                if ((s & 15) == 0 && s >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
+                if ((s & 15) == 0) {
+                    if (lane == 0) *reinterpret_cast<volatile int *>(&ctl.chain_pos) = s;  // steps < s are done
+                    if (s >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
 #pragma unroll
-                    for (int b = 0; b < NBULK; ++b) wait_ge(&ctl.bulk_pos[b], s - 30);
+                        for (int b = 0; b < NBULK; ++b) wait_ge_relaxed(&ctl.bulk_pos[b], s - 24);
+                    }
                 }
                 const double2 p0 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8);
                 const double2 p1 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 2);
                 const double2 p2 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 4);
                 const double w_j = w[j];
-                const int ow = (int)((j >> 1) & (BL - 1)) >> 5;
-                wait_ge(&ctl.bulk_pos[ow], s - LAG + 1 > 1 ? s - LAG + 1 : 1);
-                double x = xq[s & (QR - 1)];
+                // Qw[j] as of update s-LAG-1, published by the owning update lane
+                double x = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag0 | (unsigned)(s + 1));
                 x = __dadd_rn(x, __dmul_rn(d3, p2.y));  // delta_{s-3} * Q[j_s][j_{s-3}]
                 x = __dadd_rn(x, __dmul_rn(d2, p2.x));
                 x = __dadd_rn(x, __dmul_rn(d1, p1.y));
                 double delta, aw, w_new;
                 cd_update(p0.x, p0.y, p1.x, x, w_j, l1, delta, aw, w_new);
                 w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
-                if (lane == 0) dq[s & (QR - 1)] = delta;
-                __syncwarp();
-                if (lane == 0) st_release(&ctl.chain_pos, s + 1);
+                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag0 | (unsigned)(s + 1));
                 const double d = fabs(delta);
                 d_w_max = (aw >= 0.0 && d > d_w_max) ? d : d_w_max;
                 w_max = (aw > w_max) ? aw : w_max;
@@ -378,14 +403,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             }
             for (int s = 0; s <= LAG && s < n_active; ++s) {  // entries the chain needs before any update
                 const uint32_t js = jz[s];
-                if ((int)((js >> 1) & (BL - 1)) == bt) xq[s] = Qw[js];
+                if ((int)((js >> 1) & (BL - 1)) == bt) put_tagged(xq_s + (uint32_t)s * 16u, Qw[js], tag0 | (unsigned)(s + 1));
             }
-            __syncwarp();
-            if (lane == 0) st_release(&ctl.bulk_pos[b], 1);
             for (int t = 0; t < n_active; ++t) {
                 const int slot = t % RING;
-                wait_ge(&ctl.chain_pos, t + 1);
-                const double delta = dq[t & (QR - 1)];
+                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (unsigned)(t + 1));
                 cp_async_wait<RING - 1>();  // this lane's pairs of row t have landed
                 if (delta != 0.0) {
                     const double *row = ring + (size_t)slot * CP;
@@ -402,18 +424,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
                 if (sp1 < n_active) {
                     const uint32_t js = jz[sp1];
-                    if ((int)((js >> 1) & (BL - 1)) == bt) xq[sp1 & (QR - 1)] = Qw[js];
+                    if ((int)((js >> 1) & (BL - 1)) == bt)
+                        put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (unsigned)(sp1 + 1));
                 }
                 if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
                 cp_async_commit();
-                __syncwarp();
-                if (lane == 0) st_release(&ctl.bulk_pos[b], t + 2);
+                if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
             }
             cp_async_wait<0>();
         } else if (warp == PK_WARP) {
             // -------- packager: operands of 32 chain steps at a time
             for (int base = 0; base < n_active; base += 32) {
-                if (base >= QR) wait_ge(&ctl.chain_pos, base - 32);  // slots of batch base-64 are free
+                if (base >= QR) wait_ge_relaxed(&ctl.chain_pos, base - 32);  // slots of batch base-64 are free
                 const int s = base + lane;
                 if (s < n_active) {
                     const uint32_t j = jz[s];
@@ -440,6 +462,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 }
             }
         }
+        ++sweep_no;
         __syncthreads();
     };
 
@@ -533,7 +556,7 @@ template <int NPB>
 int launch_select(const SelectParams &P, cudaStream_t stream) {
     constexpr int CP = 2 * 32 * NBULK * NPB;
     constexpr int RING = RingDepth<NPB>::value;
-    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 10 * sizeof(double) +
+    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 12 * sizeof(double) +
                         (size_t)CP * (4 * sizeof(uint32_t) + 1) + 16;
     static bool configured = false;
     if (!configured) {
