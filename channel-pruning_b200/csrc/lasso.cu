@@ -150,16 +150,16 @@ __device__ __forceinline__ void wait_ge_relaxed(const int *p, int target) {
 }
 // Tagged 16-byte records {value, tag}: written with ONE st.shared.v2.f64 and read with ONE ld.shared.v2.f64, so
 // value and tag always travel together -- no separate flag, no fence on the serial chain.
-__device__ __forceinline__ void put_tagged(uint32_t slot_saddr, double v, unsigned long long tag) {
+__device__ __forceinline__ void put_tagged(uint32_t slot_saddr, double v, uint32_t tag) {
     asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot_saddr), "d"(v),
-                 "d"(__longlong_as_double((long long)tag))
+                 "d"(__hiloint2double(0, (int)tag))
                  : "memory");
 }
-__device__ __forceinline__ double get_tagged(uint32_t slot_saddr, unsigned long long tag) {
+__device__ __forceinline__ double get_tagged(uint32_t slot_saddr, uint32_t tag) {
     double v, t;
     for (uint32_t spin = 0;; ++spin) {
         asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(slot_saddr) : "memory");
-        if ((unsigned long long)__double_as_longlong(t) == tag) break;
+        if ((uint32_t)__double2loint(t) == tag) break;
         if (spin > (1u << 26)) __trap();
     }
     return v;
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
     double *dg = qv + CP;
     double *ring = dg + CP;                 // [RING][CP]
     double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1, r2, r3
-    double *dq = pk + QR * 8;               // [QR][2] published {delta, tag}
-    double *xq = dq + QR * 2;               // [QR][2] published {Qw entry, tag}
+    double *dq = pk + QR * 8;               // [QR][4] published {delta, tag, |w_new|, tag}
+    double *xq = dq + QR * 4;               // [QR][2] published {Qw entry, tag}
     uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR * 2);
     uint32_t *jz = active + CP;             // coordinate sequence of the sweep / eviction list of the screening
     uint32_t *raw = jz + CP;                // [2][CP] xorshift states (this sweep / next sweep)
@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         excluded[e] = 0;
     }
     for (int e = tid; e < RING * CP; e += WS_THREADS) ring[e] = 0.0;  // padding pairs stay zero
-    for (int e = tid; e < QR * 4; e += WS_THREADS) dq[e] = 0.0;        // dq and xq: tag 0 never matches
+    for (int e = tid; e < QR * 6; e += WS_THREADS) dq[e] = 0.0;        // dq and xq: tag 0 never matches
     __syncthreads();
-    unsigned long long sweep_no = 0;  // tags are (sweep_no << 32) | (step + 1): unique over the whole launch
+    uint32_t sweep_no = 1;  // tags are (sweep_no << 12) | (step + 1): unique over the whole launch (< 2^20 sweeps)
 
     const double tolS = __dmul_rn(P.tol, yn2);
     int probe = 0, status = 0;
@@ -318,10 +318,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         const double mag = __dadd_rn(fabs(tmp), -l1);
         // fsign(tmp) * fmax(|tmp| - l1, 0) / Qjj  (Qjj > 0): signed zero when thresholded away
         const double wn = mag > 0.0 ? div_markstein(copysign(mag, tmp), Qjj, rj) : (tmp < 0.0 ? -0.0 : 0.0);
-        const bool live = Qjj != 0.0;  // model: "if Qjj == 0: continue"
-        w_new = live ? wn : w_j;
-        delta = live ? __dadd_rn(wn, -w_j) : 0.0;
-        aw = live ? fabs(wn) : -1.0;
+        // model: "if Qjj == 0: continue" -- cannot trigger here: the first screening of every fit removes
+        // zero-diagonal columns from the active set, and only active coordinates are visited
+        w_new = wn;
+        delta = __dadd_rn(wn, -w_j);
+        aw = fabs(wn);
     };
     auto sweep = [&](int n_active, bool fresh, uint32_t seed, int cur, double l1) {
         uint32_t *raw_cur = raw + cur * CP, *raw_nxt = raw + (cur ^ 1) * CP;
@@ -347,11 +348,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             }
         }
         __syncthreads();
-        const unsigned long long tag0 = sweep_no << 32;
+        const uint32_t tag0 = sweep_no << 12;
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         if (warp == 0) {
             // -------- chain warp: the serial recurrence and nothing else
-            double d1 = 0.0, d2 = 0.0, d3 = 0.0, w_max = 0.0, d_w_max = 0.0;
+            double d1 = 0.0, d2 = 0.0, d3 = 0.0;
             for (int s = 0; s < n_active; ++s) {
                 const uint32_t j = jz[s];
                 if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
@@ -367,22 +368,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 const double2 p2 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 4);
                 const double w_j = w[j];
                 // Qw[j] as of update s-LAG-1, published by the owning update lane
-                double x = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag0 | (unsigned)(s + 1));
+                double x = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag0 | (uint32_t)(s + 1));
                 x = __dadd_rn(x, __dmul_rn(d3, p2.y));  // delta_{s-3} * Q[j_s][j_{s-3}]
                 x = __dadd_rn(x, __dmul_rn(d2, p2.x));
                 x = __dadd_rn(x, __dmul_rn(d1, p1.y));
                 double delta, aw, w_new;
                 cd_update(p0.x, p0.y, p1.x, x, w_j, l1, delta, aw, w_new);
                 w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
-                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag0 | (unsigned)(s + 1));
-                const double d = fabs(delta);
-                d_w_max = (aw >= 0.0 && d > d_w_max) ? d : d_w_max;
-                w_max = (aw > w_max) ? aw : w_max;
+                if (lane == 0) {
+                    const uint32_t slot = dq_s + (uint32_t)(s & (QR - 1)) * 32u;
+                    put_tagged(slot, delta, tag0 | (uint32_t)(s + 1));
+                    put_tagged(slot + 16u, aw, tag0 | (uint32_t)(s + 1));  // for the sweep statistics (update warp 0)
+                }
                 d3 = d2; d2 = d1; d1 = delta;
-            }
-            if (lane == 0) {
-                ctl.w_max = w_max;
-                ctl.d_w_max = d_w_max;
             }
         } else if (warp <= NBULK) {
             // -------- pair-update warps
@@ -403,11 +401,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             }
             for (int s = 0; s <= LAG && s < n_active; ++s) {  // entries the chain needs before any update
                 const uint32_t js = jz[s];
-                if ((int)((js >> 1) & (BL - 1)) == bt) put_tagged(xq_s + (uint32_t)s * 16u, Qw[js], tag0 | (unsigned)(s + 1));
+                if ((int)((js >> 1) & (BL - 1)) == bt) put_tagged(xq_s + (uint32_t)s * 16u, Qw[js], tag0 | (uint32_t)(s + 1));
             }
+            double w_max = 0.0, d_w_max = 0.0;
             for (int t = 0; t < n_active; ++t) {
                 const int slot = t % RING;
-                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (unsigned)(t + 1));
+                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 32u, tag0 | (uint32_t)(t + 1));
                 cp_async_wait<RING - 1>();  // this lane's pairs of row t have landed
                 if (delta != 0.0) {
                     const double *row = ring + (size_t)slot * CP;
@@ -425,13 +424,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 if (sp1 < n_active) {
                     const uint32_t js = jz[sp1];
                     if ((int)((js >> 1) & (BL - 1)) == bt)
-                        put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (unsigned)(sp1 + 1));
+                        put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (uint32_t)(sp1 + 1));
                 }
                 if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
                 cp_async_commit();
+                if (b == 0) {  // sweep statistics, off the chain warp
+                    const double aw = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 32u + 16u, tag0 | (uint32_t)(t + 1));
+                    d_w_max = fmax(d_w_max, fabs(delta));
+                    w_max = fmax(w_max, aw);
+                }
                 if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
             }
             cp_async_wait<0>();
+            if (b == 0 && lane == 0) {
+                ctl.w_max = w_max;
+                ctl.d_w_max = d_w_max;
+            }
         } else if (warp == PK_WARP) {
             // -------- packager: operands of 32 chain steps at a time
             for (int base = 0; base < n_active; base += 32) {
@@ -556,7 +564,7 @@ template <int NPB>
 int launch_select(const SelectParams &P, cudaStream_t stream) {
     constexpr int CP = 2 * 32 * NBULK * NPB;
     constexpr int RING = RingDepth<NPB>::value;
-    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 12 * sizeof(double) +
+    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 14 * sizeof(double) +
                         (size_t)CP * (4 * sizeof(uint32_t) + 1) + 16;
     static bool configured = false;
     if (!configured) {

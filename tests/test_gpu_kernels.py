@@ -154,7 +154,7 @@ def test_lasso_build_matches_centred_design(engine, c, n, N, k):
 
 
 @pytest.mark.parametrize("c,n,N,k,rank", [(32, 16, 600, 3, 27), (96, 32, 800, 1, 83), (131, 24, 1000, 3, 113),
-                                           (300, 24, 1000, 3, 260), (600, 8, 2000, 1, 520), (1100, 4, 2000, 1, 950)])
+                                           (300, 24, 1000, 3, 260), (600, 8, 2000, 1, 520), (1100, 16, 3000, 1, 950)])
 def test_lasso_select_bit_exact_vs_gram_model(engine, c, n, N, k, rank):
     """Device alpha search == oracle/cd_oracle.c:cp_enet_cd_gram driven by the same search loop,
     fed the device-built (Q, q, |y|^2): identical probes, iteration counts, coefficients (bitwise)."""
