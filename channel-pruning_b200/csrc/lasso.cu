@@ -385,13 +385,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         } else if (warp <= NBULK) {
             // -------- pair-update warps
             const int b = warp - 1, bt = b * 32 + lane;
+            const double *Qmine = Q + 2 * bt;                  // this lane's first pair of any row
+            double *ring_mine = ring + 2 * bt;
             auto prefetch_row = [&](uint32_t j, int slot) {
-                const double *src = Q + (int64_t)j * ldq;
-                double *dst = ring + (size_t)slot * CP;
+                const double *src = Qmine + (uint32_t)(j * (uint32_t)ldq);  // c * ldq < 2^31
+                double *dst = ring_mine + (uint32_t)(slot * CP);
 #pragma unroll
                 for (int sp = 0; sp < NPB; ++sp) {
-                    const int e = 2 * BL * sp + 2 * bt;
-                    if (e < c) cp_async16(dst + e, src + e);
+                    if (2 * BL * sp + 2 * bt < c) cp_async16(dst + 2 * BL * sp, src + 2 * BL * sp);
                 }
             };
 #pragma unroll
@@ -423,8 +424,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
                 if (sp1 < n_active) {
                     const uint32_t js = jz[sp1];
-                    if ((int)((js >> 1) & (BL - 1)) == bt)
-                        put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (uint32_t)(sp1 + 1));
+                    const int ob = (int)((js >> 1) & (BL - 1));
+                    if ((ob >> 5) == b) {  // warp-uniform: only the owning warp looks for the owning lane
+                        if ((ob & 31) == lane)
+                            put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (uint32_t)(sp1 + 1));
+                    }
                 }
                 if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
                 cp_async_commit();
