@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
     double *dg = qv + CP;
     double *ring = dg + CP;                 // [RING][CP]
     double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1, r2, r3
-    double *dq = pk + QR * 8;               // [QR][4] published {delta, tag, |w_new|, tag}
-    double *xq = dq + QR * 4;               // [QR][2] published {Qw entry, tag}
+    double *dq = pk + QR * 8;               // [QR][2] published {delta, tag}
+    double *xq = dq + QR * 2;               // [QR][2] published {Qw entry, tag}
     uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR * 2);
     uint32_t *jz = active + CP;             // coordinate sequence of the sweep / eviction list of the screening
     uint32_t *raw = jz + CP;                // [2][CP] xorshift states (this sweep / next sweep)
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         excluded[e] = 0;
     }
     for (int e = tid; e < RING * CP; e += WS_THREADS) ring[e] = 0.0;  // padding pairs stay zero
-    for (int e = tid; e < QR * 6; e += WS_THREADS) dq[e] = 0.0;        // dq and xq: tag 0 never matches
+    for (int e = tid; e < QR * 4; e += WS_THREADS) dq[e] = 0.0;        // dq and xq: tag 0 never matches
     __syncthreads();
     uint32_t sweep_no = 1;  // tags are (sweep_no << 12) | (step + 1): unique over the whole launch (< 2^20 sweeps)
 
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         if (warp == 0) {
             // -------- chain warp: the serial recurrence and nothing else
-            double d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            double d1 = 0.0, d2 = 0.0, d3 = 0.0, w_max = 0.0, d_w_max = 0.0;
             for (int s = 0; s < n_active; ++s) {
                 const uint32_t j = jz[s];
                 if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
@@ -375,12 +375,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 double delta, aw, w_new;
                 cd_update(p0.x, p0.y, p1.x, x, w_j, l1, delta, aw, w_new);
                 w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
-                if (lane == 0) {
-                    const uint32_t slot = dq_s + (uint32_t)(s & (QR - 1)) * 32u;
-                    put_tagged(slot, delta, tag0 | (uint32_t)(s + 1));
-                    put_tagged(slot + 16u, aw, tag0 | (uint32_t)(s + 1));  // for the sweep statistics (update warp 0)
-                }
+                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag0 | (uint32_t)(s + 1));
+                d_w_max = fmax(d_w_max, fabs(delta));
+                w_max = fmax(w_max, aw);
                 d3 = d2; d2 = d1; d1 = delta;
+            }
+            if (lane == 0) {
+                ctl.w_max = w_max;
+                ctl.d_w_max = d_w_max;
             }
         } else if (warp <= NBULK) {
             // -------- pair-update warps
@@ -404,10 +406,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 const uint32_t js = jz[s];
                 if ((int)((js >> 1) & (BL - 1)) == bt) put_tagged(xq_s + (uint32_t)s * 16u, Qw[js], tag0 | (uint32_t)(s + 1));
             }
-            double w_max = 0.0, d_w_max = 0.0;
             for (int t = 0; t < n_active; ++t) {
                 const int slot = t % RING;
-                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 32u, tag0 | (uint32_t)(t + 1));
+                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
                 cp_async_wait<RING - 1>();  // this lane's pairs of row t have landed
                 if (delta != 0.0) {
                     const double *row = ring + (size_t)slot * CP;
@@ -432,18 +433,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 }
                 if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
                 cp_async_commit();
-                if (b == 0) {  // sweep statistics, off the chain warp
-                    const double aw = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 32u + 16u, tag0 | (uint32_t)(t + 1));
-                    d_w_max = fmax(d_w_max, fabs(delta));
-                    w_max = fmax(w_max, aw);
-                }
                 if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
             }
             cp_async_wait<0>();
-            if (b == 0 && lane == 0) {
-                ctl.w_max = w_max;
-                ctl.d_w_max = d_w_max;
-            }
         } else if (warp == PK_WARP) {
             // -------- packager: operands of 32 chain steps at a time
             for (int base = 0; base < n_active; base += 32) {
@@ -568,7 +560,7 @@ template <int NPB>
 int launch_select(const SelectParams &P, cudaStream_t stream) {
     constexpr int CP = 2 * 32 * NBULK * NPB;
     constexpr int RING = RingDepth<NPB>::value;
-    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 14 * sizeof(double) +
+    const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 12 * sizeof(double) +
                         (size_t)CP * (4 * sizeof(uint32_t) + 1) + 16;
     static bool configured = false;
     if (!configured) {
