@@ -32,7 +32,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "conv_layers_pruned_per_sec"
 UNIT = "layers/s"
-WORKLOAD = "vgg16_conv_stack_13_layers_N5000"
+WORKLOADS = {"vgg16": "vgg16_conv_stack_13_layers_N5000", "resnet50": "resnet50_bottlenecks_48_problems_N5000"}
+
+
+def workload_shapes(args):
+    import cpb200
+
+    shapes = cpb200.synth.vgg16_layers() if args.workload == "vgg16" else cpb200.synth.resnet50_layers()
+    return select_shapes(shapes, args.layers)
 
 
 def parse():
@@ -46,7 +53,9 @@ def parse():
                     help="arithmetic of the big Gram products: tc = tcgen05 3xTF32 (default), fp64 = DFMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--layers", default="", help="comma list of VGG layer names (debug); default all 13")
+    ap.add_argument("--layers", default="", help="comma list of layer names (debug); default: all of the workload")
+    ap.add_argument("--workload", default="vgg16", choices=["vgg16", "resnet50"],
+                    help="vgg16 = BASELINE configs[1] (13 conv layers); resnet50 = configs[3] (48 bottleneck problems)")
     return ap.parse_args()
 
 
@@ -119,7 +128,7 @@ def run_reference(args):
         return
     import cpb200
 
-    shapes = select_shapes(cpb200.synth.vgg16_layers(), args.layers)
+    shapes = workload_shapes(args)
     for _ in range(args.warmup):
         cpu_pass(shapes)
     vals, secs = [], []
@@ -133,7 +142,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * len(shapes) / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of lib/net.py + lib/decompose.py (oracle port); "
+        "config": {"workload": WORKLOADS[args.workload], "note": "CPU restatement of lib/net.py + lib/decompose.py (oracle port); "
                    "the Python reference itself cannot travel to the GPU box"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,7 +231,7 @@ def run_gpu(args):
     lib = cpb200._cabi.load()[1]
     dev = eng.device
 
-    base = select_shapes(cpb200.synth.vgg16_layers(), args.layers)
+    base = workload_shapes(args)
     shapes = [s for _ in range(world) for s in base]  # one network per GPU in the pool (weak scaling)
     owner = pruner.assign_layers([s.cost() for s in shapes], world)
     mine = [i for i, o in enumerate(owner) if o == rank]
@@ -342,7 +351,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "tf32x3+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "layers_per_network": len(base), "networks": world,
+            "config": {"workload": WORKLOADS[args.workload], "layers_per_network": len(base), "networks": world,
                        "N_patches": base[0].N, "l2": "inputs (feature maps, ~%.1f GB per network) exceed L2; no flush needed"
                        % (sum(4.0 * s.N // (s.B * s.P) * s.B * s.c * s.H * s.W for s in base) / 1e9),
                        "streams": args.streams, "kept_channels_rank0": kept},

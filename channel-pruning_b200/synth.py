@@ -28,6 +28,37 @@ VGG16 = [
 
 C_RATIO = 1.15  # lib/net.py:1327
 
+# BASELINE config 4: ResNet-50 bottleneck problems.  (name, c_in, n_out, k, H_in, stride, pad, kept) where `kept`
+# is the number of surviving INPUT channels recorded in the reference's released pruned net
+# temp/resnet-50-cp.prototxt (branch2a: the block's input selector `<prev>_Filter.num_output`; branch2b /
+# branch2c: `num_output` of the producing conv).  kept == c_in means the layer was left alone (LS only).
+RESNET50 = [
+    ('res2a_branch2a', 64, 64, 1, 56, 1, 0, 35), ('res2a_branch2b', 64, 64, 3, 56, 1, 1, 64),
+    ('res2a_branch2c', 64, 256, 1, 56, 1, 0, 55), ('res2b_branch2a', 256, 64, 1, 56, 1, 0, 101),
+    ('res2b_branch2b', 64, 64, 3, 56, 1, 1, 51), ('res2b_branch2c', 64, 256, 1, 56, 1, 0, 39),
+    ('res2c_branch2a', 256, 64, 1, 56, 1, 0, 97), ('res2c_branch2b', 64, 64, 3, 56, 1, 1, 50),
+    ('res2c_branch2c', 64, 256, 1, 56, 1, 0, 37), ('res3a_branch2a', 256, 128, 1, 56, 2, 0, 144),
+    ('res3a_branch2b', 128, 128, 3, 28, 1, 1, 128), ('res3a_branch2c', 128, 512, 1, 28, 1, 0, 106),
+    ('res3b_branch2a', 512, 128, 1, 28, 1, 0, 205), ('res3b_branch2b', 128, 128, 3, 28, 1, 1, 105),
+    ('res3b_branch2c', 128, 512, 1, 28, 1, 0, 72), ('res3c_branch2a', 512, 128, 1, 28, 1, 0, 198),
+    ('res3c_branch2b', 128, 128, 3, 28, 1, 1, 105), ('res3c_branch2c', 128, 512, 1, 28, 1, 0, 72),
+    ('res3d_branch2a', 512, 128, 1, 28, 1, 0, 288), ('res3d_branch2b', 128, 128, 3, 28, 1, 1, 128),
+    ('res3d_branch2c', 128, 512, 1, 28, 1, 0, 110), ('res4a_branch2a', 512, 256, 1, 28, 2, 0, 278),
+    ('res4a_branch2b', 256, 256, 3, 14, 1, 1, 256), ('res4a_branch2c', 256, 1024, 1, 14, 1, 0, 225),
+    ('res4b_branch2a', 1024, 256, 1, 14, 1, 0, 418), ('res4b_branch2b', 256, 256, 3, 14, 1, 1, 209),
+    ('res4b_branch2c', 256, 1024, 1, 14, 1, 0, 147), ('res4c_branch2a', 1024, 256, 1, 14, 1, 0, 407),
+    ('res4c_branch2b', 256, 256, 3, 14, 1, 1, 204), ('res4c_branch2c', 256, 1024, 1, 14, 1, 0, 158),
+    ('res4d_branch2a', 1024, 256, 1, 14, 1, 0, 423), ('res4d_branch2b', 256, 256, 3, 14, 1, 1, 212),
+    ('res4d_branch2c', 256, 1024, 1, 14, 1, 0, 155), ('res4e_branch2a', 1024, 256, 1, 14, 1, 0, 412),
+    ('res4e_branch2b', 256, 256, 3, 14, 1, 1, 211), ('res4e_branch2c', 256, 1024, 1, 14, 1, 0, 148),
+    ('res4f_branch2a', 1024, 256, 1, 14, 1, 0, 595), ('res4f_branch2b', 256, 256, 3, 14, 1, 1, 256),
+    ('res4f_branch2c', 256, 1024, 1, 14, 1, 0, 213), ('res5a_branch2a', 1024, 512, 1, 14, 2, 0, 606),
+    ('res5a_branch2b', 512, 512, 3, 7, 1, 1, 512), ('res5a_branch2c', 512, 2048, 1, 7, 1, 0, 433),
+    ('res5b_branch2a', 2048, 512, 1, 7, 1, 0, 1222), ('res5b_branch2b', 512, 512, 3, 7, 1, 1, 512),
+    ('res5b_branch2c', 512, 2048, 1, 7, 1, 0, 437), ('res5c_branch2a', 2048, 512, 1, 7, 1, 0, 1147),
+    ('res5c_branch2b', 512, 512, 3, 7, 1, 1, 512), ('res5c_branch2c', 512, 2048, 1, 7, 1, 0, 440),
+]
+
 
 class LayerShape:
     def __init__(self, name, c, n, H, k=3, pad=1, stride=1, N=5000, B=10, P=10, rank=None):
@@ -52,6 +83,11 @@ class LayerShape:
 
 def vgg16_layers(N=5000, B=10, P=10):
     return [LayerShape(nm, c, n, H, N=N, B=B, P=P) for nm, c, n, H in VGG16]
+
+
+def resnet50_layers(N=5000, B=10, P=10):
+    return [LayerShape(nm, c, n, H, k=k, pad=pad, stride=st, N=N, B=B, P=P, rank=kept)
+            for nm, c, n, k, H, st, pad, kept in RESNET50]
 
 
 def make_problem_numpy(shape: LayerShape, seed: int, noise=0.01):

@@ -190,3 +190,56 @@ def test_full_size_properties_conv4_shape(engine):
     R = Yc - Xs @ Wd.T - bd
     assert float(R.mean(0).abs().max()) <= 1e-9
     assert float((Xs.T @ R).abs().max()) <= 1e-6 * float((Xs.T @ Yc).abs().max())
+
+
+@pytest.mark.parametrize("name", ["res2a_branch2a", "res2b_branch2a", "res3a_branch2a", "res2b_branch2b", "res3b_branch2c"])
+def test_resnet50_bottleneck_problem_vs_oracle(engine, name):
+    """BASELINE configs[3] shapes (1x1 / 3x3 / stride-2 bottleneck convs, target counts from the reference's
+    released resnet-50-cp.prototxt) through the batched pipeline (pruner.prune_layers) against the oracle's
+    dictionary_kernel on the same data, N=1000."""
+    import cpb200
+
+    row = [r for r in cpb200.synth.RESNET50 if r[0] == name][0]
+    nm, c, n, k, H, st, pad, kept = row
+    s = cpb200.synth.LayerShape(nm, c, n, H, k=k, pad=pad, stride=st, N=1000, rank=kept)
+    d = cpb200.synth.make_problem_device(s, 77, engine)
+    res = cpb200.pruner.prune_layers(engine, [s], [d], right0=1e-3)[0]
+    torch.cuda.synchronize()
+    fm = d["fmap"].cpu().numpy()
+    pd = {"nPointsPerLayer": s.P, "nBatches": s.nbatch}
+    for b in range(s.nbatch):
+        pd[(b, "y", "randx")] = d["randx"][b].cpu().numpy()
+        pd[(b, "y", "randy")] = d["randy"][b].cpu().numpy()
+    forward = lambda b: {"x": fm[b * s.B:(b + 1) * s.B]}  # noqa: E731
+    st_ = O.DictState(alpha=1e-3)
+    info = {}
+
+    class _Seeds:  # the oracle draws its CD seeds from an RNG object: feed it the device's seed list
+        def __init__(self, seeds):
+            self.seeds, self.i = list(seeds), 0
+
+        def randint(self, lo, hi):
+            v = self.seeds[self.i]
+            self.i += 1
+            return v
+
+    import cp_oracle
+
+    orig = cp_oracle.LassoCD.__init__
+
+    def patched(self, alpha, **kw):
+        orig(self, alpha, **kw)
+        self.rng = _Seeds(d["seeds"])
+
+    cp_oracle.LassoCD.__init__ = patched
+    try:
+        oi, oW, oB = O.dictionary_kernel(forward, "x", O.ConvSpec("y", "x", k, pad, st), d["W2"].cpu().numpy(),
+                                         d["b2"].cpu().numpy(), d["feats"].cpu().numpy().astype(np.float64), pd, kept,
+                                         state=st_, samples=d["samples"].cpu().numpy(), info=info)
+    finally:
+        cp_oracle.LassoCD.__init__ = orig
+    assert np.array_equal(res.idxs, oi)
+    if kept != c:
+        assert res.alpha == st_.alpha and res.nprobe == len(info["probes"])
+    W = res.W.cpu().numpy().reshape(oW.shape)
+    assert _rel(W, oW) <= W_TOL and np.abs(res.b.cpu().numpy() - oB).max() <= W_TOL
