@@ -12,6 +12,8 @@ libcpb200.so construction fails.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -34,13 +36,15 @@ class LassoResult:
 
 
 class Engine:
-    def __init__(self, device=None, nstreams: int = 1, gram_mode: int = GRAM_FP64):
+    def __init__(self, device=None, nstreams: int = 1, gram_mode: int = None):
         if not torch.cuda.is_available():
             raise RuntimeError("cpb200: no CUDA device visible; the solver has no CPU path")
         self.ffi, self.lib = _cabi.load()
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        if gram_mode is None:  # tensor cores by default; CPB200_GRAM=fp64 selects the exact-product DFMA mode
+            gram_mode = GRAM_FP64 if os.environ.get("CPB200_GRAM", "tc").lower() == "fp64" else GRAM_3XTF32
         self.gram_mode = gram_mode
         self._handles = []
         self.streams = []

@@ -21,7 +21,7 @@ def golden_dir():
 
 
 @pytest.fixture(scope="session")
-def engine():
+def _engine_session():
     import torch
 
     if not torch.cuda.is_available():
@@ -29,3 +29,10 @@ def engine():
     import cpb200
 
     return cpb200.get_engine()
+
+
+@pytest.fixture
+def engine(_engine_session):
+    """The process-wide engine, reset to the product default (tensor-core Gram) before every test."""
+    _engine_session.gram_mode = 1
+    return _engine_session

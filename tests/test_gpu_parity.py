@@ -22,8 +22,9 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["fp64", "3xtf32"])
 @pytest.mark.parametrize("name", list(cases.DICTIONARY_CASES))
-def test_dictionary_matches_reference_golden(engine, golden_dir, name):
+def test_dictionary_matches_reference_golden(engine, golden_dir, name, mode):
     import cpb200
     from cpb200.lib import cfgs, decompose
 
@@ -32,23 +33,28 @@ def test_dictionary_matches_reference_golden(engine, golden_dir, name):
     X, W2, Y = cases.dictionary_inputs(**spec["gen"])
     cfgs.alpha = spec["alpha0"]
     cfgs.c.dic.rank_tol = spec.get("rank_tol", .1)
+    old_mode, engine.gram_mode = engine.gram_mode, mode
     try:
         np.random.seed(spec["np_seed"])
         idxs, W, B = decompose.dictionary(X.astype(np.float64), W2, Y, rank=spec["rank"], B2=np.zeros(W2.shape[0]))
         after = np.random.randint(0, 1 << 30)
     finally:
         cfgs.c.dic.rank_tol = .1
+        engine.gram_mode = old_mode
     assert idxs.dtype == np.bool_ and np.array_equal(idxs, g["idxs"])  # exact channel set
     assert after == int(g["rng_after"])  # consumed the same global RNG draws as the reference
     assert cfgs.alpha == float(g["alpha_final"])
     assert W.dtype == np.float64 and W.shape == g["W"].shape
     assert _rel(W, g["W"]) <= W_TOL
-    assert _rel(W, g["W"]) <= 1e-7  # what the fp64 path actually delivers
-    assert np.abs(B - g["B"]).max() <= 1e-7 * max(1.0, np.abs(g["B"]).max())
+    tight = 1e-7 if mode == 0 else 2e-5  # what the two arithmetic modes actually deliver
+    assert _rel(W, g["W"]) <= tight
+    assert np.abs(B - g["B"]).max() <= tight * max(1.0, np.abs(g["B"]).max())
 
 
 def test_dictionary_accepts_cuda_tensors(engine, golden_dir):
     from cpb200.lib import cfgs, decompose
+
+    engine.gram_mode = 0
 
     spec = cases.DICTIONARY_CASES["c32"]
     g = np.load(os.path.join(golden_dir, "dictionary_c32.npz"))
@@ -62,6 +68,8 @@ def test_dictionary_accepts_cuda_tensors(engine, golden_dir):
 
 def test_fc_kernel_matches_oracle(engine):
     from cpb200.lib import decompose
+
+    engine.gram_mode = 0
 
     r = np.random.RandomState(8)
     X = np.maximum(r.standard_normal((900, 250)), 0).astype(np.float32)
@@ -99,6 +107,7 @@ def test_net_methods_match_reference_golden(engine, golden_dir, name):
     g = np.load(os.path.join(golden_dir, "net_%s.npz" % name))
     images, specs, weights, biases = cases.net_inputs(**spec["gen"])
     fnp = _forward_np(images, specs, weights, biases)
+    engine.gram_mode = 0
 
     def forward(net, batch):  # feature provider: the same blobs the reference saw, on the device
         return {k: torch.as_tensor(v, device=engine.device) for k, v in fnp(batch).items()}
@@ -148,13 +157,16 @@ def test_baseline_config1_mask_bit_compare(engine):
     assert _rel(W, oW) <= W_TOL and np.abs(B - oB).max() <= W_TOL
 
 
-def test_full_size_properties_conv4_shape(engine):
+@pytest.mark.parametrize("mode", [0, 1], ids=["fp64", "3xtf32"])
+def test_full_size_properties_conv4_shape(engine, mode):
     """c=n=512, k=3, N=5000 (VGG conv4_x; too slow for the CPU oracle in a unit test): check what
     must hold for ANY correct solution -- LASSO KKT conditions on the device-built statistics and
     the normal equations of the reconstruction -- plus agreement of the Gram-form statistics with
     a torch fp64 evaluation."""
     import cpb200
 
+    engine.gram_mode = mode
+    gtol, netol = (1e-11, 1e-6) if mode == 0 else (2e-6, 1e-4)
     s = cpb200.synth.LayerShape("conv4_x", 512, 512, 28, N=5000)
     d = cpb200.synth.make_problem_device(s, 123, engine)
     X = engine.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
@@ -169,8 +181,9 @@ def test_full_size_properties_conv4_shape(engine):
     # Gram statistics vs torch fp64 on a sub-block
     X64 = X[:, :300].double()
     Yc = d["feats"].double() - d["b2"].double()
-    assert torch.allclose(g_full["G"][:300, :300], X64.T @ X64, rtol=1e-11, atol=1e-8)
-    assert torch.allclose(g_full["B"][:300], X64.T @ Yc, rtol=1e-10, atol=1e-8)
+    Gref, Bref = X64.T @ X64, X64.T @ Yc
+    assert float((g_full["G"][:300, :300] - Gref).abs().max()) <= gtol * float(Gref.abs().max())
+    assert float((g_full["B"][:300] - Bref).abs().max()) <= 10 * gtol * float(Bref.abs().max())
     # KKT of the final LASSO fit (duality gap criterion => subgradient condition up to the gap)
     gs = engine.gram(X, d["feats"], y_bias=d["b2"], rows=d["samples"], want_yy=True, mode=0)
     gw = engine.gram(W2m, None, want_B=False, mode=0)
@@ -188,8 +201,8 @@ def test_full_size_properties_conv4_shape(engine):
     cols = torch.as_tensor((np.flatnonzero(idxs)[:, None] * 9 + np.arange(9)).reshape(-1), device=engine.device)
     Xs = X[:, cols].double()
     R = Yc - Xs @ Wd.T - bd
-    assert float(R.mean(0).abs().max()) <= 1e-9
-    assert float((Xs.T @ R).abs().max()) <= 1e-6 * float((Xs.T @ Yc).abs().max())
+    assert float(R.mean(0).abs().max()) <= (1e-9 if mode == 0 else 1e-6)
+    assert float((Xs.T @ R).abs().max()) <= netol * float((Xs.T @ Yc).abs().max())
 
 
 @pytest.mark.parametrize("name", ["res2a_branch2a", "res2b_branch2a", "res3a_branch2a", "res2b_branch2b", "res3b_branch2c"])
