@@ -42,13 +42,14 @@ ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const 
 }
 
 // ---------------------------------------------------------------- 64x64 diagonal block: L and L^-1
-// One CTA of 256 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 4 m (m = 0..15) of
-// column j in registers.  Right-looking factorisation: at step k the 4 threads of column k publish the
-// raw column (pivot included) to shared memory, ONE barrier (8 warps), then every thread applies the
+// One CTA of 1024 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 16 m (m = 0..3) of
+// column j in registers.  Right-looking factorisation: at step k the 16 threads of column k publish the
+// raw column (pivot included) to shared memory, ONE barrier, then every thread applies the
 // rank-1 update to its registers.  The inverse is a forward substitution with the same ownership (one
 // barrier per row).  1/sqrt(pivot) comes from the fp32 MUFU seed + two fp64 Newton steps.
-constexpr int PT = 256;
-constexpr int PR = 16;  // rows per thread
+constexpr int PT = 1024;
+constexpr int PR = 4;   // rows per thread
+constexpr int PG = 64 / PR;  // row groups
 constexpr size_t POTRF_SMEM = (size_t)(NB * (NB + 1) + 5 * NB) * sizeof(double);
 
 __device__ __forceinline__ double rsqrt_newton(double d) {
@@ -70,7 +71,7 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
     double a[PR], x[PR];
 #pragma unroll
     for (int m = 0; m < PR; ++m) {
-        const int i = ig + 4 * m;
+        const int i = ig + PG * m;
         double v = 0.0;
         if (i < nb && j < nb && j <= i) v = A[(int64_t)i * ld + j];
         if (i >= nb && i == j) v = 1.0;  // identity padding keeps the arithmetic finite
@@ -81,7 +82,7 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
         double *ck = col + (k & 1) * NB;
         if (j == k) {
 #pragma unroll
-            for (int m = 0; m < PR; ++m) ck[ig + 4 * m] = a[m];
+            for (int m = 0; m < PR; ++m) ck[ig + PG * m] = a[m];
         }
         __syncthreads();
         double d = ck[k];
@@ -95,7 +96,7 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
         if (j == k) {
 #pragma unroll
             for (int m = 0; m < PR; ++m) {
-                const int i = ig + 4 * m;
+                const int i = ig + PG * m;
                 Ls[i * (NB + 1) + k] = (i > k) ? ck[i] * rs : (i == k ? d * rs : 0.0);
             }
             if (ig == 0) rsd[k] = rs;
@@ -104,7 +105,7 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
             const double ljk = -ck[j] * rs * rs;  // -L[j][k] / sqrt(d)
 #pragma unroll
             for (int m = 0; m < PR; ++m) {
-                const int i = ig + 4 * m;
+                const int i = ig + PG * m;
                 if (i >= j) a[m] = fma(ck[i], ljk, a[m]);
             }
         }
@@ -113,8 +114,8 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
     // X = L^-1: row k of X is final once rows < k have been eliminated
     for (int k = 0; k < NB; ++k) {
         double *xr = xrow + (k & 1) * NB;
-        if (ig == (k & 3)) {
-            const int mk = k >> 2;
+        if (ig == (k & (PG - 1))) {
+            const int mk = k / PG;
             double xv = 0.0;
 #pragma unroll
             for (int m = 0; m < PR; ++m) xv = (m == mk) ? x[m] : xv;
@@ -127,14 +128,14 @@ potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv
             const double xk = xr[j];
 #pragma unroll
             for (int m = 0; m < PR; ++m) {
-                const int i = ig + 4 * m;
+                const int i = ig + PG * m;
                 if (i > k) x[m] = fma(-Ls[i * (NB + 1) + k], xk, x[m]);
             }
         }
     }
 #pragma unroll
     for (int m = 0; m < PR; ++m) {
-        const int i = ig + 4 * m;
+        const int i = ig + PG * m;
         if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = Ls[i * (NB + 1) + j];
     }
 }
