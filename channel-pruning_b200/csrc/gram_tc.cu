@@ -40,15 +40,16 @@ namespace {
 constexpr int TM = 128, TN = 128, KB = 32;           // output tile, rows per k-block
 constexpr int RAW_TILE = KB * TM * 4;                // 16 KB raw fp32 box
 constexpr int OP_TILE = TM * 128;                    // 16 KB operand tile (128 rows x 128 B)
-constexpr int STAGES = 2;
+constexpr int STAGES = 2;      // operand stages (hi/lo, K-major swizzled)
+constexpr int RSTAGES = 3;     // raw fp32 stages in flight (TMA latency x bandwidth needs ~64 KB per SM)
 constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 converters/epilogue
 constexpr int NCONV = 256;
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_OPS = 0;                                    // STAGES x {Ahi, Alo, Bhi, Blo}
-constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // STAGES x {rawA, rawB}
-constexpr int OFF_SHIFT = OFF_RAW + STAGES * 2 * RAW_TILE;    // shiftA[128], shiftB[128] fp32
+constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // RSTAGES x {rawA, rawB}
+constexpr int OFF_SHIFT = OFF_RAW + RSTAGES * 2 * RAW_TILE;    // shiftA[128], shiftB[128] fp32
 constexpr int OFF_BAR = OFF_SHIFT + 2 * TM * 4;               // mbarriers
-constexpr int NBAR = 4 * STAGES + 1;
+constexpr int NBAR = 2 * RSTAGES + 2 * STAGES + 1;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
 
@@ -147,16 +148,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nkb = (int)((r_end - r_begin + KB - 1) / KB);
 
     auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
-    // barrier indices: raw_full[s] = s, raw_empty[s] = STAGES+s, ops_full[s] = 2*STAGES+s, ops_empty[s] = 3*STAGES+s
-    const int ACC_FULL = 4 * STAGES;
+    // barrier indices
+    constexpr int RAW_FULL = 0, RAW_EMPTY = RSTAGES, OPS_FULL = 2 * RSTAGES, OPS_EMPTY = 2 * RSTAGES + STAGES;
+    constexpr int ACC_FULL = 2 * RSTAGES + 2 * STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     if (threadIdx.x == 0) {
+        for (int s = 0; s < RSTAGES; ++s) {
+            mbar_init(bar(RAW_FULL + s), 1);
+            mbar_init(bar(RAW_EMPTY + s), NCONV);
+        }
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar(s), 1);
-            mbar_init(bar(STAGES + s), NCONV);
-            mbar_init(bar(2 * STAGES + s), NCONV);
-            mbar_init(bar(3 * STAGES + s), 1);
+            mbar_init(bar(OPS_FULL + s), NCONV);
+            mbar_init(bar(OPS_EMPTY + s), 1);
         }
         mbar_init(bar(ACC_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,13 +186,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ===================== TMA producer =====================
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(bar(STAGES + s), ph ^ 1);  // slot free (fresh barrier passes immediately)
-                mbar_arrive_expect_tx(bar(s), diag ? RAW_TILE : 2 * RAW_TILE);
+                const int s = kb % RSTAGES;
+                const uint32_t ph = (kb / RSTAGES) & 1;
+                mbar_wait(bar(RAW_EMPTY + s), ph ^ 1);  // slot free (fresh barrier passes immediately)
+                mbar_arrive_expect_tx(bar(RAW_FULL + s), diag ? RAW_TILE : 2 * RAW_TILE);
                 const int row = (int)(r_begin + (int64_t)kb * KB);
-                tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, &mapA, bar(s), ti * TM, row);
-                if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, &mapB, bar(s), tj * TN, row);
+                tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, &mapA, bar(RAW_FULL + s), ti * TM, row);
+                if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, &mapB, bar(RAW_FULL + s), tj * TN, row);
             }
         }
     } else if (warp == 1) {
@@ -199,7 +203,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(bar(2 * STAGES + s), ph);
+                mbar_wait(bar(OPS_FULL + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ops = sbase + OFF_OPS + s * 4 * OP_TILE;
                 const uint32_t a_hi = ops, a_lo = ops + OP_TILE;
@@ -215,7 +219,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
                     umma_tf32(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
                 }
-                umma_commit(bar(3 * STAGES + s));  // operand stage free once these MMAs have read it
+                umma_commit(bar(OPS_EMPTY + s));  // operand stage free once these MMAs have read it
             }
             umma_commit(bar(ACC_FULL));  // accumulator complete
         }
@@ -224,9 +228,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int t = threadIdx.x - 64;   // 0..255
         const int m = t & 127;            // column of the raw box = row of the K-major operand
         const int kh = t >> 7;            // which half of the 32-row k-block this thread converts
-        auto convert = [&](int s, int which, int nvalid, auto full_tag) {
+        auto convert = [&](int rs, int s, int which, int nvalid, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (s * 2 + which) * RAW_TILE);
+            const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (rs * 2 + which) * RAW_TILE);
             unsigned char *hi = smem + OFF_OPS + (s * 4 + which * 2) * OP_TILE + m * 128;
             unsigned char *lo = hi + OP_TILE;
             const float sh = which == 0 ? shA[m] : shB[m];
@@ -250,22 +254,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         };
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(bar(s), ph);                    // raw boxes landed
-            mbar_wait(bar(3 * STAGES + s), ph ^ 1);   // operand stage no longer read by the tensor core
+            const int s = kb % STAGES, rs = kb % RSTAGES;
+            const uint32_t ph = (kb / STAGES) & 1, rph = (kb / RSTAGES) & 1;
+            mbar_wait(bar(RAW_FULL + rs), rph);       // raw boxes landed
+            mbar_wait(bar(OPS_EMPTY + s), ph ^ 1);    // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
             if (nvalid == KB) {
-                convert(s, 0, KB, std::true_type{});
-                if (!diag) convert(s, 1, KB, std::true_type{});
+                convert(rs, s, 0, KB, std::true_type{});
+                if (!diag) convert(rs, s, 1, KB, std::true_type{});
             } else {
-                convert(s, 0, nvalid, std::false_type{});
-                if (!diag) convert(s, 1, nvalid, std::false_type{});
+                convert(rs, s, 0, nvalid, std::false_type{});
+                if (!diag) convert(rs, s, 1, nvalid, std::false_type{});
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
-            mbar_arrive(bar(2 * STAGES + s));  // operands ready
-            mbar_arrive(bar(STAGES + s));      // raw stage free
+            mbar_arrive(bar(OPS_FULL + s));    // operands ready
+            mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
         }
         // ---- epilogue: TMEM -> fp32 partial tile
         mbar_wait(bar(ACC_FULL), 0);
