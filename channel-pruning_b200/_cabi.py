@@ -11,7 +11,8 @@ import cffi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "cpb200.h")
-LIBRARY = os.path.join(_HERE, "libcpb200.so")
+# CPB200_LIBRARY: load another build of the same ABI (the profiling build `make timing`)
+LIBRARY = os.environ.get("CPB200_LIBRARY") or os.path.join(_HERE, "libcpb200.so")
 
 _ffi = None
 _lib = None

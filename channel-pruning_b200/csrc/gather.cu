@@ -13,6 +13,8 @@
 // NHWC path: a window row is k*c contiguous floats; the CTA stages the k*k x c tile
 // in shared memory with coalesced loads (channel fastest) and writes it back
 // transposed to (c, k*k) column order, again coalesced.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -20,31 +22,37 @@ namespace {
 template <int KS>
 __global__ void __launch_bounds__(256)
 patch_gather_nchw(const float *__restrict__ fmap, const int32_t *__restrict__ randx,
-                  const int32_t *__restrict__ randy, float *__restrict__ X, int64_t ldx, int B, int c, int H,
-                  int W, int P, int k_rt, int pad, int stride, int relu) {
+                  const int32_t *__restrict__ randy, float *__restrict__ X, int64_t ldx, int64_t rows, int B, int c,
+                  int H, int W, int P, int k_rt, int pad, int stride, int relu) {
     const int k = KS > 0 ? KS : k_rt;
     const int k2 = k * k;
-    const int64_t r = blockIdx.x;
-    const int img_in_batch = (int)(r % B);
-    const int64_t bp = r / B;  // batch*P + point
-    const int batch = (int)(bp / P);
-    const int y0 = stride * randx[bp] - pad;  // window origin, rows   (net.py: feat[:,:,x,y], x indexes H)
-    const int x0 = stride * randy[bp] - pad;  // window origin, cols
-    const float *src = fmap + ((int64_t)batch * B + img_in_batch) * c * H * W;
-    float *dst = X + r * ldx;
     const int K = c * k2;
-    for (int col = threadIdx.x; col < K; col += blockDim.x) {
-        const int a = col / k2;
-        const int p = col - a * k2;
-        const int py = p / k;
-        const int px = p - py * k;
-        const int yy = y0 + py, xx = x0 + px;
-        float v = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(src + ((int64_t)a * H + yy) * W + xx);
-        if (relu) v = fmaxf(v, 0.f);
-        dst[col] = v;
+    // one CTA per output row when the map is in HBM; a small persistent grid strides over the rows when the
+    // map is read in place from pinned host memory (PCIe-bound: more CTAs only block SMs other layers need)
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int img_in_batch = (int)(r % B);
+        const int64_t bp = r / B;  // batch*P + point
+        const int batch = (int)(bp / P);
+        const int y0 = stride * randx[bp] - pad;  // window origin, rows   (net.py: feat[:,:,x,y], x indexes H)
+        const int x0 = stride * randy[bp] - pad;  // window origin, cols
+        const float *src = fmap + ((int64_t)batch * B + img_in_batch) * c * H * W;
+        float *dst = X + r * ldx;
+#pragma unroll 4
+        for (int col = threadIdx.x; col < K; col += blockDim.x) {
+            const int a = col / k2;
+            const int p = col - a * k2;
+            const int py = p / k;
+            const int px = p - py * k;
+            const int yy = y0 + py, xx = x0 + px;
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(src + ((int64_t)a * H + yy) * W + xx);
+            if (relu) v = fmaxf(v, 0.f);
+            dst[col] = v;
+        }
     }
 }
+
+constexpr int64_t CP_HOST_GATHER_CTAS = 64;  // grid of the in-place (zero-copy) reader
 
 // NHWC: tile = k2 spatial taps x CT channels staged through shared memory.
 constexpr int NHWC_CT = 128;  // channels per tile
@@ -119,13 +127,23 @@ extern "C" int cp_patch_gather(cp_handle_t h, const float *fmap, int nbatch, int
     if (rows == 0) return CP_OK;
     CP_REQUIRE(rows < (1ll << 31), "cp_patch_gather: too many rows");
     if (layout == CP_LAYOUT_NCHW) {
-        dim3 grid((unsigned)rows);
+        // map in (pinned, UVA-mapped) host memory?  then the kernel is a PCIe reader: keep its footprint small
+        cudaPointerAttributes pa;
+        const bool host_src = cudaPointerGetAttributes(&pa, fmap) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        static const int64_t host_ctas = [] {
+            const char *e = getenv("CPB200_HOST_GATHER_CTAS");  // tuning knob (profiles/e2e_breakdown.py)
+            const long v = e ? atol(e) : 0;
+            return (int64_t)(v > 0 ? v : CP_HOST_GATHER_CTAS);
+        }();
+        const int64_t ncta = host_src ? (rows < host_ctas ? rows : host_ctas) : rows;
+        dim3 grid((unsigned)ncta);
         if (k == 3)
-            patch_gather_nchw<3><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, B, c, H, W, P, k, pad, stride, relu);
+            patch_gather_nchw<3><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, rows, B, c, H, W, P, k, pad, stride, relu);
         else if (k == 1)
-            patch_gather_nchw<1><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, B, c, H, W, P, k, pad, stride, relu);
+            patch_gather_nchw<1><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, rows, B, c, H, W, P, k, pad, stride, relu);
         else
-            patch_gather_nchw<0><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, B, c, H, W, P, k, pad, stride, relu);
+            patch_gather_nchw<0><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, rows, B, c, H, W, P, k, pad, stride, relu);
     } else {
         const size_t smem = (size_t)k * k * (NHWC_CT + 1) * sizeof(float);
         CP_REQUIRE(smem <= 48 * 1024, "cp_patch_gather: kernel_size %d too large for the NHWC tile", k);

@@ -116,9 +116,27 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // round-to-nearest (ties away) to the 10-bit tf32 mantissa with two full-rate integer ops; identical to
 // cvt.rna.tf32.f32 for finite inputs, but not issued on the quarter-rate conversion pipe
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+
+// ------------------------------------------------------------------ optional in-kernel timeline (profiling builds only)
+#ifdef CP_TC_TIMING
+__device__ long long cp_tc_times[64][16];
+#define TC_T(slot) do { if (timed) cp_tc_times[blockIdx.x][slot] = clock64(); } while (0)
+#define TC_ACC(slot, expr) do { long long _a = clock64(); expr; if (timed) cp_tc_times[blockIdx.x][slot] += clock64() - _a; } while (0)
+#else
+#define TC_T(slot) do { } while (0)
+#define TC_ACC(slot, expr) do { expr; } while (0)
+#endif
 
 // ------------------------------------------------------------------ main kernel
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -127,6 +145,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef CP_TC_TIMING
+    const bool timed = blockIdx.x < 64 && blockIdx.y == 3 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
+    if (timed && threadIdx.x == 0) { for (int i = 8; i < 16; ++i) cp_tc_times[blockIdx.x][i] = 0; }
+    if (threadIdx.x == 0) TC_T(0);
+#endif
 
     // ---- work item
     int l = blockIdx.x, ti, tj;
@@ -164,6 +187,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mbar_init(bar(ACC_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first RSTAGES boxes need nothing but their barriers: get them in flight before the rest of the set-up
+        for (int kb = 0; kb < nkb && kb < RSTAGES; ++kb) {
+            mbar_arrive_expect_tx(bar(RAW_FULL + kb), diag ? RAW_TILE : 2 * RAW_TILE);
+            const int row = (int)(r_begin + (int64_t)kb * KB);
+            tma_load_2d(sbase + OFF_RAW + (kb * 2 + 0) * RAW_TILE, &mapA, bar(RAW_FULL + kb), ti * TM, row);
+            if (!diag) tma_load_2d(sbase + OFF_RAW + (kb * 2 + 1) * RAW_TILE, &mapB, bar(RAW_FULL + kb), tj * TN, row);
+        }
     }
     if (warp == 1) {  // TMEM: all 512 columns = 4 fp32 accumulators of 128 columns, used round-robin by k-block
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -181,14 +211,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_T(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = RSTAGES; kb < nkb; ++kb) {
                 const int s = kb % RSTAGES;
                 const uint32_t ph = (kb / RSTAGES) & 1;
-                mbar_wait(bar(RAW_EMPTY + s), ph ^ 1);  // slot free (fresh barrier passes immediately)
+                TC_ACC(8, mbar_wait(bar(RAW_EMPTY + s), ph ^ 1));  // slot free (fresh barrier passes immediately)
                 mbar_arrive_expect_tx(bar(RAW_FULL + s), diag ? RAW_TILE : 2 * RAW_TILE);
                 const int row = (int)(r_begin + (int64_t)kb * KB);
                 tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, &mapA, bar(RAW_FULL + s), ti * TM, row);
@@ -203,7 +234,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(bar(OPS_FULL + s), ph);
+                TC_ACC(9, mbar_wait(bar(OPS_FULL + s), ph));
+                if (kb == 0) TC_T(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ops = sbase + OFF_OPS + s * 4 * OP_TILE;
                 const uint32_t a_hi = ops, a_lo = ops + OP_TILE;
@@ -222,57 +254,76 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 umma_commit(bar(OPS_EMPTY + s));  // operand stage free once these MMAs have read it
             }
             umma_commit(bar(ACC_FULL));  // accumulator complete
+            TC_T(4);
         }
     } else {
         // ===================== converters (then epilogue) =====================
         const int t = threadIdx.x - 64;   // 0..255
         const int m = t & 127;            // column of the raw box = row of the K-major operand
         const int kh = t >> 7;            // which half of the 32-row k-block this thread converts
-        auto convert = [&](int rs, int s, int which, int nvalid, auto full_tag) {
+        // Shared-space (32-bit) addresses and explicit ld/st.shared: through the aligned generic pointer the
+        // compiler emits generic LD/ST and, fearing aliasing, serialises load -> split -> store per 4 values.
+        // All 16 (or 32) raw values of the thread are loaded first so that their latency overlaps.
+        float shv[2];
+        shv[0] = shA[m];
+        shv[1] = shB[m];
+        auto convert = [&](int rs, int s, int nops, int nvalid, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            const float *raw = reinterpret_cast<const float *>(smem + OFF_RAW + (rs * 2 + which) * RAW_TILE);
-            unsigned char *hi = smem + OFF_OPS + (s * 4 + which * 2) * OP_TILE + m * 128;
-            unsigned char *lo = hi + OP_TILE;
-            const float sh = which == 0 ? shA[m] : shB[m];
+            float v[2][16];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const int q = kh * 4 + q4;
-                float v[4];
+            for (int which = 0; which < 2; ++which) {
+                if (which < nops) {
+                    const uint32_t raw = sbase + OFF_RAW + (rs * 2 + which) * RAW_TILE + (uint32_t)(kh * 16 * TM + m) * 4u;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * q + e;
-                    const float x = raw[k * TM + m];
-                    v[e] = (FULL || k < nvalid) ? __fsub_rn(x, sh) : 0.f;
+                    for (int e = 0; e < 16; ++e) v[which][e] = lds_f32(raw + (uint32_t)e * TM * 4u);
                 }
-                float4 h, l4;
-                h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
-                l4.x = tf32_rn(__fsub_rn(v[0], h.x)); l4.y = tf32_rn(__fsub_rn(v[1], h.y));
-                l4.z = tf32_rn(__fsub_rn(v[2], h.z)); l4.w = tf32_rn(__fsub_rn(v[3], h.w));
-                const int off = (q ^ (m & 7)) << 4;  // Swizzle<3,4,3>: 16B chunk ^= row & 7
-                *reinterpret_cast<float4 *>(hi + off) = h;
-                *reinterpret_cast<float4 *>(lo + off) = l4;
+            }
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (which < nops) {
+                    const uint32_t hi = sbase + OFF_OPS + (s * 4 + which * 2) * OP_TILE + (uint32_t)m * 128u;
+                    const float sh = shv[which];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int q = kh * 4 + q4;
+                        float x[4], h[4], l[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = 4 * q + e;
+                            x[e] = (FULL || k < nvalid) ? __fsub_rn(v[which][4 * q4 + e], sh) : 0.f;
+                            h[e] = tf32_rn(x[e]);
+                            l[e] = tf32_rn(__fsub_rn(x[e], h[e]));
+                        }
+                        const uint32_t off = (uint32_t)((q ^ (m & 7)) << 4);  // Swizzle<3,4,3>: 16B chunk ^= row & 7
+                        sts_v4(hi + off, h[0], h[1], h[2], h[3]);
+                        sts_v4(hi + OP_TILE + off, l[0], l[1], l[2], l[3]);
+                    }
+                }
             }
         };
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES, rs = kb % RSTAGES;
             const uint32_t ph = (kb / STAGES) & 1, rph = (kb / RSTAGES) & 1;
-            mbar_wait(bar(RAW_FULL + rs), rph);       // raw boxes landed
-            mbar_wait(bar(OPS_EMPTY + s), ph ^ 1);    // operand stage no longer read by the tensor core
+            TC_ACC(10, mbar_wait(bar(RAW_FULL + rs), rph));     // raw boxes landed
+            if (kb == 0) TC_T(2);
+            TC_ACC(11, mbar_wait(bar(OPS_EMPTY + s), ph ^ 1));  // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
             if (nvalid == KB) {
-                convert(rs, s, 0, KB, std::true_type{});
-                if (!diag) convert(rs, s, 1, KB, std::true_type{});
+                if (diag) convert(rs, s, 1, KB, std::true_type{});
+                else convert(rs, s, 2, KB, std::true_type{});
             } else {
-                convert(rs, s, 0, nvalid, std::false_type{});
-                if (!diag) convert(rs, s, 1, nvalid, std::false_type{});
+                if (diag) convert(rs, s, 1, nvalid, std::false_type{});
+                else convert(rs, s, 2, nvalid, std::false_type{});
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(bar(OPS_FULL + s));    // operands ready
             mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
         }
         // ---- epilogue: TMEM -> fp32 partial tile
+        TC_T(12);
         mbar_wait(bar(ACC_FULL), 0);
+        TC_T(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
         const int mrow = quad * 32 + lane;  // row of the output tile
@@ -305,12 +356,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 *reinterpret_cast<float4 *>(dst + cb + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
         }
     }
+    if (threadIdx.x == 64) TC_T(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    if (threadIdx.x == 32) TC_T(7);
 }
 
 // ------------------------------------------------------------------ small kernels around it
@@ -448,6 +501,12 @@ int make_map(cp_handle_t h, CUtensorMap *map, const float *base, int64_t rows, i
 }
 
 }  // namespace
+
+#ifdef CP_TC_TIMING
+extern "C" int cp_debug_tc_times(long long *host_out) {  // 64 x 16 clock64 stamps of the last gram_tc_kernel launch
+    return (int)cudaMemcpyFromSymbol(host_out, cp_tc_times, sizeof(long long) * 64 * 16);
+}
+#endif
 
 bool cp_gram_tc_eligible(const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n, int64_t ldy,
                          const int32_t *rows, bool wantB) {

@@ -56,6 +56,9 @@ class Engine:
                 self.streams.append(torch.cuda.Stream(self.device) if nstreams > 1 else None)
         self._cur = 0
         self.launches = 0  # libcpb200 calls issued (each launches >= 1 kernel)
+        self._pinned = {}   # (key, shape, dtype) -> page-locked host buffer, allocated once (cudaHostAlloc is slow)
+        self._staging = {}  # (key, shape) -> device staging buffer for maps that are cheaper to DMA whole
+        self._xfer = None   # (zero-copy gather stream, DMA stream) of the host-resident input path
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -68,6 +71,27 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def pinned(self, key, shape, dtype):
+        """Engine-owned page-locked host buffer, reused across calls (contents valid until the next call that
+        asks for the same key)."""
+        k = (key, tuple(shape), dtype)
+        t = self._pinned.get(k)
+        if t is None:
+            t = self._pinned[k] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        return t
+
+    def staging(self, key, shape):
+        k = (key, tuple(shape))
+        t = self._staging.get(k)
+        if t is None:
+            t = self._staging[k] = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+        return t
+
+    def xfer_streams(self):
+        if self._xfer is None:
+            self._xfer = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._xfer
 
     def use_slot(self, i: int):
         """Select which (handle, stream) pair subsequent calls use."""

@@ -12,6 +12,8 @@ coupled and this sharding does not apply (use lib.net.Net.R3 on one GPU).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -73,10 +75,12 @@ class LayerResult:
     __slots__ = ("idxs", "W", "b", "alpha", "nprobe", "probes", "info")
 
 
-def prune_layers(eng: Engine, shapes, datas, right0=1e-3, rank_tol=.1, from_host=False, to_host=False):
+def prune_layers(eng: Engine, shapes, datas, right0=1e-3, rank_tol=.1, from_host=False, to_host=False, trace=None):
     """Runs the layer problems ``shapes[i]`` / ``datas[i]`` (see synth.make_problem_device) on
     ``eng``.  from_host: feature maps are taken from pinned host memory (datas[i]['fmap_host'])
     and copied in the pipeline; to_host: results are copied back to pinned host memory.
+    trace: optional dict; filled with {layer name: [(label, timing event), ...]} plus '_t0' (device timeline
+    of the step: profiles/e2e_breakdown.py prints it).
     Returns a list of LayerResult (W, b as device fp64 tensors unless to_host)."""
     nslots = len(eng.streams)
     main = torch.cuda.current_stream(eng.device)
@@ -85,11 +89,76 @@ def prune_layers(eng: Engine, shapes, datas, right0=1e-3, rank_tol=.1, from_host
     inv = {orig: pos for pos, orig in enumerate(order)}
     shapes_o = [shapes[i] for i in order]
     datas_o = [datas[i] for i in order]
-    res_o = _prune_layers_ordered(eng, shapes_o, datas_o, right0, rank_tol, from_host, to_host, main)
+    if trace is not None:
+        trace["_t0"] = torch.cuda.Event(enable_timing=True)
+        trace["_t0"].record()
+    res_o = _prune_layers_ordered(eng, shapes_o, datas_o, right0, rank_tol, from_host, to_host, main, trace)
     return [res_o[inv[i]] for i in range(len(shapes))]
 
 
-def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_host, main):
+def _zero_copy_seconds(s):
+    """Model of the in-place gather over PCIe: it is bound by the number of read requests (one per 128-byte
+    line touched: the k rows of a window are W*4 bytes apart), ~4.5e8 lines/s measured (profiles/r1c_summary.md)."""
+    row = s.W * 4 if hasattr(s, "W") else 4 * 64
+    lines = min(s.k, -(-((s.k - 1) * row + s.k * 4) // 128) + 1) if s.k > 1 else 1
+    return s.N * s.c * lines / 4.5e8
+
+
+def h2d_plan(shapes, datas, from_host):
+    """Per layer: 'zc' (gather kernel reads the windows in place from pinned host memory) or 'dma' (copy engine
+    moves the whole map at full PCIe bandwidth, gather from HBM).  DMA pays off when the windows cover most of
+    the map (small spatial maps: conv5_x).  CPB200_DMA_MAX_MB caps the size of a map that may be staged."""
+    if from_host == "zc":
+        return ["zc"] * len(shapes)
+    if from_host == "copy":
+        return ["dma"] * len(shapes)
+    cap = float(os.environ.get("CPB200_DMA_MAX_MB", "300")) * 1e6
+    ratio = float(os.environ.get("CPB200_DMA_RATIO", "0.8"))
+    plan = []
+    for s, d in zip(shapes, datas):
+        nbytes = d["fmap_host"].numel() * 4
+        t_dma = nbytes / 50e9 + 1e-4
+        plan.append("dma" if (nbytes <= cap and t_dma < ratio * _zero_copy_seconds(s)) else "zc")
+    return plan
+
+
+def _mark(trace, name, label):
+    if trace is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        trace.setdefault(name, []).append((label, e))
+
+
+def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_host, main, trace=None):
+    # ---- host-resident inputs: PCIe is the shared resource, so the transfers are issued in the (longest-first)
+    # layer order on two dedicated streams -- zero-copy gathers on one, whole-map DMAs on the copy engine --
+    # and each layer stream waits only for its own transfer.
+    pre = [None] * len(shapes)
+    if from_host and len(eng.streams) > 1 and eng.streams[0] is not None:
+        plan = h2d_plan(shapes, datas, from_host)
+        zc_stream, dma_stream = eng.xfer_streams()
+        zc_stream.wait_stream(main)
+        dma_stream.wait_stream(main)
+        dma_order = sorted((i for i in range(len(shapes)) if plan[i] == "dma"),
+                           key=lambda i: (datas[i]["fmap_host"].numel(), i))
+        for i in dma_order:
+            with torch.cuda.stream(dma_stream):
+                st = eng.staging(("fmap", i), datas[i]["fmap_host"].shape)
+                st.copy_(datas[i]["fmap_host"], non_blocking=True)
+                _mark(trace, shapes[i].name, "dma_done")
+                ev = torch.cuda.Event()
+                ev.record()
+            pre[i] = ("dma", st, ev)
+        for i, (s, d) in enumerate(zip(shapes, datas)):
+            if plan[i] != "zc":
+                continue
+            eng.use_slot(i)
+            with torch.cuda.stream(zc_stream):
+                X = eng.patch_gather(d["fmap_host"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+                _mark(trace, s.name, "zc_done")
+                ev = torch.cuda.Event()
+                ev.record()
+            pre[i] = ("zc", X, ev)
     phase1 = []
     for i, (s, d) in enumerate(zip(shapes, datas)):
         stream = eng.use_slot(i)
@@ -97,8 +166,16 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
         with ctx:
             if stream is not None:
                 stream.wait_stream(main)
-            if from_host == "copy":
-                fmap = torch.empty(d["fmap_host"].shape, dtype=torch.float32, device=eng.device)
+            X = None
+            if pre[i] is not None:
+                kind, obj, ev = pre[i]
+                stream.wait_event(ev)
+                if kind == "zc":
+                    X = obj
+                else:
+                    fmap = obj
+            elif from_host == "copy":
+                fmap = eng.staging(("fmap", i), d["fmap_host"].shape)
                 fmap.copy_(d["fmap_host"], non_blocking=True)
             elif from_host:
                 # zero-copy: the gather kernel reads the sampled windows straight out of pinned host memory;
@@ -106,7 +183,8 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
                 fmap = d["fmap_host"]
             else:
                 fmap = d["fmap"]
-            X = eng.patch_gather(fmap, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+            if X is None:
+                X = eng.patch_gather(fmap, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
             W2m = d["W2"].reshape(s.n, s.K)
             if s.rank == s.c:
                 g_full = eng.gram(X, d["feats"], y_bias=d["b2"])
@@ -115,10 +193,10 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             else:
                 g_full, res = eng.select_channels_async(X, W2m, d["feats"], d["b2"], d["samples"], s.c, s.k * s.k,
                                                         s.rank, rank_tol, right0, d["seeds"])
-                host = (torch.empty(4, dtype=torch.float64, pin_memory=True),
-                        torch.empty(s.c, dtype=torch.uint8, pin_memory=True))
+                host = (eng.pinned(("scal", i), (4,), torch.float64), eng.pinned(("idxs", i), (s.c,), torch.uint8))
                 host[0].copy_(res.scalars, non_blocking=True)
                 host[1].copy_(res.idxs, non_blocking=True)
+            _mark(trace, s.name, "select_done")
             ev = torch.cuda.Event()
             ev.record()
         phase1.append((X, g_full, res, host, ev))
@@ -142,14 +220,16 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
         with ctx:
             W, b, info = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], r.idxs, s.k * s.k)
             if to_host:
-                Wh = torch.empty(W.shape, dtype=torch.float64, pin_memory=True)
-                bh = torch.empty(b.shape, dtype=torch.float64, pin_memory=True)
+                # engine-owned pinned buffers: valid until the next prune_layers call on this engine
+                Wh = eng.pinned(("W", i), W.shape, torch.float64)
+                bh = eng.pinned(("b", i), b.shape, torch.float64)
                 Wh.copy_(W, non_blocking=True)
                 bh.copy_(b, non_blocking=True)
                 r.W, r.b = Wh, bh
             else:
                 r.W, r.b = W, b
             r.info = info
+            _mark(trace, s.name, "ls_done")
         r.probes = res
         out[i] = r
     for st in eng.streams:

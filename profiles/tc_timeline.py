@@ -1,0 +1,33 @@
+"""In-kernel clock64 timeline of gram_tc_kernel (profiling build: `make -C channel-pruning_b200/csrc timing`).
+    CPB200_LIBRARY=channel-pruning_b200/libcpb200_timing.so python profiles/tc_timeline.py [N K n]
+Prints, for CTAs blockIdx.x < 64 of row chunk 3 of the X'X launch, cycles from kernel entry to each stage and
+the cycles each role spent waiting on its barriers."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import cpb200
+from cpb200 import _cabi
+
+N, K, n = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (5000, 4608, 512)
+eng = cpb200.Engine(gram_mode=1)
+X = torch.rand(N, K, device="cuda")
+for _ in range(2):
+    g = eng.gram(X, None, mode=1)   # G only -> the last gram_tc_kernel launch is the X'X one
+torch.cuda.synchronize()
+L = ctypes.CDLL(_cabi.LIBRARY)
+buf = (ctypes.c_longlong * (64 * 16))()
+assert L.cp_debug_tc_times(buf) == 0
+T = np.array(buf, dtype=np.int64).reshape(64, 16)
+names = ["entry", "setup_done", "first_raw_full", "first_ops_full", "mma_all_issued", "acc_full", "epilogue_done", "exit"]
+rel = T[:, :8] - T[:, :1]
+print("N=%d K=%d: cycles from CTA entry (median / min / max over 64 CTAs)" % (N, K))
+for i, nm in enumerate(names):
+    print("  %-16s %8d %8d %8d" % (nm, np.median(rel[:, i]), rel[:, i].min(), rel[:, i].max()))
+print("  %-16s %8d   (converter loop end)" % ("conv_loop_done", np.median(T[:, 12] - T[:, 0])))
+for i, nm in zip(range(8, 12), ["producer waits raw_empty", "mma waits ops_full", "converter waits raw_full", "converter waits ops_empty"]):
+    print("  %-26s %8d cycles total (median)" % (nm, np.median(T[:, i])))
