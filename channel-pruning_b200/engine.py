@@ -81,6 +81,12 @@ class Engine:
             t = self._pinned[k] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         return t
 
+    def _ring(self):
+        """Rotating index for small pinned staging buffers: a buffer is rewritten by the host only 256 calls
+        after the asynchronous copy that read it was enqueued (every step synchronises on each layer's search)."""
+        self._seq = (getattr(self, "_seq", -1) + 1) % 256
+        return self._seq
+
     def staging(self, key, shape):
         k = (key, tuple(shape))
         t = self._staging.get(k)
@@ -215,7 +221,16 @@ class Engine:
             Qp = torch.zeros(c, c + (c & 1), dtype=torch.float64, device=self.device)
             Qp[:, :c] = Q
             Q = Qp[:, :c]
-        seeds_d = torch.as_tensor(np.asarray(seeds, dtype=np.int64), device=self.device).to(torch.int32)
+        if isinstance(seeds, torch.Tensor) and seeds.is_cuda:
+            assert seeds.dtype == torch.int32 and seeds.is_contiguous()
+            seeds_d = seeds
+        else:
+            # staged through an engine-owned pinned buffer: a pageable H2D copy would make torch synchronise
+            # the stream, i.e. block the host until everything queued on this layer's stream has run
+            sh = np.asarray(seeds, dtype=np.int64).astype(np.int32)
+            pin = self.pinned(("seeds", self._ring()), sh.shape, torch.int32)
+            pin.numpy()[...] = sh
+            seeds_d = pin.to(self.device, non_blocking=True)
         maxp = seeds_d.numel()
         idxs = self.empty(c, dtype=torch.uint8)
         coef = self.empty(c)
@@ -277,7 +292,9 @@ class Engine:
         """LS on the surviving channels (device outputs; no host sync)."""
         sel = np.flatnonzero(idxs_host)
         cols = (sel[:, None] * k2 + np.arange(k2)[None, :]).reshape(-1).astype(np.int32)
-        cols_d = torch.as_tensor(cols, device=self.device)
+        pin = self.pinned(("cols", self._ring()), (g_full["K"],), torch.int32)  # no pageable (synchronising) copy
+        pin.numpy()[:cols.size] = cols
+        cols_d = pin[:cols.size].to(self.device, non_blocking=True)
         if g_full["N"] - 1 >= cols.size:
             return self.ls_solve(g_full, cols_d)
         return self.ls_solve_dual(X, Y, y_bias, cols_d)
