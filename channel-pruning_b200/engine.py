@@ -53,7 +53,10 @@ class Engine:
                 hp = self.ffi.new("cp_handle_t*")
                 _cabi.check(self.lib.cp_create(hp, self.device.index))
                 self._handles.append(hp[0])
-                self.streams.append(torch.cuda.Stream(self.device) if nstreams > 1 else None)
+                # the pipeline hands its most expensive problems to the first slots: give those streams priority,
+                # so that the chains that decide the makespan are not queued behind the short ones' big grids
+                prio = -1 if (i < nstreams // 2 and os.environ.get("CPB200_STREAM_PRIORITY", "1") == "1") else 0
+                self.streams.append(torch.cuda.Stream(self.device, priority=prio) if nstreams > 1 else None)
         self._cur = 0
         self.launches = 0  # libcpb200 calls issued (each launches >= 1 kernel)
         self._pinned = {}   # (key, shape, dtype) -> page-locked host buffer, allocated once (cudaHostAlloc is slow)

@@ -13,6 +13,7 @@ coupled and this sharding does not apply (use lib.net.Net.R3 on one GPU).
 from __future__ import annotations
 
 import os
+import time
 
 import numpy as np
 import torch
@@ -201,7 +202,16 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             ev.record()
         phase1.append((X, g_full, res, host, ev))
     out = [None] * len(shapes)
-    for i in reversed(range(len(shapes))):  # shortest first: their searches finish first
+    # phase 2 in COMPLETION order of the searches (which layer finishes first depends on sizes and, with
+    # host-resident inputs, on the transfer order): poll the events, reconstruct whichever is ready
+    pending = list(reversed(range(len(shapes))))
+    while pending:
+        ready = [i for i in pending if phase1[i][2] is None or phase1[i][4].query()]
+        if not ready:
+            time.sleep(2e-5)
+            continue
+        i = ready[0]
+        pending.remove(i)
         s, d = shapes[i], datas[i]
         X, g_full, res, host, ev = phase1[i]
         stream = eng.use_slot(i)
@@ -210,7 +220,6 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             r.idxs = np.ones(s.c, dtype=bool)
             r.alpha, r.nprobe = 1e-4, 0  # lib/decompose.py:386 argument default survives (:627)
         else:
-            ev.synchronize()
             scal = host[0].numpy()
             if int(scal[2]) != 0:
                 raise RuntimeError("layer %s: alpha search hit the probe cap" % s.name)
