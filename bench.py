@@ -294,9 +294,12 @@ def run_gpu(args):
         for _ in range(min(args.warmup, 3)):
             step(True)
         ms_e, _, res_e = timed(args.steps, True)
-        # zero-copy: the feature maps stay in pinned host memory and the gather kernel pulls the sampled
-        # k x k x c windows over PCIe; the bytes that must cross are the gathered patches (4*N*K per layer)
-        h2d = sum(int(s.N) * s.K * 4 for s in my_shapes)
+        # the feature maps stay in pinned host memory; per layer either the gather kernel pulls the sampled
+        # k x k x c windows over PCIe in place (bytes that must cross: 4*N*K) or, where the windows cover most of
+        # the map (conv5_x), the copy engine moves the whole map (bytes: the map) -- pruner.h2d_plan decides
+        plan = pruner.h2d_plan(my_shapes, datas, True)
+        h2d = sum(int(d["fmap_host"].numel()) * 4 if p == "dma" else int(s.N) * s.K * 4
+                  for s, d, p in zip(my_shapes, datas, plan))
         host_resident = sum(int(d["fmap_host"].numel()) * 4 for d in datas)
         d2h = sum(int(r.W.numel() + r.b.numel()) * 8 + s.c + 32 for r, s in zip(res_e, my_shapes))
         if world > 1:
@@ -305,8 +308,9 @@ def run_gpu(args):
             h2d, d2h = int(t[0].item()), int(t[1].item())
         e2e = {"value": total_layers / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / args.steps, "host_resident_input_bytes": host_resident,
-               "input_path": "feature maps in pinned host memory, read in place by cp_patch_gather (zero-copy over "
-                             "PCIe); h2d_bytes_per_step counts the gathered windows, not the whole maps"}
+               "h2d_plan": "".join("D" if p == "dma" else "z" for p in plan),
+               "input_path": "feature maps in pinned host memory; per layer (h2d_plan, z/D) read in place by "
+                             "cp_patch_gather (zero-copy over PCIe, bytes = gathered windows) or DMA'd whole (bytes = map)"}
 
     # ---- roofline of the dominant kernel: Gram statistics of the widest layer, timed alone
     roof = None
