@@ -49,17 +49,17 @@ constexpr int OFF_OPS = 0;                                    // STAGES x {Ahi, 
 constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // RSTAGES x {rawA, rawB}
 constexpr int OFF_SHIFT = OFF_RAW + RSTAGES * 2 * RAW_TILE;    // shiftA[128], shiftB[128] fp32
 constexpr int OFF_BAR = OFF_SHIFT + 2 * TM * 4;               // mbarriers
-constexpr int NBAR = 2 * RSTAGES + 2 * STAGES + 1;
+constexpr int NBAR = 2 * RSTAGES + 2 * STAGES + 2;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
 
 struct TcParams {
     const float *shiftA;  // K   fp32 column shifts of X
-    const float *shiftB;  // K or n: shifts of the B operand (X again, or Y)
-    float *partial;       // [nchunks][ntiles][128][128]
-    int K, nB;            // columns of A source, columns of B source
+    const float *shiftB;  // n   fp32 column shifts of Y (B operand of the X'Y tiles)
+    float *partial;       // [nsplit][ntiles][128][128]
+    int K, nB;            // columns of X, columns of Y
     int64_t N;
-    int rows_per_chunk;
+    int rows_per_chunk;   // rows per split (one CTA per tile and split)
     int tiles_sym;        // number of upper-triangular G tiles (0 when G is not requested)
     int tk;               // ceil(K / 128)
     int tnb;              // ceil(nB / 128) for the X'Y tiles
@@ -139,14 +139,33 @@ __device__ long long cp_tc_times[64][16];
 #endif
 
 // ------------------------------------------------------------------ main kernel
+// One CTA = one 128x128 output tile x one row split.  The rows of the split are consumed in sub-chunks of
+// CHUNK_KB k-blocks (256 rows); sub-chunk c accumulates into TMEM accumulator pair (c & 1) -- two accumulators
+// alternating by k-block, so no fp32 accumulator takes more than 48 truncating additions -- while the
+// converter warps drain pair ((c-1) & 1) into fp32 registers (round-to-nearest adds).  One fp32 partial
+// tile per CTA leaves the kernel.
+constexpr int CHUNK_KB = 8;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, const TcParams P) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef CP_TC_TIMING
-    const bool timed = blockIdx.x < 64 && blockIdx.y == 3 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
+    const bool timed = blockIdx.x < 64 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
     if (timed && threadIdx.x == 0) { for (int i = 8; i < 16; ++i) cp_tc_times[blockIdx.x][i] = 0; }
     if (threadIdx.x == 0) TC_T(0);
 #endif
@@ -165,15 +184,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tj = l - ti * P.tnb;
     }
     const bool diag = !is_xy && ti == tj;  // A and B operands are the same tile
+    const CUtensorMap *mapA = &mapX, *mapB = is_xy ? &mapY : &mapX;
     const int64_t r_begin = (int64_t)blockIdx.y * P.rows_per_chunk;
     int64_t r_end = r_begin + P.rows_per_chunk;
     if (r_end > P.N) r_end = P.N;
     const int nkb = (int)((r_end - r_begin + KB - 1) / KB);
+    const int nchunk = (nkb + CHUNK_KB - 1) / CHUNK_KB;
 
     auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
     // barrier indices
     constexpr int RAW_FULL = 0, RAW_EMPTY = RSTAGES, OPS_FULL = 2 * RSTAGES, OPS_EMPTY = 2 * RSTAGES + STAGES;
-    constexpr int ACC_FULL = 2 * RSTAGES + 2 * STAGES;
+    constexpr int ACC_FULL = 2 * RSTAGES + 2 * STAGES;  // two: one per accumulator pair
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     if (threadIdx.x == 0) {
@@ -185,17 +206,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(bar(OPS_FULL + s), NCONV);
             mbar_init(bar(OPS_EMPTY + s), 1);
         }
-        mbar_init(bar(ACC_FULL), 1);
+        mbar_init(bar(ACC_FULL + 0), 1);
+        mbar_init(bar(ACC_FULL + 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the first RSTAGES boxes need nothing but their barriers: get them in flight before the rest of the set-up
         for (int kb = 0; kb < nkb && kb < RSTAGES; ++kb) {
             mbar_arrive_expect_tx(bar(RAW_FULL + kb), diag ? RAW_TILE : 2 * RAW_TILE);
             const int row = (int)(r_begin + (int64_t)kb * KB);
-            tma_load_2d(sbase + OFF_RAW + (kb * 2 + 0) * RAW_TILE, &mapA, bar(RAW_FULL + kb), ti * TM, row);
-            if (!diag) tma_load_2d(sbase + OFF_RAW + (kb * 2 + 1) * RAW_TILE, &mapB, bar(RAW_FULL + kb), tj * TN, row);
+            tma_load_2d(sbase + OFF_RAW + (kb * 2 + 0) * RAW_TILE, mapA, bar(RAW_FULL + kb), ti * TM, row);
+            if (!diag) tma_load_2d(sbase + OFF_RAW + (kb * 2 + 1) * RAW_TILE, mapB, bar(RAW_FULL + kb), tj * TN, row);
         }
     }
-    if (warp == 1) {  // TMEM: all 512 columns = 4 fp32 accumulators of 128 columns, used round-robin by k-block
+    if (warp == 1) {  // TMEM: all 512 columns = 2 pairs of fp32 accumulators of 128 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -205,7 +227,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int ca = ti * TM + threadIdx.x;
         shA[threadIdx.x] = ca < P.K ? P.shiftA[ca] : 0.f;
         const int cb = tj * TN + threadIdx.x;
-        shB[threadIdx.x] = cb < P.nB ? P.shiftB[cb] : 0.f;
+        const int nB = is_xy ? P.nB : P.K;
+        const float *shiftB = is_xy ? P.shiftB : P.shiftA;
+        shB[threadIdx.x] = cb < nB ? shiftB[cb] : 0.f;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -219,11 +243,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = RSTAGES; kb < nkb; ++kb) {
                 const int s = kb % RSTAGES;
                 const uint32_t ph = (kb / RSTAGES) & 1;
-                TC_ACC(8, mbar_wait(bar(RAW_EMPTY + s), ph ^ 1));  // slot free (fresh barrier passes immediately)
+                TC_ACC(8, mbar_wait(bar(RAW_EMPTY + s), ph ^ 1));  // slot free
                 mbar_arrive_expect_tx(bar(RAW_FULL + s), diag ? RAW_TILE : 2 * RAW_TILE);
                 const int row = (int)(r_begin + (int64_t)kb * KB);
-                tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, &mapA, bar(RAW_FULL + s), ti * TM, row);
-                if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, &mapB, bar(RAW_FULL + s), tj * TN, row);
+                tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, mapA, bar(RAW_FULL + s), ti * TM, row);
+                if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, mapB, bar(RAW_FULL + s), tj * TN, row);
             }
         }
     } else if (warp == 1) {
@@ -234,30 +258,32 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
+                const int c = kb / CHUNK_KB, kk = kb - c * CHUNK_KB;
                 TC_ACC(9, mbar_wait(bar(OPS_FULL + s), ph));
                 if (kb == 0) TC_T(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ops = sbase + OFF_OPS + s * 4 * OP_TILE;
                 const uint32_t a_hi = ops, a_lo = ops + OP_TILE;
                 const uint32_t b_hi = diag ? a_hi : ops + 2 * OP_TILE, b_lo = diag ? a_lo : ops + 3 * OP_TILE;
+                // The tensor core truncates when it adds into the fp32 accumulator, so long positive sums drift
+                // low in proportion to the number of additions: two accumulators per pair, alternating by k-block.
+                // Pair (c & 1) was drained by the converters before they delivered this sub-chunk's operands.
+                const uint32_t acc = tmem_base + (uint32_t)(((c & 1) * 2 + (kk & 1)) * TN);
 #pragma unroll
                 for (int ks = 0; ks < KB / 8; ++ks) {
                     const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzled row
-                    // The tensor core truncates when it adds into the fp32 accumulator, so long positive sums
-                    // drift low in proportion to the number of additions: rotate over 4 accumulators.
-                    const uint32_t acc = tmem_base + (uint32_t)((kb & 3) * TN);
-                    const uint32_t first = (kb < 4 && ks == 0) ? 0u : 1u;
+                    const uint32_t first = (kk < 2 && ks == 0) ? 0u : 1u;
                     umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
                     umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
                     umma_tf32(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
                 }
                 umma_commit(bar(OPS_EMPTY + s));  // operand stage free once these MMAs have read it
+                if (kk == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(bar(ACC_FULL + (c & 1)));  // pair complete
             }
-            umma_commit(bar(ACC_FULL));  // accumulator complete
             TC_T(4);
         }
     } else {
-        // ===================== converters (then epilogue) =====================
+        // ===================== converters + drain =====================
         const int t = threadIdx.x - 64;   // 0..255
         const int m = t & 127;            // column of the raw box = row of the K-major operand
         const int kh = t >> 7;            // which half of the 32-row k-block this thread converts
@@ -301,12 +327,37 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
         };
+        // drain: this thread owns row (quad*32 + lane) x 64 columns of the tile
+        const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
+        const int chalf = (warp - 2) >> 2;  // two warps share a lane quadrant: each drains 64 of the 128 columns
+        float accv[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) accv[e] = 0.f;
+        auto drain = [&](int c) {
+            TC_ACC(11, mbar_wait(bar(ACC_FULL + (c & 1)), (uint32_t)((c >> 1) & 1)));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kbc = nkb - c * CHUNK_KB;  // k-blocks of this sub-chunk: one of them -> only the first accumulator is live
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                if (a == 1 && kbc < 2) break;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(((c & 1) * 2 + a) * TN + chalf * 64 + g * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) accv[g * 32 + e] = __fadd_rn(accv[g * 32 + e], __uint_as_float(r[e]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        };
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES, rs = kb % RSTAGES;
             const uint32_t ph = (kb / STAGES) & 1, rph = (kb / RSTAGES) & 1;
+            const int c = kb / CHUNK_KB, kk = kb - c * CHUNK_KB;
             TC_ACC(10, mbar_wait(bar(RAW_FULL + rs), rph));     // raw boxes landed
             if (kb == 0) TC_T(2);
-            TC_ACC(11, mbar_wait(bar(OPS_EMPTY + s), ph ^ 1));  // operand stage no longer read by the tensor core
+            TC_ACC(12, mbar_wait(bar(OPS_EMPTY + s), ph ^ 1));  // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
             if (nvalid == KB) {
@@ -319,42 +370,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
             mbar_arrive(bar(OPS_FULL + s));    // operands ready
             mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
-        }
-        // ---- epilogue: TMEM -> fp32 partial tile
-        TC_T(12);
-        mbar_wait(bar(ACC_FULL), 0);
-        TC_T(5);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
-        const int mrow = quad * 32 + lane;  // row of the output tile
-        const int chalf = (warp - 2) >> 2;  // two warps share a lane quadrant: each drains 64 of the 128 columns
-        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)mrow * TN;
-        const int nacc = nkb < 4 ? nkb : 4;
-#pragma unroll
-        for (int cb = chalf * 64; cb < chalf * 64 + 64; cb += 32) {
-            float accv[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) accv[e] = 0.f;
-            for (int a = 0; a < nacc; ++a) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TN + cb);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int e = 0; e < 32; ++e) accv[e] += __uint_as_float(r[e]);
+            // the previous sub-chunk's pair is complete by now (the tensor core is at most two k-blocks behind):
+            // drain it while the MMAs of this sub-chunk run on the other pair
+            if (c > 0) {
+                const int kbc = nkb - c * CHUNK_KB;
+                const int dpoint = kbc > 2 ? 2 : kbc - 1;
+                if (kk == dpoint) drain(c - 1);
             }
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4 *>(dst + cb + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
         }
+        TC_T(5);
+        drain(nchunk - 1);
+        // ---- fp32 partial tile
+        const int mrow = quad * 32 + lane;  // row of the output tile
+        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)mrow * TN + chalf * 64;
+#pragma unroll
+        for (int e = 0; e < 64; e += 4)
+            *reinterpret_cast<float4 *>(dst + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
     }
     if (threadIdx.x == 64) TC_T(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -528,14 +559,25 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
     const int tiles_sym = G ? tk * (tk + 1) / 2 : 0;
     const int tnb = wantB ? cp_cdiv(n, TN) : 0;
     const int ntiles = tiles_sym + tk * tnb;
-    // rows per chunk: enough CTAs for >= 2 waves, 128 <= rows <= 512 (short fp32 accumulations), multiple of 32
-    int nchunks = ntiles > 0 ? cp_cdiv(2 * h->num_sms, ntiles) : 1;
-    const int cmin = cp_cdiv(N, 512), cmax = cp_cdiv(N, 128);
-    if (nchunks < cmin) nchunks = cmin;
-    if (nchunks > cmax) nchunks = cmax;
-    if (nchunks < 1) nchunks = 1;
-    int rpc = cp_cdiv(cp_cdiv(N, nchunks), KB) * KB;
-    nchunks = cp_cdiv(N, rpc);
+    // Row splits: every CTA pays a fixed prologue/epilogue (~10k cycles) and ~1.4k cycles per 32-row k-block, and the
+    // grid runs in waves of num_sms CTAs (one per SM: 224 KB of shared memory each).  Pick the number of splits
+    // that minimises waves x CTA time; splits are multiples of the 256-row sub-chunk.
+    int nchunks = 1, rpc = (int)(cp_cdiv(N, CHUNK_KB * KB) * CHUNK_KB * KB);
+    if (ntiles > 0) {
+        double best = 1e300;
+        const int max_ns = (int)cp_cdiv(N, CHUNK_KB * KB);
+        for (int ns = 1; ns <= max_ns && ns <= 64; ++ns) {
+            const int64_t r = cp_cdiv(cp_cdiv(N, ns), CHUNK_KB * KB) * CHUNK_KB * KB;
+            const int ns_eff = (int)cp_cdiv(N, r);
+            const double waves = (double)cp_cdiv((int64_t)ntiles * ns_eff, h->num_sms);
+            const double cost = waves * (10000.0 + 1400.0 * (double)(r / KB));
+            if (cost < best * 0.97) {  // prefer fewer splits (less partial traffic) unless clearly better
+                best = cost;
+                nchunks = ns_eff;
+                rpc = (int)r;
+            }
+        }
+    }
 
     const size_t part_bytes = (size_t)nchunks * ntiles * TM * TN * sizeof(float);
     const size_t need = cp_carver::need(part_bytes, 1) + 2 * cp_carver::need(K, 8) + cp_carver::need(n > 0 ? n : 1, 8) +
@@ -575,31 +617,23 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
         CUtensorMap mapA, mapB;
         rc = make_map(h, &mapA, X, N, K, ldx);
         if (rc) return rc;
+        if (wantB) {
+            rc = make_map(h, &mapB, Y, N, n, ldy);
+            if (rc) return rc;
+        } else {
+            mapB = mapA;
+        }
         TcParams P{};
-        P.shiftA = shX; P.partial = partial; P.K = K; P.N = N; P.rows_per_chunk = rpc;
-        P.tiles_sym = tiles_sym; P.tk = tk; P.ntiles = ntiles;
+        P.shiftA = shX; P.shiftB = shY; P.partial = partial; P.K = K; P.nB = n; P.N = N; P.rows_per_chunk = rpc;
+        P.tiles_sym = tiles_sym; P.tk = tk; P.tnb = tnb; P.ntiles = ntiles;
         static bool configured = false;
         if (!configured) {
             CP_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             configured = true;
         }
-        // X'X tiles and X'Y tiles need different B sources -> two launches over disjoint tile ranges of
-        // the same partial buffer (blockIdx.x offsets are folded into tiles_sym / tnb).
-        if (tiles_sym > 0) {
-            TcParams Pg = P;
-            Pg.shiftB = shX; Pg.nB = K; Pg.tnb = 0; Pg.ntiles = ntiles;
-            gram_tc_kernel<<<dim3(tiles_sym, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapA, Pg);
-            CP_CHECK_LAUNCH();
-        }
-        if (wantB) {
-            rc = make_map(h, &mapB, Y, N, n, ldy);
-            if (rc) return rc;
-            TcParams Pb = P;
-            Pb.shiftB = shY; Pb.nB = n; Pb.tnb = tnb; Pb.tiles_sym = 0; Pb.ntiles = ntiles;
-            Pb.partial = partial + (size_t)tiles_sym * TM * TN;  // tile slots after the symmetric ones
-            gram_tc_kernel<<<dim3(tk * tnb, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, Pb);
-            CP_CHECK_LAUNCH();
-        }
+        // one launch: X'X upper tiles first, then the X'Y tiles (B operand from the Y map)
+        gram_tc_kernel<<<dim3(ntiles, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, P);
+        CP_CHECK_LAUNCH();
         if (tiles_sym > 0) {
             reduce_tc<<<dim3(tiles_sym, 4), 256, 0, stream>>>(partial, nchunks, ntiles, 0, 0, 1, tk, shX, TX, shX, nullptr, TX, SQX, Nd,
                                                     K, K, G, K);
