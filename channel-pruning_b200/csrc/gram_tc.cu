@@ -40,13 +40,13 @@ namespace {
 constexpr int TM = 128, TN = 128, KB = 32;           // output tile, rows per k-block
 constexpr int RAW_TILE = KB * TM * 4;                // 16 KB raw fp32 box
 constexpr int OP_TILE = TM * 128;                    // 16 KB operand tile (128 rows x 128 B)
-constexpr int STAGES = 2;      // operand stages (hi/lo, K-major swizzled)
-constexpr int RSTAGES = 3;     // raw fp32 stages in flight (TMA latency x bandwidth needs ~64 KB per SM)
+constexpr int STAGES = 3;      // operand stages: B hi/lo in shared memory (K-major swizzled), A hi/lo in TMEM
+constexpr int RSTAGES = 4;     // raw fp32 stages in flight
 constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 converters/epilogue
 constexpr int NCONV = 256;
 // shared memory map (bytes, from a 1024-aligned base)
-constexpr int OFF_OPS = 0;                                    // STAGES x {Ahi, Alo, Bhi, Blo}
-constexpr int OFF_RAW = OFF_OPS + STAGES * 4 * OP_TILE;       // RSTAGES x {rawA, rawB}
+constexpr int OFF_OPS = 0;                                    // STAGES x {Bhi, Blo}
+constexpr int OFF_RAW = OFF_OPS + STAGES * 2 * OP_TILE;       // RSTAGES x {rawA, rawB}
 constexpr int OFF_SHIFT = OFF_RAW + RSTAGES * 2 * RAW_TILE;    // shiftA[128], shiftB[128] fp32
 constexpr int OFF_BAR = OFF_SHIFT + 2 * TM * 4;               // mbarriers
 constexpr int NBAR = 2 * RSTAGES + 2 * STAGES + 2;
@@ -103,12 +103,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// A operand from tensor memory (lanes = rows of A, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -144,7 +153,8 @@ __device__ long long cp_tc_times[64][16];
 // alternating by k-block, so no fp32 accumulator takes more than 48 truncating additions -- while the
 // converter warps drain pair ((c-1) & 1) into fp32 registers (round-to-nearest adds).  One fp32 partial
 // tile per CTA leaves the kernel.
-constexpr int CHUNK_KB = 8;
+constexpr int CHUNK_KB = 4;
+constexpr uint32_t TM_ACC = 0, TM_A = 2 * TN;  // TMEM columns: two accumulators, then STAGES x {A hi (32), A lo (32)}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -262,20 +272,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 TC_ACC(9, mbar_wait(bar(OPS_FULL + s), ph));
                 if (kb == 0) TC_T(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ops = sbase + OFF_OPS + s * 4 * OP_TILE;
-                const uint32_t a_hi = ops, a_lo = ops + OP_TILE;
-                const uint32_t b_hi = diag ? a_hi : ops + 2 * OP_TILE, b_lo = diag ? a_lo : ops + 3 * OP_TILE;
+                const uint32_t b_hi = sbase + OFF_OPS + s * 2 * OP_TILE, b_lo = b_hi + OP_TILE;
+                const uint32_t a_hi = tmem_base + TM_A + (uint32_t)(s * 2 * KB), a_lo = a_hi + KB;
                 // The tensor core truncates when it adds into the fp32 accumulator, so long positive sums drift
-                // low in proportion to the number of additions: two accumulators per pair, alternating by k-block.
-                // Pair (c & 1) was drained by the converters before they delivered this sub-chunk's operands.
-                const uint32_t acc = tmem_base + (uint32_t)(((c & 1) * 2 + (kk & 1)) * TN);
+                // low in proportion to the number of additions: a sub-chunk (4 k-blocks, 48 additions) per accumulator.
+                // Accumulator (c & 1) was drained by the converters before they delivered this sub-chunk's operands.
+                const uint32_t acc = tmem_base + TM_ACC + (uint32_t)((c & 1) * TN);
 #pragma unroll
                 for (int ks = 0; ks < KB / 8; ++ks) {
                     const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzled row
-                    const uint32_t first = (kk < 2 && ks == 0) ? 0u : 1u;
-                    umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
-                    umma_tf32(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
-                    umma_tf32(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
+                    const uint32_t first = (kk == 0 && ks == 0) ? 0u : 1u;
+                    umma_tf32_ts(acc, a_hi + ks * 8, umma_desc_k_sw128(b_hi + off), idesc, first);
+                    umma_tf32_ts(acc, a_hi + ks * 8, umma_desc_k_sw128(b_lo + off), idesc, 1u);
+                    umma_tf32_ts(acc, a_lo + ks * 8, umma_desc_k_sw128(b_hi + off), idesc, 1u);
                 }
                 umma_commit(bar(OPS_EMPTY + s));  // operand stage free once these MMAs have read it
                 if (kk == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(bar(ACC_FULL + (c & 1)));  // pair complete
@@ -284,70 +293,75 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         }
     } else {
         // ===================== converters + drain =====================
-        const int t = threadIdx.x - 64;   // 0..255
-        const int m = t & 127;            // column of the raw box = row of the K-major operand
-        const int kh = t >> 7;            // which half of the 32-row k-block this thread converts
+        // thread -> (m, kh): m = row of the operands (column of the raw boxes) = TMEM lane, which a warp can only
+        // reach inside its own quadrant (warp % 4); kh = which half of the 32-row k-block this thread converts
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const int kh = (warp - 2) >> 2;
         // Shared-space (32-bit) addresses and explicit ld/st.shared: through the aligned generic pointer the
         // compiler emits generic LD/ST and, fearing aliasing, serialises load -> split -> store per 4 values.
-        // All 16 (or 32) raw values of the thread are loaded first so that their latency overlaps.
-        float shv[2];
-        shv[0] = shA[m];
-        shv[1] = shB[m];
-        auto convert = [&](int rs, int s, int nops, int nvalid, auto full_tag) {
+        // All raw values of the thread are loaded first so that their latency overlaps.
+        const float shva = shA[m], shvb = shB[m];
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        auto convert = [&](int rs, int s, bool same, int nvalid, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            float v[2][16];
+            float va[16], vb[16];
+            const uint32_t rawa = sbase + OFF_RAW + (rs * 2 + 0) * RAW_TILE + (uint32_t)(kh * 16 * TM + m) * 4u;
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                if (which < nops) {
-                    const uint32_t raw = sbase + OFF_RAW + (rs * 2 + which) * RAW_TILE + (uint32_t)(kh * 16 * TM + m) * 4u;
+            for (int e = 0; e < 16; ++e) va[e] = lds_f32(rawa + (uint32_t)e * TM * 4u);
+            if (!same) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[which][e] = lds_f32(raw + (uint32_t)e * TM * 4u);
-                }
+                for (int e = 0; e < 16; ++e) vb[e] = lds_f32(rawa + RAW_TILE + (uint32_t)e * TM * 4u);
             }
+            // A: shift, split, straight into tensor memory (columns = k)
+            float ah[16], al[16];
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                if (which < nops) {
-                    const uint32_t hi = sbase + OFF_OPS + (s * 4 + which * 2) * OP_TILE + (uint32_t)m * 128u;
-                    const float sh = shv[which];
+            for (int e = 0; e < 16; ++e) {
+                const float x = (FULL || kh * 16 + e < nvalid) ? __fsub_rn(va[e], shva) : 0.f;
+                ah[e] = tf32_rn(x);
+                al[e] = tf32_rn(__fsub_rn(x, ah[e]));
+            }
+            const uint32_t ta = lane_addr + TM_A + (uint32_t)(s * 2 * KB + kh * 16);
+            tmem_st16(ta, ah);
+            tmem_st16(ta + KB, al);
+            // B: K-major 128B-swizzled shared memory (the same values when the tile is on the diagonal)
+            const uint32_t hi = sbase + OFF_OPS + s * 2 * OP_TILE + (uint32_t)m * 128u;
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int q = kh * 4 + q4;
-                        float x[4], h[4], l[4];
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int q = kh * 4 + q4;
+                float h[4], l[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = 4 * q + e;
-                            x[e] = (FULL || k < nvalid) ? __fsub_rn(v[which][4 * q4 + e], sh) : 0.f;
-                            h[e] = tf32_rn(x[e]);
-                            l[e] = tf32_rn(__fsub_rn(x[e], h[e]));
-                        }
-                        const uint32_t off = (uint32_t)((q ^ (m & 7)) << 4);  // Swizzle<3,4,3>: 16B chunk ^= row & 7
-                        sts_v4(hi + off, h[0], h[1], h[2], h[3]);
-                        sts_v4(hi + OP_TILE + off, l[0], l[1], l[2], l[3]);
+                for (int e = 0; e < 4; ++e) {
+                    if (same) {
+                        h[e] = ah[4 * q4 + e];
+                        l[e] = al[4 * q4 + e];
+                    } else {
+                        const float x = (FULL || 4 * q + e < nvalid) ? __fsub_rn(vb[4 * q4 + e], shvb) : 0.f;
+                        h[e] = tf32_rn(x);
+                        l[e] = tf32_rn(__fsub_rn(x, h[e]));
                     }
                 }
+                const uint32_t off = (uint32_t)((q ^ (m & 7)) << 4);  // Swizzle<3,4,3>: 16B chunk ^= row & 7
+                sts_v4(hi + off, h[0], h[1], h[2], h[3]);
+                sts_v4(hi + OP_TILE + off, l[0], l[1], l[2], l[3]);
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
         // drain: this thread owns row (quad*32 + lane) x 64 columns of the tile
-        const int quad = warp & 3;          // TMEM lanes 32*quad .. +31 are accessible to this warp
-        const int chalf = (warp - 2) >> 2;  // two warps share a lane quadrant: each drains 64 of the 128 columns
+        const int chalf = kh;  // two warps share a lane quadrant: each drains 64 of the 128 columns
         float accv[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) accv[e] = 0.f;
         auto drain = [&](int c) {
-            TC_ACC(11, mbar_wait(bar(ACC_FULL + (c & 1)), (uint32_t)((c >> 1) & 1)));
+            TC_ACC(11, mbar_wait(bar(ACC_FULL + (c & 1)), (uint32_t)((c >> 1) & 1)));  // sub-chunk c is the (c>>1)-th use
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kbc = nkb - c * CHUNK_KB;  // k-blocks of this sub-chunk: one of them -> only the first accumulator is live
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                if (a == 1 && kbc < 2) break;
+            for (int g = 0; g < 2; ++g) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + TM_ACC + (uint32_t)((c & 1) * TN + chalf * 64 + g * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(((c & 1) * 2 + a) * TN + chalf * 64 + g * 32), r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) accv[g * 32 + e] = __fadd_rn(accv[g * 32 + e], __uint_as_float(r[e]));
-                }
+                for (int e = 0; e < 32; ++e) accv[g * 32 + e] = __fadd_rn(accv[g * 32 + e], __uint_as_float(r[e]));
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         };
@@ -360,14 +374,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             TC_ACC(12, mbar_wait(bar(OPS_EMPTY + s), ph ^ 1));  // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
-            if (nvalid == KB) {
-                if (diag) convert(rs, s, 1, KB, std::true_type{});
-                else convert(rs, s, 2, KB, std::true_type{});
-            } else {
-                if (diag) convert(rs, s, 1, nvalid, std::false_type{});
-                else convert(rs, s, 2, nvalid, std::false_type{});
-            }
+            if (nvalid == KB) convert(rs, s, diag, KB, std::true_type{});
+            else convert(rs, s, diag, nvalid, std::false_type{});
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st (A) ordered before the arrive
             mbar_arrive(bar(OPS_FULL + s));    // operands ready
             mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
             // the previous sub-chunk's pair is complete by now (the tensor core is at most two k-blocks behind):

@@ -23,11 +23,10 @@ L = ctypes.CDLL(_cabi.LIBRARY)
 buf = (ctypes.c_longlong * (64 * 16))()
 assert L.cp_debug_tc_times(buf) == 0
 T = np.array(buf, dtype=np.int64).reshape(64, 16)
-names = ["entry", "setup_done", "first_raw_full", "first_ops_full", "mma_all_issued", "acc_full", "epilogue_done", "exit"]
+names = ["entry", "setup_done", "first_raw_full", "first_ops_full", "mma_all_issued", "conv_loop_done", "partial_written", "exit"]
 rel = T[:, :8] - T[:, :1]
 print("N=%d K=%d: cycles from CTA entry (median / min / max over 64 CTAs)" % (N, K))
 for i, nm in enumerate(names):
     print("  %-16s %8d %8d %8d" % (nm, np.median(rel[:, i]), rel[:, i].min(), rel[:, i].max()))
-print("  %-16s %8d   (converter loop end)" % ("conv_loop_done", np.median(T[:, 12] - T[:, 0])))
-for i, nm in zip(range(8, 12), ["producer waits raw_empty", "mma waits ops_full", "converter waits raw_full", "converter waits ops_empty"]):
-    print("  %-26s %8d cycles total (median)" % (nm, np.median(T[:, i])))
+for i, nm in zip(range(8, 13), ["producer waits raw_empty", "mma waits ops_full", "converter waits raw_full", "converter waits acc_full (drain)", "converter waits ops_empty"]):
+    print("  %-34s %8d cycles total (median)" % (nm, np.median(T[:, i])))
