@@ -44,6 +44,7 @@ constexpr int STAGES = 3;      // operand stages: B hi/lo in shared memory (K-ma
 constexpr int RSTAGES = 4;     // raw fp32 stages in flight
 constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 converters/epilogue
 constexpr int NCONV = 256;
+constexpr int NCONV_WARPS = NCONV / 32;  // barrier arrivals are per warp (one elected lane after __syncwarp)
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_OPS = 0;                                    // STAGES x {Bhi, Blo}
 constexpr int OFF_RAW = OFF_OPS + STAGES * 2 * OP_TILE;       // RSTAGES x {rawA, rawB}
@@ -79,19 +80,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+template <bool TEST_WAIT>
+__device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 24)) __trap();
+        if (TEST_WAIT) {  // non-blocking probe: the thread keeps polling instead of being suspended
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        }
+        if (spin > (1u << 26)) __trap();
     }
 }
+// ablation builds (make ablate): CP_TC_ABLATE_MASK is a compile-time constant, so the product build carries none of it
+// bit0: converters skip their work, bit1: no MMAs, bit2: no TMA loads, bit3: no fences, bit4: no drain, bit6: test_wait
+#ifndef CP_TC_ABLATE_MASK
+#define CP_TC_ABLATE_MASK 0
+#endif
+#define TC_ABLATE(bit) ((CP_TC_ABLATE_MASK) & (bit))
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_impl<(TC_ABLATE(64) != 0)>(bar, parity); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -141,7 +160,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
 #ifdef CP_TC_TIMING
 __device__ long long cp_tc_times[64][16];
 #define TC_T(slot) do { if (timed) cp_tc_times[blockIdx.x][slot] = clock64(); } while (0)
-#define TC_ACC(slot, expr) do { long long _a = clock64(); expr; if (timed) cp_tc_times[blockIdx.x][slot] += clock64() - _a; } while (0)
+#define TC_ACC(slot, expr) do { long long _a = 0; if (timed) _a = clock64(); expr; if (timed) cp_tc_times[blockIdx.x][slot] += clock64() - _a; } while (0)
 #else
 #define TC_T(slot) do { } while (0)
 #define TC_ACC(slot, expr) do { expr; } while (0)
@@ -210,10 +229,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < RSTAGES; ++s) {
             mbar_init(bar(RAW_FULL + s), 1);
-            mbar_init(bar(RAW_EMPTY + s), NCONV);
+            mbar_init(bar(RAW_EMPTY + s), NCONV_WARPS);
         }
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar(OPS_FULL + s), NCONV);
+            mbar_init(bar(OPS_FULL + s), NCONV_WARPS);
             mbar_init(bar(OPS_EMPTY + s), 1);
         }
         mbar_init(bar(ACC_FULL + 0), 1);
@@ -221,6 +240,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the first RSTAGES boxes need nothing but their barriers: get them in flight before the rest of the set-up
         for (int kb = 0; kb < nkb && kb < RSTAGES; ++kb) {
+            if (TC_ABLATE(4)) { mbar_arrive(bar(RAW_FULL + kb)); continue; }
             mbar_arrive_expect_tx(bar(RAW_FULL + kb), diag ? RAW_TILE : 2 * RAW_TILE);
             const int row = (int)(r_begin + (int64_t)kb * KB);
             tma_load_2d(sbase + OFF_RAW + (kb * 2 + 0) * RAW_TILE, mapA, bar(RAW_FULL + kb), ti * TM, row);
@@ -254,6 +274,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 const int s = kb % RSTAGES;
                 const uint32_t ph = (kb / RSTAGES) & 1;
                 TC_ACC(8, mbar_wait(bar(RAW_EMPTY + s), ph ^ 1));  // slot free
+                if (TC_ABLATE(4)) { mbar_arrive(bar(RAW_FULL + s)); continue; }
                 mbar_arrive_expect_tx(bar(RAW_FULL + s), diag ? RAW_TILE : 2 * RAW_TILE);
                 const int row = (int)(r_begin + (int64_t)kb * KB);
                 tma_load_2d(sbase + OFF_RAW + (s * 2 + 0) * RAW_TILE, mapA, bar(RAW_FULL + s), ti * TM, row);
@@ -280,6 +301,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 const uint32_t acc = tmem_base + TM_ACC + (uint32_t)((c & 1) * TN);
 #pragma unroll
                 for (int ks = 0; ks < KB / 8; ++ks) {
+                    if (TC_ABLATE(2)) break;
                     const uint32_t off = ks * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzled row
                     const uint32_t first = (kk == 0 && ks == 0) ? 0u : 1u;
                     umma_tf32_ts(acc, a_hi + ks * 8, umma_desc_k_sw128(b_hi + off), idesc, first);
@@ -374,18 +396,26 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             TC_ACC(12, mbar_wait(bar(OPS_EMPTY + s), ph ^ 1));  // operand stage no longer read by the tensor core
             const int64_t row0 = r_begin + (int64_t)kb * KB;
             const int nvalid = (int)((r_end - row0) < KB ? (r_end - row0) : KB);
-            if (nvalid == KB) convert(rs, s, diag, KB, std::true_type{});
+            if (TC_ABLATE(1)) { }
+            else if (nvalid == KB) convert(rs, s, diag, KB, std::true_type{});
             else convert(rs, s, diag, nvalid, std::false_type{});
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st (A) ordered before the arrive
-            mbar_arrive(bar(OPS_FULL + s));    // operands ready
-            mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
+            if (!TC_ABLATE(8)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // tcgen05.st (A) ordered before the arrive
+            }
+            // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in shared memory
+            // (~500 cycles per k-block, measured with profiles/tc_timeline.py)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar(OPS_FULL + s));    // operands ready
+                mbar_arrive(bar(RAW_EMPTY + rs));  // raw stage free
+            }
             // the previous sub-chunk's pair is complete by now (the tensor core is at most two k-blocks behind):
             // drain it while the MMAs of this sub-chunk run on the other pair
             if (c > 0) {
                 const int kbc = nkb - c * CHUNK_KB;
                 const int dpoint = kbc > 2 ? 2 : kbc - 1;
-                if (kk == dpoint) drain(c - 1);
+                if (kk == dpoint && !TC_ABLATE(16)) drain(c - 1);
             }
         }
         TC_T(5);
