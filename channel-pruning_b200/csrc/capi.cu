@@ -26,17 +26,25 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->ws = nullptr;
     h->ws_bytes = 0;
     h->tmap_encode = nullptr;
+    h->side = nullptr;
+    h->ev_panel = nullptr;
+    h->ev_side = nullptr;
     *out = h;
     return CP_OK;
 }
 
 extern "C" int cp_destroy(cp_handle_t h) {
     if (!h) return CP_OK;
-    if (h->ws) {
+    if (h->ws || h->side) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(h->device);
-        cudaFree(h->ws);
+        if (h->ws) cudaFree(h->ws);
+        if (h->side) {
+            cudaStreamDestroy(h->side);
+            cudaEventDestroy(h->ev_panel);
+            cudaEventDestroy(h->ev_side);
+        }
         cudaSetDevice(cur);
     }
     delete h;

@@ -13,6 +13,9 @@ struct cp_handle_s {
     void *ws;          // scratch, grown on demand
     size_t ws_bytes;
     void *tmap_encode; // cuTensorMapEncodeTiled entry point (resolved lazily)
+    // look-ahead of the blocked Cholesky (ls.cu): low-priority side stream + fork/join events, created lazily
+    cudaStream_t side;
+    cudaEvent_t ev_panel, ev_side;
 };
 
 extern thread_local char cp_err_buf[512];

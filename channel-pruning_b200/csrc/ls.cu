@@ -185,7 +185,7 @@ int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
 // In-place: M is (Kd + n) x Kd (leading dimension ld), rows 0..Kd-1 an SPD matrix (lower part
 // used), rows Kd.. the transposed right-hand sides.  On return rows Kd.. hold the transposed
 // solution  (SPD^-1 Rhs)'.  Linv: scratch of ceil(Kd/64) * 64*64 doubles.
-static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv, const double *diag0,
+static int chol_solve_inplace(cp_handle_t h, double *M, int64_t ld, int Kd, int n, double *Linv, const double *diag0,
                               int32_t *info, cudaStream_t stream) {
     using namespace cpgemm;
     const int Ktot = Kd + n;
@@ -200,6 +200,17 @@ static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv
     // dimension 256 (4x fewer, 4x deeper tile GEMMs than a plain 64-wide right-looking sweep).
     constexpr int NBO = 4 * NB;
     (void)npanel;
+    // Look-ahead: the trailing update of an outer panel is split into the next panel's columns (needed at once, stays
+    // on the caller's stream) and the rest, which runs on a low-priority side stream concurrently with the next
+    // panel's (latency-bound, one-CTA-at-a-time) factorisation.
+    if (!h->side) {
+        int lo = 0, hi = 0;
+        CP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+        CP_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+        CP_CUDA(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+    }
+    bool side_pending = false;
     for (int J0 = 0; J0 < Kd; J0 += NBO) {
         const int w = Kd - J0 < NBO ? Kd - J0 : NBO;
         const int J1 = J0 + w;
@@ -225,12 +236,29 @@ static int chol_solve_inplace(double *M, int64_t ld, int Kd, int n, double *Linv
         }
         const int ncols = Kd - J1;
         if (ncols > 0) {  // trailing (lower) -= panel * panel', inner dimension w
+            const int w2 = ncols < NBO ? ncols : NBO;  // columns of the next outer panel
+            const bool fork = ncols > w2;
+            if (fork) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // panel J0..J1 is final
+            if (side_pending) {  // the previous panel's far update also touched the columns updated next
+                CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
+                side_pending = false;
+            }
             double *Pn = M + (int64_t)J1 * ld + J0;
-            int rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)J1 * ld + J1, ld, Ktot - J1, ncols, w, -1.0, 1.0, TILES_LOWER,
-                                  stream);
+            int rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)J1 * ld + J1, ld, Ktot - J1, w2, w, -1.0, 1.0, TILES_LOWER, stream);
             if (rc) return rc;
+            if (fork) {
+                const int J2 = J1 + w2;
+                double *Pf = M + (int64_t)J2 * ld + J0;
+                CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
+                rc = dgemm<false>(Pf, ld, Pf, ld, M + (int64_t)J2 * ld + J2, ld, Ktot - J2, ncols - w2, w, -1.0, 1.0, TILES_LOWER,
+                                  h->side);
+                if (rc) return rc;
+                CP_CUDA(cudaEventRecord(h->ev_side, h->side));
+                side_pending = true;
+            }
         }
     }
+    if (side_pending) CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
     // backward: Wt * L = Zt, outer panels last to first, inner blocks last to first
     double *Zt = M + (int64_t)Kd * ld;
     const int nouter = (Kd + NBO - 1) / NBO;
@@ -283,7 +311,7 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     dim3 grid(cp_cdiv(Ksel, 256), Ksel + n);
     ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld, diag0);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(M, ld, Ksel, n, Linv, diag0, info_out, stream);
+    rc = chol_solve_inplace(h, M, ld, Ksel, n, Linv, diag0, info_out, stream);
     if (rc) return rc;
     ls_output<<<n, 256, 0, stream>>>(M + (int64_t)Ksel * ld, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
     CP_CHECK_LAUNCH();
@@ -415,7 +443,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     else
         dual_rhs<double><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(M, ldm, Ni, n, Linv, diag0, info_out, stream);
+    rc = chol_solve_inplace(h, M, ldm, Ni, n, Linv, diag0, info_out, stream);
     if (rc) return rc;
     // Wt = At * Xc   (C[t, i] = sum_r At[t, r] * Xc[r, i])
     rc = dgemm<true>(M + (int64_t)Ni * ldm, ldm, Xc, ldc, Wt, ldc, n, Ksel, Ni, 1.0, 0.0, TILES_ALL, stream);
