@@ -73,3 +73,47 @@ def test_dictionary_with_tc_gram_meets_north_star_tolerance(engine):
     rel = np.linalg.norm(W - oW) / np.linalg.norm(oW)
     print("rel weight error with 3xTF32 Gram: %.2e" % rel)
     assert rel <= 1e-4 and np.abs(B - oB).max() <= 1e-4
+
+
+@pytest.mark.parametrize("N,K,n", [(64, 64, 4), (65, 128, 1), (257, 192, 130), (8191, 256, 64), (300, 1000, 12)])
+def test_gram_tc_edge_shapes(engine, N, K, n):
+    """Row counts that are not multiples of the 32-row k-block / 128-row sub-chunk, a single sub-chunk, many
+    row splits (tall-skinny: few tiles), one target column, K and n that leave partial tiles."""
+    r = np.random.RandomState(7 * N + K)
+    X = (r.standard_normal((N, K)) * r.uniform(0.1, 3.0, K) + r.uniform(-2, 2, K)).astype(np.float32)
+    ldy = (n + 3) // 4 * 4
+    Y = r.standard_normal((N, n)).astype(np.float32)
+    Yp = torch.zeros(N, ldy, dtype=torch.float32, device=engine.device)
+    Yp[:, :n] = _dev(Y, engine)
+    g = engine.gram(_dev(X, engine), Yp[:, :n], mode=1)
+    X64, Y64 = X.astype(np.float64), Y.astype(np.float64)
+    Gr, Br = X64.T @ X64, X64.T @ Y64
+    dx, dy = np.sqrt(np.diag(Gr)), np.sqrt((Y64 ** 2).sum(0))
+    assert (np.abs(g["G"].cpu().numpy() - Gr) / np.outer(dx, dx)).max() <= 1e-6
+    assert (np.abs(g["B"].cpu().numpy() - Br) / np.outer(dx, dy)).max() <= 1e-6
+    np.testing.assert_array_equal(g["G"].cpu().numpy(), g["G"].cpu().numpy().T)
+
+
+def test_gram_tc_single_products(engine):
+    """G only and X'Y only (one launch covers both tile kinds; either may be absent)."""
+    r = np.random.RandomState(11)
+    N, K, n = 1500, 384, 96
+    X = np.maximum(r.standard_normal((N, K)), 0).astype(np.float32)
+    Y = r.standard_normal((N, n)).astype(np.float32)
+    X64, Y64 = X.astype(np.float64), Y.astype(np.float64)
+    g1 = engine.gram(_dev(X, engine), None, mode=1)
+    assert g1["B"] is None
+    np.testing.assert_allclose(g1["G"].cpu().numpy(), X64.T @ X64, rtol=0, atol=1e-6 * np.diag(X64.T @ X64).max())
+    g2 = engine.gram(_dev(X, engine), _dev(Y, engine), want_G=False, mode=1)
+    assert g2["G"] is None
+    ref = X64.T @ Y64
+    assert np.abs(g2["B"].cpu().numpy() - ref).max() <= 1e-6 * np.sqrt(np.diag(X64.T @ X64).max() * (Y64 ** 2).sum(0).max())
+
+
+def test_gram_tc_is_bitwise_reproducible(engine):
+    r = np.random.RandomState(5)
+    X = _dev(r.standard_normal((3000, 640)).astype(np.float32), engine)
+    Y = _dev(r.standard_normal((3000, 64)).astype(np.float32), engine)
+    a = engine.gram(X, Y, mode=1)
+    b = engine.gram(X, Y, mode=1)
+    assert torch.equal(a["G"], b["G"]) and torch.equal(a["B"], b["B"])

@@ -256,3 +256,46 @@ def test_resnet50_bottleneck_problem_vs_oracle(engine, name):
         assert res.alpha == st_.alpha and res.nprobe == len(info["probes"])
     W = res.W.cpu().numpy().reshape(oW.shape)
     assert _rel(W, oW) <= W_TOL and np.abs(res.b.cpu().numpy() - oB).max() <= W_TOL
+
+
+@pytest.mark.parametrize("policy", [True, "zc", "copy"])
+def test_host_resident_pipeline_equals_device_resident(policy):
+    """prune_layers with the feature maps in pinned host memory (in-place gather over PCIe, whole-map DMA, or the
+    per-layer plan) must return bit-identical masks and weights to the device-resident run, and results copied
+    back to host buffers must equal the device ones."""
+    import cpb200
+    from cpb200 import pruner
+
+    eng = cpb200.Engine(nstreams=4)
+    shapes = [cpb200.synth.LayerShape("a", 32, 24, 14, N=600, B=4, P=5), cpb200.synth.LayerShape("b", 48, 16, 28, N=800, B=4, P=5),
+              cpb200.synth.LayerShape("c", 16, 16, 56, N=400, B=4, P=5), cpb200.synth.LayerShape("d", 64, 32, 7, N=600, B=4, P=5),
+              cpb200.synth.LayerShape("e", 24, 8, 20, k=1, pad=0, N=400, B=4, P=5)]
+    datas = [cpb200.synth.make_problem_device(s, 40 + i, eng, pinned_host=True) for i, s in enumerate(shapes)]
+    ref = pruner.prune_layers(eng, shapes, datas)
+    torch.cuda.synchronize()
+    got = pruner.prune_layers(eng, shapes, datas, from_host=policy, to_host=True)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, got):
+        assert np.array_equal(a.idxs, b.idxs) and a.alpha == b.alpha and a.nprobe == b.nprobe
+        assert not b.W.is_cuda and b.W.is_pinned()
+        assert torch.equal(a.W.cpu(), b.W) and torch.equal(a.b.cpu(), b.b)
+    eng.close()
+
+
+def test_pipeline_trace_records_every_stage():
+    import cpb200
+    from cpb200 import pruner
+
+    eng = cpb200.Engine(nstreams=2)
+    shapes = [cpb200.synth.LayerShape("a", 32, 24, 14, N=600, B=4, P=5), cpb200.synth.LayerShape("b", 16, 16, 28, N=400, B=4, P=5)]
+    datas = [cpb200.synth.make_problem_device(s, 3 + i, eng, pinned_host=True) for i, s in enumerate(shapes)]
+    tr = {}
+    pruner.prune_layers(eng, shapes, datas, from_host="zc", to_host=True, trace=tr)
+    torch.cuda.synchronize()
+    t0 = tr.pop("_t0")
+    for s in shapes:
+        labels = [lab for lab, _ in tr[s.name]]
+        assert labels == ["zc_done", "select_done", "ls_done"]
+        times = [t0.elapsed_time(e) for _, e in tr[s.name]]
+        assert times == sorted(times) and times[0] >= 0
+    eng.close()

@@ -167,3 +167,33 @@ def test_two_rank_allgather_reassembles_every_layer(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_h2d_plan_stages_small_maps_and_reads_large_ones_in_place(monkeypatch):
+    """Transfer plan of the host-resident input path: maps that the sampled windows mostly cover (conv5_x: 14x14)
+    are DMA'd whole, the others are read in place; explicit policies override."""
+    import torch
+
+    import cpb200
+    from cpb200 import pruner
+
+    monkeypatch.delenv("CPB200_DMA_MAX_MB", raising=False)
+    monkeypatch.delenv("CPB200_DMA_RATIO", raising=False)
+    shapes = cpb200.synth.vgg16_layers()
+
+    class FakeMap:  # only .numel() is used by the plan
+        def __init__(self, n):
+            self._n = n
+
+        def numel(self):
+            return self._n
+
+    datas = [dict(fmap_host=FakeMap(s.nbatch * s.B * s.c * s.H * s.W)) for s in shapes]
+    plan = pruner.h2d_plan(shapes, datas, True)
+    by_name = {s.name: p for s, p in zip(shapes, plan)}
+    assert all(by_name[n] == "dma" for n in ("conv5_1", "conv5_2", "conv5_3"))
+    assert all(by_name[n] == "zc" for n in ("conv1_2", "conv2_2", "conv3_2", "conv4_2"))
+    assert pruner.h2d_plan(shapes, datas, "zc") == ["zc"] * len(shapes)
+    assert pruner.h2d_plan(shapes, datas, "copy") == ["dma"] * len(shapes)
+    monkeypatch.setenv("CPB200_DMA_MAX_MB", "1")
+    assert pruner.h2d_plan(shapes, datas, True) == ["zc"] * len(shapes)
