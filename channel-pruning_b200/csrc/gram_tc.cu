@@ -42,8 +42,19 @@ constexpr int RAW_TILE = KB * TM * 4;                // 16 KB raw fp32 box
 constexpr int OP_TILE = TM * 128;                    // 16 KB operand tile (128 rows x 128 B)
 constexpr int STAGES = 3;      // operand stages: B hi/lo in shared memory (K-major swizzled), A hi/lo in TMEM
 constexpr int RSTAGES = 4;     // raw fp32 stages in flight
-constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 converters/epilogue
-constexpr int NCONV = 256;
+#ifndef CP_TC_CONV_WARPS
+#define CP_TC_CONV_WARPS 8
+#endif
+constexpr int NCONV = 32 * CP_TC_CONV_WARPS;   // converter / drain threads (8 or 16 warps)
+constexpr int NTHREADS = NCONV + 64;           // converters first, then the TMA warp, then the MMA warp
+// Warp roles.  The two single-thread roles take the HIGHEST warp ids: the warp scheduler favours high warp ids, and
+// with the roles at warps 0/1 the polling converter warps starved the TMA / MMA issuers of issue slots.
+constexpr int W_TMA = CP_TC_CONV_WARPS, W_MMA = CP_TC_CONV_WARPS + 1;
+constexpr int T_TMA = 32 * W_TMA, T_MMA = 32 * W_MMA;
+constexpr int WPQ = CP_TC_CONV_WARPS / 4;      // converter warps per TMEM lane quadrant
+constexpr int KPT = KB / WPQ;                  // k-values (rows of the k-block) converted per thread and operand
+constexpr int CPT = TN / WPQ;                  // accumulator columns drained per thread
+static_assert(KPT == 8 || KPT == 16, "converter layout");
 constexpr int NCONV_WARPS = NCONV / 32;  // barrier arrivals are per warp (one elected lane after __syncwarp)
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_OPS = 0;                                    // STAGES x {Bhi, Blo}
@@ -131,12 +142,18 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+__device__ __forceinline__ __attribute__((unused)) void tmem_st(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
           "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ __attribute__((unused)) void tmem_st(uint32_t taddr, const float (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -194,9 +211,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef CP_TC_TIMING
-    const bool timed = blockIdx.x < 64 && blockIdx.y == 0 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
-    if (timed && threadIdx.x == 0) { for (int i = 8; i < 16; ++i) cp_tc_times[blockIdx.x][i] = 0; }
-    if (threadIdx.x == 0) TC_T(0);
+    const bool timed = blockIdx.x < 64 && blockIdx.y == 0 && (threadIdx.x == T_TMA || threadIdx.x == T_MMA || threadIdx.x == 0);
+    if (timed && threadIdx.x == T_TMA) { for (int i = 8; i < 16; ++i) cp_tc_times[blockIdx.x][i] = 0; }
+    if (threadIdx.x == T_TMA) TC_T(0);
 #endif
 
     // ---- work item
@@ -226,7 +243,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     constexpr int ACC_FULL = 2 * RSTAGES + 2 * STAGES;  // two: one per accumulator pair
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == T_TMA) {
         for (int s = 0; s < RSTAGES; ++s) {
             mbar_init(bar(RAW_FULL + s), 1);
             mbar_init(bar(RAW_EMPTY + s), NCONV_WARPS);
@@ -247,7 +264,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             if (!diag) tma_load_2d(sbase + OFF_RAW + (kb * 2 + 1) * RAW_TILE, mapB, bar(RAW_FULL + kb), tj * TN, row);
         }
     }
-    if (warp == 1) {  // TMEM: all 512 columns = 2 pairs of fp32 accumulators of 128 columns
+    if (warp == W_MMA) {  // TMEM: all 512 columns = 2 pairs of fp32 accumulators of 128 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -265,9 +282,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) TC_T(1);
+    if (threadIdx.x == T_TMA) TC_T(1);
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             for (int kb = RSTAGES; kb < nkb; ++kb) {
@@ -281,7 +298,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 if (!diag) tma_load_2d(sbase + OFF_RAW + (s * 2 + 1) * RAW_TILE, mapB, bar(RAW_FULL + s), tj * TN, row);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // InstrDescriptor: c_format F32 (1<<4) | a,b TF32 (2<<7, 2<<10) | K-major | N>>3 at 17 | M>>4 at 24
@@ -316,10 +333,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     } else {
         // ===================== converters + drain =====================
         // thread -> (m, kh): m = row of the operands (column of the raw boxes) = TMEM lane, which a warp can only
-        // reach inside its own quadrant (warp % 4); kh = which half of the 32-row k-block this thread converts
+        // reach inside its own quadrant (warp % 4); kh = which KPT-row slice of the 32-row k-block this thread converts
         const int quad = warp & 3;
         const int m = quad * 32 + lane;
-        const int kh = (warp - 2) >> 2;
+        const int kh = warp >> 2;
         // Shared-space (32-bit) addresses and explicit ld/st.shared: through the aligned generic pointer the
         // compiler emits generic LD/ST and, fearing aliasing, serialises load -> split -> store per 4 values.
         // All raw values of the thread are loaded first so that their latency overlaps.
@@ -327,30 +344,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         auto convert = [&](int rs, int s, bool same, int nvalid, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            float va[16], vb[16];
-            const uint32_t rawa = sbase + OFF_RAW + (rs * 2 + 0) * RAW_TILE + (uint32_t)(kh * 16 * TM + m) * 4u;
+            float va[KPT], vb[KPT];
+            const uint32_t rawa = sbase + OFF_RAW + (rs * 2 + 0) * RAW_TILE + (uint32_t)(kh * KPT * TM + m) * 4u;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) va[e] = lds_f32(rawa + (uint32_t)e * TM * 4u);
+            for (int e = 0; e < KPT; ++e) va[e] = lds_f32(rawa + (uint32_t)e * TM * 4u);
             if (!same) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) vb[e] = lds_f32(rawa + RAW_TILE + (uint32_t)e * TM * 4u);
+                for (int e = 0; e < KPT; ++e) vb[e] = lds_f32(rawa + RAW_TILE + (uint32_t)e * TM * 4u);
             }
             // A: shift, split, straight into tensor memory (columns = k)
-            float ah[16], al[16];
+            float ah[KPT], al[KPT];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float x = (FULL || kh * 16 + e < nvalid) ? __fsub_rn(va[e], shva) : 0.f;
+            for (int e = 0; e < KPT; ++e) {
+                const float x = (FULL || kh * KPT + e < nvalid) ? __fsub_rn(va[e], shva) : 0.f;
                 ah[e] = tf32_rn(x);
                 al[e] = tf32_rn(__fsub_rn(x, ah[e]));
             }
-            const uint32_t ta = lane_addr + TM_A + (uint32_t)(s * 2 * KB + kh * 16);
-            tmem_st16(ta, ah);
-            tmem_st16(ta + KB, al);
+            const uint32_t ta = lane_addr + TM_A + (uint32_t)(s * 2 * KB + kh * KPT);
+            tmem_st(ta, ah);
+            tmem_st(ta + KB, al);
             // B: K-major 128B-swizzled shared memory (the same values when the tile is on the diagonal)
             const uint32_t hi = sbase + OFF_OPS + s * 2 * OP_TILE + (uint32_t)m * 128u;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const int q = kh * 4 + q4;
+            for (int q4 = 0; q4 < KPT / 4; ++q4) {
+                const int q = kh * (KPT / 4) + q4;
                 float h[4], l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -370,17 +387,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
         // drain: this thread owns row (quad*32 + lane) x 64 columns of the tile
-        const int chalf = kh;  // two warps share a lane quadrant: each drains 64 of the 128 columns
-        float accv[64];
+        // drain: this thread owns row m x CPT columns (slice kh) of the tile
+        float accv[CPT];
 #pragma unroll
-        for (int e = 0; e < 64; ++e) accv[e] = 0.f;
+        for (int e = 0; e < CPT; ++e) accv[e] = 0.f;
         auto drain = [&](int c) {
             TC_ACC(11, mbar_wait(bar(ACC_FULL + (c & 1)), (uint32_t)((c >> 1) & 1)));  // sub-chunk c is the (c>>1)-th use
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < CPT / 32; ++g) {
                 uint32_t r[32];
-                tmem_ld32(lane_addr + TM_ACC + (uint32_t)((c & 1) * TN + chalf * 64 + g * 32), r);
+                tmem_ld32(lane_addr + TM_ACC + (uint32_t)((c & 1) * TN + kh * CPT + g * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int e = 0; e < 32; ++e) accv[g * 32 + e] = __fadd_rn(accv[g * 32 + e], __uint_as_float(r[e]));
@@ -421,20 +438,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         TC_T(5);
         drain(nchunk - 1);
         // ---- fp32 partial tile
-        const int mrow = quad * 32 + lane;  // row of the output tile
-        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)mrow * TN + chalf * 64;
+        float *dst = P.partial + ((size_t)blockIdx.y * P.ntiles + blockIdx.x) * (size_t)(TM * TN) + (size_t)m * TN + kh * CPT;
 #pragma unroll
-        for (int e = 0; e < 64; e += 4)
+        for (int e = 0; e < CPT; e += 4)
             *reinterpret_cast<float4 *>(dst + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
     }
-    if (threadIdx.x == 64) TC_T(6);
+    if (threadIdx.x == 0) TC_T(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
-    if (threadIdx.x == 32) TC_T(7);
+    if (threadIdx.x == T_MMA) TC_T(7);
 }
 
 // ------------------------------------------------------------------ small kernels around it
