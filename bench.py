@@ -203,6 +203,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# profiles/r1c_gram_tc_full.ncu-rep: gram_tc_kernel on the X'X tiles of conv4_2 (666 of the 810 tiles of the cp_gram
+# call the roofline times): dram__bytes_read.sum 92.5 MB (= X once) + dram__bytes_write.sum 49.8 MB (fp32 partials)
+NCU_TRAFFIC = {"bytes": 92545536 + 49779200,
+               "source": "profiles/r1c_gram_tc_full.ncu-rep (gram_tc_kernel, X'X tiles of conv4_2 N=5000; read 92.5 MB = X once, "
+                         "write 49.8 MB partials)"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -340,7 +347,12 @@ def run_gpu(args):
             peak, peak_note = peaks["bf16_tflops"] / 2.0, "tf32 = half of the %s bf16 cuBLAS peak" % which
         roof = {"kernel": "cp_gram (X'X upper tiles + X'Y) on %s: N=%d K=%d n=%d" % (s.name, s.N, s.K, s.n),
                 "bound": "tensor" if eng.gram_mode != cpb200.engine.GRAM_FP64 else "fp64-pipe",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                # DRAM bytes of the dominant kernel from the committed ncu --set full capture (not re-measured here):
+                # only valid for the shape and mode it was captured on
+                "traffic": NCU_TRAFFIC["bytes"] if (eng.gram_mode != cpb200.engine.GRAM_FP64 and s.name == "conv4_2"
+                                                     and s.N == 5000) else None,
+                "traffic_source": NCU_TRAFFIC["source"],
                 "ms": t_ms, "algorithmic_flops": flops, "peak_source": peak_note,
                 "mode": "fp64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "3xtf32"}
 

@@ -11,20 +11,26 @@
 //   xs = hi + lo                    hi = tf32_rn(xs), lo = tf32_rn(xs - hi)  (22 mantissa bits kept)
 //   P += hi'hi + hi'lo + lo'hi      three kind::tf32 MMAs per k-step, fp32 accumulation in TMEM
 //
-// and keeps each fp32 accumulation short: the N rows are cut into chunks, every (tile, chunk)
-// is one CTA writing an fp32 partial tile, and a second kernel sums the partials in fp64 and
-// undoes the shift exactly (G = P + s T' + T s' + N s s',  T = column sums of xs in fp64).
+// and keeps each fp32 accumulation short (the tensor core truncates when it adds into its fp32 accumulator):
+// the N rows are cut into row splits (one CTA per 128x128 output tile and split) and, inside a CTA, into
+// 128-row sub-chunks that alternate between two TMEM accumulators; finished sub-chunks are added into fp32
+// registers with round-to-nearest, every CTA writes ONE fp32 partial tile, and a second kernel sums the
+// partials of the splits in fp64 and undoes the shift exactly
+// (G = P + s T' + T s' + N s s',  T = column sums of xs in fp64).  The diagonal comes from an fp64 pass.
 //
-// CTA anatomy (192 threads, one 128x128 output tile, K-major SWIZZLE_128B operands):
-//   warp 0     TMA producer: cp.async.bulk.tensor 2D boxes of raw fp32 X (32 rows x 128 cols),
-//              two-stage ring, mbarrier complete_tx
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of 128x128x8 per
-//              32-row k-block), tcgen05.commit frees operand stages / signals the epilogue
-//   warps 2-5  converters: shift, split hi/lo, TRANSPOSE the row-major box into the K-major
-//              128B-swizzled operand layout (X is "MN-major" in memory; the transposition is
-//              free here because the data passes through registers for the split anyway),
-//              fence.proxy.async, then the epilogue: tcgen05.ld 32x32b -> fp32 partial tile.
-// Bound: tensor pipe (3 passes -> at most 1/3 of the dense TF32 rate in algorithmic flops).
+// CTA anatomy (8 converter warps + 2 single-thread roles on the highest warp ids, one CTA per SM):
+//   TMA warp     cp.async.bulk.tensor 2D boxes of raw fp32 X (32 rows x 128 cols for A and for B), 4-stage ring,
+//                mbarrier complete_tx; the first boxes are issued before the rest of the set-up
+//   MMA warp     TMEM allocator + single-thread tcgen05.mma issuer: TS mode (A from tensor memory, B from shared
+//                memory), 12 MMAs of 128x128x8 per 32-row k-block, tcgen05.commit frees the operand stage and,
+//                at the end of a sub-chunk, publishes the accumulator
+//   converters   thread = one operand row (= its TMEM lane) x 16 k-values: shift, split hi/lo, A -> tcgen05.st
+//                (columns = k), B -> K-major 128B-swizzled shared memory (X is "MN-major" in memory; the
+//                transposition is free because the data passes through registers for the split anyway);
+//                between k-blocks they drain the accumulator of the PREVIOUS sub-chunk (tcgen05.ld) into
+//                registers, so the epilogue overlaps the MMAs; finally one fp32 partial tile per CTA.
+// Bound: tensor pipe (3 passes -> at most 1/3 of the dense TF32 rate in algorithmic flops); measured state and
+// the ablation study are in profiles/r1c_summary.md.
 #include <cuda.h>
 
 #include <type_traits>
