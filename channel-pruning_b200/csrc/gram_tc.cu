@@ -624,12 +624,16 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
     // Row splits: every CTA pays a fixed prologue/epilogue (~10k cycles) and ~1.4k cycles per 32-row k-block, and the
     // grid runs in waves of num_sms CTAs (one per SM: 224 KB of shared memory each).  Pick the number of splits
     // that minimises waves x CTA time; splits are multiples of the 256-row sub-chunk.
-    int nchunks = 1, rpc = (int)(cp_cdiv(N, CHUNK_KB * KB) * CHUNK_KB * KB);
+    // A CTA adds its sub-chunks in fp32 registers (round to nearest): at most MAX_SPLIT_ROWS rows (32 sub-chunks)
+    // per split keeps that error below 4e-7 of the partial sum whatever N is.
+    constexpr int64_t SUB = CHUNK_KB * KB, MAX_SPLIT_ROWS = 32 * SUB;
+    const int ns_min = (int)cp_cdiv(N, MAX_SPLIT_ROWS);
+    int nchunks = ns_min, rpc = (int)(cp_cdiv(cp_cdiv(N, ns_min), SUB) * SUB);
     if (ntiles > 0) {
         double best = 1e300;
-        const int max_ns = (int)cp_cdiv(N, CHUNK_KB * KB);
-        for (int ns = 1; ns <= max_ns && ns <= 64; ++ns) {
-            const int64_t r = cp_cdiv(cp_cdiv(N, ns), CHUNK_KB * KB) * CHUNK_KB * KB;
+        const int max_ns = (int)cp_cdiv(N, SUB);
+        for (int ns = ns_min; ns <= max_ns && ns < ns_min + 64; ++ns) {
+            const int64_t r = cp_cdiv(cp_cdiv(N, ns), SUB) * SUB;
             const int ns_eff = (int)cp_cdiv(N, r);
             const double waves = (double)cp_cdiv((int64_t)ntiles * ns_eff, h->num_sms);
             const double cost = waves * (10000.0 + 1400.0 * (double)(r / KB));

@@ -75,10 +75,12 @@ def test_dictionary_with_tc_gram_meets_north_star_tolerance(engine):
     assert rel <= 1e-4 and np.abs(B - oB).max() <= 1e-4
 
 
-@pytest.mark.parametrize("N,K,n", [(64, 64, 4), (65, 128, 1), (257, 192, 130), (8191, 256, 64), (300, 1000, 12)])
+@pytest.mark.parametrize("N,K,n", [(64, 64, 4), (65, 128, 1), (257, 192, 130), (8191, 256, 64), (300, 1000, 12),
+                                   (20000, 256, 64)])
 def test_gram_tc_edge_shapes(engine, N, K, n):
     """Row counts that are not multiples of the 32-row k-block / 128-row sub-chunk, a single sub-chunk, many
-    row splits (tall-skinny: few tiles), one target column, K and n that leave partial tiles."""
+    row splits (tall-skinny: few tiles), one target column, K and n that leave partial tiles, N beyond one
+    split's row cap (SURVEY 8d config 5 sweeps N up to 1e5 at this kernel)."""
     r = np.random.RandomState(7 * N + K)
     X = (r.standard_normal((N, K)) * r.uniform(0.1, 3.0, K) + r.uniform(-2, 2, K)).astype(np.float32)
     ldy = (n + 3) // 4 * 4
