@@ -244,6 +244,21 @@ def run_gpu(args):
     mine = [i for i, o in enumerate(owner) if o == rank]
     my_shapes = [shapes[i] for i in mine]
     want_e2e = not args.no_e2e
+    e2e_skip = None
+    if want_e2e:
+        # the e2e leg keeps every owned feature map in pinned host memory (18 GB per VGG-16 network and rank):
+        # refuse up front, on every rank alike, rather than die inside cudaHostAlloc on a small host
+        need = max(sum(shapes[i].nbatch * shapes[i].B * shapes[i].c * shapes[i].H * shapes[i].W * 4
+                       for i in range(len(shapes)) if owner[i] == r) for r in range(world)) * world
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:  # pragma: no cover
+            avail = None
+        if avail is not None and need > 0.6 * avail:
+            want_e2e = False
+            e2e_skip = "host has %.0f GB available, the pinned feature maps of %d ranks need %.0f GB" % (
+                avail / 1e9, world, need / 1e9)
     datas = [cpb200.synth.make_problem_device(shapes[i], 1000 + i, eng, pinned_host=want_e2e) for i in mine]
     sizes = [pruner.slot_size(s.c, s.n, s.k * s.k, s.rank, .1) for s in shapes]
     per_rank = [sum(sizes[i] for i in range(len(shapes)) if owner[i] == r) for r in range(world)]
@@ -371,7 +386,7 @@ def run_gpu(args):
                        "N_patches": base[0].N, "l2": "inputs (feature maps, ~%.1f GB per network) exceed L2; no flush needed"
                        % (sum(4.0 * s.N // (s.B * s.P) * s.B * s.c * s.H * s.W for s in base) / 1e9),
                        "streams": args.streams, "kept_channels_rank0": kept},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches // max(1, args.steps)),
+            "clocks": clocks, "e2e": e2e if e2e is not None or e2e_skip is None else {"unavailable": e2e_skip}, "gpu_launches": int(launches // max(1, args.steps)),
             "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
