@@ -197,3 +197,34 @@ def test_h2d_plan_stages_small_maps_and_reads_large_ones_in_place(monkeypatch):
     assert pruner.h2d_plan(shapes, datas, "copy") == ["dma"] * len(shapes)
     monkeypatch.setenv("CPB200_DMA_MAX_MB", "1")
     assert pruner.h2d_plan(shapes, datas, True) == ["zc"] * len(shapes)
+
+
+def test_reference_arm_rebounds_later_steps(monkeypatch):
+    """bench.py --impl reference: the first pass times every (c,n,k) class, later passes re-time only the classes
+    that fit the remaining budget and keep the earlier timing of the others (whole run stays within minutes)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import cpb200
+
+    cost = {64: 1.0, 128: 4.0, 256: 10.0, 512: 40.0, 3: 0.1}
+    calls = []
+
+    def fake_seconds(shape, seed):
+        calls.append(shape.c)
+        return cost[shape.c]
+
+    monkeypatch.setattr(bench, "cpu_layer_seconds", fake_seconds)
+    shapes = cpb200.synth.vgg16_layers()
+    cache = {}
+    v1, m1, d1 = bench.cpu_pass(shapes, cache, None)
+    assert len(calls) == len(bench.shape_classes(shapes)) and "re-timed" not in d1
+    calls.clear()
+    v2, m2, d2 = bench.cpu_pass(shapes, cache, 6.0)
+    assert sorted(calls) == [3, 64, 64] and "re-timed" in d2   # 0.1 + 1 + 1 fit 6 s, the next class (4 s) does not
+    assert v2 == v1 and m2 < m1
+    calls.clear()
+    bench.cpu_pass(shapes, cache, 11.0)
+    assert sorted(calls) == [3, 64, 64, 128, 128]
