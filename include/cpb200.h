@@ -71,7 +71,10 @@ int64_t cp_workspace_bytes(cp_handle_t h);
  * Sparse-point im2col -- replaces Net.extract_XY (lib/net.py:534-684, w1=None
  * branch) plus the relu of Net.dictionary_kernel (lib/net.py:1720) when relu != 0.
  *
- *   fmap   : nbatch*B images, layout NCHW (B,c,H,W) or NHWC (B,H,W,c), fp32.
+ *   fmap   : nbatch*B images, layout NCHW (B,c,H,W) or NHWC (B,H,W,c), fp32.  Device memory, or -- NCHW --
+ *            page-locked host memory mapped under UVA (cudaHostAlloc / pinned torch tensor): the kernel then
+ *            reads the sampled windows in place over PCIe with a small persistent grid (the reference keeps
+ *            its feature maps in host RAM; only the windows have to cross).
  *   randx  : nbatch*P sampled output rows   (points_dict[(batch, Y, "randx")])
  *   randy  : nbatch*P sampled output cols
  *   window : rows [stride*x - pad, +k), cols [stride*y - pad, +k) of the bottom
