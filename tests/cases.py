@@ -24,6 +24,8 @@ DICTIONARY_CASES = {
     "under": dict(gen=dict(c=64, n=16, N=400, k=3, seed=15), rank=55, np_seed=9, alpha0=1e-3),  # N-1 < K'
     "carry": dict(gen=dict(c=48, n=24, N=800, k=3, seed=16), rank=41, np_seed=10, alpha0=0.016),  # carried alpha
     "tol2": dict(gen=dict(c=40, n=24, N=800, k=3, seed=17), rank=30, np_seed=11, alpha0=1e-3, rank_tol=.2),
+    # rank_tol >= 1 is an ABSOLUTE slack on the channel count (decompose.py:493-494): window [24, 27]
+    "tolabs": dict(gen=dict(c=36, n=20, N=700, k=3, seed=18), rank=24, np_seed=12, alpha0=1e-3, rank_tol=3),
 }
 
 
