@@ -280,6 +280,10 @@ def run_gpu(args):
             avail = psutil.virtual_memory().available
         except Exception:  # pragma: no cover
             avail = None
+        if world > 1:  # one decision for all ranks (they probe at slightly different times): the smallest view wins
+            t = torch.tensor([float(avail if avail is not None else 1e18)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            avail = None if t.item() >= 1e18 else t.item()
         if avail is not None and need > 0.6 * avail:
             want_e2e = False
             e2e_skip = "host has %.0f GB available, the pinned feature maps of %d ranks need %.0f GB" % (
