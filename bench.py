@@ -5,18 +5,23 @@
     python bench.py --gpus 1 --steps K --warmup W
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU restatement of the reference, same metric
+    python bench.py --workload sweep          # BASELINE configs[4]: N in {1k,5k,20k,100k} on the conv4_3 shape
 
 One "step" = the whole hot path (sparse-point im2col -> Gram statistics -> LASSO channel
-selection -> least-squares reconstruction) over one pool of layer problems.  At N GPUs the pool
-holds N networks (13*N independent layer problems, weak scaling), assigned to ranks by LPT, and
-every step ends with the single all_gather that re-assembles the pruned weight dict on all ranks.
+selection -> least-squares reconstruction) over one pool of layer problems.
 
-value : layers/s with the feature maps already resident in HBM (device timed, max over ranks)
-e2e   : the same metric with feature maps in pinned HOST memory (H2D inside the timed region) and
-        the results copied back to the host
+value : layers/s with the feature maps already resident in HBM (device timed, max over ranks).  WEAK scaling: at N
+        GPUs the pool holds N networks (13*N independent layer problems) assigned to ranks by LPT, and every step
+        ends with the single all_gather that re-assembles the pruned weight dict on all ranks.
+strong: (N > 1, extra object) ONE network's 13 problems split over the N GPUs -- north_star's sharding; bounded by
+        the critical path of the largest layer, reported with the per-rank device times.
+e2e   : the weak metric with feature maps in pinned HOST memory (H2D inside the timed region) and the results copied
+        back to the host.
+parity: every run checks its own output: two of the timed layer problems are re-solved by the CPU oracle on the
+        same arrays (mask, alpha-probe sequence, weights, bias).
 Inputs per step (~18 GB of feature maps per network) are far larger than the 126 MB L2, so no L2
-flush is needed between timed iterations of the step; the stand-alone kernel timing for the
-roofline flushes L2 explicitly.
+flush is needed between timed iterations of the step; the stand-alone kernel timings for the
+rooflines flush L2 explicitly.
 """
 import argparse
 import json
@@ -32,7 +37,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "conv_layers_pruned_per_sec"
 UNIT = "layers/s"
-WORKLOADS = {"vgg16": "vgg16_conv_stack_13_layers_N5000", "resnet50": "resnet50_bottlenecks_48_problems_N5000"}
+WORKLOADS = {"vgg16": "vgg16_conv_stack_13_layers_N5000", "resnet50": "resnet50_bottlenecks_48_problems_N5000",
+             "sweep": "conv4_3_patch_count_sweep_N1k_5k_20k_100k"}
+PARITY_LAYERS = {"vgg16": ("conv2_2", "conv3_2"), "resnet50": ("res3b_branch2b", "res4b_branch2a")}
 
 
 def workload_shapes(args):
@@ -53,10 +60,21 @@ def parse():
                     help="arithmetic of the big Gram products: tc = tcgen05 3xTF32 (default), fp64 = DFMA")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg")
     ap.add_argument("--layers", default="", help="comma list of layer names (debug); default: all of the workload")
-    ap.add_argument("--workload", default="vgg16", choices=["vgg16", "resnet50"],
-                    help="vgg16 = BASELINE configs[1] (13 conv layers); resnet50 = configs[3] (48 bottleneck problems)")
+    ap.add_argument("--workload", default="vgg16", choices=["vgg16", "resnet50", "sweep"],
+                    help="vgg16 = BASELINE configs[1] (13 conv layers); resnet50 = configs[3] (48 bottleneck problems); "
+                         "sweep = configs[4] (Gram roofline and LASSO data-form kernel against N)")
     return ap.parse_args()
+
+
+def config_dict(args, base, world):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOADS[args.workload], "layers_per_network": len(base), "networks": world,
+            "N_patches": base[0].N,
+            "l2": "inputs (feature maps, ~%.1f GB per network) exceed L2; no flush needed"
+                  % (sum(4.0 * s.N // (s.B * s.P) * s.B * s.c * s.H * s.W for s in base) / 1e9)}
 
 
 # ------------------------------------------------------------------------------ CPU arm (oracle)
@@ -68,61 +86,63 @@ def shape_classes(shapes):
     return classes
 
 
-def cpu_layer_seconds(shape, seed):
-    """Times the oracle (restated reference: numpy patch gather + sklearn-faithful LASSO search +
-    gelsd least squares, float64) on one layer problem.  Returns seconds."""
+def oracle_on_arrays(shape, fmap, randx, randy, W2, b2, feats, samples, seeds, form="dense"):
+    """Runs the oracle (restated reference: numpy patch gather + sklearn-faithful LASSO search + gelsd least squares,
+    float64) on one layer problem given as host arrays.  Returns (idxs, W, B, info) with info['t_*'] phase seconds."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
 
     import cp_oracle as O
+
+    pd = {"nPointsPerLayer": shape.P, "nBatches": shape.nbatch}
+    for b in range(shape.nbatch):
+        pd[(b, "y", "randx")] = randx[b]
+        pd[(b, "y", "randy")] = randy[b]
+    forward = lambda b: {"x": fmap[b * shape.B:(b + 1) * shape.B]}  # noqa: E731
+    spec = O.ConvSpec("y", "x", shape.k, shape.pad, shape.stride)
+    info = {}
+    st = O.DictState(alpha=1e-3)
+    rng = O.SeedFeeder(seeds) if seeds is not None else None
+    idxs, W, B = O.dictionary_kernel(forward, "x", spec, W2, b2, np.asarray(feats, dtype=np.float64), pd, shape.rank,
+                                     state=st, samples=samples, form=form, info=info, rng=rng)
+    return idxs, W, B, info
+
+
+def cpu_layer_seconds(shape, seed):
+    """Times the oracle on one synthetic layer problem.  Returns (seconds, phase dict)."""
     import cpb200
 
     d = cpb200.synth.make_problem_numpy(shape, seed)
-    pd = {"nPointsPerLayer": shape.P, "nBatches": shape.nbatch}
-    for b in range(shape.nbatch):
-        pd[(b, "y", "randx")] = d["randx"][b]
-        pd[(b, "y", "randy")] = d["randy"][b]
-    fm = d["fmap"]
-    forward = lambda b: {"x": fm[b * shape.B:(b + 1) * shape.B]}  # noqa: E731
-    spec = O.ConvSpec("y", "x", shape.k, shape.pad, shape.stride)
-    feats = d["feats"].astype(np.float64)
-    st = O.DictState(alpha=1e-3)
     t0 = time.perf_counter()
-    O.dictionary_kernel(forward, "x", spec, d["W2"], d["b2"], feats, pd, shape.rank, state=st, samples=d["samples"])
-    return time.perf_counter() - t0
+    _, _, _, info = oracle_on_arrays(shape, d["fmap"], d["randx"], d["randy"], d["W2"], d["b2"], d["feats"], d["samples"],
+                                     None)
+    return time.perf_counter() - t0, {k: info.get(k, 0.0) for k in ("t_gather", "t_lasso", "t_ls")}
 
 
-def cpu_pass(shapes, cache=None, budget_s=None):
-    """One CPU 'step' = one problem per shape class, extrapolated to the 13-layer stack by class
-    multiplicity.  With ``cache`` (class -> seconds from an earlier step of this run) and ``budget_s`` the step
-    re-times a bounded sample -- the cheapest classes that fit the budget -- and reuses this run's earlier
-    measurement for the others, so that K steps stay within minutes (a full pass is ~70 s of 64-thread CPU).
-    Returns (layers_per_sec, seconds_measured, description)."""
+def class_rep(members):
+    """The class member with the smallest map (identical solver work, less host memory for the maps), capped at
+    28x28: a 224x224x64-channel map set is 6.4 GB of host RAM and ~20 s of random-number generation per layer."""
     import cpb200
 
+    rep = min(members, key=lambda s: s.H)
+    return cpb200.synth.LayerShape(rep.name, rep.c, rep.n, min(rep.H, 28), k=rep.k, pad=rep.pad, stride=rep.stride,
+                                   N=rep.N, B=rep.B, P=rep.P, rank=rep.rank)
+
+
+def stack_rate(shapes, cache):
     classes = shape_classes(shapes)
-    cache = {} if cache is None else cache
-    order = sorted(classes.items(), key=lambda kv: cache.get(kv[0], 0.0))
-    measured, retimed, left = 0.0, 0, budget_s
-    for i, (key, members) in enumerate(order):
-        if key in cache and left is not None and cache[key] > left:
-            continue  # keep this run's earlier timing of the class
-        # use the smallest map of the class: identical solver work, less host memory for the maps
-        rep = min(members, key=lambda s: s.H)
-        small = cpb200.synth.LayerShape(rep.name, rep.c, rep.n, min(rep.H, 28), k=rep.k, pad=rep.pad, stride=rep.stride,
-                                        N=rep.N, B=rep.B, P=rep.P)
-        t = cpu_layer_seconds(small, 900 + sorted(classes).index(key))
-        cache[key] = t
-        measured += t
-        retimed += 1
-        if left is not None:
-            left -= t
-    total = sum(cache[key] * len(members) for key, members in classes.items())
-    desc = "one layer problem per distinct (c,n,k) class (%d classes, feature maps capped at 28x28), " \
-           "times class multiplicity = full %d-layer stack" % (len(classes), len(shapes))
-    if retimed < len(classes):
-        desc += "; this step re-timed the %d cheapest classes, the others keep this run's first-pass timing" % retimed
-    return len(shapes) / total, measured, desc
+    total = sum(cache[key]["s"] * len(members) for key, members in classes.items())
+    return len(shapes) / total
+
+
+def cpu_full_pass(shapes, cache):
+    """One problem per shape class (cost-ascending), stored in cache[class] = {s, phases, n}."""
+    classes = shape_classes(shapes)
+    t0 = time.perf_counter()
+    for key in sorted(classes, key=lambda k: k[0] * k[0] * k[1]):
+        t, ph = cpu_layer_seconds(class_rep(classes[key]), 900 + sorted(classes).index(key))
+        cache[key] = {"s": t, "phases": ph, "n": 1}
+    return time.perf_counter() - t0
 
 
 def host_threads():
@@ -135,41 +155,78 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-REF_BUDGET_S = 170.0
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
+REF_BUDGET_S = 165.0
+SAMPLE_DESC = ("one layer problem per distinct (c,n,k) class of the stack (feature maps capped at 28x28: solver work "
+               "is independent of the map size and a full-size conv1_2 map set alone is 6.4 GB of host RAM), "
+               "value = layers / sum(class multiplicity x class seconds)")
 
 
 def run_reference(args):
+    """CPU arm.  A step is a BOUNDED sample: one class problem of the stack (classes visited round-robin in
+    cost-ascending order; a class whose last timing no longer fits the run budget is skipped in favour of the most
+    expensive one that does).  ms_per_step is the measured mean wall time of the timed steps -- what was run --;
+    value extrapolates the classes' mean seconds to the 13-layer stack by multiplicity (stated in `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import cpb200
-
+    ncores = use_all_host_threads()
     shapes = workload_shapes(args)
-    # whole run bounded to ~REF_BUDGET_S: the first pass times every class, later passes re-time what fits
+    classes = shape_classes(shapes)
+    order = sorted(classes, key=lambda k: k[0] * k[0] * k[1])
     cache, t_run = {}, time.perf_counter()
     nsteps = max(1, args.steps)
     todo = args.warmup + nsteps
-    vals, secs, desc = [], [], ""
+    step_secs, timed_layers = [], 0
     for it in range(todo):
-        spent = time.perf_counter() - t_run
-        budget = None if it == 0 else max(0.0, (REF_BUDGET_S - spent) / (todo - it))
+        left = REF_BUDGET_S - (time.perf_counter() - t_run)
+        key = order[it % len(order)]
+        if key in cache and cache[key]["s"] > left / max(1, todo - it):
+            fits = [k for k in order if k not in cache or cache[k]["s"] <= left / max(1, todo - it)]
+            key = fits[-1] if fits else order[0]
         t0 = time.perf_counter()
-        v, m, d = cpu_pass(shapes, cache, budget)
-        if it == 0:
-            desc = d
+        t, ph = cpu_layer_seconds(class_rep(classes[key]), 900 + sorted(classes).index(key) + 17 * it)
+        c = cache.setdefault(key, {"s": 0.0, "phases": {k: 0.0 for k in ph}, "n": 0})
+        c["s"] = (c["s"] * c["n"] + t) / (c["n"] + 1)
+        for k in ph:
+            c["phases"][k] = (c["phases"][k] * c["n"] + ph[k]) / (c["n"] + 1)
+        c["n"] += 1
         if it >= args.warmup:
-            secs.append(time.perf_counter() - t0)
-            vals.append(v)
-    if todo > 1:
-        desc += "; steps after the first re-time the cheapest classes within a %.0f s run budget" % REF_BUDGET_S
-    v = statistics.mean(vals)
+            step_secs.append(time.perf_counter() - t0)
+            timed_layers += 1
+    missing = [k for k in order if k not in cache]
+    for key in missing:  # fewer steps than classes: the estimate still needs every class once
+        t, ph = cpu_layer_seconds(class_rep(classes[key]), 900 + sorted(classes).index(key))
+        cache[key] = {"s": t, "phases": ph, "n": 1}
+    v = stack_rate(shapes, cache)
+    phases = {k: sum(cache[key]["phases"][k] * len(m) for key, m in classes.items()) for k in ("t_gather", "t_lasso", "t_ls")}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * len(shapes) / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "note": "CPU restatement of lib/net.py + lib/decompose.py (oracle port); "
-                   "the Python reference itself cannot travel to the GPU box"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc},
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(step_secs), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, shapes, max(1, args.gpus)),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "blas_threads": host_threads(), "kind": "port",
+                         "sample": SAMPLE_DESC + "; a step = ONE class problem (round-robin, cost-ascending; classes that "
+                         "no longer fit the %.0f s run budget keep their earlier timing); %d problems in %d timed steps%s"
+                         % (REF_BUDGET_S, timed_layers, nsteps,
+                            "; %d classes timed once outside the steps" % len(missing) if missing else ""),
+                         "stack_seconds": {"gather": phases["t_gather"], "lasso": phases["t_lasso"], "ls": phases["t_ls"]},
+                         "class_seconds": {"%dx%dk%d" % k: round(cache[k]["s"], 3) for k in order},
+                         "note": "CPU restatement of lib/net.py + lib/decompose.py (oracle port: numpy + C coordinate "
+                                 "descent following sklearn _cd_fast.pyx, LAPACK gelsd); the Python reference itself "
+                                 "cannot travel to the GPU box",
+                         "env": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,11 +285,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# profiles/r1c_gram_tc_full.ncu-rep: gram_tc_kernel on the X'X tiles of conv4_2 (666 of the 810 tiles of the cp_gram
-# call the roofline times): dram__bytes_read.sum 92.5 MB (= X once) + dram__bytes_write.sum 49.8 MB (fp32 partials)
-NCU_TRAFFIC = {"bytes": 92545536 + 49779200,
-               "source": "profiles/r1c_gram_tc_full.ncu-rep (gram_tc_kernel, X'X tiles of conv4_2 N=5000; read 92.5 MB = X once, "
-                         "write 49.8 MB partials)"}
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed ncu --set full captures (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
 
 
 def measured_peaks():
@@ -241,6 +299,79 @@ def measured_peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def library_peaks(torch, dev):
+    """cuBLAS TF32 and FP64 GEMM throughput on THIS box (denominators only; MEASURED_PEAKS.json holds bf16 and HBM).
+    Burst figures: best of 5 after warm-up, CUDA events."""
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, n, dt, tf32 in (("tf32_tflops", 8192, torch.float32, True), ("fp64_tflops", 4096, torch.float64, False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=dev, dtype=dt)
+            b = torch.randn(n, n, device=dev, dtype=dt)
+            best = 1e9
+            for it in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    best = min(best, e0.elapsed_time(e1))
+            out[name] = 2.0 * n ** 3 / (best / 1e3) / 1e12
+            del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
+def timed_alone(torch, dev, fn, reps=6, skip=2):
+    """Mean CUDA-event time (ms) of fn() run alone with an L2 flush before every repetition."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for it in range(reps):
+        flush.fill_(it)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if it >= skip:
+            times.append(a.elapsed_time(b))
+    return statistics.mean(times)
+
+
+def parity_check(shapes, datas, results, names):
+    """Re-solves the named layer problems with the CPU oracle on the SAME arrays the GPU just used and compares."""
+    import numpy as np
+
+    out = {"layers_checked": [], "mask_equal": True, "probes_equal": True, "rel_W_max": 0.0, "rel_b_max": 0.0,
+           "oracle": "cp_oracle.dictionary_kernel (sklearn data-form coordinate descent restated in C, LAPACK gelsd)",
+           "tolerance": {"rel_W": 1e-4, "rel_b": 1e-4}}
+    for s, d, r in zip(shapes, datas, results):
+        if s.name not in names or s.name in out["layers_checked"]:
+            continue
+        t0 = time.perf_counter()
+        oi, oW, oB, info = oracle_on_arrays(s, d["fmap"].cpu().numpy(), d["randx"].cpu().numpy(), d["randy"].cpu().numpy(),
+                                            d["W2"].cpu().numpy(), d["b2"].cpu().numpy(), d["feats"].cpu().numpy(),
+                                            d["samples"].cpu().numpy(), d["seeds"])
+        W = (r.W if not r.W.is_cuda else r.W.cpu()).numpy().reshape(-1)
+        b = (r.b if not r.b.is_cuda else r.b.cpu()).numpy()
+        same = bool(np.array_equal(r.idxs, oi))
+        out["mask_equal"] &= same
+        if r.probes is not None:
+            plog = r.probes.probe_log[:r.nprobe].cpu().numpy()
+            out["probes_equal"] &= [(float(a), int(z)) for a, z, _, _ in plog] == info["probes"]
+        if same:
+            out["rel_W_max"] = max(out["rel_W_max"], float(np.linalg.norm(W - oW.reshape(-1)) / np.linalg.norm(oW)))
+            out["rel_b_max"] = max(out["rel_b_max"], float(np.abs(b - oB).max() / max(1.0, np.abs(oB).max())))
+        out["layers_checked"].append(s.name)
+        out.setdefault("oracle_seconds", {})[s.name] = round(time.perf_counter() - t0, 2)
+    out["pass"] = bool(out["layers_checked"] and out["mask_equal"] and out["probes_equal"] and
+                       out["rel_W_max"] <= 1e-4 and out["rel_b_max"] <= 1e-4)
+    return out
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -294,40 +425,44 @@ def run_gpu(args):
     gbuf = torch.zeros(max(per_rank), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
-    def step(from_host):
-        res = pruner.prune_layers(eng, my_shapes, datas, right0=1e-3, rank_tol=.1, from_host=from_host,
-                                  to_host=from_host)
+    def step(from_host, shp=my_shapes, dat=datas, idx=mine, all_shapes=shapes, all_sizes=sizes):
+        res = pruner.prune_layers(eng, shp, dat, right0=1e-3, rank_tol=.1, from_host=from_host, to_host=from_host)
         if world > 1:
             off = 0
-            for j, i in enumerate(mine):
-                s = shapes[i]
-                pruner.pack_result(gbuf, off, res[j].idxs, res[j].W.to(dev, non_blocking=True) if from_host else res[j].W,
-                                   res[j].b.to(dev, non_blocking=True) if from_host else res[j].b, res[j].alpha,
-                                   res[j].nprobe, s.c, s.n, s.k * s.k)
-                off += sizes[i]
+            for j, i in enumerate(idx):
+                s = all_shapes[i]
+                pruner.pack_result(gbuf, off, res[j].idxs, res[j].W, res[j].b, res[j].alpha, res[j].nprobe, s.c, s.n,
+                                   s.k * s.k, eng=eng, slot=j)
+                off += all_sizes[i]
             pruner.allgather_results(gbuf, world)
         return res
 
-    def timed(nsteps, from_host):
+    def timed(nsteps, fn):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.cp_launch_count()
+        t_host = time.perf_counter()
         e0.record()
         res = None
         for _ in range(nsteps):
-            res = step(from_host)
+            res = fn()
         e1.record()
+        host_issue = time.perf_counter() - t_host  # host time spent ISSUING the steps (incl. the mask read-backs)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms_local = e0.elapsed_time(e1)
+        ms = ms_local
         launches = lib.cp_launch_count() - l0
+        per_rank_ms = [ms_local]
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+            allt = torch.empty(world, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(allt, t)
+            per_rank_ms = [float(x) for x in allt.cpu()]
+            ms = max(per_rank_ms)
             dist.barrier()
-        return ms, launches, res
+        return ms, launches, res, host_issue, per_rank_ms
 
     for _ in range(args.warmup):
         step(False)
@@ -335,16 +470,24 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches, res = timed(args.steps, False)
+    ms, launches, res, host_issue, _ = timed(args.steps, lambda: step(False))
     clocks = sampler.stop() if rank == 0 else None
     total_layers = len(shapes) * args.steps
     value = total_layers / (ms / 1e3)
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(my_shapes, datas, res, PARITY_LAYERS.get(args.workload, ()))
+    ls_paths = {}
+    for s, r in zip(my_shapes, res):
+        ls_paths[r.info.get("verdict", "?")] = ls_paths.get(r.info.get("verdict", "?"), 0) + 1
+    min_ratio = min([r.info.get("pivot_ratio", 1.0) for r in res] + [1.0])
 
     e2e = None
     if want_e2e:
         for _ in range(min(args.warmup, 3)):
             step(True)
-        ms_e, _, res_e = timed(args.steps, True)
+        ms_e, _, res_e, _, _ = timed(args.steps, lambda: step(True))
         # the feature maps stay in pinned host memory; per layer either the gather kernel pulls the sampled
         # k x k x c windows over PCIe in place (bytes that must cross: 4*N*K) or, where the windows cover most of
         # the map (conv5_x), the copy engine moves the whole map (bytes: the map) -- pruner.h2d_plan decides
@@ -363,60 +506,92 @@ def run_gpu(args):
                "input_path": "feature maps in pinned host memory; per layer (h2d_plan, z/D) read in place by "
                              "cp_patch_gather (zero-copy over PCIe, bytes = gathered windows) or DMA'd whole (bytes = map)"}
 
-    # ---- roofline of the dominant kernel: Gram statistics of the widest layer, timed alone
-    roof = None
+    # ---- strong scaling (north_star's split): ONE network's problems over the N GPUs
+    strong = None
+    if world > 1 and not args.no_strong:
+        s_owner = pruner.assign_layers([s.cost() for s in base], world)
+        s_mine = [i for i, o in enumerate(s_owner) if o == rank]
+        s_shapes = [base[i] for i in s_mine]
+        have = {i: d for i, d in zip(mine, datas)}
+        s_datas = [have[i] if i in have else cpb200.synth.make_problem_device(base[i], 1000 + i, eng) for i in s_mine]
+        s_sizes = [pruner.slot_size(s.c, s.n, s.k * s.k, s.rank, .1) for s in base]
+
+        def sstep():
+            return step(False, s_shapes, s_datas, s_mine, base, s_sizes)
+
+        for _ in range(max(2, args.warmup // 2)):
+            sstep()
+        ms_s, _, _, _, per_rank_ms = timed(args.steps, sstep)
+        strong = {"value": len(base) * args.steps / (ms_s / 1e3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
+                  "networks": 1, "scaling": "strong",
+                  "per_rank_ms_per_step": [round(x / args.steps, 3) for x in per_rank_ms],
+                  "layers_per_rank": [sum(1 for o in s_owner if o == r) for r in range(world)],
+                  "note": "one network split by LPT; the step cannot be shorter than the critical path of its largest "
+                          "layer (gather + Gram -> LASSO search -> least squares)"}
+
+    # ---- rooflines of the two kernels north_star names, each timed alone after an L2 flush
+    roof = roof_g = None
+    peaks_lib = None
     if rank == 0:
         peaks, which = measured_peaks()
+        peaks_lib = library_peaks(torch, dev)
+        traffic = ncu_traffic()
         s = max(base, key=lambda q: q.K)
-        d = datas[[shapes[i].name for i in mine].index(s.name)] if s.name in [shapes[i].name for i in mine] else \
-            cpb200.synth.make_problem_device(s, 5, eng)
+        names = [shapes[i].name for i in mine]
+        d = datas[names.index(s.name)] if s.name in names else cpb200.synth.make_problem_device(s, 5, eng)
         X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        times = []
-        for it in range(6):
-            flush.fill_(it)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False)
-            b.record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                times.append(a.elapsed_time(b))
-        t_ms = statistics.mean(times)
+        t_ms = timed_alone(torch, dev, lambda: eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False))
         flops = float(s.N) * s.K * (s.K + 1) + 2.0 * s.N * s.K * s.n  # symmetric half + X'Y
         achieved = flops / (t_ms / 1e3) / 1e12
         if eng.gram_mode == cpb200.engine.GRAM_FP64:
-            peak, peak_note = 40.0, "nominal B200 FP64 (no measured FP64 figure in MEASURED_PEAKS.json)"
+            peak, peak_note = peaks_lib["fp64_tflops"], "cuBLAS FP64 GEMM 4096^3 measured in this run"
         else:
-            peak, peak_note = peaks["bf16_tflops"] / 2.0, "tf32 = half of the %s bf16 cuBLAS peak" % which
+            peak, peak_note = peaks_lib["tf32_tflops"], "cuBLAS TF32 GEMM 8192^3 measured in this run (bf16 burst in " \
+                "MEASURED_PEAKS.json: %.0f, %s); 3xTF32 issues 3 MMAs per product: ceiling 1/3" % (peaks["bf16_tflops"], which)
+        tr = traffic.get("gram_tc_kernel") if eng.gram_mode != cpb200.engine.GRAM_FP64 else None
         roof = {"kernel": "cp_gram (X'X upper tiles + X'Y) on %s: N=%d K=%d n=%d" % (s.name, s.N, s.K, s.n),
                 "bound": "tensor" if eng.gram_mode != cpb200.engine.GRAM_FP64 else "fp64-pipe",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # DRAM bytes of the dominant kernel from the committed ncu --set full capture (not re-measured here):
-                # only valid for the shape and mode it was captured on
-                "traffic": NCU_TRAFFIC["bytes"] if (eng.gram_mode != cpb200.engine.GRAM_FP64 and s.name == "conv4_2"
-                                                     and s.N == 5000) else None,
-                "traffic_source": NCU_TRAFFIC["source"],
+                "traffic": tr["bytes"] if tr and s.name == "conv4_2" and s.N == 5000 else None,
+                "traffic_source": tr["source"] if tr else None,
                 "ms": t_ms, "algorithmic_flops": flops, "peak_source": peak_note,
                 "mode": "fp64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "3xtf32"}
+        t_g = timed_alone(torch, dev, lambda: eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad,
+                                                               s.stride, relu=True, out=X))
+        gbytes = 8.0 * s.N * s.K  # unique patch elements read + X written
+        trg = traffic.get("patch_gather")
+        roof_g = {"kernel": "cp_patch_gather (sparse-point im2col, NCHW) on %s: N=%d K=%d" % (s.name, s.N, s.K),
+                  "bound": "hbm", "achieved": gbytes / (t_g / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": gbytes / (t_g / 1e3) / 1e9 / peaks["hbm_gbs"],
+                  "traffic": trg["bytes"] if trg else None, "traffic_source": trg["source"] if trg else None,
+                  "ms": t_g, "algorithmic_bytes": gbytes, "peak_source": "%s copy bandwidth (MEASURED_PEAKS.json)" % which}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, m, desc = cpu_pass(base)
-        cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc, "seconds": m}
+        ncores = use_all_host_threads()
+        cache = {}
+        secs = cpu_full_pass(base, cache)
+        classes = shape_classes(base)
+        cpu = {"value": stack_rate(base, cache), "unit": UNIT, "cores": ncores, "blas_threads": host_threads(),
+               "kind": "port", "sample": SAMPLE_DESC, "seconds": secs,
+               "stack_seconds": {k[2:]: sum(cache[key]["phases"][k] * len(m) for key, m in classes.items())
+                                 for k in ("t_gather", "t_lasso", "t_ls")}}
 
     if rank == 0:
         kept = [int(r.idxs.sum()) for r in res]
+        cfg = config_dict(args, base, world)
+        cfg.update(streams=args.streams, kept_channels_rank0=kept)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "tf32x3+f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "layers_per_network": len(base), "networks": world,
-                       "N_patches": base[0].N, "l2": "inputs (feature maps, ~%.1f GB per network) exceed L2; no flush needed"
-                       % (sum(4.0 * s.N // (s.B * s.P) * s.B * s.c * s.H * s.W for s in base) / 1e9),
-                       "streams": args.streams, "kept_channels_rank0": kept},
-            "clocks": clocks, "e2e": e2e if e2e is not None or e2e_skip is None else {"unavailable": e2e_skip}, "gpu_launches": int(launches // max(1, args.steps)),
-            "roofline": roof, "cpu_baseline": cpu,
+            "config": cfg, "clocks": clocks,
+            "e2e": e2e if e2e is not None or e2e_skip is None else {"unavailable": e2e_skip},
+            "gpu_launches": int(launches // max(1, args.steps)),
+            "host_issue_ms_per_step": 1e3 * host_issue / max(1, args.steps),
+            "roofline": roof, "roofline_im2col": roof_g, "library_peaks": peaks_lib, "parity": parity,
+            "ls_policy": {"paths": ls_paths, "min_pivot_ratio": min_ratio, "ratio_min_for_tc": cpb200.engine.LS_RATIO_MIN},
+            "strong": strong, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -426,7 +601,11 @@ def run_gpu(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "sweep":
+        from profiles import sweep_config5
+
+        sweep_config5.main(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

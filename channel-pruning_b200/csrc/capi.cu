@@ -2,11 +2,11 @@
 #include "common.cuh"
 
 thread_local char cp_err_buf[512] = "";
-unsigned long long cp_launch_counter = 0;
+std::atomic<unsigned long long> cp_launch_counter{0};
 
-extern "C" int64_t cp_launch_count(void) { return (int64_t)cp_launch_counter; }
+extern "C" int64_t cp_launch_count(void) { return (int64_t)cp_launch_counter.load(std::memory_order_relaxed); }
 
-extern "C" int cp_version(void) { return 100; }  // 0.1.0
+extern "C" int cp_version(void) { return 200; }  // 0.2.0
 
 extern "C" const char *cp_last_error(void) { return cp_err_buf; }
 
@@ -29,17 +29,23 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->side = nullptr;
     h->ev_panel = nullptr;
     h->ev_side = nullptr;
+    h->potrf_configured = false;
+    h->fac = nullptr;
+    h->fac_bytes = 0;
+    h->fac_K = h->fac_Kfull = 0;
+    h->fac_N = 0;
     *out = h;
     return CP_OK;
 }
 
 extern "C" int cp_destroy(cp_handle_t h) {
     if (!h) return CP_OK;
-    if (h->ws || h->side) {
+    if (h->ws || h->side || h->fac) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(h->device);
         if (h->ws) cudaFree(h->ws);
+        if (h->fac) cudaFree(h->fac);
         if (h->side) {
             cudaStreamDestroy(h->side);
             cudaEventDestroy(h->ev_panel);

@@ -16,6 +16,43 @@ struct cp_handle_s {
     // look-ahead of the blocked Cholesky (ls.cu): low-priority side stream + fork/join events, created lazily
     cudaStream_t side;
     cudaEvent_t ev_panel, ev_side;
+    bool potrf_configured;  // opt-in shared memory of potrf128 set on this handle's device
+    // factor kept between cp_ls_factor and cp_ls_resolve (own allocation: the scratch above is reused by every call)
+    void *fac;
+    size_t fac_bytes;
+    int fac_K, fac_Kfull;
+    int64_t fac_N;
+};
+
+// Entry points run on the handle's device whatever the caller's current device is (restored on return).
+struct cp_device_guard {
+    int prev;
+    bool ok;
+    explicit cp_device_guard(int dev) : prev(-1), ok(true) {
+        int cur = -1;
+        ok = cudaGetDevice(&cur) == cudaSuccess;
+        if (ok && cur != dev) {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            if (ok) prev = cur;
+        }
+    }
+    ~cp_device_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define CP_DEVICE_GUARD(h)                                                             \
+    cp_device_guard guard__((h)->device);                                              \
+    if (!guard__.ok) CP_FAIL(CP_ERR_CUDA, "cannot switch to device %d of the handle", (h)->device)
+
+// cudaFuncSetAttribute is per DEVICE: one flag per device ordinal for every kernel that opts into large shared memory
+constexpr int CP_MAX_DEVICES = 64;
+struct cp_per_device_flag {
+    bool done[CP_MAX_DEVICES] = {};
+    bool *slot() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        return &done[cur >= 0 && cur < CP_MAX_DEVICES ? cur : 0];
+    }
 };
 
 extern thread_local char cp_err_buf[512];
@@ -34,16 +71,17 @@ extern thread_local char cp_err_buf[512];
     } while (0)
 
 // every kernel launch of the library goes through one of these two, so the counter is exact
-extern unsigned long long cp_launch_counter;
-#define CP_CHECK_LAUNCH()              \
-    do {                               \
-        ++cp_launch_counter;           \
-        CP_CUDA(cudaGetLastError());   \
+#include <atomic>
+extern std::atomic<unsigned long long> cp_launch_counter;
+#define CP_CHECK_LAUNCH()                                             \
+    do {                                                              \
+        cp_launch_counter.fetch_add(1, std::memory_order_relaxed);    \
+        CP_CUDA(cudaGetLastError());                                  \
     } while (0)
-#define CP_GEMM_LAUNCH(call)           \
-    do {                               \
-        ++cp_launch_counter;           \
-        CP_CUDA((call));               \
+#define CP_GEMM_LAUNCH(call)                                          \
+    do {                                                              \
+        cp_launch_counter.fetch_add(1, std::memory_order_relaxed);    \
+        CP_CUDA((call));                                              \
     } while (0)
 
 #define CP_REQUIRE(cond, ...)                         \

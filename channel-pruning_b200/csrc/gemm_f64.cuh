@@ -236,11 +236,14 @@ inline int num_tiles(int M, int Nn, int mode) {
 template <typename TA, typename TB, bool A_MC, bool B_NC>
 inline cudaError_t launch(const Args &g, cudaStream_t stream) {
     auto kern = gemm_kernel<TA, TB, A_MC, B_NC>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static bool configured[64] = {};  // per instantiation and per device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &done = configured[dev >= 0 && dev < 64 ? dev : 0];
+    if (!done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        done = true;
     }
     dim3 grid((unsigned)num_tiles(g.M, g.Nn, g.tile_mode), (unsigned)(g.nsplit > 1 ? g.nsplit : 1));
     if (grid.x == 0) return cudaSuccess;

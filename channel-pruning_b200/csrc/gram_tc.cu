@@ -692,10 +692,10 @@ int cp_gram_tc(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, con
         TcParams P{};
         P.shiftA = shX; P.shiftB = shY; P.partial = partial; P.K = K; P.nB = n; P.N = N; P.rows_per_chunk = rpc;
         P.tiles_sym = tiles_sym; P.tk = tk; P.tnb = tnb; P.ntiles = ntiles;
-        static bool configured = false;
-        if (!configured) {
+        static cp_per_device_flag configured;
+        if (bool *done = configured.slot(); !*done) {
             CP_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            configured = true;
+            *done = true;
         }
         // one launch: X'X upper tiles first, then the X'Y tiles (B operand from the Y map)
         gram_tc_kernel<<<dim3(ntiles, nchunks), NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, P);

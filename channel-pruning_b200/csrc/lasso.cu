@@ -103,7 +103,11 @@ struct SelectParams {
 };
 
 constexpr int MAXC = 2048;   // largest channel count (shared-memory bound)
-constexpr int LAG = 3;       // deltas the chain warp applies itself (slack of the update warps)
+#ifndef CP_LASSO_LAG
+#define CP_LASSO_LAG 5
+#endif
+constexpr int LAG = CP_LASSO_LAG;  // deltas the chain warp applies itself (slack of the update warps), 1..5
+static_assert(LAG >= 1 && LAG <= 5, "the packaged record holds at most 5 lag entries");
 constexpr int NBULK = 4;     // pair-update warps
 constexpr int PK_WARP = 1 + NBULK, SEQ_WARP = 2 + NBULK;
 constexpr int WS_THREADS = 32 * (3 + NBULK);
@@ -165,6 +169,11 @@ __device__ __forceinline__ double get_tagged(uint32_t slot_saddr, uint32_t tag) 
     return v;
 }
 
+// the same record read WITHOUT waiting for the tag: the caller checks it later (after the latency has been hidden)
+__device__ __forceinline__ void peek_tagged(uint32_t slot_saddr, double &v, double &t) {
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(slot_saddr) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum_butterfly(double v) {  // model: p[l] + p[l ^ off], off = 16..1
 #pragma unroll
     for (int off = 16; off; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
     double *qv = Qw + CP;
     double *dg = qv + CP;
     double *ring = dg + CP;                 // [RING][CP]
-    double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1, r2, r3
+    double *pk = ring + (size_t)RING * CP;  // [QR][8]: q, Qjj, 1/Qjj, r1 .. r5
     double *dq = pk + QR * 8;               // [QR][2] published {delta, tag}
     double *xq = dq + QR * 2;               // [QR][2] published {Qw entry, tag}
     uint32_t *active = reinterpret_cast<uint32_t *>(xq + QR * 2);
@@ -351,44 +360,82 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         const uint32_t tag0 = sweep_no << 12;
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         if (warp == 0) {
-            // -------- chain warp: the serial recurrence and nothing else
-            double d1 = 0.0, d2 = 0.0, d3 = 0.0, w_max = 0.0, d_w_max = 0.0;
-            for (int s = 0; s < n_active; ++s) {
-                const uint32_t j = jz[s];
+            // -------- chain warp: the serial recurrence and nothing else.  Software pipelined: the operands of step
+            // s+1 (coordinate, packaged scalars, w[j], the published Qw entry) are fetched BEFORE the dependent
+            // arithmetic of step s, so that per step only  delta -> x -> soft threshold -> division -> delta  remains
+            // on the chain (8 dependent fp64 operations), not the shared-memory round trips.
+            double dl[LAG];  // dl[i-1] = delta of step s-i
+#pragma unroll
+            for (int i = 0; i < LAG; ++i) dl[i] = 0.0;
+            double w_max = 0.0, d_w_max = 0.0;
+            auto fetch = [&](int s, uint32_t &j_, double (&p)[8], double &wj_, double &xv_, double &xt_) {
                 if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
                 if ((s & 15) == 0) {
-                    if (lane == 0) *reinterpret_cast<volatile int *>(&ctl.chain_pos) = s;  // steps < s are done
+                    // operands of steps < s are in registers: their slots may be reused
+                    if (lane == 0) *reinterpret_cast<volatile int *>(&ctl.chain_pos) = s;
                     if (s >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
 #pragma unroll
                         for (int b = 0; b < NBULK; ++b) wait_ge_relaxed(&ctl.bulk_pos[b], s - 24);
                     }
                 }
-                const double2 p0 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8);
-                const double2 p1 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 2);
-                const double2 p2 = *reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8 + 4);
-                const double w_j = w[j];
-                // Qw[j] as of update s-LAG-1, published by the owning update lane
-                double x = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag0 | (uint32_t)(s + 1));
-                x = __dadd_rn(x, __dmul_rn(d3, p2.y));  // delta_{s-3} * Q[j_s][j_{s-3}]
-                x = __dadd_rn(x, __dmul_rn(d2, p2.x));
-                x = __dadd_rn(x, __dmul_rn(d1, p1.y));
+                j_ = jz[s];
+                const double2 *rec = reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 v = rec[q];
+                    p[2 * q] = v.x;
+                    p[2 * q + 1] = v.y;
+                }
+                wj_ = w[j_];
+                // Qw[j] as of update s-LAG-1, published by the owning update lane (tag checked at use)
+                peek_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, xv_, xt_);
+            };
+            uint32_t j = 0;
+            double pc[8];  // q, Qjj, 1/Qjj, r1..r5
+            double w_j = 0.0, xv = 0.0, xt = 0.0;
+            fetch(0, j, pc, w_j, xv, xt);
+            for (int s = 0; s < n_active; ++s) {
+                const bool has_next = s + 1 < n_active;
+                uint32_t jn = 0;
+                double pn[8];
+                double wjn = 0.0, xvn = 0.0, xtn = 0.0;
+                if (has_next) fetch(s + 1, jn, pn, wjn, xvn, xtn);
+                asm volatile("" ::: "memory");  // the loads above stay above the arithmetic below
+                const uint32_t tag = tag0 | (uint32_t)(s + 1);
+                if ((uint32_t)__double2loint(xt) != tag) xv = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag);
+                double x = xv;
+#pragma unroll
+                for (int i = LAG; i >= 1; --i) x = __dadd_rn(x, __dmul_rn(dl[i - 1], pc[2 + i]));  // oldest delta first
                 double delta, aw, w_new;
-                cd_update(p0.x, p0.y, p1.x, x, w_j, l1, delta, aw, w_new);
+                cd_update(pc[0], pc[1], pc[2], x, w_j, l1, delta, aw, w_new);
                 w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
-                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag0 | (uint32_t)(s + 1));
+                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag);
                 d_w_max = fmax(d_w_max, fabs(delta));
                 w_max = fmax(w_max, aw);
-                d3 = d2; d2 = d1; d1 = delta;
+#pragma unroll
+                for (int i = LAG - 1; i >= 1; --i) dl[i] = dl[i - 1];
+                dl[0] = delta;
+                if (has_next) {
+                    if (jn == j) wjn = w_new;  // the same coordinate twice in a row: the prefetched w[j] was stale
+                    j = jn;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pc[q] = pn[q];
+                    w_j = wjn; xv = xvn; xt = xtn;
+                }
             }
             if (lane == 0) {
                 ctl.w_max = w_max;
                 ctl.d_w_max = d_w_max;
             }
         } else if (warp <= NBULK) {
-            // -------- pair-update warps
+            // -------- pair-update warps: this lane's NPB pairs of Qw live in REGISTERS for the whole sweep (loaded from /
+            // written back to shared memory at its ends); the pairs of row t are in registers before delta_t arrives
             const int b = warp - 1, bt = b * 32 + lane;
             const double *Qmine = Q + 2 * bt;                  // this lane's first pair of any row
             double *ring_mine = ring + 2 * bt;
+            double2 qw[NPB], row[NPB];
+#pragma unroll
+            for (int sp = 0; sp < NPB; ++sp) qw[sp] = *reinterpret_cast<const double2 *>(Qw + 2 * BL * sp + 2 * bt);
             auto prefetch_row = [&](uint32_t j, int slot) {
                 const double *src = Qmine + (uint32_t)(j * (uint32_t)ldq);  // c * ldq < 2^31
                 double *dst = ring_mine + (uint32_t)(slot * CP);
@@ -397,45 +444,57 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                     if (2 * BL * sp + 2 * bt < c) cp_async16(dst + 2 * BL * sp, src + 2 * BL * sp);
                 }
             };
+            auto load_row = [&](int slot) {
+                const double *r = ring_mine + (uint32_t)(slot * CP);
+#pragma unroll
+                for (int sp = 0; sp < NPB; ++sp) row[sp] = *reinterpret_cast<const double2 *>(r + 2 * BL * sp);
+            };
+            // entry js of Qw if this lane owns it (element 2*BL*sp + 2*bt + h)
+            auto publish = [&](int step) {
+                const uint32_t js = jz[step];
+                const int ob = (int)((js >> 1) & (BL - 1));
+                if ((ob >> 5) == b) {  // warp-uniform: only the owning warp looks for the owning lane
+                    if ((ob & 31) == lane) {
+                        const int spj = (int)(js >> 1) / BL;
+                        double v = 0.0;
+#pragma unroll
+                        for (int sp = 0; sp < NPB; ++sp)
+                            if (sp == spj) v = (js & 1) ? qw[sp].y : qw[sp].x;
+                        put_tagged(xq_s + (uint32_t)(step & (QR - 1)) * 16u, v, tag0 | (uint32_t)(step + 1));
+                    }
+                }
+            };
 #pragma unroll
             for (int d = 0; d < RING; ++d) {
                 if (d < n_active) prefetch_row(jz[d], d);
                 cp_async_commit();
             }
-            for (int s = 0; s <= LAG && s < n_active; ++s) {  // entries the chain needs before any update
-                const uint32_t js = jz[s];
-                if ((int)((js >> 1) & (BL - 1)) == bt) put_tagged(xq_s + (uint32_t)s * 16u, Qw[js], tag0 | (uint32_t)(s + 1));
-            }
+            for (int s = 0; s <= LAG && s < n_active; ++s) publish(s);  // entries the chain needs before any update
+            cp_async_wait<RING - 1>();  // this lane's pairs of row 0 have landed
+            load_row(0);
             for (int t = 0; t < n_active; ++t) {
                 const int slot = t % RING;
                 const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
-                cp_async_wait<RING - 1>();  // this lane's pairs of row t have landed
                 if (delta != 0.0) {
-                    const double *row = ring + (size_t)slot * CP;
 #pragma unroll
                     for (int sp = 0; sp < NPB; ++sp) {
-                        const int e = 2 * BL * sp + 2 * bt;
-                        const double2 r = *reinterpret_cast<const double2 *>(row + e);
-                        double2 v = *reinterpret_cast<double2 *>(Qw + e);
-                        v.x = __dadd_rn(v.x, __dmul_rn(delta, r.x));
-                        v.y = __dadd_rn(v.y, __dmul_rn(delta, r.y));
-                        *reinterpret_cast<double2 *>(Qw + e) = v;
+                        qw[sp].x = __dadd_rn(qw[sp].x, __dmul_rn(delta, row[sp].x));
+                        qw[sp].y = __dadd_rn(qw[sp].y, __dmul_rn(delta, row[sp].y));
                     }
                 }
                 const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
-                if (sp1 < n_active) {
-                    const uint32_t js = jz[sp1];
-                    const int ob = (int)((js >> 1) & (BL - 1));
-                    if ((ob >> 5) == b) {  // warp-uniform: only the owning warp looks for the owning lane
-                        if ((ob & 31) == lane)
-                            put_tagged(xq_s + (uint32_t)(sp1 & (QR - 1)) * 16u, Qw[js], tag0 | (uint32_t)(sp1 + 1));
-                    }
-                }
-                if (t + RING < n_active) prefetch_row(jz[t + RING], slot);
+                if (sp1 < n_active) publish(sp1);
+                if (t + RING < n_active) prefetch_row(jz[t + RING], slot);  // row t is in registers: its slot is free
                 cp_async_commit();
+                if (t + 1 < n_active) {
+                    cp_async_wait<RING - 1>();  // row t+1 has landed
+                    load_row((t + 1) % RING);
+                }
                 if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
             }
             cp_async_wait<0>();
+#pragma unroll
+            for (int sp = 0; sp < NPB; ++sp) *reinterpret_cast<double2 *>(Qw + 2 * BL * sp + 2 * bt) = qw[sp];
         } else if (warp == PK_WARP) {
             // -------- packager: operands of 32 chain steps at a time
             for (int base = 0; base < n_active; base += 32) {
@@ -445,13 +504,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                     const uint32_t j = jz[s];
                     const double d = dg[j];
                     const double *qrow = Q + (int64_t)j * ldq;
-                    const double r1 = s >= 1 ? __ldg(qrow + jz[s - 1]) : 0.0;
-                    const double r2 = s >= 2 ? __ldg(qrow + jz[s - 2]) : 0.0;
-                    const double r3 = s >= 3 ? __ldg(qrow + jz[s - 3]) : 0.0;
+                    double rr[5];
+#pragma unroll
+                    for (int i = 1; i <= 5; ++i) rr[i - 1] = (i <= LAG && s >= i) ? __ldg(qrow + jz[s - i]) : 0.0;
                     double *o = pk + (s & (QR - 1)) * 8;
                     *reinterpret_cast<double2 *>(o) = make_double2(qv[j], d);
-                    *reinterpret_cast<double2 *>(o + 2) = make_double2(d != 0.0 ? __drcp_rn(d) : 0.0, r1);
-                    *reinterpret_cast<double2 *>(o + 4) = make_double2(r2, r3);
+                    *reinterpret_cast<double2 *>(o + 2) = make_double2(d != 0.0 ? __drcp_rn(d) : 0.0, rr[0]);
+                    *reinterpret_cast<double2 *>(o + 4) = make_double2(rr[1], rr[2]);
+                    *reinterpret_cast<double2 *>(o + 6) = make_double2(rr[3], rr[4]);
                 }
                 __syncwarp();
                 if (lane == 0) st_release(&ctl.pk_pos, base + 32 < n_active ? base + 32 : n_active);
@@ -562,10 +622,10 @@ int launch_select(const SelectParams &P, cudaStream_t stream) {
     constexpr int RING = RingDepth<NPB>::value;
     const size_t smem = (size_t)CP * (4 + RING) * sizeof(double) + (size_t)QR * 12 * sizeof(double) +
                         (size_t)CP * (4 * sizeof(uint32_t) + 1) + 16;
-    static bool configured = false;
-    if (!configured) {
+    static cp_per_device_flag configured;  // per instantiation, per device
+    if (bool *done = configured.slot(); !*done) {
         CP_CUDA(cudaFuncSetAttribute(lasso_select_kernel<NPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        *done = true;
     }
     lasso_select_kernel<NPB><<<1, WS_THREADS, smem, stream>>>(P);
     CP_CHECK_LAUNCH();

@@ -5,23 +5,42 @@
 //                        equations on the principal sub-block of the Gram matrix.
 //   cp_ls_solve_dual  <- the same call when N-1 < K' (gelsd's minimum-norm answer),
 //                        through the dual (row) normal equations.
+//   cp_ls_factor / cp_ls_resolve
+//                     <- nonlinear_fc (lib/decompose.py:671-685): 50 refits against the SAME X --
+//                        factor the centred Gram once, then one forward/backward substitution per refit.
 //
-// Both reduce to one routine: blocked right-looking Cholesky (panel 64) of an SPD matrix
-// with the right-hand sides appended as extra ROWS of the same array, so that the forward
-// substitution happens for free inside the panel TRSM / trailing update; the diagonal
-// blocks are inverted once (64x64, one CTA) and every other operation is an fp64 tile
-// GEMM (cpgemm::gemm_kernel).  The backward substitution reuses the inverted blocks.
-// Bound: FP64 pipe for the trailing updates (K'^3/3 flop), latency for the 64x64 panels.
+// All of them run one routine: right-looking blocked Cholesky with 128-wide panels.
+//   * the diagonal block of a panel is factored AND inverted by ONE CTA entirely in shared
+//     memory (potrf128: 32-wide sub-panels; the 32 x 32 pivot blocks are factored by a single
+//     warp in registers with shuffles -- the only truly serial part, ~100 ns per pivot);
+//   * the rows below are multiplied by the inverted block (a GEMM, not a triangular solve);
+//   * the trailing update is split three ways: the next panel's columns stay on the caller's
+//     stream (small 64 x 64 tiles: few flops, many CTAs, short latency), the panel after that
+//     and the rest run on a low-priority side stream underneath the next panel's factorisation.
+//   * right-hand sides ride along as extra ROWS of the matrix, so the forward substitution
+//     happens inside the panel steps; the backward substitution reuses the inverted blocks.
+// The factor goes to a second array (L), the trailing matrix is updated in place (M): no step
+// reads and writes the same tile, whatever the tile shape.
+// Bound: the dependency chain of ~K'/128 x (potrf128 + 2 small GEMMs) for the factorisation,
+// the FP64 pipe for the far updates (K'^3/3 flop).
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include "gemm_small.cuh"
 
 namespace {
 
-constexpr int NB = 64;
+constexpr int PB = 128;          // panel width
+constexpr int SB = 32;           // sub-block factored by one warp
+constexpr int NSB = PB / SB;     // 4
+constexpr int LDA_S = PB + 1;    // padded leading dimension of the shared-memory panel
+constexpr int LDX_S = SB + 1;
+constexpr int P128_T = 512;
+constexpr size_t P128_SMEM =
+    (size_t)(PB * LDA_S + 2 * NSB * SB * LDX_S + 3 * SB * LDX_S + 3 * PB) * sizeof(double);
 
 // ---------------------------------------------------------------- assemble
-// M rows 0..Ks-1    : G[sel_i, sel_j] - sx_i sx_j / N           (Ks x Ks)
-// M rows Ks..Ks+n-1 : Bxy[sel_j, t]   - sx_j sy_t / N           (n  x Ks)   (right-hand sides, transposed)
+// M rows 0..Ks-1    : G[sel_i, sel_j] - sx_i sx_j / N   (lower triangle only)
+// M rows Ks..Ks+n-1 : Bxy[sel_j, t]   - sx_j sy_t / N   (right-hand sides, transposed)
 __global__ void __launch_bounds__(256)
 ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const double *__restrict__ sx,
             const double *__restrict__ sy, double invN, int K, int n, const int32_t *__restrict__ sel, int Ks,
@@ -29,29 +48,20 @@ ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const 
     const int j = blockIdx.x * 256 + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= Ks) return;
-    const int sj = sel[j];
+    const int sj = sel ? sel[j] : j;
     if (i < Ks) {
-        const int si = sel[i];
+        if (j > i) return;
+        const int si = sel ? sel[i] : i;
         const double v = G[(int64_t)si * K + sj] - sx[si] * sx[sj] * invN;
         M[(int64_t)i * ld + j] = v;
         if (i == j) diag0[i] = v;
-    } else {
+    } else if (Bxy) {
         const int t = i - Ks;
         M[(int64_t)i * ld + j] = Bxy[(int64_t)sj * n + t] - sx[sj] * sy[t] * invN;
     }
 }
 
-// ---------------------------------------------------------------- 64x64 diagonal block: L and L^-1
-// One CTA of 1024 threads; thread (j = tid % 64, ig = tid / 64) keeps rows i = ig + 16 m (m = 0..3) of
-// column j in registers.  Right-looking factorisation: at step k the 16 threads of column k publish the
-// raw column (pivot included) to shared memory, ONE barrier, then every thread applies the
-// rank-1 update to its registers.  The inverse is a forward substitution with the same ownership (one
-// barrier per row).  1/sqrt(pivot) comes from the fp32 MUFU seed + two fp64 Newton steps.
-constexpr int PT = 1024;
-constexpr int PR = 4;   // rows per thread
-constexpr int PG = 64 / PR;  // row groups
-constexpr size_t POTRF_SMEM = (size_t)(NB * (NB + 1) + 5 * NB) * sizeof(double);
-
+// ---------------------------------------------------------------- 128 x 128 diagonal block: L and L^-1
 __device__ __forceinline__ double rsqrt_newton(double d) {
     double y = (double)rsqrtf((float)d);
     y = y * (1.5 - 0.5 * d * y * y);
@@ -59,84 +69,238 @@ __device__ __forceinline__ double rsqrt_newton(double d) {
     return y;
 }
 
-__global__ void __launch_bounds__(PT, 1)
-potrf_diag(double *__restrict__ A, int64_t ld, int nb, double *__restrict__ Linv, int32_t *__restrict__ info,
-           int j0, const double *__restrict__ diag0) {
-    extern __shared__ __align__(16) double psm[];
-    double *Ls = psm;                      // [64][65] finished factor (row-major)
-    double *col = psm + NB * (NB + 1);     // [2][64] raw column k (double buffered)
-    double *xrow = col + 2 * NB;           // [2][64] finished row k of the inverse
-    double *rsd = xrow + 2 * NB;           // [64] 1 / L[k][k]
-    const int tid = threadIdx.x, j = tid & 63, ig = tid >> 6;
-    double a[PR], x[PR];
+__device__ __forceinline__ void atomic_min_pos(double *addr, double v) {  // v > 0: bit patterns order like the values
+    atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// One warp factors the 32 x 32 block at (k0, k0) of the shared-memory panel.  Lane i owns row i in
+// registers; per pivot: broadcast the pivot, 1/sqrt (fp32 seed + two fp64 Newton steps), scale the
+// column, rank-1 update of the rows to the right with the column entries fetched by shuffle.
+__device__ __forceinline__ void potrf32_warp(double *As, int k0, const double *thr_s, double *rinv_s, int32_t *info,
+                                             int jglob, int lane, double &ratio_min, const double *inv0_s) {
+    double a[SB];
 #pragma unroll
-    for (int m = 0; m < PR; ++m) {
-        const int i = ig + PG * m;
-        double v = 0.0;
-        if (i < nb && j < nb && j <= i) v = A[(int64_t)i * ld + j];
-        if (i >= nb && i == j) v = 1.0;  // identity padding keeps the arithmetic finite
-        a[m] = v;
-        x[m] = (i == j) ? 1.0 : 0.0;
+    for (int j = 0; j < SB; ++j) a[j] = (j <= lane) ? As[(k0 + lane) * LDA_S + k0 + j] : 0.0;
+    const double thr = thr_s[k0 + lane];
+    double myrs = 1.0;
+#pragma unroll
+    for (int k = 0; k < SB; ++k) {
+        double dk = __shfl_sync(0xffffffffu, a[k], k);
+        const double tk = __shfl_sync(0xffffffffu, thr, k);
+        // pivot must stay above 1e-12 of the original diagonal entry: the squared form of the
+        // sigma < 1e-6 sigma_max cut-off LinearRegression applies (sklearn _base.py:752-753, cond=tol=1e-6)
+        if (!(dk > tk)) {
+            if (lane == 0) atomicCAS(info, 0, jglob + k0 + k + 1);
+            dk = 1.0;
+        }
+        const double rs = rsqrt_newton(dk);
+        double l = (lane > k) ? a[k] * rs : 0.0;
+        if (lane == k) {
+            l = dk * rs;
+            myrs = rs;
+            const double i0 = inv0_s[k0 + k];
+            if (i0 > 0.0) ratio_min = fmin(ratio_min, dk * i0);
+        }
+        a[k] = l;
+#pragma unroll
+        for (int j = k + 1; j < SB; ++j) {
+            const double ljk = __shfl_sync(0xffffffffu, l, j);
+            a[j] = fma(-l, ljk, a[j]);  // entries right of the diagonal (j > lane) are never read
+        }
     }
-    for (int k = 0; k < NB; ++k) {
-        double *ck = col + (k & 1) * NB;
-        if (j == k) {
 #pragma unroll
-            for (int m = 0; m < PR; ++m) ck[ig + PG * m] = a[m];
+    for (int j = 0; j < SB; ++j)
+        if (j <= lane) As[(k0 + lane) * LDA_S + k0 + j] = a[j];
+    rinv_s[k0 + lane] = myrs;
+}
+
+// out[r * dr + c * dc] = sign * sum_terms sum_q A_t[r * sa_t + q] * B_t[c * sb_t + q]   (32 x 32 blocks)
+struct MmTerm {
+    const double *A;
+    int sa;
+    const double *B;
+    int sb;
+};
+struct MmTask {
+    double *dst;
+    int dr, dc;
+    double sign;
+    int nterm;
+    MmTerm t[3];
+};
+__device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
+    for (int e = threadIdx.x; e < ntask * SB * SB; e += P128_T) {
+        const MmTask &tk = tasks[e >> 10];
+        const int r = (e >> 5) & 31, c = e & 31;
+        double s = 0.0;
+        for (int u = 0; u < tk.nterm; ++u) {
+            const double *ap = tk.t[u].A + r * tk.t[u].sa;
+            const double *bp = tk.t[u].B + c * tk.t[u].sb;
+#pragma unroll 8
+            for (int q = 0; q < SB; ++q) s = fma(ap[q], bp[q], s);
+        }
+        tk.dst[r * tk.dr + c * tk.dc] = tk.sign * s;
+    }
+}
+
+// A: the (updated) diagonal block in the trailing matrix; Lout: where the factor goes; Linv: 128 x 128
+// row-major (zero above the diagonal).  nb < 128 (last panel) is padded with the identity.
+__global__ void __launch_bounds__(P128_T, 1)
+potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__ Lout, int64_t ldl,
+         double *__restrict__ Linv, int32_t *__restrict__ info, double *__restrict__ ratio_out, int j0,
+         const double *__restrict__ diag0) {
+    extern __shared__ __align__(16) double psm[];
+    double *As = psm;                             // [128][129]  lower: L ; strictly-upper blocks: (L^-1)^T
+    double *Xd = As + PB * LDA_S;                 // [4][32][33] inverses of the diagonal sub-blocks
+    double *Xdt = Xd + NSB * SB * LDX_S;          // the same, transposed
+    double *Tt = Xdt + NSB * SB * LDX_S;          // [3][32][33] temporaries of the block inversion (transposed)
+    double *rinv = Tt + 3 * SB * LDX_S;           // [128] 1 / L[k][k]
+    double *thr = rinv + PB;                      // [128] pivot thresholds
+    double *inv0 = thr + PB;                      // [128] 1 / original diagonal
+    __shared__ MmTask tasks[3];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int e = tid; e < PB * PB; e += P128_T) {
+        const int i = e >> 7, j = e & (PB - 1);
+        double v = 0.0;
+        if (i < nb && j <= i) v = A[(int64_t)i * lda + j];
+        else if (i >= nb && i == j) v = 1.0;
+        As[i * LDA_S + j] = v;
+    }
+    if (tid < PB) {
+        const double d0 = tid < nb ? diag0[j0 + tid] : 0.0;
+        thr[tid] = tid < nb ? 1e-12 * d0 : 0.0;
+        inv0[tid] = d0 > 0.0 ? 1.0 / d0 : 0.0;
+    }
+    __syncthreads();
+
+    double ratio_min = 1e300;
+    for (int sp = 0; sp < NSB; ++sp) {
+        const int k0 = sp * SB;
+        if (warp == 0) potrf32_warp(As, k0, thr, rinv, info, j0, lane, ratio_min, inv0);
+        __syncthreads();
+        const int r0 = k0 + SB, T = PB - r0;
+        if (T == 0) break;
+        // rows below the pivot block:  x * L32' = a  (one thread per row, right-looking over the 32 columns)
+        if (tid < T) {
+            double a[SB];
+            double *row = As + (r0 + tid) * LDA_S + k0;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) a[j] = row[j];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const double x = a[k] * rinv[k0 + k];
+                a[k] = x;
+#pragma unroll
+                for (int j = k + 1; j < SB; ++j) a[j] = fma(-x, As[(k0 + j) * LDA_S + k0 + k], a[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < SB; ++j) row[j] = a[j];
         }
         __syncthreads();
-        double d = ck[k];
-        // pivot must stay above 1e-12 of the original diagonal entry: the squared form of the
-        // sigma < 1e-6 sigma_max cut-off LinearRegression applies (sklearn _base.py:752-753)
-        if (!(d > (k < nb ? 1e-12 * diag0[j0 + k] : 0.0))) {
-            if (tid == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
-            d = 1.0;
-        }
-        const double rs = rsqrt_newton(d);
-        if (j == k) {
+        // trailing block -= P P'   (4 x 4 micro-tiles on interleaved rows: conflict-free shared-memory reads)
+        const int nt = T >> 2;
+        for (int idx = tid; idx < nt * nt; idx += P128_T) {
+            const int ti = idx / nt, tj = idx - ti * nt;
+            double acc[4][4];
 #pragma unroll
-            for (int m = 0; m < PR; ++m) {
-                const int i = ig + PG * m;
-                Ls[i * (NB + 1) + k] = (i > k) ? ck[i] * rs : (i == k ? d * rs : 0.0);
-            }
-            if (ig == 0) rsd[k] = rs;
-        }
-        if (j > k) {
-            const double ljk = -ck[j] * rs * rs;  // -L[j][k] / sqrt(d)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int m = 0; m < PR; ++m) {
-                const int i = ig + PG * m;
-                if (i >= j) a[m] = fma(ck[i], ljk, a[m]);
+                for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+            const double *pa = As + (r0 + ti) * LDA_S + k0;
+            const double *pb = As + (r0 + tj) * LDA_S + k0;
+#pragma unroll 4
+            for (int k = 0; k < SB; ++k) {
+                double av[4], bv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    av[u] = pa[u * nt * LDA_S + k];
+                    bv[u] = pb[u * nt * LDA_S + k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int ri = r0 + ti + nt * u, cj = r0 + tj + nt * v;
+                    if (ri >= cj) As[ri * LDA_S + cj] -= acc[u][v];
+                }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) ratio_min = fmin(ratio_min, __shfl_xor_sync(0xffffffffu, ratio_min, off));
+        if (lane == 0 && ratio_min < 1e299 && ratio_out) atomic_min_pos(ratio_out, ratio_min > 0.0 ? ratio_min : 1e-300);
+    }
+    // ---- the factor leaves now (coalesced rows); the shared copy stays for the inversion
+    for (int e = tid; e < PB * PB; e += P128_T) {
+        const int i = e >> 7, j = e & (PB - 1);
+        if (i < nb && j <= i) Lout[(int64_t)i * ldl + j] = As[i * LDA_S + j];
+    }
+    // ---- inverse of the four 32 x 32 diagonal sub-blocks: lane c solves L x = e_c
+    if (warp < NSB) {
+        const int b = warp, c = lane;
+        const double *Lb = As + (b * SB) * LDA_S + b * SB;
+        double x[SB];
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; ++j) s = fma(-Lb[i * LDA_S + j], x[j], s);
+            x[i] = s * rinv[b * SB + i];
+        }
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+            Xd[(b * SB + i) * LDX_S + c] = x[i];
+            Xdt[(b * SB + c) * LDX_S + i] = x[i];
         }
     }
     __syncthreads();
-    // X = L^-1: row k of X is final once rows < k have been eliminated
-    for (int k = 0; k < NB; ++k) {
-        double *xr = xrow + (k & 1) * NB;
-        if (ig == (k & (PG - 1))) {
-            const int mk = k / PG;
-            double xv = 0.0;
-#pragma unroll
-            for (int m = 0; m < PR; ++m) xv = (m == mk) ? x[m] : xv;
-            xv *= rsd[k];
-            xr[j] = xv;
-            Linv[k * NB + j] = (j <= k) ? xv : 0.0;
+    // ---- off-diagonal blocks of X = L^-1, sub-diagonal by sub-diagonal:
+    //      X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj ;  X_ij (i > j) is kept TRANSPOSED in the upper block (j, i) of As
+    auto Lblk = [&](int i, int k) { return As + (i * SB) * LDA_S + k * SB; };        // L_ik[r][q]   stride LDA_S
+    auto XoffT = [&](int k, int j) { return As + (j * SB) * LDA_S + k * SB; };       // X_kj[q][c] at [c][q], stride LDA_S
+    for (int d = 1; d < NSB; ++d) {
+        const int ntask = NSB - d;
+        if (tid < ntask) {
+            const int j = tid, i = j + d;
+            MmTask t;
+            t.dst = Tt + tid * SB * LDX_S;
+            t.dr = 1; t.dc = LDX_S; t.sign = 1.0; t.nterm = d;
+            for (int u = 0; u < d; ++u) {
+                const int k = j + u;
+                t.t[u].A = Lblk(i, k); t.t[u].sa = LDA_S;
+                if (k == j) { t.t[u].B = Xdt + (j * SB) * LDX_S; t.t[u].sb = LDX_S; }
+                else { t.t[u].B = XoffT(k, j); t.t[u].sb = LDA_S; }
+            }
+            tasks[tid] = t;
         }
         __syncthreads();
-        if (j <= k) {  // columns right of the diagonal stay zero
-            const double xk = xr[j];
-#pragma unroll
-            for (int m = 0; m < PR; ++m) {
-                const int i = ig + PG * m;
-                if (i > k) x[m] = fma(-Ls[i * (NB + 1) + k], xk, x[m]);
-            }
+        run_tasks(tasks, ntask);
+        __syncthreads();
+        if (tid < ntask) {
+            const int j = tid, i = j + d;
+            MmTask t;
+            t.dst = XoffT(i, j);
+            t.dr = 1; t.dc = LDA_S; t.sign = -1.0; t.nterm = 1;
+            t.t[0].A = Xd + (i * SB) * LDX_S; t.t[0].sa = LDX_S;
+            t.t[0].B = Tt + tid * SB * LDX_S; t.t[0].sb = LDX_S;
+            tasks[tid] = t;
         }
+        __syncthreads();
+        run_tasks(tasks, ntask);
+        __syncthreads();
     }
-#pragma unroll
-    for (int m = 0; m < PR; ++m) {
-        const int i = ig + PG * m;
-        if (i < nb && j < nb && j <= i) A[(int64_t)i * ld + j] = Ls[i * (NB + 1) + j];
+    for (int e = tid; e < PB * PB; e += P128_T) {
+        const int i = e >> 7, j = e & (PB - 1);
+        double v = 0.0;
+        if (j <= i) v = ((i >> 5) == (j >> 5)) ? Xd[((i >> 5) * SB + (i & 31)) * LDX_S + (j & 31)] : As[j * LDA_S + i];
+        Linv[e] = v;
     }
 }
 
@@ -151,7 +315,7 @@ ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ 
     for (int i = threadIdx.x; i < Ks; i += 256) {
         const double w = src[i];
         W_out[(int64_t)t * Ks + i] = w;
-        s = fma(sx[sel[i]], w, s);
+        s = fma(sx[sel ? sel[i] : i], w, s);
     }
     red[threadIdx.x] = s;
     __syncthreads();
@@ -164,9 +328,9 @@ ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ 
 
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
-template <bool B_NC>
-int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
-          int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
+// 128 x 128 tiles (throughput: the far trailing updates)
+int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
+              int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
     using namespace cpgemm;
     Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
@@ -176,33 +340,26 @@ int dgemm(const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
     g.a_vec = al16(A) && (lda % 2 == 0);
     g.b_vec = al16(B) && (ldb % 2 == 0);
     if (M <= 0 || Nn <= 0) return CP_OK;
-    CP_GEMM_LAUNCH((launch<double, double, false, B_NC>(g, stream)));
+    CP_GEMM_LAUNCH((launch<double, double, false, false>(g, stream)));
+    return CP_OK;
+}
+// 64 x 64 tiles (latency: everything on the dependency chain)
+template <bool B_NC>
+int dgemm_small(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
+                int R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
+    using namespace cpsmall;
+    Args g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.M = M; g.Nn = Nn; g.R = R;
+    g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode;
+    g.a_vec = al16(A) && (lda % 2 == 0);
+    g.b_vec = al16(B) && (ldb % 2 == 0);
+    if (M <= 0 || Nn <= 0) return CP_OK;
+    CP_GEMM_LAUNCH((launch<B_NC>(g, stream)));
     return CP_OK;
 }
 
-}  // namespace
-
-// In-place: M is (Kd + n) x Kd (leading dimension ld), rows 0..Kd-1 an SPD matrix (lower part
-// used), rows Kd.. the transposed right-hand sides.  On return rows Kd.. hold the transposed
-// solution  (SPD^-1 Rhs)'.  Linv: scratch of ceil(Kd/64) * 64*64 doubles.
-static int chol_solve_inplace(cp_handle_t h, double *M, int64_t ld, int Kd, int n, double *Linv, const double *diag0,
-                              int32_t *info, cudaStream_t stream) {
-    using namespace cpgemm;
-    const int Ktot = Kd + n;
-    const int npanel = (Kd + NB - 1) / NB;
-    static bool configured = false;
-    if (!configured) {
-        CP_CUDA(cudaFuncSetAttribute(potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
-        configured = true;
-    }
-    // Two-level blocking: 256-wide outer panels are factored with 64-wide inner blocks whose updates
-    // stay inside the panel; the trailing matrix is then updated ONCE per outer panel with inner
-    // dimension 256 (4x fewer, 4x deeper tile GEMMs than a plain 64-wide right-looking sweep).
-    constexpr int NBO = 4 * NB;
-    (void)npanel;
-    // Look-ahead: the trailing update of an outer panel is split into the next panel's columns (needed at once, stays
-    // on the caller's stream) and the rest, which runs on a low-priority side stream concurrently with the next
-    // panel's (latency-bound, one-CTA-at-a-time) factorisation.
+int ensure_side(cp_handle_t h) {
     if (!h->side) {
         int lo = 0, hi = 0;
         CP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -210,110 +367,255 @@ static int chol_solve_inplace(cp_handle_t h, double *M, int64_t ld, int Kd, int 
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     }
+    return CP_OK;
+}
+
+int configure_potrf(cp_handle_t h) {
+    if (!h->potrf_configured) {  // the attribute is per device: remembered per handle (one handle = one device)
+        CP_CUDA(cudaFuncSetAttribute(potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P128_SMEM));
+        h->potrf_configured = true;
+    }
+    return CP_OK;
+}
+
+}  // namespace
+
+// Factorisation.  M: (Kd + nrhs) x Kd (leading dimension ld): rows 0..Kd-1 an SPD matrix (lower part used, destroyed),
+// rows Kd.. transposed right-hand sides (destroyed).  L (same shape, same ld) receives the factor in rows 0..Kd-1
+// and the forward-substituted right-hand sides  (L^-1 Rhs)'  in rows Kd.. .  Linv: ceil(Kd/128) blocks of 128 x 128.
+static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, int nrhs, double *Linv,
+                       const double *diag0, int32_t *info, double *ratio, cudaStream_t stream) {
+    using namespace cpgemm;
+    const int Ktot = Kd + nrhs;
+    int rc = ensure_side(h);
+    if (rc) return rc;
+    rc = configure_potrf(h);
+    if (rc) return rc;
     bool side_pending = false;
-    for (int J0 = 0; J0 < Kd; J0 += NBO) {
-        const int w = Kd - J0 < NBO ? Kd - J0 : NBO;
-        const int J1 = J0 + w;
-        for (int jb = J0; jb < J1; jb += NB) {
-            const int nb = J1 - jb < NB ? J1 - jb : NB;
-            const int j1 = jb + nb;
-            double *Lp = Linv + (size_t)(jb / NB) * NB * NB;
-            potrf_diag<<<1, PT, POTRF_SMEM, stream>>>(M + (int64_t)jb * ld + jb, ld, nb, Lp, info, jb, diag0);
-            CP_CHECK_LAUNCH();
-            const int below = Ktot - j1;
-            if (below > 0) {
-                // block column <- block column * L_d^-T (all rows below, right-hand-side rows included), in place
-                double *Pn = M + (int64_t)j1 * ld + jb;
-                int rc = dgemm<false>(Pn, ld, Lp, NB, Pn, ld, below, nb, nb, 1.0, 0.0, TILES_ALL, stream);
-                if (rc) return rc;
-                const int nin = J1 - j1;  // columns of this outer panel still to be factored
-                if (nin > 0) {
-                    rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, below, nin, nb, -1.0, 1.0, TILES_ALL,
-                                      stream);
-                    if (rc) return rc;
-                }
-            }
+    for (int j0 = 0; j0 < Kd; j0 += PB) {
+        const int nb = Kd - j0 < PB ? Kd - j0 : PB;
+        const int j1 = j0 + nb;
+        double *Lp = Linv + (size_t)(j0 / PB) * PB * PB;
+        potrf128<<<1, P128_T, P128_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, L + (int64_t)j0 * ld + j0, ld, Lp, info,
+                                                   ratio, j0, diag0);
+        CP_CHECK_LAUNCH();
+        const int below = Ktot - j1;
+        if (below <= 0) break;
+        // block column of the factor: rows below * L_d^-T  (right-hand-side rows included)
+        rc = dgemm_small<false>(M + (int64_t)j1 * ld + j0, ld, Lp, PB, L + (int64_t)j1 * ld + j0, ld, below, nb, nb, 1.0, 0.0,
+                                cpsmall::TILES_ALL, stream);
+        if (rc) return rc;
+        const int ncols = Kd - j1;
+        if (ncols <= 0) continue;
+        const int w2 = ncols < PB ? ncols : PB;
+        const bool fork = ncols > w2;
+        if (fork) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // block column j0..j1 of L is final
+        if (side_pending) {  // the previous panel's far update also wrote the columns updated next
+            CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
+            side_pending = false;
         }
-        const int ncols = Kd - J1;
-        if (ncols > 0) {  // trailing (lower) -= panel * panel', inner dimension w
-            const int w2 = ncols < NBO ? ncols : NBO;  // columns of the next outer panel
-            const bool fork = ncols > w2;
-            if (fork) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // panel J0..J1 is final
-            if (side_pending) {  // the previous panel's far update also touched the columns updated next
-                CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
-                side_pending = false;
-            }
-            double *Pn = M + (int64_t)J1 * ld + J0;
-            int rc = dgemm<false>(Pn, ld, Pn, ld, M + (int64_t)J1 * ld + J1, ld, Ktot - J1, w2, w, -1.0, 1.0, TILES_LOWER, stream);
+        const double *Pn = L + (int64_t)j1 * ld + j0;
+        rc = dgemm_small<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, Ktot - j1, w2, nb, -1.0, 1.0,
+                                cpsmall::TILES_LOWER, stream);
+        if (rc) return rc;
+        if (fork) {
+            const int j2 = j1 + w2;
+            const int w3 = Kd - j2 < PB ? Kd - j2 : PB;
+            const double *Pf = L + (int64_t)j2 * ld + j0;
+            CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
+            rc = dgemm_big(Pf, ld, Pf, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, w3, nb, -1.0, 1.0, TILES_LOWER, h->side);
             if (rc) return rc;
-            if (fork) {
-                const int J2 = J1 + w2;
-                double *Pf = M + (int64_t)J2 * ld + J0;
-                CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
-                rc = dgemm<false>(Pf, ld, Pf, ld, M + (int64_t)J2 * ld + J2, ld, Ktot - J2, ncols - w2, w, -1.0, 1.0, TILES_LOWER,
-                                  h->side);
+            CP_CUDA(cudaEventRecord(h->ev_side, h->side));
+            side_pending = true;
+            const int j3 = j2 + w3;
+            if (Kd - j3 > 0) {
+                const double *Pg = L + (int64_t)j3 * ld + j0;
+                rc = dgemm_big(Pg, ld, Pg, ld, M + (int64_t)j3 * ld + j3, ld, Ktot - j3, Kd - j3, nb, -1.0, 1.0, TILES_LOWER,
+                               h->side);
                 if (rc) return rc;
-                CP_CUDA(cudaEventRecord(h->ev_side, h->side));
-                side_pending = true;
             }
         }
     }
-    if (side_pending) CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
-    // backward: Wt * L = Zt, outer panels last to first, inner blocks last to first
-    double *Zt = M + (int64_t)Kd * ld;
-    const int nouter = (Kd + NBO - 1) / NBO;
-    for (int P = nouter - 1; P >= 0; --P) {
-        const int J0 = P * NBO;
-        const int w = Kd - J0 < NBO ? Kd - J0 : NBO;
-        const int nin = (w + NB - 1) / NB;
-        for (int b = nin - 1; b >= 0; --b) {
-            const int jb = J0 + b * NB;
-            const int nb = J0 + w - jb < NB ? J0 + w - jb : NB;
-            double *Lp = Linv + (size_t)(jb / NB) * NB * NB;
-            // Wt_b = Zt_b * Linv_b   (C[t, i] = sum_r Zt[t, jb + r] * Linv[r, i]), in place
-            int rc = dgemm<true>(Zt + jb, ld, Lp, NB, Zt + jb, ld, n, nb, nb, 1.0, 0.0, TILES_ALL, stream);
-            if (rc) return rc;
-            if (jb > J0) {  // remaining columns of this outer panel
-                rc = dgemm<true>(Zt + jb, ld, M + (int64_t)jb * ld + J0, ld, Zt + J0, ld, n, jb - J0, nb, -1.0, 1.0, TILES_ALL,
-                                 stream);
-                if (rc) return rc;
-            }
-        }
-        if (J0 > 0) {  // Zt[:, 0:J0] -= Wt_P * L[J0:J0+w, 0:J0], inner dimension w
-            int rc = dgemm<true>(Zt + J0, ld, M + (int64_t)J0 * ld, ld, Zt, ld, n, J0, w, -1.0, 1.0, TILES_ALL, stream);
+    // whatever the side stream still holds must be ordered before the next user of this workspace
+    CP_CUDA(cudaEventRecord(h->ev_side, h->side));
+    CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
+    return CP_OK;
+}
+
+// Forward substitution of further right-hand sides: Zt (n x Kd, ld) is destroyed, F (n x Kd, ld) receives (L^-1 Rhs)'.
+static int chol_forward(const double *L, int64_t ld, int Kd, const double *Linv, double *Zt, double *F, int64_t ldz, int n,
+                        cudaStream_t stream) {
+    for (int j0 = 0; j0 < Kd; j0 += PB) {
+        const int nb = Kd - j0 < PB ? Kd - j0 : PB;
+        const int j1 = j0 + nb;
+        const double *Lp = Linv + (size_t)(j0 / PB) * PB * PB;
+        int rc = dgemm_small<false>(Zt + j0, ldz, Lp, PB, F + j0, ldz, n, nb, nb, 1.0, 0.0, cpsmall::TILES_ALL, stream);
+        if (rc) return rc;
+        if (Kd - j1 > 0) {  // Zt[:, j1:] -= F_b * L[j1:, j0:j1]'
+            rc = dgemm_small<false>(F + j0, ldz, L + (int64_t)j1 * ld + j0, ld, Zt + j1, ldz, n, Kd - j1, nb, -1.0, 1.0,
+                                    cpsmall::TILES_ALL, stream);
             if (rc) return rc;
         }
     }
     return CP_OK;
 }
 
+// Backward substitution: F (n x Kd, ldf; destroyed) holds (L^-1 Rhs)'; Wt (n x Kd, ldw) receives (SPD^-1 Rhs)'.
+static int chol_backward(const double *L, int64_t ld, int Kd, const double *Linv, double *F, int64_t ldf, double *Wt,
+                         int64_t ldw, int n, cudaStream_t stream) {
+    const int npanel = (Kd + PB - 1) / PB;
+    for (int p = npanel - 1; p >= 0; --p) {
+        const int j0 = p * PB;
+        const int nb = Kd - j0 < PB ? Kd - j0 : PB;
+        const double *Lp = Linv + (size_t)p * PB * PB;
+        // Wt_b = F_b * Linv_b   (C[t, i] = sum_r F[t, j0 + r] * Linv[r, i])
+        int rc = dgemm_small<true>(F + j0, ldf, Lp, PB, Wt + j0, ldw, n, nb, nb, 1.0, 0.0, cpsmall::TILES_ALL, stream);
+        if (rc) return rc;
+        if (j0 > 0) {  // F[:, 0:j0] -= Wt_b * L[j0:j0+nb, 0:j0]
+            rc = dgemm_small<true>(Wt + j0, ldw, L + (int64_t)j0 * ld, ld, F, ldf, n, j0, nb, -1.0, 1.0, cpsmall::TILES_ALL,
+                                   stream);
+            if (rc) return rc;
+        }
+    }
+    return CP_OK;
+}
+
+static inline int64_t ld_for(int K) { return (K + 7) / 8 * 8; }
+
 extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
                            int64_t N, int K, int n, const int32_t *sel_cols, int Ksel, double *W_out, double *b_out,
-                           int32_t *info_out, cp_stream_t stream_) {
-    CP_REQUIRE(h && G && Bxy && sx && sy && sel_cols && W_out && b_out && info_out, "cp_ls_solve: NULL argument");
+                           int32_t *info_out, double *stat_out, cp_stream_t stream_) {
+    CP_REQUIRE(h && G && Bxy && sx && sy && W_out && b_out && info_out, "cp_ls_solve: NULL argument");
     CP_REQUIRE(K > 0 && n > 0 && Ksel > 0 && Ksel <= K && N > 0, "cp_ls_solve: bad shape");
+    CP_REQUIRE(sel_cols || Ksel == K, "cp_ls_solve: sel_cols may be NULL only when every column is used");
     CP_REQUIRE(N - 1 >= Ksel, "cp_ls_solve: N-1=%lld < K'=%d: centred Gram is singular, use cp_ls_solve_dual",
                (long long)(N - 1), Ksel);
+    CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t ld = (Ksel + 7) / 8 * 8;
-    const int npanel = (Ksel + NB - 1) / NB;
-    const size_t need = cp_carver::need((size_t)(Ksel + n) * ld, 8) + cp_carver::need((size_t)npanel * NB * NB, 8) +
-                        cp_carver::need(Ksel, 8);
+    const int64_t ld = ld_for(Ksel);
+    const int npanel = (Ksel + PB - 1) / PB;
+    const size_t nM = (size_t)(Ksel + n) * ld;
+    const size_t need = 2 * cp_carver::need(nM, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) +
+                        cp_carver::need((size_t)n * ld, 8) + cp_carver::need(Ksel, 8) + cp_carver::need(1, 8);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
-    double *M = cv.take<double>((size_t)(Ksel + n) * ld);
-    double *Linv = cv.take<double>((size_t)npanel * NB * NB);
+    double *M = cv.take<double>(nM);
+    double *L = cv.take<double>(nM);
+    double *Linv = cv.take<double>((size_t)npanel * PB * PB);
+    double *Wt = cv.take<double>((size_t)n * ld);
     double *diag0 = cv.take<double>(Ksel);
+    double *ratio = cv.take<double>(1);
     CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
+    CP_CUDA(cudaMemsetAsync(ratio, 0x7f, sizeof(double), stream));  // 1.4e306: "no pivot seen yet"
     const double invN = 1.0 / (double)N;
     dim3 grid(cp_cdiv(Ksel, 256), Ksel + n);
     ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld, diag0);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(h, M, ld, Ksel, n, Linv, diag0, info_out, stream);
+    rc = chol_factor(h, M, L, ld, Ksel, n, Linv, diag0, info_out, ratio, stream);
     if (rc) return rc;
-    ls_output<<<n, 256, 0, stream>>>(M + (int64_t)Ksel * ld, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
+    rc = chol_backward(L, ld, Ksel, Linv, L + (int64_t)Ksel * ld, ld, Wt, ld, n, stream);
+    if (rc) return rc;
+    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
+    CP_CHECK_LAUNCH();
+    if (stat_out) CP_CUDA(cudaMemcpyAsync(stat_out, ratio, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    return CP_OK;
+}
+
+// ---------------------------------------------------------------- factor once, solve many (nonlinear_fc)
+extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, int64_t N, int K,
+                            const int32_t *sel_cols, int Ksel, int32_t *info_out, double *stat_out,
+                            cp_stream_t stream_) {
+    CP_REQUIRE(h && G && sx && info_out, "cp_ls_factor: NULL argument");
+    CP_REQUIRE(K > 0 && Ksel > 0 && Ksel <= K && N > 0, "cp_ls_factor: bad shape");
+    CP_REQUIRE(sel_cols || Ksel == K, "cp_ls_factor: sel_cols may be NULL only when every column is used");
+    CP_REQUIRE(N - 1 >= Ksel, "cp_ls_factor: N-1=%lld < K'=%d: centred Gram is singular", (long long)(N - 1), Ksel);
+    CP_DEVICE_GUARD(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t ld = ld_for(Ksel);
+    const int npanel = (Ksel + PB - 1) / PB;
+    const size_t nM = (size_t)Ksel * ld;
+    // the factor outlives this call: it lives in its own allocation, not in the shared scratch
+    const size_t fac_need = cp_carver::need(nM, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) + cp_carver::need(1, 8);
+    if (fac_need > h->fac_bytes) {
+        if (h->fac) CP_CUDA(cudaFree(h->fac));
+        h->fac = nullptr;
+        h->fac_bytes = 0;
+        cudaError_t e = cudaMalloc(&h->fac, fac_need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            CP_FAIL(CP_ERR_WORKSPACE, "factor allocation of %zu bytes failed: %s", fac_need, cudaGetErrorString(e));
+        }
+        h->fac_bytes = fac_need;
+    }
+    h->fac_K = 0;
+    cp_carver fc(h->fac);
+    double *L = fc.take<double>(nM);
+    double *Linv = fc.take<double>((size_t)npanel * PB * PB);
+    double *ratio = fc.take<double>(1);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, cp_carver::need(nM, 8) + cp_carver::need(Ksel, 8), &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    double *M = cv.take<double>(nM);
+    double *diag0 = cv.take<double>(Ksel);
+    CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
+    CP_CUDA(cudaMemsetAsync(ratio, 0x7f, sizeof(double), stream));  // 1.4e306: "no pivot seen yet"
+    dim3 grid(cp_cdiv(Ksel, 256), Ksel);
+    ls_assemble<<<grid, 256, 0, stream>>>(G, nullptr, sx, nullptr, 1.0 / (double)N, K, 0, sel_cols, Ksel, M, ld, diag0);
+    CP_CHECK_LAUNCH();
+    rc = chol_factor(h, M, L, ld, Ksel, 0, Linv, diag0, info_out, ratio, stream);
+    if (rc) return rc;
+    if (stat_out) CP_CUDA(cudaMemcpyAsync(stat_out, ratio, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    h->fac_K = Ksel;
+    h->fac_Kfull = K;
+    h->fac_N = N;
+    return CP_OK;
+}
+
+namespace {
+// rows of the right-hand sides, transposed and centred: Zt[t, j] = Bxy[sel_j, t] - sx[sel_j] sy[t] / N
+__global__ void __launch_bounds__(256)
+rhs_assemble(const double *__restrict__ Bxy, const double *__restrict__ sx, const double *__restrict__ sy, double invN,
+             int n, const int32_t *__restrict__ sel, int Ks, double *__restrict__ Zt, int64_t ld) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int t = blockIdx.y;
+    if (j >= Ks) return;
+    const int sj = sel ? sel[j] : j;
+    Zt[(int64_t)t * ld + j] = Bxy[(int64_t)sj * n + t] - sx[sj] * sy[t] * invN;
+}
+}  // namespace
+
+extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const double *sy, int n,
+                             const int32_t *sel_cols, double *W_out, double *b_out, cp_stream_t stream_) {
+    CP_REQUIRE(h && Bxy && sx && sy && W_out && b_out, "cp_ls_resolve: NULL argument");
+    CP_REQUIRE(h->fac_K > 0, "cp_ls_resolve: no factor on this handle (call cp_ls_factor first)");
+    CP_REQUIRE(n > 0, "cp_ls_resolve: bad shape");
+    CP_REQUIRE(sel_cols || h->fac_K == h->fac_Kfull, "cp_ls_resolve: sel_cols needed (the factor used a column subset)");
+    CP_DEVICE_GUARD(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int Ksel = h->fac_K;
+    const int64_t ld = ld_for(Ksel);
+    const int npanel = (Ksel + PB - 1) / PB;
+    cp_carver fc(h->fac);
+    const double *L = fc.take<double>((size_t)Ksel * ld);
+    const double *Linv = fc.take<double>((size_t)npanel * PB * PB);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, 3 * cp_carver::need((size_t)n * ld, 8), &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    double *Zt = cv.take<double>((size_t)n * ld);
+    double *F = cv.take<double>((size_t)n * ld);
+    double *Wt = cv.take<double>((size_t)n * ld);
+    const double invN = 1.0 / (double)h->fac_N;
+    rhs_assemble<<<dim3(cp_cdiv(Ksel, 256), n), 256, 0, stream>>>(Bxy, sx, sy, invN, n, sel_cols, Ksel, Zt, ld);
+    CP_CHECK_LAUNCH();
+    rc = chol_forward(L, ld, Ksel, Linv, Zt, F, ld, n, stream);
+    if (rc) return rc;
+    rc = chol_backward(L, ld, Ksel, Linv, F, ld, Wt, ld, n, stream);
+    if (rc) return rc;
+    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }
@@ -351,7 +653,7 @@ center_sel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__
            const double *__restrict__ mean, double *__restrict__ Xc, int64_t ld) {
     const int j = blockIdx.x * 256 + threadIdx.x;
     const int64_t r = blockIdx.y;
-    if (j < Ks) Xc[r * ld + j] = (double)__ldg(X + r * ldx + sel[j]) - mean[j];
+    if (j < Ks) Xc[r * ld + j] = (double)__ldg(X + r * ldx + (sel ? sel[j] : j)) - mean[j];
 }
 
 // rows N..N+n-1 of the augmented matrix: Yc' (n x N):  M[N + t, r] = Y[r, t] - bias_t - ymean_t
@@ -398,32 +700,40 @@ dual_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict_
 
 extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw,
                                 int y_dtype, int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel,
-                                double *W_out, double *b_out, int32_t *info_out, cp_stream_t stream_) {
+                                double *W_out, double *b_out, int32_t *info_out, double *stat_out, cp_stream_t stream_) {
     using namespace cpgemm;
-    CP_REQUIRE(h && X && Yraw && sel_cols && W_out && b_out && info_out, "cp_ls_solve_dual: NULL argument");
+    CP_REQUIRE(h && X && Yraw && W_out && b_out && info_out, "cp_ls_solve_dual: NULL argument");
     CP_REQUIRE(N > 1 && N < (1 << 15) && K > 0 && n > 0 && Ksel > 0 && Ksel <= K && ldx >= K && ldy >= n,
                "cp_ls_solve_dual: bad shape (N must be < 32768)");
+    CP_REQUIRE(sel_cols || Ksel == K, "cp_ls_solve_dual: sel_cols may be NULL only when every column is used");
+    CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_solve_dual: unknown y_dtype %d", y_dtype);
+    CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int Ni = (int)N;
-    const int64_t ldc = (Ksel + 7) / 8 * 8;  // Xc
-    const int64_t ldm = (Ni + 7) / 8 * 8;    // dual system
-    const int npanel = (Ni + NB - 1) / NB;
-    const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + cp_carver::need((size_t)(Ni + n) * ldm, 8) +
-                        cp_carver::need((size_t)npanel * NB * NB, 8) + cp_carver::need((size_t)n * ldc, 8) +
-                        cp_carver::need(Ksel, 8) + cp_carver::need(n, 8) + cp_carver::need(Ni, 8);
+    const int64_t ldc = ld_for(Ksel);  // Xc
+    const int64_t ldm = ld_for(Ni);    // dual system
+    const int npanel = (Ni + PB - 1) / PB;
+    const size_t nM = (size_t)(Ni + n) * ldm;
+    const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + 2 * cp_carver::need(nM, 8) +
+                        cp_carver::need((size_t)npanel * PB * PB, 8) + cp_carver::need((size_t)n * ldm, 8) +
+                        cp_carver::need((size_t)n * ldc, 8) + cp_carver::need(Ksel, 8) + cp_carver::need(n, 8) +
+                        cp_carver::need(Ni, 8) + cp_carver::need(1, 8);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     double *Xc = cv.take<double>((size_t)Ni * ldc);
-    double *M = cv.take<double>((size_t)(Ni + n) * ldm);
-    double *Linv = cv.take<double>((size_t)npanel * NB * NB);
+    double *M = cv.take<double>(nM);
+    double *L = cv.take<double>(nM);
+    double *Linv = cv.take<double>((size_t)npanel * PB * PB);
+    double *At = cv.take<double>((size_t)n * ldm);
     double *Wt = cv.take<double>((size_t)n * ldc);
     double *xmean = cv.take<double>(Ksel);
     double *ymean = cv.take<double>(n);
     double *diag0 = cv.take<double>(Ni);
+    double *ratio = cv.take<double>(1);
     CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
-    CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_solve_dual: unknown y_dtype %d", y_dtype);
+    CP_CUDA(cudaMemsetAsync(ratio, 0x7f, sizeof(double), stream));  // 1.4e306: "no pivot seen yet"
     colmean_sel<float><<<cp_cdiv(Ksel, 32), 256, 0, stream>>>(X, ldx, sel_cols, Ksel, N, nullptr, xmean);
     CP_CHECK_LAUNCH();
     if (y_dtype == CP_F32)
@@ -434,7 +744,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     center_sel<<<dim3(cp_cdiv(Ksel, 256), Ni), 256, 0, stream>>>(X, ldx, sel_cols, Ksel, xmean, Xc, ldc);
     CP_CHECK_LAUNCH();
     // H = Xc Xc' (lower tiles) + 1/N
-    rc = dgemm<false>(Xc, ldc, Xc, ldc, M, ldm, Ni, Ni, Ksel, 1.0, 0.0, TILES_LOWER, stream);
+    rc = dgemm_big(Xc, ldc, Xc, ldc, M, ldm, Ni, Ni, Ksel, 1.0, 0.0, TILES_LOWER, stream);
     if (rc) return rc;
     add_const_lower<<<dim3(cp_cdiv(Ni, 256), Ni), 256, 0, stream>>>(M, ldm, Ni, 1.0 / (double)N, diag0);
     CP_CHECK_LAUNCH();
@@ -443,12 +753,23 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     else
         dual_rhs<double><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
     CP_CHECK_LAUNCH();
-    rc = chol_solve_inplace(h, M, ldm, Ni, n, Linv, diag0, info_out, stream);
+    rc = chol_factor(h, M, L, ldm, Ni, n, Linv, diag0, info_out, ratio, stream);
+    if (rc) return rc;
+    rc = chol_backward(L, ldm, Ni, Linv, L + (int64_t)Ni * ldm, ldm, At, ldm, n, stream);
     if (rc) return rc;
     // Wt = At * Xc   (C[t, i] = sum_r At[t, r] * Xc[r, i])
-    rc = dgemm<true>(M + (int64_t)Ni * ldm, ldm, Xc, ldc, Wt, ldc, n, Ksel, Ni, 1.0, 0.0, TILES_ALL, stream);
-    if (rc) return rc;
+    {
+        Args g{};
+        g.A = At; g.lda = ldm; g.B = Xc; g.ldb = ldc; g.C = Wt; g.ldc = ldc;
+        g.M = n; g.Nn = Ksel; g.R = Ni;
+        g.nsplit = 1; g.r_per_split = Ni;
+        g.alpha = 1.0; g.beta = 0.0; g.tile_mode = TILES_ALL;
+        g.a_vec = al16(At) && (ldm % 2 == 0);
+        g.b_vec = al16(Xc) && (ldc % 2 == 0);
+        CP_GEMM_LAUNCH((launch<double, double, false, true>(g, stream)));
+    }
     dual_output<<<n, 256, 0, stream>>>(Wt, ldc, xmean, ymean, Ksel, W_out, b_out);
     CP_CHECK_LAUNCH();
+    if (stat_out) CP_CUDA(cudaMemcpyAsync(stat_out, ratio, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     return CP_OK;
 }

@@ -21,6 +21,11 @@ from . import _cabi
 
 RAND_R_MAX = 2147483647
 MAX_PROBES = 64
+# Least squares from tensor-core (3xTF32) statistics is accepted only while the smallest Cholesky pivot keeps at
+# least this fraction of its original diagonal entry (1 - R^2 of the most collinear column).  Below it the ~4e-7
+# relative error of the 3xTF32 Gram is amplified past the 1e-4 weight tolerance, and the layer is re-solved from
+# exact-product fp64 statistics (tests/test_gpu_conditioning.py maps error against this ratio).
+LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.05"))
 
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
 GRAM_FP64, GRAM_3XTF32 = 0, 1
@@ -200,7 +205,7 @@ class Engine:
                                     rows.numel() if rows is not None else 0, self._p(G, "double*"),
                                     self._p(Bxy, "double*"), self._p(sx, "double*"), self._p(sy, "double*"),
                                     self._p(yy, "double*"), self.gram_mode if mode is None else mode, self._s()))
-        out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n)
+        out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n, mode=self.gram_mode if mode is None else mode)
         return out
 
     def lasso_build(self, gs, gw, W2m, c, k2, S):
@@ -249,33 +254,59 @@ class Engine:
         return LassoResult(idxs, coef, scalars, plog, seeds_d)
 
     def ls_solve(self, g, sel_cols):
-        """Centred normal-equation LS on columns ``sel_cols`` (int32 device tensor, ascending).
-        Returns (W (n, Ksel) fp64, b (n,) fp64, info (1,) int32) on device."""
-        Ks = sel_cols.numel()
+        """Centred normal-equation LS on columns ``sel_cols`` (int32 device tensor, ascending; None = all).
+        Returns (W (n, Ksel) fp64, b (n,) fp64, info (1,) int32, stat (1,) fp64) on device; stat is the smallest
+        pivot / original-diagonal ratio of the Cholesky (conditioning signal, see include/cpb200.h)."""
+        Ks = sel_cols.numel() if sel_cols is not None else g["K"]
         n = g["n"]
         W = self.empty(n, Ks)
         b = self.empty(n)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        stat = self.empty(1)
         self._call(self.lib.cp_ls_solve(self.h, self._p(g["G"], "const double*"), self._p(g["B"], "const double*"),
                                         self._p(g["sx"], "const double*"), self._p(g["sy"], "const double*"),
                                         g["N"], g["K"], n, self._p(sel_cols, "const int32_t*"), Ks,
                                         self._p(W, "double*"), self._p(b, "double*"), self._p(info, "int32_t*"),
-                                        self._s()))
-        return W, b, info
+                                        self._p(stat, "double*"), self._s()))
+        return W, b, info, stat
 
     def ls_solve_dual(self, X, Y, y_bias, sel_cols):
         N, K = X.shape
         n = Y.shape[1]
-        Ks = sel_cols.numel()
+        Ks = sel_cols.numel() if sel_cols is not None else K
         W = self.empty(n, Ks)
         b = self.empty(n)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        stat = self.empty(1)
         self._call(self.lib.cp_ls_solve_dual(self.h, self._p(X, "const float*"), N, K, X.stride(0),
                                              self._p(Y, "const void*"), 0 if Y.dtype == torch.float32 else 1, n,
                                              Y.stride(0), self._p(y_bias, "const float*"),
                                              self._p(sel_cols, "const int32_t*"), Ks, self._p(W, "double*"),
-                                             self._p(b, "double*"), self._p(info, "int32_t*"), self._s()))
-        return W, b, info
+                                             self._p(b, "double*"), self._p(info, "int32_t*"),
+                                             self._p(stat, "double*"), self._s()))
+        return W, b, info, stat
+
+    def ls_factor(self, g, sel_cols=None):
+        """Keeps the Cholesky factor of the centred Gram (columns ``sel_cols``) on the CURRENT handle for
+        subsequent ls_resolve calls.  Returns (info (1,) int32, stat (1,) fp64)."""
+        Ks = sel_cols.numel() if sel_cols is not None else g["K"]
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        stat = self.empty(1)
+        self._call(self.lib.cp_ls_factor(self.h, self._p(g["G"], "const double*"), self._p(g["sx"], "const double*"),
+                                         g["N"], g["K"], self._p(sel_cols, "const int32_t*"), Ks,
+                                         self._p(info, "int32_t*"), self._p(stat, "double*"), self._s()))
+        return info, stat
+
+    def ls_resolve(self, Bxy, sx, sy, sel_cols=None, Ks=None):
+        """Solve against the factor kept by ls_factor: Bxy (K, n) = X'U, sy (n,) = 1'U.  Returns (W (n, Ksel), b (n,))."""
+        n = Bxy.shape[1]
+        Ks = (sel_cols.numel() if sel_cols is not None else Bxy.shape[0]) if Ks is None else Ks
+        W = self.empty(n, Ks)
+        b = self.empty(n)
+        self._call(self.lib.cp_ls_resolve(self.h, self._p(Bxy, "const double*"), self._p(sx, "const double*"),
+                                          self._p(sy, "const double*"), n, self._p(sel_cols, "const int32_t*"),
+                                          self._p(W, "double*"), self._p(b, "double*"), self._s()))
+        return W, b
 
     # ------------------------------------------------------------------ composite: one layer problem
     def select_channels_async(self, X, W2m, Y, y_bias, samples, c, k2, rank, rank_tol, right0, seeds):
@@ -291,16 +322,34 @@ class Engine:
         res = self.lasso_select(Q, qv, yn2, float(S) * n, rank, lbound, rbound, right0, seeds)
         return g_full, res
 
-    def reconstruct_async(self, g_full, X, Y, y_bias, idxs_host, k2):
-        """LS on the surviving channels (device outputs; no host sync)."""
+    def _cols_device(self, idxs_host, k2, K):
         sel = np.flatnonzero(idxs_host)
         cols = (sel[:, None] * k2 + np.arange(k2)[None, :]).reshape(-1).astype(np.int32)
-        pin = self.pinned(("cols", self._ring()), (g_full["K"],), torch.int32)  # no pageable (synchronising) copy
+        pin = self.pinned(("cols", self._ring()), (K,), torch.int32)  # no pageable (synchronising) copy
         pin.numpy()[:cols.size] = cols
-        cols_d = pin[:cols.size].to(self.device, non_blocking=True)
-        if g_full["N"] - 1 >= cols.size:
+        return pin[:cols.size].to(self.device, non_blocking=True)
+
+    def reconstruct_async(self, g_full, X, Y, y_bias, idxs_host, k2):
+        """LS on the surviving channels (device outputs; no host sync).  Returns (W, b, info, stat)."""
+        cols_d = self._cols_device(idxs_host, k2, g_full["K"])
+        if g_full["N"] - 1 >= cols_d.numel():
             return self.ls_solve(g_full, cols_d)
         return self.ls_solve_dual(X, Y, y_bias, cols_d)
+
+    def reconstruct_exact_async(self, X, Y, y_bias, idxs_host, k2):
+        """The same solve from exact-product fp64 statistics (the slow path of the conditioning policy)."""
+        g = self.gram(X, Y, y_bias=y_bias, mode=GRAM_FP64)
+        return self.reconstruct_async(g, X, Y, y_bias, idxs_host, k2)
+
+    @staticmethod
+    def ls_verdict(info, stat, mode, dual=False):
+        """'ok' | 'redo' (tensor-core statistics too inaccurate for this conditioning: re-solve in fp64) |
+        'singular' (a pivot fell below sklearn's rank cut-off even with exact statistics)."""
+        if mode == GRAM_FP64 or dual:
+            return "singular" if info else "ok"
+        if info or not (stat >= LS_RATIO_MIN):
+            return "redo"
+        return "ok"
 
 
 def window(rank, rank_tol):

@@ -135,14 +135,34 @@ def _dictionary_device(eng, Xd, W2m, Yd, y_bias, c, h, rank, alpha=1e-4):
                                % (MAX_PROBES, info["probes"]))
         alpha = float(scal[0])
         idxs = res.idxs.cpu().numpy().astype(bool)
-    Wd, bd, info_d = eng.reconstruct_async(g_full, Xd, Yd, y_bias, idxs, k2)
-    fail = int(info_d.cpu()[0])
-    if fail:
-        raise np.linalg.LinAlgError("least-squares system not positive definite at pivot %d" % fail)
+    Wd, bd = _solve_ls(eng, g_full, Xd, Yd, y_bias, idxs, k2, info)
     cfgs.alpha = alpha  # :626-627
     info["alpha"] = alpha
     DictionaryInfo.last = info
     return idxs, Wd, bd
+
+
+def _solve_ls(eng, g_full, Xd, Yd, y_bias, idxs, k2, info=None):
+    """LS on the surviving channels with the conditioning policy of engine.LS_RATIO_MIN: statistics from the
+    tensor-core Gram are used while the Cholesky stays well conditioned, otherwise the layer is re-solved from
+    exact-product fp64 statistics; a pivot below sklearn's rank cut-off (cond=1e-6, _base.py:752) raises."""
+    Wd, bd, info_d, stat_d = eng.reconstruct_async(g_full, Xd, Yd, y_bias, idxs, k2)
+    dual = not (g_full["N"] - 1 >= int(np.count_nonzero(idxs)) * k2)
+    fail, ratio = int(info_d.cpu()[0]), float(stat_d.cpu()[0])
+    verdict = eng.ls_verdict(fail, ratio, g_full["mode"], dual)
+    if info is not None:
+        info["ls"] = {"pivot_ratio": ratio, "verdict": verdict}
+    if verdict == "redo":
+        Wd, bd, info_d, stat_d = eng.reconstruct_exact_async(Xd, Yd, y_bias, idxs, k2)
+        fail, ratio = int(info_d.cpu()[0]), float(stat_d.cpu()[0])
+        verdict = "singular" if fail else "ok"
+        if info is not None:
+            info["ls"].update(pivot_ratio_exact=ratio, verdict="redo->" + verdict)
+    if verdict == "singular":
+        raise np.linalg.LinAlgError(
+            "least-squares system is numerically rank deficient (pivot %d below 1e-12 of its diagonal: the "
+            "reference's gelsd would truncate here)" % fail)
+    return Wd, bd
 
 
 def fc_kernel(X, Y, copy_X=True, W=None, B=None, ret_reg=False, fit_intercept=True):
@@ -159,14 +179,7 @@ def fc_kernel(X, Y, copy_X=True, W=None, B=None, ret_reg=False, fit_intercept=Tr
     Yd = _dev_y(Y, eng)
     g = eng.gram(Xd, Yd)
     K = Xd.shape[1]
-    cols = torch.arange(K, dtype=torch.int32, device=eng.device)
-    if g["N"] - 1 >= K:
-        Wd, bd, info_d = eng.ls_solve(g, cols)
-    else:
-        Wd, bd, info_d = eng.ls_solve_dual(Xd, Yd, None, cols)
-    fail = int(info_d.cpu()[0])
-    if fail:
-        raise np.linalg.LinAlgError("least-squares system not positive definite at pivot %d" % fail)
+    Wd, bd = _solve_ls(eng, g, Xd, Yd, None, np.ones(K, dtype=bool), 1)
     return Wd.cpu().numpy(), bd.cpu().numpy()
 
 

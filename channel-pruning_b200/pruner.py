@@ -42,9 +42,21 @@ def slot_size(c, n, k2, rank, rank_tol):
     return 4 + c + n + n * cmax * k2
 
 
-def pack_result(buf, offset, idxs, W, b, alpha, nprobe, c, n, k2):
-    """buf: 1-D float64 tensor (any device).  Layout: [c', alpha, nprobe, 0, idxs(c), b(n), W(n*c'*k2)]."""
+def pack_result(buf, offset, idxs, W, b, alpha, nprobe, c, n, k2, eng=None, slot=0):
+    """buf: 1-D float64 tensor (any device).  Layout: [c', alpha, nprobe, 0, idxs(c), b(n), W(n*c'*k2)].
+    With ``eng`` the host-side scalars/mask are staged through an engine-owned PINNED buffer and every copy is
+    asynchronous on the current stream (a pageable copy would make torch synchronise the stream: the pattern
+    engine.lasso_select documents as a serialising bug); W / b may live on the device or in pinned host memory."""
     cp = int(idxs.sum())
+    if eng is not None:
+        head = eng.pinned(("pack", slot), (4 + c,), torch.float64)
+        hn = head.numpy()
+        hn[0], hn[1], hn[2], hn[3] = cp, alpha, nprobe, 0.0
+        hn[4:] = idxs
+        buf[offset:offset + 4 + c].copy_(head, non_blocking=True)
+        buf[offset + 4 + c:offset + 4 + c + n].copy_(b.reshape(-1), non_blocking=True)
+        buf[offset + 4 + c + n:offset + 4 + c + n + n * cp * k2].copy_(W.reshape(-1), non_blocking=True)
+        return
     head = torch.tensor([cp, alpha, nprobe, 0.0], dtype=torch.float64)
     buf[offset:offset + 4] = head.to(buf.device)
     buf[offset + 4:offset + 4 + c] = torch.as_tensor(idxs.astype(np.float64)).to(buf.device)
@@ -205,6 +217,7 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
     # phase 2 in COMPLETION order of the searches (which layer finishes first depends on sizes and, with
     # host-resident inputs, on the transfer order): poll the events, reconstruct whichever is ready
     pending = list(reversed(range(len(shapes))))
+    checks = []
     while pending:
         ready = [i for i in pending if phase1[i][2] is None or phase1[i][4].query()]
         if not ready:
@@ -227,24 +240,56 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             r.alpha, r.nprobe = float(scal[0]), int(scal[1])
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
         with ctx:
-            W, b, info = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], r.idxs, s.k * s.k)
-            if to_host:
-                # engine-owned pinned buffers: valid until the next prune_layers call on this engine
-                Wh = eng.pinned(("W", i), W.shape, torch.float64)
-                bh = eng.pinned(("b", i), b.shape, torch.float64)
-                Wh.copy_(W, non_blocking=True)
-                bh.copy_(b, non_blocking=True)
-                r.W, r.b = Wh, bh
-            else:
-                r.W, r.b = W, b
-            r.info = info
+            W, b, info, stat = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], r.idxs, s.k * s.k)
+            chk = (eng.pinned(("lsinfo", i), (1,), torch.int32), eng.pinned(("lsstat", i), (1,), torch.float64))
+            chk[0].copy_(info, non_blocking=True)
+            chk[1].copy_(stat, non_blocking=True)
+            r.W, r.b = _maybe_to_host(eng, i, W, b, to_host)  # eager: the copy overlaps the other layers' solves
+            ev_ls = torch.cuda.Event()
+            ev_ls.record()
             _mark(trace, s.name, "ls_done")
         r.probes = res
+        r.info = {"mode": g_full["mode"], "dual": not (g_full["N"] - 1 >= int(r.idxs.sum()) * s.k * s.k)}
         out[i] = r
+        checks.append((i, chk, ev_ls))
+    # ---- every reconstruction is CHECKED before it is handed out: Cholesky status + conditioning signal.
+    # Tensor-core statistics are accepted only for well-conditioned systems (engine.LS_RATIO_MIN); otherwise the
+    # layer is re-solved from exact-product fp64 statistics; a system that is rank deficient by sklearn's cut-off
+    # raises (the reference's gelsd would silently truncate there).
+    for i, chk, ev_ls in checks:
+        ev_ls.synchronize()
+        s, d, r = shapes[i], datas[i], out[i]
+        fail, ratio = int(chk[0][0]), float(chk[1][0])
+        verdict = eng.ls_verdict(fail, ratio, r.info["mode"], r.info["dual"])
+        r.info.update(pivot_ratio=ratio, verdict=verdict)
+        if verdict == "redo":
+            stream = eng.use_slot(i)
+            ctx = torch.cuda.stream(stream) if stream is not None else _null()
+            with ctx:
+                X = phase1[i][0]
+                W, b, info, stat = eng.reconstruct_exact_async(X, d["feats"], d["b2"], r.idxs, s.k * s.k)
+                fail, ratio = int(info.cpu()[0]), float(stat.cpu()[0])
+                r.W, r.b = _maybe_to_host(eng, i, W, b, to_host)
+            verdict = "singular" if fail else "ok"
+            r.info.update(pivot_ratio_exact=ratio, verdict="redo->" + verdict)
+        if verdict == "singular":
+            raise np.linalg.LinAlgError("layer %s: least-squares system numerically rank deficient (pivot %d)"
+                                        % (s.name, fail))
     for st in eng.streams:
         if st is not None:
             main.wait_stream(st)
     return out
+
+
+def _maybe_to_host(eng, i, W, b, to_host):
+    if not to_host:
+        return W, b
+    # engine-owned pinned buffers: valid until the next prune_layers call on this engine
+    Wh = eng.pinned(("W", i), W.shape, torch.float64)
+    bh = eng.pinned(("b", i), b.shape, torch.float64)
+    Wh.copy_(W, non_blocking=True)
+    bh.copy_(b, non_blocking=True)
+    return Wh, bh
 
 
 class _null:
@@ -270,7 +315,8 @@ def prune_network_sharded(eng: Engine, shapes, make_data, rank, world_size, righ
     off = 0
     for j, i in enumerate(mine):
         s = shapes[i]
-        pack_result(buf, off, res[j].idxs, res[j].W, res[j].b, res[j].alpha, res[j].nprobe, s.c, s.n, s.k * s.k)
+        pack_result(buf, off, res[j].idxs, res[j].W, res[j].b, res[j].alpha, res[j].nprobe, s.c, s.n, s.k * s.k,
+                    eng=eng, slot=j)
         off += sizes[i]
     if world_size > 1:
         allbuf = allgather_results(buf, world_size, group)

@@ -154,16 +154,19 @@ int cp_lasso_select(cp_handle_t h, const double *Q, int ldq, const double *qv, c
  * Least-squares reconstruction on the surviving channels -- replaces fc_kernel /
  * LinearRegression(fit_intercept=True).fit (lib/decompose.py:622-623, 665-669) by
  * the centred normal equations on the principal sub-block of G:
- *   Gc = G[sel,sel] - sx sx'/N,  Bc = Bxy[sel,:] - sx sy'/N,  Gc W = Bc  (Cholesky)
+ *   Gc = G[sel,sel] - sx sx'/N,  Bc = Bxy[sel,:] - sx sy'/N,  Gc W = Bc  (blocked Cholesky)
  *   b  = (sy - sx' W)/N
- * sel_cols : Ksel int32 column indices (device), ascending.
+ * sel_cols : Ksel int32 column indices (device), ascending; NULL = all K columns (Ksel == K).
  * W_out : n x Ksel fp64 row-major (== coef_, i.e. newW2.reshape(n, c', k, k));
- * b_out : n fp64.  info_out : 1 int32 (0 ok, j>0: pivot j not positive).
+ * b_out : n fp64.  info_out : 1 int32 (0 ok, j>0: pivot j fell below 1e-12 of its original diagonal entry --
+ * the squared form of the sigma < 1e-6 sigma_max cut-off of LinearRegression, sklearn _base.py:752-753).
+ * stat_out : NULL or 1 double: the smallest pivot / original-diagonal ratio met (1 - R^2 of the most collinear
+ * column given its predecessors) -- the caller's conditioning signal for choosing the Gram arithmetic.
  * Requires N - 1 >= Ksel (otherwise use cp_ls_solve_dual).
  */
 int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
                 int64_t N, int K, int n, const int32_t *sel_cols, int Ksel, double *W_out, double *b_out,
-                int32_t *info_out, cp_stream_t stream);
+                int32_t *info_out, double *stat_out, cp_stream_t stream);
 
 /*
  * Minimum-norm least squares for N - 1 < Ksel (what gelsd returns for the
@@ -173,7 +176,19 @@ int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double 
  */
 int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
                      int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, double *W_out,
-                     double *b_out, int32_t *info_out, cp_stream_t stream);
+                     double *b_out, int32_t *info_out, double *stat_out, cp_stream_t stream);
+
+/*
+ * Factor once, refit many -- replaces the loop of nonlinear_fc (lib/decompose.py:671-685): 50 calls of
+ * fc_kernel(X, U, ret_reg=True) with the SAME X and changing targets U.  cp_ls_factor keeps the Cholesky factor
+ * of the centred Gram of the selected columns inside the handle (until the next cp_ls_factor on that handle);
+ * cp_ls_resolve solves for new targets given their cross products Bxy = X'U (K x n) and column sums sy = 1'U:
+ *   W_out (n x Ksel), b_out (n)  as in cp_ls_solve.  sx / sel_cols must be the ones given to cp_ls_factor.
+ */
+int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, int64_t N, int K, const int32_t *sel_cols,
+                 int Ksel, int32_t *info_out, double *stat_out, cp_stream_t stream);
+int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const double *sy, int n,
+                  const int32_t *sel_cols, double *W_out, double *b_out, cp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -212,8 +212,23 @@ class DictState:
         self.rank_tol = rank_tol
 
 
+class SeedFeeder:
+    """Stands in for the numpy global RandomState where a test must hand the CD solver the SAME per-fit seeds the
+    device path was given (``rng.randint(0, RAND_R_MAX)`` is the only call Lasso.fit makes, _cd_fast.pyx:374)."""
+
+    def __init__(self, seeds):
+        self.seeds = [int(v) for v in seeds]
+        self.used = 0
+
+    def randint(self, lo, hi=None, size=None):
+        assert size is None
+        v = self.seeds[self.used]
+        self.used += 1
+        return v
+
+
 def dictionary(X, W2, Y, alpha=1e-4, rank=None, DEBUG=0, B2=None, rank_tol=.1, verbose=0, *, state=None,
-               samples=None, form="dense", engine="restated", max_probes=200, info=None):
+               samples=None, form="dense", engine="restated", max_probes=200, info=None, rng=None):
     """lib/decompose.py:386-634 on the default configuration of ``train.py -action c3``
     (dcfgs.autodet=False, solver='sklearn', ls='linear', dic.alter=0, dic.debug=0,
     fc_ridge=0, nonlinear_fc=0, nofc=0).
@@ -228,6 +243,9 @@ def dictionary(X, W2, Y, alpha=1e-4, rank=None, DEBUG=0, B2=None, rank_tol=.1, v
     ``max_probes`` guards the reference's unguarded ``while True`` loops
     (decompose.py:502,516); hitting it raises.
     """
+    import time as _time
+
+    _t0 = _time.perf_counter()
     state = state if state is not None else DictState()
     rank_tol = state.rank_tol  # decompose.py:393 (argument ignored)
     X = np.asarray(X)
@@ -251,7 +269,7 @@ def dictionary(X, W2, Y, alpha=1e-4, rank=None, DEBUG=0, B2=None, rank_tol=.1, v
 
             _solver = Lasso(alpha=alpha, warm_start=True, selection='random')  # (:449)
         else:
-            _solver = LassoCD(alpha=alpha, form=form)
+            _solver = LassoCD(alpha=alpha, form=form, rng=rng)
 
         def solve(a):  # decompose.py:453-466
             if len(probes) >= max_probes:
@@ -293,9 +311,13 @@ def dictionary(X, W2, Y, alpha=1e-4, rank=None, DEBUG=0, B2=None, rank_tol=.1, v
             info["coef"] = np.array(_solver.coef_)
             if engine != "sklearn":
                 info["cd_history"] = list(_solver.history)
+    _t1 = _time.perf_counter()
     # least squares on the survivors (:621-623)
     newW2, newB2 = fc_kernel(X[:, idxs, ...].reshape((N, -1)), Y,
                              W=np.asarray(W2)[:, idxs, ...].reshape(n, -1), B=B2)
+    if info is not None:
+        info["t_lasso"] = _t1 - _t0
+        info["t_ls"] = _time.perf_counter() - _t1
     newW2 = newW2.reshape((n, rank, h, w))
     state.alpha = alpha  # (:626-627); NB: with rank == c this is the *argument default*
     if info is not None:
@@ -401,9 +423,14 @@ def extract_XY(forward, X_name, Y_spec, points_dict):
 
 
 def dictionary_kernel(forward, X_name, Y_spec, W2, B2, feats_Y, points_dict, d_prime, *, state=None,
-                      samples=None, form="dense", engine="restated", info=None):
+                      samples=None, form="dense", engine="restated", info=None, rng=None):
     """lib/net.py:1685-1735 for the VGG branch (relu on X, resY = 0)."""
+    import time as _time
+
+    _t0 = _time.perf_counter()
     X = extract_XY(forward, X_name, Y_spec, points_dict)  # :1698
+    if info is not None:
+        info["t_gather"] = _time.perf_counter() - _t0
     h = W2.shape[-1]
     w = h
     newX = np.rollaxis(X.reshape((-1, h, w, X.shape[1])), 3, 1).copy()  # :1702
@@ -413,7 +440,7 @@ def dictionary_kernel(forward, X_name, Y_spec, W2, B2, feats_Y, points_dict, d_p
     if info is not None:
         info["rMSE"] = rel_error(newX.reshape((newX.shape[0], -1)).dot(W2.reshape((W2.shape[0], -1)).T), gtY)
     return dictionary(newX, W2, Y, rank=d_prime, B2=B2, state=state, samples=samples, form=form,
-                      engine=engine, info=info)
+                      engine=engine, info=info, rng=rng)
 
 
 def prune_block_R3(forward, conv_specs, weights, biases, feats_dict, points_dict, pairs, c_ratio=1.15, *,

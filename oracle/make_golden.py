@@ -30,7 +30,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 def run_dictionary_cases(D, CF):
     for name, spec in cases.DICTIONARY_CASES.items():
-        X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+        X, W2, Y = cases.case_inputs(spec)
         CF.alpha = spec["alpha0"]
         CF.c.dic.rank_tol = spec.get("rank_tol", .1)
         np.random.seed(spec["np_seed"])
@@ -39,7 +39,10 @@ def run_dictionary_cases(D, CF):
         np.savez_compressed(os.path.join(OUT, "dictionary_%s.npz" % name), idxs=idxs, W=W, B=B,
                             alpha_final=CF.alpha, rng_after=after,
                             checksum=np.array([X.sum(dtype=np.float64), W2.sum(dtype=np.float64), Y.sum()]))
-        print(name, "kept", int(idxs.sum()), "of", len(idxs), "alpha", CF.alpha)
+        Xs = X[:, idxs].reshape(X.shape[0], -1).astype(np.float64)
+        sv = np.linalg.svd(Xs - Xs.mean(0), compute_uv=False)
+        print(name, "kept", int(idxs.sum()), "of", len(idxs), "alpha", CF.alpha,
+              "cond(centred Gram of kept columns) %.2e" % ((sv[0] / sv[-1]) ** 2))
     CF.c.dic.rank_tol = .1
 
 

@@ -15,6 +15,47 @@ def dictionary_inputs(c, n, N, k, seed, noise=0.01):
     return X, W2, Y
 
 
+def correlated_inputs(c, n, N, k, seed, noise=0.01, H=20, collinear=None):
+    """Realistic conditioning: post-ReLU features of a random 3x3 conv over SMOOTH images (low-pass filtered
+    noise), so that channels and neighbouring taps are strongly correlated (cond of the centred Gram >= 1e4,
+    against ~1e1-1e3 for the iid inputs above).  ``collinear=(a, b, eps)`` makes channel b an almost exact
+    multiple of channel a (relative perturbation eps).  Same return convention as dictionary_inputs."""
+    r = np.random.RandomState(seed)
+    nimg = -(-N // 16)
+    img = r.standard_normal((nimg, 3, H + 8, H + 8))
+    for _ in range(3):  # separable box blur, three passes ~ gaussian
+        img = (img + np.roll(img, 1, 2) + np.roll(img, -1, 2)) / 3.0
+        img = (img + np.roll(img, 1, 3) + np.roll(img, -1, 3)) / 3.0
+    img = (img / img.std()).astype(np.float32)
+    w1 = (r.standard_normal((c, 3, 3, 3)) * np.sqrt(2.0 / 27)).astype(np.float32)
+    b1 = (0.1 * r.standard_normal(c)).astype(np.float32)
+    Hf = H + 6
+    feat = np.zeros((nimg, c, Hf, Hf), dtype=np.float32)
+    for dy in range(3):
+        for dx in range(3):
+            feat += np.einsum("bchw,oc->bohw", img[:, :, dy:dy + Hf, dx:dx + Hf], w1[:, :, dy, dx]).astype(np.float32)
+    feat = np.maximum(feat + b1[None, :, None, None], 0).astype(np.float32)
+    if collinear is not None:
+        a, b, eps = collinear
+        feat[:, b] = (feat[:, a] * np.float32(1.5) * (1 + eps * r.standard_normal(feat[:, a].shape))).astype(np.float32)
+    ys = r.randint(0, Hf - k + 1, N)
+    xs = r.randint(0, Hf - k + 1, N)
+    ims = r.randint(0, nimg, N)
+    X = np.stack([feat[i, :, y:y + k, x:x + k] for i, y, x in zip(ims, ys, xs)]).astype(np.float32)
+    W2 = (r.standard_normal((n, c, k, k)) * np.sqrt(2.0 / (c * k * k))).astype(np.float32)
+    Y = X.reshape(N, -1).astype(np.float64) @ W2.reshape(n, -1).T.astype(np.float64)
+    Y = Y + noise * Y.std() * r.standard_normal(Y.shape)
+    Y = Y.astype(np.float32).astype(np.float64)
+    return X, W2, Y
+
+
+def case_inputs(spec):
+    """Inputs of a DICTIONARY_CASES entry (iid generator unless the case names another one)."""
+    if spec.get("generator") == "correlated":
+        return correlated_inputs(**spec["gen"])
+    return dictionary_inputs(**spec["gen"])
+
+
 DICTIONARY_CASES = {
     # name: generator args, target rank, np.random.seed before the call, cfgs.alpha on entry
     "c32": dict(gen=dict(c=32, n=16, N=600, k=3, seed=11), rank=27, np_seed=5, alpha0=1e-3),
@@ -26,6 +67,13 @@ DICTIONARY_CASES = {
     "tol2": dict(gen=dict(c=40, n=24, N=800, k=3, seed=17), rank=30, np_seed=11, alpha0=1e-3, rank_tol=.2),
     # rank_tol >= 1 is an ABSOLUTE slack on the channel count (decompose.py:493-494): window [24, 27]
     "tolabs": dict(gen=dict(c=36, n=20, N=700, k=3, seed=18), rank=24, np_seed=12, alpha0=1e-3, rank_tol=3),
+    # correlated (real-conv-like) features: ill-conditioned least squares, the regime of real networks
+    "corr": dict(generator="correlated", gen=dict(c=32, n=24, N=1600, k=3, seed=19), rank=27, np_seed=13, alpha0=1e-3),
+    "corrbig": dict(generator="correlated", gen=dict(c=48, n=32, N=2400, k=3, seed=20), rank=41, np_seed=14,
+                    alpha0=1e-3),
+    # one channel an almost exact multiple of another (relative perturbation 1e-4): near-collinear columns
+    "collin": dict(generator="correlated", gen=dict(c=24, n=16, N=1200, k=3, seed=21, collinear=(3, 11, 1e-4)),
+                   rank=20, np_seed=15, alpha0=1e-3, w_tol=5e-5),
 }
 
 

@@ -230,7 +230,7 @@ def test_ls_solve_matches_lstsq(engine, N, K, n, nsel):
     Y = (X @ r.standard_normal((K, n)) + r.standard_normal((N, n))).astype(np.float32)
     sel = np.sort(r.choice(K, nsel, replace=False)).astype(np.int32)
     g = engine.gram(_dev(X, engine), _dev(Y, engine), mode=0)
-    W, b, info = engine.ls_solve(g, _dev(sel, engine))
+    W, b, info, _ = engine.ls_solve(g, _dev(sel, engine))
     assert int(info.cpu()[0]) == 0
     coef, icpt = O.linear_regression(X[:, sel].astype(np.float64), Y.astype(np.float64))
     assert np.linalg.norm(W.cpu().numpy() - coef) <= 1e-9 * np.linalg.norm(coef)
@@ -243,7 +243,7 @@ def test_ls_solve_dual_minimum_norm(engine):
     X = np.maximum(r.standard_normal((N, K)), 0).astype(np.float32)
     Y = r.standard_normal((N, n)).astype(np.float32)
     sel = np.arange(K, dtype=np.int32)
-    W, b, info = engine.ls_solve_dual(_dev(X, engine), _dev(Y, engine), None, _dev(sel, engine))
+    W, b, info, _ = engine.ls_solve_dual(_dev(X, engine), _dev(Y, engine), None, _dev(sel, engine))
     assert int(info.cpu()[0]) == 0
     coef, icpt = O.linear_regression(X.astype(np.float64), Y.astype(np.float64))
     assert np.linalg.norm(W.cpu().numpy() - coef) <= 1e-8 * np.linalg.norm(coef)
@@ -256,5 +256,5 @@ def test_ls_solve_flags_singular_system(engine):
     X[:, 7] = X[:, 3]  # exactly collinear columns
     Y = r.standard_normal((400, 3)).astype(np.float32)
     g = engine.gram(_dev(X, engine), _dev(Y, engine), mode=0)
-    W, b, info = engine.ls_solve(g, _dev(np.arange(20, dtype=np.int32), engine))
+    W, b, info, _ = engine.ls_solve(g, _dev(np.arange(20, dtype=np.int32), engine))
     assert int(info.cpu()[0]) != 0

@@ -30,7 +30,7 @@ def test_dictionary_matches_reference_golden(engine, golden_dir, name, mode):
 
     spec = cases.DICTIONARY_CASES[name]
     g = np.load(os.path.join(golden_dir, "dictionary_%s.npz" % name))
-    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    X, W2, Y = cases.case_inputs(spec)
     cfgs.alpha = spec["alpha0"]
     cfgs.c.dic.rank_tol = spec.get("rank_tol", .1)
     old_mode, engine.gram_mode = engine.gram_mode, mode
@@ -46,7 +46,9 @@ def test_dictionary_matches_reference_golden(engine, golden_dir, name, mode):
     assert cfgs.alpha == float(g["alpha_final"])
     assert W.dtype == np.float64 and W.shape == g["W"].shape
     assert _rel(W, g["W"]) <= W_TOL
-    tight = 1e-7 if mode == 0 else 2e-5  # what the two arithmetic modes actually deliver
+    # what the two arithmetic modes actually deliver; the near-collinear case (cond of the centred Gram 2e10) is
+    # limited by the normal equations in fp64, cond * 2e-16
+    tight = spec.get("w_tol", 1e-7 if mode == 0 else 2e-5)
     assert _rel(W, g["W"]) <= tight
     assert np.abs(B - g["B"]).max() <= tight * max(1.0, np.abs(g["B"]).max())
 
@@ -58,7 +60,7 @@ def test_dictionary_accepts_cuda_tensors(engine, golden_dir):
 
     spec = cases.DICTIONARY_CASES["c32"]
     g = np.load(os.path.join(golden_dir, "dictionary_c32.npz"))
-    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    X, W2, Y = cases.case_inputs(spec)
     cfgs.alpha = spec["alpha0"]
     np.random.seed(spec["np_seed"])
     idxs, W, B = decompose.dictionary(torch.as_tensor(X, device=engine.device), torch.as_tensor(W2, device=engine.device),
@@ -196,7 +198,7 @@ def test_full_size_properties_conv4_shape(engine, mode):
     assert float((grad[active] - l1 * torch.sign(w[active])).abs().max()) <= 5e-2 * l1
     # reconstruction: centred normal equations  Xc'(Yc - Xc W - b) = 0
     idxs = res.idxs.cpu().numpy().astype(bool)
-    Wd, bd, info = engine.reconstruct_async(g_full, X, d["feats"], d["b2"], idxs, 9)
+    Wd, bd, info, _ = engine.reconstruct_async(g_full, X, d["feats"], d["b2"], idxs, 9)
     assert int(info.cpu()[0]) == 0
     cols = torch.as_tensor((np.flatnonzero(idxs)[:, None] * 9 + np.arange(9)).reshape(-1), device=engine.device)
     Xs = X[:, cols].double()

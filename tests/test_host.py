@@ -199,32 +199,38 @@ def test_h2d_plan_stages_small_maps_and_reads_large_ones_in_place(monkeypatch):
     assert pruner.h2d_plan(shapes, datas, True) == ["zc"] * len(shapes)
 
 
-def test_reference_arm_rebounds_later_steps(monkeypatch):
-    """bench.py --impl reference: the first pass times every (c,n,k) class, later passes re-time only the classes
-    that fit the remaining budget and keep the earlier timing of the others (whole run stays within minutes)."""
+def test_reference_arm_reports_what_it_ran(monkeypatch, capsys):
+    """bench.py --impl reference: a step is ONE class problem (round-robin, cost-ascending), ms_per_step is the
+    measured wall time of the timed steps (so steps x ms_per_step is what the run really took), and the value
+    extrapolates the class timings to the 13-layer stack by multiplicity."""
     import importlib.util
+    import json
+    import types
 
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     import cpb200
 
-    cost = {64: 1.0, 128: 4.0, 256: 10.0, 512: 40.0, 3: 0.1}
+    cost = {64: .01, 128: .04, 256: .10, 512: .40, 3: .001}
     calls = []
 
     def fake_seconds(shape, seed):
-        calls.append(shape.c)
-        return cost[shape.c]
+        calls.append((shape.c, shape.n))
+        return cost[shape.c], {"t_gather": 0.1 * cost[shape.c], "t_lasso": 0.4 * cost[shape.c], "t_ls": 0.5 * cost[shape.c]}
 
     monkeypatch.setattr(bench, "cpu_layer_seconds", fake_seconds)
+    monkeypatch.delenv("RANK", raising=False)
+    args = types.SimpleNamespace(gpus=1, steps=10, warmup=2, workload="vgg16", layers="")
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     shapes = cpb200.synth.vgg16_layers()
-    cache = {}
-    v1, m1, d1 = bench.cpu_pass(shapes, cache, None)
-    assert len(calls) == len(bench.shape_classes(shapes)) and "re-timed" not in d1
-    calls.clear()
-    v2, m2, d2 = bench.cpu_pass(shapes, cache, 6.0)
-    assert sorted(calls) == [3, 64, 64] and "re-timed" in d2   # 0.1 + 1 + 1 fit 6 s, the next class (4 s) does not
-    assert v2 == v1 and m2 < m1
-    calls.clear()
-    bench.cpu_pass(shapes, cache, 11.0)
-    assert sorted(calls) == [3, 64, 64, 128, 128]
+    classes = bench.shape_classes(shapes)
+    assert len(calls) == 12 and set(calls) == set((c, n) for c, n, _ in classes)  # 12 steps cover the 8 classes
+    want = len(shapes) / sum(cost[c] * len(m) for (c, n, k), m in classes.items())
+    assert abs(line["value"] - want) <= 1e-9 * want
+    assert line["impl"] == "reference" and line["steps"] == 10 and line["cpu_baseline"]["kind"] == "port"
+    assert line["ms_per_step"] * line["steps"] < 5e3  # the fake problems take no time: what was RUN, not 13 layers/step
+    st = line["cpu_baseline"]["stack_seconds"]
+    assert abs(st["lasso"] + st["ls"] + st["gather"] - len(shapes) / want) <= 1e-9
+    assert line["config"] == bench.config_dict(args, shapes, 1)

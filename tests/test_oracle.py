@@ -18,7 +18,7 @@ def _load(golden_dir, name):
 def test_dictionary_matches_reference_golden(golden_dir, name, form):
     spec = cases.DICTIONARY_CASES[name]
     g = _load(golden_dir, "dictionary_%s.npz" % name)
-    X, W2, Y = cases.dictionary_inputs(**spec["gen"])
+    X, W2, Y = cases.case_inputs(spec)
     np.testing.assert_array_equal(g["checksum"], [X.sum(dtype=np.float64), W2.sum(dtype=np.float64), Y.sum()])
     st = O.DictState(alpha=spec["alpha0"], rank_tol=spec.get("rank_tol", .1))
     np.random.seed(spec["np_seed"])
