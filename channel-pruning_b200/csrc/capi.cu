@@ -34,6 +34,7 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->fac_bytes = 0;
     h->fac_K = h->fac_Kfull = 0;
     h->fac_N = 0;
+    h->fac_rows = 0;
     *out = h;
     return CP_OK;
 }

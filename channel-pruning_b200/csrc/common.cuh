@@ -22,6 +22,7 @@ struct cp_handle_s {
     size_t fac_bytes;
     int fac_K, fac_Kfull;
     int64_t fac_N;
+    int fac_rows;  // rows of L stored in `fac` (Ksel, or Ksel + n when right-hand sides rode along)
 };
 
 // Entry points run on the handle's device whatever the caller's current device is (restored on return).

@@ -307,14 +307,14 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
 __global__ void __launch_bounds__(256)
 ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ sx, const double *__restrict__ sy,
           const int32_t *__restrict__ sel, int Ks, double invN, double *__restrict__ W_out,
-          double *__restrict__ b_out) {
+          double *__restrict__ b_out, int accumulate) {
     __shared__ double red[256];
     const int t = blockIdx.x;
     const double *src = Wt + (int64_t)t * ld;
     double s = 0.0;
     for (int i = threadIdx.x; i < Ks; i += 256) {
         const double w = src[i];
-        W_out[(int64_t)t * Ks + i] = w;
+        W_out[(int64_t)t * Ks + i] = accumulate ? W_out[(int64_t)t * Ks + i] + w : w;
         s = fma(sx[sel ? sel[i] : i], w, s);
     }
     red[threadIdx.x] = s;
@@ -323,7 +323,10 @@ ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ 
         if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
         __syncthreads();
     }
-    if (threadIdx.x == 0) b_out[t] = (sy[t] - red[0]) * invN;
+    if (threadIdx.x == 0) {
+        const double v = (sy[t] - red[0]) * invN;
+        b_out[t] = accumulate ? b_out[t] + v : v;
+    }
 }
 
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
@@ -482,6 +485,32 @@ static int chol_backward(const double *L, int64_t ld, int Kd, const double *Linv
 
 static inline int64_t ld_for(int K) { return (K + 7) / 8 * 8; }
 
+// The factor (L: rows x ld, then the inverted 128 x 128 diagonal blocks, then the pivot-ratio scalar) lives in the
+// handle's own allocation, not in the shared scratch: it must survive the calls that follow a solve (refinement
+// against the same factor, cp_ls_resolve) and every other entry point reuses the scratch.
+static int fac_reserve(cp_handle_t h, size_t rows, int64_t ld, int npanel, double **L, double **Linv, double **ratio) {
+    const size_t need = cp_carver::need(rows * (size_t)ld, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) +
+                        cp_carver::need(1, 8);
+    if (need > h->fac_bytes) {
+        if (h->fac) CP_CUDA(cudaFree(h->fac));  // synchronises: nothing in flight still reads the old block
+        h->fac = nullptr;
+        h->fac_bytes = 0;
+        const size_t want = cp_align_up(need + need / 8, (size_t)1 << 20);
+        cudaError_t e = cudaMalloc(&h->fac, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            CP_FAIL(CP_ERR_WORKSPACE, "factor allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        h->fac_bytes = want;
+    }
+    h->fac_K = 0;
+    cp_carver fc(h->fac);
+    *L = fc.take<double>(rows * (size_t)ld);
+    *Linv = fc.take<double>((size_t)npanel * PB * PB);
+    *ratio = fc.take<double>(1);
+    return CP_OK;
+}
+
 extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, const double *sx, const double *sy,
                            int64_t N, int K, int n, const int32_t *sel_cols, int Ksel, double *W_out, double *b_out,
                            int32_t *info_out, double *stat_out, cp_stream_t stream_) {
@@ -495,18 +524,17 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     const int64_t ld = ld_for(Ksel);
     const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)(Ksel + n) * ld;
-    const size_t need = 2 * cp_carver::need(nM, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) +
-                        cp_carver::need((size_t)n * ld, 8) + cp_carver::need(Ksel, 8) + cp_carver::need(1, 8);
+    double *L = nullptr, *Linv = nullptr, *ratio = nullptr;
+    int rc = fac_reserve(h, (size_t)(Ksel + n), ld, npanel, &L, &Linv, &ratio);
+    if (rc) return rc;
+    const size_t need = cp_carver::need(nM, 8) + cp_carver::need((size_t)n * ld, 8) + cp_carver::need(Ksel, 8);
     void *ws = nullptr;
-    int rc = cp_ws_reserve(h, need, &ws);
+    rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     double *M = cv.take<double>(nM);
-    double *L = cv.take<double>(nM);
-    double *Linv = cv.take<double>((size_t)npanel * PB * PB);
     double *Wt = cv.take<double>((size_t)n * ld);
     double *diag0 = cv.take<double>(Ksel);
-    double *ratio = cv.take<double>(1);
     CP_CUDA(cudaMemsetAsync(info_out, 0, sizeof(int32_t), stream));
     CP_CUDA(cudaMemsetAsync(ratio, 0x7f, sizeof(double), stream));  // 1.4e306: "no pivot seen yet"
     const double invN = 1.0 / (double)N;
@@ -517,9 +545,13 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     if (rc) return rc;
     rc = chol_backward(L, ld, Ksel, Linv, L + (int64_t)Ksel * ld, ld, Wt, ld, n, stream);
     if (rc) return rc;
-    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
+    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out, 0);
     CP_CHECK_LAUNCH();
     if (stat_out) CP_CUDA(cudaMemcpyAsync(stat_out, ratio, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    h->fac_K = Ksel;  // the factor stays valid for cp_ls_resolve (refinement of this very solve)
+    h->fac_Kfull = K;
+    h->fac_N = N;
+    h->fac_rows = Ksel + n;
     return CP_OK;
 }
 
@@ -536,26 +568,11 @@ extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, in
     const int64_t ld = ld_for(Ksel);
     const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)Ksel * ld;
-    // the factor outlives this call: it lives in its own allocation, not in the shared scratch
-    const size_t fac_need = cp_carver::need(nM, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) + cp_carver::need(1, 8);
-    if (fac_need > h->fac_bytes) {
-        if (h->fac) CP_CUDA(cudaFree(h->fac));
-        h->fac = nullptr;
-        h->fac_bytes = 0;
-        cudaError_t e = cudaMalloc(&h->fac, fac_need);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            CP_FAIL(CP_ERR_WORKSPACE, "factor allocation of %zu bytes failed: %s", fac_need, cudaGetErrorString(e));
-        }
-        h->fac_bytes = fac_need;
-    }
-    h->fac_K = 0;
-    cp_carver fc(h->fac);
-    double *L = fc.take<double>(nM);
-    double *Linv = fc.take<double>((size_t)npanel * PB * PB);
-    double *ratio = fc.take<double>(1);
+    double *L = nullptr, *Linv = nullptr, *ratio = nullptr;
+    int rc = fac_reserve(h, (size_t)Ksel, ld, npanel, &L, &Linv, &ratio);
+    if (rc) return rc;
     void *ws = nullptr;
-    int rc = cp_ws_reserve(h, cp_carver::need(nM, 8) + cp_carver::need(Ksel, 8), &ws);
+    rc = cp_ws_reserve(h, cp_carver::need(nM, 8) + cp_carver::need(Ksel, 8), &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     double *M = cv.take<double>(nM);
@@ -571,6 +588,7 @@ extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, in
     h->fac_K = Ksel;
     h->fac_Kfull = K;
     h->fac_N = N;
+    h->fac_rows = Ksel;
     return CP_OK;
 }
 
@@ -588,7 +606,8 @@ rhs_assemble(const double *__restrict__ Bxy, const double *__restrict__ sx, cons
 }  // namespace
 
 extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const double *sy, int n,
-                             const int32_t *sel_cols, double *W_out, double *b_out, cp_stream_t stream_) {
+                             const int32_t *sel_cols, double *W_out, double *b_out, int accumulate,
+                             cp_stream_t stream_) {
     CP_REQUIRE(h && Bxy && sx && sy && W_out && b_out, "cp_ls_resolve: NULL argument");
     CP_REQUIRE(h->fac_K > 0, "cp_ls_resolve: no factor on this handle (call cp_ls_factor first)");
     CP_REQUIRE(n > 0, "cp_ls_resolve: bad shape");
@@ -599,7 +618,7 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     const int64_t ld = ld_for(Ksel);
     const int npanel = (Ksel + PB - 1) / PB;
     cp_carver fc(h->fac);
-    const double *L = fc.take<double>((size_t)Ksel * ld);
+    const double *L = fc.take<double>((size_t)h->fac_rows * ld);
     const double *Linv = fc.take<double>((size_t)npanel * PB * PB);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, 3 * cp_carver::need((size_t)n * ld, 8), &ws);
@@ -615,7 +634,74 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     if (rc) return rc;
     rc = chol_backward(L, ld, Ksel, Linv, F, ld, Wt, ld, n, stream);
     if (rc) return rc;
-    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out);
+    ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out, accumulate);
+    CP_CHECK_LAUNCH();
+    return CP_OK;
+}
+
+// ---------------------------------------------------------------- residual of a solve (iterative refinement)
+namespace {
+// Wf (n x K, zero for unselected columns) <- W (n x Ksel)
+__global__ void __launch_bounds__(256)
+scatter_cols(const double *__restrict__ W, int Ks, const int32_t *__restrict__ sel, double *__restrict__ Wf, int K) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int t = blockIdx.y;
+    if (j < Ks) Wf[(int64_t)t * K + (sel ? sel[j] : j)] = W[(int64_t)t * Ks + j];
+}
+// C[r, t] = Y[r, t] - y_bias[t] - b[t]
+template <typename T>
+__global__ void __launch_bounds__(256)
+residual_init(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ y_bias, const double *__restrict__ b,
+              int64_t N, int n, double *__restrict__ C) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    const double off = (y_bias ? (double)y_bias[t] : 0.0) + b[t];
+    for (int64_t r = blockIdx.y; r < N; r += gridDim.y) C[r * n + t] = (double)Y[r * ldy + t] - off;
+}
+__global__ void __launch_bounds__(256)
+to_float(const double *__restrict__ C, int64_t count, int n, float *__restrict__ R, int64_t ldr) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e < count) R[(e / n) * ldr + (e % n)] = (float)C[e];
+}
+}  // namespace
+
+extern "C" int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                              int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, const double *W,
+                              const double *b, float *R_out, int64_t ldr, cp_stream_t stream_) {
+    using namespace cpgemm;
+    CP_REQUIRE(h && X && Yraw && W && b && R_out, "cp_ls_residual: NULL argument");
+    CP_REQUIRE(N > 0 && K > 0 && n > 0 && Ksel > 0 && Ksel <= K && ldx >= K && ldy >= n && ldr >= n, "cp_ls_residual: bad shape");
+    CP_REQUIRE(sel_cols || Ksel == K, "cp_ls_residual: sel_cols may be NULL only when every column is used");
+    CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_residual: unknown y_dtype %d", y_dtype);
+    CP_DEVICE_GUARD(h);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t ldw = ld_for(K);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, cp_carver::need((size_t)n * ldw, 8) + cp_carver::need((size_t)N * n, 8), &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    double *Wf = cv.take<double>((size_t)n * ldw);
+    double *C = cv.take<double>((size_t)N * n);
+    CP_CUDA(cudaMemsetAsync(Wf, 0, (size_t)n * ldw * sizeof(double), stream));
+    scatter_cols<<<dim3(cp_cdiv(Ksel, 256), n), 256, 0, stream>>>(W, Ksel, sel_cols, Wf, (int)ldw);
+    CP_CHECK_LAUNCH();
+    const unsigned gy = (unsigned)(N < 4096 ? N : 4096);
+    if (y_dtype == CP_F32)
+        residual_init<float><<<dim3(cp_cdiv(n, 256), gy), 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, b, N, n, C);
+    else
+        residual_init<double><<<dim3(cp_cdiv(n, 256), gy), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, b, N, n, C);
+    CP_CHECK_LAUNCH();
+    // C -= X Wf'   (exact products of fp32 data with the fp64 weights, fp64 accumulation)
+    Args g{};
+    g.A = X; g.lda = ldx; g.B = Wf; g.ldb = ldw; g.C = C; g.ldc = n;
+    g.M = (int)N; g.Nn = n; g.R = K;
+    g.nsplit = 1; g.r_per_split = K;
+    g.alpha = -1.0; g.beta = 1.0; g.tile_mode = TILES_ALL;
+    g.a_vec = al16(X) && (ldx % 4 == 0);
+    g.b_vec = al16(Wf) && (ldw % 2 == 0);
+    CP_GEMM_LAUNCH((launch<float, double, false, false>(g, stream)));
+    const int64_t count = N * (int64_t)n;
+    to_float<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(C, count, n, R_out, ldr);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }

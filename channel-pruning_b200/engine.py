@@ -21,11 +21,14 @@ from . import _cabi
 
 RAND_R_MAX = 2147483647
 MAX_PROBES = 64
-# Least squares from tensor-core (3xTF32) statistics is accepted only while the smallest Cholesky pivot keeps at
-# least this fraction of its original diagonal entry (1 - R^2 of the most collinear column).  Below it the ~4e-7
-# relative error of the 3xTF32 Gram is amplified past the 1e-4 weight tolerance, and the layer is re-solved from
-# exact-product fp64 statistics (tests/test_gpu_conditioning.py maps error against this ratio).
-LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.05"))
+# Least squares from tensor-core (3xTF32) statistics: the ~4e-7 relative error of that Gram is amplified by the
+# conditioning of the system (profiles/r2_conditioning.md maps it: 5e-6 of relative weight error at a pivot ratio of
+# 0.2, 2e-4 at 0.01, 5e-3 at 1e-4), so every such solve is followed by ONE step of iterative refinement against the
+# same factor with the residual taken from the data (engine.ls_refine) -- which squares the error -- and is accepted
+# only while the smallest Cholesky pivot keeps at least LS_RATIO_MIN of its original diagonal entry (1 - R^2 of the
+# most collinear column); below that the layer is re-solved from exact-product fp64 statistics.
+LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.005"))
+LS_REFINE = os.environ.get("CPB200_LS_REFINE", "1") == "1"
 
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
 GRAM_FP64, GRAM_3XTF32 = 0, 1
@@ -297,16 +300,114 @@ class Engine:
                                          self._p(info, "int32_t*"), self._p(stat, "double*"), self._s()))
         return info, stat
 
-    def ls_resolve(self, Bxy, sx, sy, sel_cols=None, Ks=None):
-        """Solve against the factor kept by ls_factor: Bxy (K, n) = X'U, sy (n,) = 1'U.  Returns (W (n, Ksel), b (n,))."""
+    def ls_resolve(self, Bxy, sx, sy, sel_cols=None, Ks=None, accumulate_into=None):
+        """Solve against the factor kept on the CURRENT handle (ls_factor, or the last ls_solve): Bxy (K, n) = X'U,
+        sy (n,) = 1'U.  Returns (W (n, Ksel), b (n,)); with accumulate_into=(W, b) the solution is ADDED to those."""
         n = Bxy.shape[1]
         Ks = (sel_cols.numel() if sel_cols is not None else Bxy.shape[0]) if Ks is None else Ks
-        W = self.empty(n, Ks)
-        b = self.empty(n)
+        if accumulate_into is None:
+            W, b, acc = self.empty(n, Ks), self.empty(n), 0
+        else:
+            (W, b), acc = accumulate_into, 1
+            assert W.shape == (n, Ks) and W.is_contiguous() and b.shape == (n,)
         self._call(self.lib.cp_ls_resolve(self.h, self._p(Bxy, "const double*"), self._p(sx, "const double*"),
                                           self._p(sy, "const double*"), n, self._p(sel_cols, "const int32_t*"),
-                                          self._p(W, "double*"), self._p(b, "double*"), self._s()))
+                                          self._p(W, "double*"), self._p(b, "double*"), acc, self._s()))
         return W, b
+
+    def ls_residual(self, X, Y, y_bias, sel_cols, W, b):
+        """fp32 residual (N, n) of the fit (W, b) on columns sel_cols, computed from the data in fp64 (cp_ls_residual)."""
+        N, K = X.shape
+        n = Y.shape[1]
+        Ks = sel_cols.numel() if sel_cols is not None else K
+        R = self.empty(N, n, dtype=torch.float32)
+        self._call(self.lib.cp_ls_residual(self.h, self._p(X, "const float*"), N, K, X.stride(0), self._p(Y, "const void*"),
+                                           0 if Y.dtype == torch.float32 else 1, n, Y.stride(0),
+                                           self._p(y_bias, "const float*"), self._p(sel_cols, "const int32_t*"), Ks,
+                                           self._p(W, "const double*"), self._p(b, "const double*"), self._p(R, "float*"),
+                                           R.stride(0), self._s()))
+        return R
+
+    def ls_refine(self, g, X, Y, y_bias, sel_cols, W, b):
+        """One step of iterative refinement of (W, b) against the factor the last ls_solve left on this handle:
+        residual from the data (exact fp64), its cross products with X on the tensor cores, forward/backward
+        substitution, correction added in place.  Removes the error tensor-core statistics put into the solution."""
+        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b)
+        gr = self.gram(X, R, want_G=False, mode=g["mode"])
+        self.ls_resolve(gr["B"], g["sx"], gr["sy"], sel_cols, accumulate_into=(W, b))
+        return W, b
+
+    # ------------------------------------------------------------------ dense fp64 blocks (3C companions)
+    def gemm(self, A, B, a_mc=False, b_nc=False, alpha=1.0, beta=0.0, out=None):
+        """C[m, nn] = alpha * sum_r a(m, r) b(nn, r) + beta * C   (cp_gemm_f64; fp64 device tensors, unit inner stride)
+        a_mc: A is (R, M) else (M, R);  b_nc: B is (R, Nn) else (Nn, R)."""
+        assert A.dtype == torch.float64 and B.dtype == torch.float64 and A.dim() == 2 and B.dim() == 2
+        assert A.stride(1) == 1 and B.stride(1) == 1
+        R, M = (A.shape[0], A.shape[1]) if a_mc else (A.shape[1], A.shape[0])
+        Rb, Nn = (B.shape[0], B.shape[1]) if b_nc else (B.shape[1], B.shape[0])
+        assert R == Rb, "inner dimensions differ: %d vs %d" % (R, Rb)
+        if out is None:
+            assert beta == 0.0
+            out = self.empty(M, Nn)
+        assert out.shape == (M, Nn) and out.dtype == torch.float64 and out.stride(1) == 1
+        self._call(self.lib.cp_gemm_f64(self.h, int(a_mc), int(b_nc), M, Nn, R, float(alpha), self._p(A, "const double*"),
+                                        A.stride(0), self._p(B, "const double*"), B.stride(0), float(beta),
+                                        self._p(out, "double*"), out.stride(0), self._s()))
+        return out
+
+    def mm(self, A, B):
+        """A @ B"""
+        return self.gemm(A, B, a_mc=False, b_nc=True)
+
+    def mm_nt(self, A, B):
+        """A @ B.T"""
+        return self.gemm(A, B, a_mc=False, b_nc=False)
+
+    def mm_tn(self, A, B):
+        """A.T @ B"""
+        return self.gemm(A, B, a_mc=True, b_nc=True)
+
+    def svd(self, F, max_sweeps=40):
+        """Thin SVD of a small dense fp64 matrix (m, n) by one-sided Jacobi (cp_svd_jacobi).  Returns (U (m, r),
+        s (r,) descending, Vh (r, n)), r = min(m, n) -- the convention of scipy.linalg.svd(full_matrices=False)."""
+        assert F.dtype == torch.float64 and F.dim() == 2
+        m, n = F.shape
+        if m < n:  # orthogonalise the columns of the taller orientation
+            U, s, Vh = self.svd(F.T.contiguous(), max_sweeps)
+            return Vh.T.contiguous(), s, U.T.contiguous()
+        Ft = F.T.contiguous()
+        Wt = self.empty(n, n)
+        sigma = self.empty(n)
+        sweeps = self.ffi.new("int32_t*")
+        tol = float(np.sqrt(m)) * 2.220446049250313e-16
+        self._call(self.lib.cp_svd_jacobi(self.h, self._p(Ft, "double*"), m, n, Ft.stride(0), self._p(Wt, "double*"),
+                                          Wt.stride(0), self._p(sigma, "double*"), 1, tol, max_sweeps, sweeps,
+                                          self._s()))
+        if sweeps[0] >= max_sweeps:
+            raise np.linalg.LinAlgError("Jacobi SVD did not converge in %d sweeps" % max_sweeps)
+        order = torch.argsort(sigma, descending=True, stable=True)
+        return Ft[order].T.contiguous(), sigma[order].contiguous(), Wt[order].contiguous()
+
+    def solve_relu(self, RUraw, bias, Z, lam, want_mean=False):
+        """U = solve_relu(RUraw + bias, Z, lam) (lib/decompose.py:51-59), optional column means of U."""
+        N, n = RUraw.shape
+        U = self.empty(N, n)
+        mean = self.empty(n) if want_mean else None
+        self._call(self.lib.cp_solve_relu(self.h, self._p(RUraw, "const double*"), RUraw.stride(0),
+                                          self._p(bias, "const double*"), self._p(Z, "const double*"), Z.stride(0),
+                                          float(lam), self._p(U, "double*"), U.stride(0), N, n, self._p(mean, "double*"),
+                                          self._s()))
+        return (U, mean) if want_mean else U
+
+    def colstats(self, X, scale=1.0, centre=False):
+        """(scale * column sums, X - that) of an fp64 matrix (cp_colstats_f64); centre with scale = 1/N."""
+        N, n = X.shape
+        assert X.dtype == torch.float64 and X.stride(1) == 1
+        cs = self.empty(n)
+        Xc = self.empty(N, n) if centre else None
+        self._call(self.lib.cp_colstats_f64(self.h, self._p(X, "const double*"), X.stride(0), N, n, float(scale),
+                                            self._p(cs, "double*"), self._p(Xc, "double*"), n, self._s()))
+        return (cs, Xc) if centre else cs
 
     # ------------------------------------------------------------------ composite: one layer problem
     def select_channels_async(self, X, W2m, Y, y_bias, samples, c, k2, rank, rank_tol, right0, seeds):
@@ -333,7 +434,13 @@ class Engine:
         """LS on the surviving channels (device outputs; no host sync).  Returns (W, b, info, stat)."""
         cols_d = self._cols_device(idxs_host, k2, g_full["K"])
         if g_full["N"] - 1 >= cols_d.numel():
-            return self.ls_solve(g_full, cols_d)
+            W, b, info, stat = self.ls_solve(g_full, cols_d)
+            if g_full["mode"] != GRAM_FP64 and LS_REFINE:
+                # statistics from the 3xTF32 Gram carry ~4e-7 relative error, which the conditioning of a wide layer
+                # amplifies to ~4e-5 in W and more in b (measured at conv4_x, N=5000): one refinement step against
+                # the same factor, with the residual taken from the data, restores fp64-level accuracy
+                self.ls_refine(g_full, X, Y, y_bias, cols_d, W, b)
+            return W, b, info, stat
         return self.ls_solve_dual(X, Y, y_bias, cols_d)
 
     def reconstruct_exact_async(self, X, Y, y_bias, idxs_host, k2):

@@ -183,17 +183,176 @@ def fc_kernel(X, Y, copy_X=True, W=None, B=None, ret_reg=False, fit_intercept=Tr
     return Wd.cpu().numpy(), bd.cpu().numpy()
 
 
-def VH_decompose(weights, rank=None, DEBUG=0, X=None, Y=None):
-    """Signature of reference lib/decompose.py:85.  Spatial (VH) decomposition is a 3C
-    companion outside the pruning hot path."""
-    raise NotImplementedError("VH_decompose: 3C companion, not part of the channel-pruning hot path yet")
+def _dev_f64(a, eng):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=eng.device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=eng.device)
 
 
-def ITQ_decompose(feature, gt_feature, weight, rank, bias=None, DEBUG=False, Wr=None):
-    """Signature of reference lib/decompose.py:163."""
-    raise NotImplementedError("ITQ_decompose: 3C companion, not part of the channel-pruning hot path yet")
+def solve_relu(RU, Z, Lambda):
+    """lib/decompose.py:51-59 (elementwise; cp_solve_relu)."""
+    eng = get_engine()
+    U = eng.solve_relu(_dev_f64(RU, eng), None, _dev_f64(Z, eng), Lambda)
+    return U if isinstance(RU, torch.Tensor) else U.cpu().numpy()
+
+
+def svd(x):
+    """lib/decompose.py:154-156: thin SVD, singular values descending (one-sided Jacobi on the device; singular
+    vectors agree with LAPACK's up to the sign of each pair)."""
+    eng = get_engine()
+    U, s, Vh = eng.svd(_dev_f64(x, eng))
+    if isinstance(x, torch.Tensor):
+        return U, s, Vh
+    return U.cpu().numpy(), s.cpu().numpy(), Vh.cpu().numpy()
+
+
+def _pinv_device(eng, x, rtol=1e-6):
+    U, s, Vh = eng.svd(x)
+    keep = s > rtol * s[0]
+    inv = torch.where(keep, 1.0 / torch.where(keep, s, torch.ones_like(s)), torch.zeros_like(s))
+    return eng.mm_tn(Vh, (U * inv[None, :]).T.contiguous())  # V diag(1/s) U'
+
+
+def pinv(x):
+    """lib/decompose.py:149-152: scipy.linalg.pinv(x, 1e-6) -- singular values below 1e-6 sigma_max dropped."""
+    eng = get_engine()
+    P = _pinv_device(eng, _dev_f64(x, eng))
+    return P if isinstance(x, torch.Tensor) else P.cpu().numpy()
+
+
+def _nonlinear_fc_device(eng, Xd, Yd):
+    """Body of nonlinear_fc on fp64 device buffers: the centred Gram of X is factored ONCE (cp_ls_factor), each of the
+    50 refits is X'U (one tall-skinny product) + two triangular substitutions (cp_ls_resolve), a prediction and the
+    elementwise ReLU-aware update.  Returns (coef (n, K), intercept (n,)) on the device."""
+    N, K = Xd.shape
+    G = eng.mm_tn(Xd, Xd)
+    sx = eng.colstats(Xd)
+    g = dict(G=G, sx=sx, N=N, K=K)
+    info_d, stat_d = eng.ls_factor(g)
+    fail = int(info_d.cpu()[0])
+    if fail:
+        raise np.linalg.LinAlgError("nonlinear_fc: X is numerically rank deficient (pivot %d); the reference's gelsd "
+                                    "would truncate here" % fail)
+    U = Yd.clone()
+    Z = torch.clamp_min(Yd, 0.)
+    its = [30, 20]
+    W = b = None
+    for epoch, l in enumerate([10 ** i for i in range(-1, 1)]):  # decompose.py:678
+        for _ in range(its[epoch]):
+            Bxy = eng.mm_tn(Xd, U)
+            sy = eng.colstats(U)
+            W, b = eng.ls_resolve(Bxy, sx, sy)  # reg = fc_kernel(X, U, ret_reg=True)
+            RUraw = eng.mm_nt(Xd, W)            # reg.predict(X) without the intercept
+            U = eng.solve_relu(RUraw, b, Z, l)
+    return W, b
 
 
 def nonlinear_fc(X, Y, copy_X=True, W=None, B=None):
-    """Signature of reference lib/decompose.py:671."""
-    raise NotImplementedError("nonlinear_fc: 3C companion, not part of the channel-pruning hot path yet")
+    """lib/decompose.py:671-685.  Returns (coef_ (n, K), intercept_ (n,)) of the last refit, float64."""
+    assert len(X.shape) == 2  # :672
+    assert copy_X == True  # noqa: E712  (:673)
+    assert W is None and B is None  # :674-675
+    eng = get_engine()
+    Wd, bd = _nonlinear_fc_device(eng, _dev_f64(X, eng), _dev_f64(Y, eng))
+    return Wd.cpu().numpy(), bd.cpu().numpy()
+
+
+def VH_decompose(weights, rank=None, DEBUG=0, X=None, Y=None):
+    """Spatial decomposition, reference lib/decompose.py:85-147.
+    weights (n, c, h, w) -> V (rank, c, h, 1), H (n, rank, 1, w), VHr (n, c, h, w) [, b (n,)]; with X (N, c, h, w) and
+    Y (N, n) the H factor is refitted on data by nonlinear_fc (:129-138).  SVD, projections and the 50 refits run on
+    the device in fp64; numpy float64 in and out like the reference."""
+    eng = get_engine()
+    Wd = _dev_f64(weights, eng)
+    n, c, h, w = Wd.shape
+    VH = Wd.permute(1, 2, 0, 3).reshape(c * h, n * w).contiguous()  # ch x nw  (:96-99)
+    Vm, sig, Hm = eng.svd(VH)
+    if rank is None:
+        rank = c * h
+    Vm = Vm[:, :rank].contiguous()                       # ch x rank
+    Hm = (sig[:rank, None] * Hm[:rank, :]).contiguous()  # rank x nw  (:105-111)
+    VHr = eng.mm(Vm, Hm).reshape(c, h, n, w)
+    H = Hm.reshape(rank, n, w, 1).permute(1, 0, 3, 2).contiguous()  # n rank 1 w
+    V = Vm.reshape(c, 1, h, rank).permute(3, 0, 2, 1).contiguous()  # rank c h 1
+    b = None
+    if X is not None:
+        Xd = _dev_f64(X, eng)
+        N = Xd.shape[0]
+        assert w == 3, "the reference reshapes H to (o, rank, 1, 3) (decompose.py:135)"
+        # Xv[N, rank, 1, w] = sum_{c,h} X[N, c, h, w] V[rank, c, h]   (:130-131)
+        Xp = Xd.permute(0, 3, 1, 2).reshape(N * w, c * h).contiguous()
+        Xv = eng.mm(Xp, Vm).reshape(N, w, rank).permute(0, 2, 1).reshape(N, rank * w).contiguous()
+        Hfit, bd = _nonlinear_fc_device(eng, Xv, _dev_f64(Y, eng))
+        H = Hfit.reshape(n, rank, 1, 3)
+        reH = H.permute(1, 0, 2, 3).reshape(rank, n * 3).contiguous()
+        VHr = eng.mm(Vm, reH).reshape(c, h, n, w)  # (:136-138)
+        b = bd.cpu().numpy()
+    VHr = VHr.permute(2, 0, 1, 3).contiguous()
+    if X is not None:
+        return V.cpu().numpy(), H.cpu().numpy(), VHr.cpu().numpy(), b
+    return V.cpu().numpy(), H.cpu().numpy(), VHr.cpu().numpy()
+
+
+def ITQ_decompose(feature, gt_feature, weight, rank, bias=None, DEBUG=False, Wr=None):
+    """Channel decomposition, reference lib/decompose.py:163-319 (the branch Net.R3 takes: weight (n, r, 1, w),
+    ``right = 1``).  Returns W1 (rank, r, 1, w), W2 (n, rank, 1, 1), B (n,), W12 (n, c, h, w), float64.
+
+    Device formulation: every N x n quantity of the loop is G times an n x n matrix (X = G M, M = pinv(G'G) G'UU), so
+    the thin SVD of the N x n matrix X (:217) is taken of the n x n matrix F = diag(sqrt(s_S)) V_S' M, which has the
+    same singular values and right singular vectors (F'F = M'(G'G)M = X'X, with G'G = V_S diag(s_S) V_S'); per
+    iteration only G'UU and G T remain tall products."""
+    eng = get_engine()
+    Yf = _dev_f64(feature, eng)
+    n_ins, nfc = Yf.shape
+    gt = _dev_f64(gt_feature, eng)
+    assert tuple(gt.shape) == (n_ins, nfc)  # :167-168
+    Z = torch.clamp_min(gt, 0.)
+    Y_mean, G = eng.colstats(Yf, 1.0 / n_ins, centre=True)  # :180-182
+    S = eng.mm_tn(G, G)
+    Us, ss, Vhs = eng.svd(S)
+    keep = ss > 1e-6 * ss[0]
+    inv = torch.where(keep, 1.0 / torch.where(keep, ss, torch.ones_like(ss)), torch.zeros_like(ss))
+    PG = eng.mm_tn(Vhs, (Us * inv[None, :]).T.contiguous())  # pinv(G'G), :189
+    E = (torch.sqrt(ss)[:, None] * Vhs).contiguous()        # E'E = G'G
+    UU = G.clone()
+    U_mean = Y_mean.clone()
+    T = None
+    for Lambda, iters in zip([0.1, 1], [30, 20]):  # :203-204
+        for _ in range(iters):
+            A1 = eng.mm_tn(G, UU)          # G'UU
+            M = eng.mm(PG, A1)             # X = G M  (:213)
+            F = eng.mm(E, M)
+            _, _, Rh = eng.svd(F)
+            Rr = Rh[:rank].contiguous()    # top right singular vectors of X
+            MP = eng.mm(eng.mm_nt(M, Rr), Rr)   # M R_r' R_r:  T_big = G (M P)  (:219)
+            T = eng.mm(PG, eng.mm(S, MP))       # PGGt.dot(T_big)  (:225)
+            RUraw = eng.mm(G, T)                # :226
+            U, U_mean_new = eng.solve_relu(RUraw, U_mean, Z, Lambda, want_mean=True)  # :228-240
+            U_mean = U_mean_new
+            UU = U - U_mean[None, :]
+    L, sigma, R = eng.svd(T)  # :250
+    L = L[:, :rank].contiguous()
+    R = (sigma[:rank, None] * R[:rank, :]).contiguous()
+    Wd = _dev_f64(weight, eng)
+    dim = tuple(Wd.shape)
+    assert len(dim) == 4
+    assert dim[3] != nfc and dim[0] == nfc, "only the branch Net.R3 takes (decompose.py:261-262) is implemented"
+    wt = Wd.permute(1, 2, 3, 0).contiguous()
+    W1 = eng.mm(wt.reshape(-1, nfc), L)  # :265-266
+    if Wr is not None:
+        wr = _dev_f64(Wr, eng).permute(1, 2, 3, 0).contiguous()
+        W12 = eng.mm(wr.reshape(-1, nfc), L)
+        shape12 = tuple(wr.shape[:3])
+    else:
+        W12 = W1
+        shape12 = tuple(wt.shape[:3])
+    W1 = W1.reshape(tuple(wt.shape[:3]) + (rank,)).permute(3, 0, 1, 2).contiguous()
+    W2 = R
+    W12 = eng.mm(W12.contiguous(), W2)
+    W2 = W2.T.contiguous().reshape(nfc, rank, 1, 1)
+    W12 = W12.reshape(shape12 + (nfc,)).permute(3, 0, 1, 2).contiguous()
+    B = -eng.mm(Y_mean[None, :].contiguous(), T)[0] + U_mean  # :304
+    B = B.cpu().numpy()
+    if bias is not None:
+        B = B + np.asarray(bias.cpu().numpy() if isinstance(bias, torch.Tensor) else bias, dtype=np.float64)
+    return W1.cpu().numpy(), W2.cpu().numpy(), B, W12.cpu().numpy()

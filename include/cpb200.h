@@ -184,11 +184,66 @@ int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ld
  * of the centred Gram of the selected columns inside the handle (until the next cp_ls_factor on that handle);
  * cp_ls_resolve solves for new targets given their cross products Bxy = X'U (K x n) and column sums sy = 1'U:
  *   W_out (n x Ksel), b_out (n)  as in cp_ls_solve.  sx / sel_cols must be the ones given to cp_ls_factor.
+ * cp_ls_solve leaves its factor on the handle too, so cp_ls_resolve can refine that very solve:
+ * accumulate != 0 ADDS the solution to W_out / b_out (one step of iterative refinement when Bxy / sy are the cross
+ * products and column sums of the residual, see cp_ls_residual).
  */
 int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, int64_t N, int K, const int32_t *sel_cols,
                  int Ksel, int32_t *info_out, double *stat_out, cp_stream_t stream);
 int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const double *sy, int n,
-                  const int32_t *sel_cols, double *W_out, double *b_out, cp_stream_t stream);
+                  const int32_t *sel_cols, double *W_out, double *b_out, int accumulate, cp_stream_t stream);
+
+/*
+ * Residual of a least-squares solve, from the DATA (not from the Gram statistics): exact products of the fp32 features
+ * with the fp64 weights, fp64 accumulation, rounded to fp32 on output --
+ *   R_out[r, t] = (Y[r, t] - y_bias[t]) - sum_j X[r, sel_j] W[t, j] - b[t]           (N x n, leading dimension ldr)
+ * With statistics from the tensor-core Gram (~4e-7 relative), refitting this residual against the same factor
+ * (cp_gram of (X, R) + cp_ls_resolve(accumulate = 1)) removes the error the statistics put into W and b: one step of
+ * iterative refinement, the reference's LinearRegression.fit (lib/decompose.py:665-666) being the fixed point.
+ */
+int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
+                   int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, const double *W, const double *b,
+                   float *R_out, int64_t ldr, cp_stream_t stream);
+
+/*
+ * ---- dense fp64 building blocks of the 3C companions (VH_decompose, nonlinear_fc, ITQ_decompose) ----
+ *
+ * General product -- replaces the np.dot / np.tensordot / np.matmul calls of lib/decompose.py:85-147, 163-319,
+ * 671-685 and reg.predict (:680):
+ *   C[m, nn] = alpha * sum_r a(m, r) * b(nn, r) + beta * C[m, nn]          (all fp64, row-major)
+ *   a(m, r)  = a_mc ? A[r * lda + m] : A[m * lda + r]
+ *   b(nn, r) = b_nc ? B[r * ldb + nn] : B[nn * ldb + r]
+ * Tall-skinny shapes (long reduction, few output tiles) are split over CTAs and summed in a fixed order.
+ */
+int cp_gemm_f64(cp_handle_t h, int a_mc, int b_nc, int M, int Nn, int64_t R, double alpha, const double *A,
+                int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, cp_stream_t stream);
+
+/*
+ * Singular value decomposition -- replaces scipy.linalg.svd(x, full_matrices=False, lapack_driver='gesvd')
+ * (lib/decompose.py:154-156) by a one-sided Jacobi (column pairs orthogonalised in round-robin order, one CTA per
+ * pair).  F is m x n, handed over TRANSPOSED: Ft is n rows of length m (row j = column j of F), leading dimension ldf.
+ * On return   row j of Ft = sigma_j * u_j  (u_j itself when normalise_left != 0),  row j of Wt (n x n) = the right
+ * singular vector v_j,  sigma[j] = sigma_j  -- UNSORTED (the caller orders them; gesvd returns descending order).
+ * tol: rotation threshold on |f_p . f_q| / (|f_p| |f_q|) (about sqrt(m) * 2.2e-16).  The number of sweeps is data
+ * dependent: this routine synchronises `stream` once per sweep.  m <= 12800.
+ */
+int cp_svd_jacobi(cp_handle_t h, double *Ft, int m, int n, int64_t ldf, double *Wt, int64_t ldw, double *sigma,
+                  int normalise_left, double tol, int max_sweeps, int32_t *sweeps_out, cp_stream_t stream);
+
+/*
+ * ReLU-aware target update -- replaces solve_relu (lib/decompose.py:51-59) and the identical block of ITQ_decompose
+ * (:231-240), fused with the bias add of the prediction:  RU = RUraw + bias (bias may be NULL);
+ *   U = argmin_u (relu(u) - Z)^2 + lambda (u - RU)^2   elementwise (N x n);  colmean_out (n, may be NULL) = U.mean(0).
+ */
+int cp_solve_relu(cp_handle_t h, const double *RUraw, int64_t ldr, const double *bias, const double *Z, int64_t ldz,
+                  double lambda, double *U, int64_t ldu, int64_t N, int n, double *colmean_out, cp_stream_t stream);
+
+/*
+ * Column statistics -- replaces ndarray.mean(0) and the centring `Y - Y_mean` (lib/decompose.py:180-182, 242-244):
+ *   colsum_out[j] = scale * sum_r X[r, j];   centred_out (may be NULL) = X - colsum_out (use scale = 1/N).
+ */
+int cp_colstats_f64(cp_handle_t h, const double *X, int64_t ldx, int64_t N, int n, double scale, double *colsum_out,
+                    double *centred_out, int64_t ldo, cp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,10 @@ restatement of the reference's algorithm, function by function:
   dictionary                   lib/decompose.py:386-634
   fc_kernel                    lib/decompose.py:636-669
   prune_block_R3               lib/net.py:1406-1459 (channel-pruning block of R3)
+  solve_relu, svd, pinv        lib/decompose.py:51-59, 154-156, 149-152
+  nonlinear_fc                 lib/decompose.py:671-685
+  VH_decompose                 lib/decompose.py:85-147
+  ITQ_decompose                lib/decompose.py:163-319
   ===========================  ==========================================
 
 Third-party arithmetic (absent from /root/reference; the reference pins no
@@ -199,6 +203,130 @@ def fc_kernel(X, Y, copy_X=True, W=None, B=None, ret_reg=False, fit_intercept=Tr
     assert len(X.shape) == 2  # decompose.py:641
     assert fit_intercept and not ret_reg
     return linear_regression(X, Y)
+
+
+# --------------------------------------------------------------------------- 3C companions
+def solve_relu(RU, Z, Lambda):
+    """lib/decompose.py:51-59: argmin_U (relu(U) - Z)^2 + Lambda (U - RU)^2, elementwise."""
+    U0 = np.minimum(RU, 0.)  # case 0: U <= 0
+    Cost0 = Z ** 2 + Lambda * (U0 - RU) ** 2
+    U1 = relu((Lambda * RU + Z) / (Lambda + 1.))  # case 1: U > 0
+    Cost1 = (U1 - Z) ** 2 + Lambda * (U1 - RU) ** 2
+    return (Cost0 <= Cost1) * U0 + (Cost0 > Cost1) * U1
+
+
+def svd(x):
+    """lib/decompose.py:154-156"""
+    import scipy.linalg
+
+    return scipy.linalg.svd(x, full_matrices=False, lapack_driver='gesvd')
+
+
+def pinv(x):
+    """lib/decompose.py:149-152 (scipy.linalg.pinv(x, 1e-6): the positional cond of the reference's scipy is
+    today's rtol -- singular values below 1e-6 * sigma_max are dropped)."""
+    import scipy.linalg
+
+    return scipy.linalg.pinv(x, rtol=1e-6)
+
+
+def nonlinear_fc(X, Y, copy_X=True, W=None, B=None):
+    """lib/decompose.py:671-685: 30 + 20 alternations of {least squares of U on X, ReLU-aware update of U}."""
+    assert len(X.shape) == 2 and copy_X == True and W is None and B is None  # noqa: E712
+    U = Y.copy()
+    Z = relu(Y)
+    its = [30, 20]
+    coef = icpt = None
+    for epoch, l in enumerate([10 ** i for i in range(-1, 1)]):
+        for _ in range(its[epoch]):
+            coef, icpt = linear_regression(X, U)  # fc_kernel(X, U, ret_reg=True)
+            RU = X @ coef.T + icpt  # reg.predict(X)
+            U = solve_relu(RU, Z, l)
+    return coef, icpt
+
+
+def VH_decompose(weights, rank=None, DEBUG=0, X=None, Y=None):
+    """lib/decompose.py:85-147: spatial decomposition W (n,c,h,w) ~ V (rank,c,h,1) then H (n,rank,1,w), H refitted
+    on data by nonlinear_fc when X, Y are given.  Returns V, H, VHr (n,c,h,w)[, b]."""
+    dim = weights.shape
+    VH = np.transpose(weights, [1, 2, 0, 3]).reshape([dim[1] * dim[2], dim[0] * dim[3]])  # ch x nw  (:96-99)
+    V, sigmaVH, H = svd(VH)
+    if rank is None:
+        rank = dim[1] * dim[2]
+    V = V[:, :rank]
+    H = np.diag(sigmaVH[:rank]).dot(H[:rank, :])  # (:105-111)
+    VHr = (V.dot(H)).reshape([dim[1], dim[2], dim[0], dim[3]])
+    H = np.transpose(H.reshape([rank, dim[0], dim[3], 1]), [1, 0, 3, 2])  # n rank 1 w  (:121-123)
+    origV = V.copy()
+    V = np.transpose(V.reshape((dim[1], 1, dim[2], rank)), [3, 0, 2, 1])  # rank c h 1  (:125-127)
+    b = None
+    if X is not None:
+        Xv = np.transpose(np.tensordot(X, V, [[1, 2], [1, 2]]), [0, 2, 3, 1])  # (:130-131)
+        N = Xv.shape[0]
+        o = H.shape[0]
+        H, b = nonlinear_fc(Xv.reshape([N, -1]), Y)
+        H = H.reshape([o, rank, 1, 3])
+        reH = np.transpose(H, [1, 0, 2, 3]).reshape([rank, -1])
+        VHr = (origV.dot(reH)).reshape([dim[1], dim[2], dim[0], dim[3]])  # (:134-138)
+    VHr = np.transpose(VHr, [2, 0, 1, 3])
+    if X is not None:
+        return V, H, VHr, b
+    return V, H, VHr
+
+
+def ITQ_decompose(feature, gt_feature, weight, rank, bias=None, DEBUG=False, Wr=None):
+    """lib/decompose.py:163-319 on the branch R3 takes (weight (n, r_vh, 1, w) with dim[3] != n, `right = 1`)."""
+    n_ins, n_filter_channels = feature.shape
+    assert gt_feature.shape == feature.shape
+    Y = feature.copy()
+    Z = relu(gt_feature)
+    Zsq = Z ** 2
+    Y_mean = Y.mean(0)
+    G = Y - Y_mean
+    PG = pinv((G.T).dot(G))  # (:182-189)
+    PGGt = PG.dot(G.T)
+    UU = G.copy()
+    U_mean = Y_mean.copy()
+    lambdas = [0.1, 1]
+    step_iters = [30, 20]
+    T = None
+    for step in range(len(lambdas)):
+        Lambda = lambdas[step]
+        for _ in range(step_iters[step]):
+            X = G.dot(PGGt.dot(UU))  # (:213)
+            L, sigma, R = svd(X)
+            T = L[:, :rank].dot(np.diag(sigma[:rank])).dot(R[:rank, :])  # (:219)
+            T = PGGt.dot(T)  # (:225)
+            RU = G.dot(T)
+            RU += U_mean
+            U0 = np.minimum(RU, 0.)
+            Cost0 = Zsq + Lambda * (U0 - RU) ** 2
+            U1 = relu((Lambda * RU + Z) / (Lambda + 1.))
+            Cost1 = (U1 - Z) ** 2 + Lambda * (U1 - RU) ** 2
+            U = (Cost0 <= Cost1) * U0 + (Cost0 > Cost1) * U1  # (:231-240)
+            U_mean = U.mean(0)
+            UU = U - U_mean
+    L, sigma, R = svd(T)  # (:250)
+    L = L[:, :rank]
+    R = np.diag(sigma[:rank]).dot(R[:rank, :])
+    dim = weight.shape
+    assert len(dim) == 4 and dim[3] != n_filter_channels and dim[0] == n_filter_channels
+    weight = np.transpose(weight, [1, 2, 3, 0])
+    W1 = weight.reshape([-1, n_filter_channels]).dot(L)  # (:265-266)
+    if Wr is not None:
+        Wr = np.transpose(Wr, [1, 2, 3, 0])
+        W12 = Wr.reshape([-1, n_filter_channels]).dot(L)
+    else:
+        W12 = W1
+    W1 = np.transpose(W1.reshape(weight.shape[:3] + (rank,)), [3, 0, 1, 2])  # (:283-284)
+    W2 = R
+    W12 = W12.dot(W2)
+    W2 = W2.T.reshape([n_filter_channels, rank, 1, 1])
+    W12 = np.transpose(W12.reshape((Wr.shape[:3] if Wr is not None else weight.shape[:3]) + (n_filter_channels,)),
+                       [3, 0, 1, 2])  # (:301-302)
+    B = - Y_mean.dot(T) + U_mean
+    B = B.T + bias if bias is not None else B.T
+    return W1, W2, B, W12
 
 
 # --------------------------------------------------------------------------- dictionary

@@ -169,12 +169,28 @@ def run_net_cases(NET, CF, D):
         print(name, "XY", XY.shape, {k: v.shape for k, v in feats_dict.items()})
 
 
+def run_3c_cases(D, CF):
+    """VH_decompose (with its nonlinear_fc refit) and ITQ_decompose of the reference on small seeded inputs."""
+    for name, spec in cases.VH_CASES.items():
+        W, X, Y = cases.vh_inputs(**spec["gen"])
+        V, H, VHr, b = D.VH_decompose(W.astype(np.float64), rank=spec["rank"], DEBUG=0, X=X.astype(np.float64), Y=Y)
+        V0, H0, VHr0 = D.VH_decompose(W.astype(np.float64), rank=spec["rank"])
+        np.savez_compressed(os.path.join(OUT, "%s.npz" % name), V=V, H=H, VHr=VHr, b=b, V0=V0, H0=H0, VHr0=VHr0)
+        print(name, "V", V.shape, "H", H.shape, "VHr", VHr.shape)
+    for name, spec in cases.ITQ_CASES.items():
+        feat, gt, H, VHr, bias = cases.itq_inputs(**spec["gen"])
+        W1, W2, B, W12 = D.ITQ_decompose(feat, gt, H, spec["rank"], bias=bias, DEBUG=0, Wr=VHr)
+        np.savez_compressed(os.path.join(OUT, "%s.npz" % name), W1=W1, W2=W2, B=B, W12=W12)
+        print(name, "W1", W1.shape, "W2", W2.shape, "W12", W12.shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     D, NET, CF = ref_shims.load_reference()
     assert NET is not None, ref_shims._loaded.get("net_error")
     run_dictionary_cases(D, CF)
     run_net_cases(NET, CF, D)
+    run_3c_cases(D, CF)
 
 
 if __name__ == "__main__":

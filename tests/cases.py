@@ -100,3 +100,39 @@ NET_CASES = {
     "k1s1": dict(gen=dict(B=3, H=8, c1=10, c2=7, k=1, pad=0, stride=1, nimgbatches=2, seed=24), nBatches=2, P=6,
                  np_seed=34, xy=("conv1", "conv2")),
 }
+
+
+def vh_inputs(c, n, N, k, seed, noise=0.05):
+    """Inputs of VH_decompose as Net.R3 calls it (lib/net.py:1355-1362): weights (n,c,k,k) fp32, X (N,c,k,k) patches of
+    the layer's bottom blob, Y (N,n) = sampled output features minus bias (pre-ReLU, both signs)."""
+    r = np.random.RandomState(seed)
+    X = np.maximum(r.standard_normal((N, c, k, k)).astype(np.float32), 0)
+    W = (r.standard_normal((n, c, k, k)) * np.sqrt(2.0 / (c * k * k))).astype(np.float32)
+    Y = X.reshape(N, -1).astype(np.float64) @ W.reshape(n, -1).T.astype(np.float64)
+    Y = (Y + noise * Y.std() * r.standard_normal(Y.shape)).astype(np.float32).astype(np.float64)
+    return W, X, Y
+
+
+VH_CASES = {
+    "vh_small": dict(gen=dict(c=12, n=20, N=900, k=3, seed=41), rank=14),
+    "vh_wide": dict(gen=dict(c=24, n=16, N=1500, k=3, seed=42), rank=22),
+}
+
+
+def itq_inputs(n, rvh, c, N, seed, k=3):
+    """Inputs of ITQ_decompose as Net.R3 calls it (lib/net.py:1387-1389): feature = features of the layer after the
+    spatial decomposition (N,n), gt_feature = the frozen original features, weight = H (n, rvh, 1, k), Wr = VHr."""
+    r = np.random.RandomState(seed)
+    base = r.standard_normal((N, n // 2)) @ r.standard_normal((n // 2, n)) + 0.3 * r.standard_normal((N, n))
+    gt = (base + 0.2).astype(np.float32).astype(np.float64)
+    feat = (gt + 0.05 * r.standard_normal((N, n))).astype(np.float32).astype(np.float64)
+    H = (r.standard_normal((n, rvh, 1, k)) * 0.2).astype(np.float64)
+    VHr = (r.standard_normal((n, c, k, k)) * 0.1).astype(np.float64)
+    bias = (0.1 * r.standard_normal(n)).astype(np.float32)
+    return feat, gt, H, VHr, bias
+
+
+ITQ_CASES = {
+    "itq_small": dict(gen=dict(n=20, rvh=9, c=8, N=700, seed=51), rank=11),
+    "itq_mid": dict(gen=dict(n=48, rvh=20, c=16, N=1600, seed=52), rank=30),
+}

@@ -154,3 +154,42 @@ def test_patch_invariant():
     X = np.rollaxis(XY.reshape((-1, k, k, XY.shape[1])), 3, 1)
     fake = O.relu(X).reshape(X.shape[0], -1) @ weights["conv2"].reshape(weights["conv2"].shape[0], -1).T + biases["conv2"]
     assert np.abs(fake - feats["conv2"]).max() < 1e-4  # CHECK_EQ tolerance, lib/utils.py:75-82
+
+
+# ---------------------------------------------------------------------------- 3C companions (VH / ITQ)
+def _sign_align(a, b, axis):
+    """Singular vectors are defined up to sign: flips slices of ``a`` along ``axis`` to agree with ``b``."""
+    a2 = np.moveaxis(a, axis, 0).copy()
+    b2 = np.moveaxis(b, axis, 0)
+    for k in range(a2.shape[0]):
+        if np.vdot(a2[k], b2[k]) < 0:
+            a2[k] = -a2[k]
+    return np.moveaxis(a2, 0, axis)
+
+
+@pytest.mark.parametrize("name", list(cases.VH_CASES))
+def test_vh_decompose_matches_reference_golden(golden_dir, name):
+    spec = cases.VH_CASES[name]
+    g = np.load(os.path.join(golden_dir, "%s.npz" % name))
+    W, X, Y = cases.vh_inputs(**spec["gen"])
+    V, H, VHr, b = O.VH_decompose(W.astype(np.float64), rank=spec["rank"], X=X.astype(np.float64), Y=Y)
+    assert V.shape == g["V"].shape and H.shape == g["H"].shape and VHr.shape == g["VHr"].shape
+    np.testing.assert_allclose(VHr, g["VHr"], rtol=0, atol=1e-9 * np.abs(g["VHr"]).max())
+    np.testing.assert_allclose(b, g["b"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(_sign_align(V, g["V"], 0), g["V"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(_sign_align(H, g["H"], 1), g["H"], rtol=0, atol=1e-8 * np.abs(g["H"]).max())
+    V0, H0, VHr0 = O.VH_decompose(W.astype(np.float64), rank=spec["rank"])
+    np.testing.assert_allclose(VHr0, g["VHr0"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(cases.ITQ_CASES))
+def test_itq_decompose_matches_reference_golden(golden_dir, name):
+    spec = cases.ITQ_CASES[name]
+    g = np.load(os.path.join(golden_dir, "%s.npz" % name))
+    feat, gt, H, VHr, bias = cases.itq_inputs(**spec["gen"])
+    W1, W2, B, W12 = O.ITQ_decompose(feat, gt, H, spec["rank"], bias=bias, Wr=VHr)
+    assert W1.shape == g["W1"].shape and W2.shape == g["W2"].shape
+    np.testing.assert_allclose(W12, g["W12"], rtol=0, atol=1e-8 * np.abs(g["W12"]).max())
+    np.testing.assert_allclose(B, g["B"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(_sign_align(W1, g["W1"], 0), g["W1"], rtol=0, atol=1e-7 * np.abs(g["W1"]).max())
+    np.testing.assert_allclose(_sign_align(W2, g["W2"], 1), g["W2"], rtol=0, atol=1e-7 * np.abs(g["W2"]).max())
