@@ -192,6 +192,17 @@ __device__ __forceinline__ double div_markstein(double num, double d, double rc)
     return __fma_rn(r, rc, q0);
 }
 
+#ifdef CP_TIMING
+constexpr int TSTEPS = 384;
+__device__ long long cp_lasso_times[TSTEPS * 8];  // per step: chain {top, fetched, confirmed, published}, update warp {poll, got, pub, end}
+#define CH_STAMP(s, i)                                                                   \
+    do {                                                                                 \
+        if (rec && lane == 0 && (s) < TSTEPS) cp_lasso_times[(s) * 8 + (i)] = clock64(); \
+    } while (0)
+#else
+#define CH_STAMP(s, i)
+#endif
+
 struct Ctl {  // CTA-wide scalars
     int chain_pos, bulk_pos[NBULK], pk_pos;
     int n_active, nnz, pad;
@@ -358,6 +369,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         }
         __syncthreads();
         const uint32_t tag0 = sweep_no << 12;
+#ifdef CP_TIMING
+        const bool rec = (probe == 0 && sweep_no == 3);
+#endif
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         if (warp == 0) {
             // -------- chain warp: the serial recurrence and nothing else.  Software pipelined: the operands of step
@@ -395,14 +409,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             double w_j = 0.0, xv = 0.0, xt = 0.0;
             fetch(0, j, pc, w_j, xv, xt);
             for (int s = 0; s < n_active; ++s) {
+                CH_STAMP(s, 0);
                 const bool has_next = s + 1 < n_active;
                 uint32_t jn = 0;
                 double pn[8];
                 double wjn = 0.0, xvn = 0.0, xtn = 0.0;
                 if (has_next) fetch(s + 1, jn, pn, wjn, xvn, xtn);
                 asm volatile("" ::: "memory");  // the loads above stay above the arithmetic below
+                CH_STAMP(s, 1);
                 const uint32_t tag = tag0 | (uint32_t)(s + 1);
                 if ((uint32_t)__double2loint(xt) != tag) xv = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag);
+                CH_STAMP(s, 2);
                 double x = xv;
 #pragma unroll
                 for (int i = LAG; i >= 1; --i) x = __dadd_rn(x, __dmul_rn(dl[i - 1], pc[2 + i]));  // oldest delta first
@@ -410,6 +427,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 cd_update(pc[0], pc[1], pc[2], x, w_j, l1, delta, aw, w_new);
                 w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
                 if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag);
+                CH_STAMP(s, 3);
                 d_w_max = fmax(d_w_max, fabs(delta));
                 w_max = fmax(w_max, aw);
 #pragma unroll
@@ -474,7 +492,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             load_row(0);
             for (int t = 0; t < n_active; ++t) {
                 const int slot = t % RING;
+#ifdef CP_TIMING
+                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 4] = clock64();
+#endif
                 const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
+#ifdef CP_TIMING
+                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 5] = clock64();
+#endif
                 if (delta != 0.0) {
 #pragma unroll
                     for (int sp = 0; sp < NPB; ++sp) {
@@ -484,6 +508,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 }
                 const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
                 if (sp1 < n_active) publish(sp1);
+#ifdef CP_TIMING
+                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 6] = clock64();
+#endif
                 if (t + RING < n_active) prefetch_row(jz[t + RING], slot);  // row t is in registers: its slot is free
                 cp_async_commit();
                 if (t + 1 < n_active) {
@@ -491,6 +518,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                     load_row((t + 1) % RING);
                 }
                 if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
+#ifdef CP_TIMING
+                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 7] = clock64();
+#endif
             }
             cp_async_wait<0>();
 #pragma unroll
@@ -633,6 +663,12 @@ int launch_select(const SelectParams &P, cudaStream_t stream) {
 }
 
 }  // namespace
+
+#ifdef CP_TIMING
+extern "C" int cp_debug_lasso_times(long long *host_out) {  // 384 steps x 8 clock64 stamps (third sweep of the first fit)
+    return (int)cudaMemcpyFromSymbol(host_out, cp_lasso_times, sizeof(long long) * 384 * 8);
+}
+#endif
 
 extern "C" int cp_lasso_build(cp_handle_t h, const double *Gs, const double *Bs, const double *sxs,
                               const double *sys, const double *yys, const double *WW, const double *sw,

@@ -143,6 +143,16 @@ __device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
     }
 }
 
+#ifdef CP_TIMING
+__device__ long long cp_ls_times[32];
+#define LS_STAMP(i)                                            \
+    do {                                                       \
+        if (threadIdx.x == 0 && j0 == 0) cp_ls_times[i] = clock64(); \
+    } while (0)
+#else
+#define LS_STAMP(i)
+#endif
+
 // A: the (updated) diagonal block in the trailing matrix; Lout: where the factor goes; Linv: 128 x 128
 // row-major (zero above the diagonal).  nb < 128 (last panel) is padded with the identity.
 __global__ void __launch_bounds__(P128_T, 1)
@@ -160,6 +170,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
     __shared__ MmTask tasks[3];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    LS_STAMP(0);
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
         double v = 0.0;
@@ -175,10 +186,13 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
     __syncthreads();
 
     double ratio_min = 1e300;
+    LS_STAMP(1);
     for (int sp = 0; sp < NSB; ++sp) {
         const int k0 = sp * SB;
+        LS_STAMP(2 + 4 * sp);
         if (warp == 0) potrf32_warp(As, k0, thr, rinv, info, j0, lane, ratio_min, inv0);
         __syncthreads();
+        LS_STAMP(3 + 4 * sp);
         const int r0 = k0 + SB, T = PB - r0;
         if (T == 0) break;
         // rows below the pivot block:  x * L32' = a  (one thread per row, right-looking over the 32 columns)
@@ -198,6 +212,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
             for (int j = 0; j < SB; ++j) row[j] = a[j];
         }
         __syncthreads();
+        LS_STAMP(4 + 4 * sp);
         // trailing block -= P P'   (4 x 4 micro-tiles on interleaved rows: conflict-free shared-memory reads)
         const int nt = T >> 2;
         for (int idx = tid; idx < nt * nt; idx += P128_T) {
@@ -231,7 +246,9 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
                 }
         }
         __syncthreads();
+        LS_STAMP(5 + 4 * sp);
     }
+    LS_STAMP(18);
     if (warp == 0) {
 #pragma unroll
         for (int off = 16; off; off >>= 1) ratio_min = fmin(ratio_min, __shfl_xor_sync(0xffffffffu, ratio_min, off));
@@ -242,6 +259,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         const int i = e >> 7, j = e & (PB - 1);
         if (i < nb && j <= i) Lout[(int64_t)i * ldl + j] = As[i * LDA_S + j];
     }
+    LS_STAMP(19);
     // ---- inverse of the four 32 x 32 diagonal sub-blocks: lane c solves L x = e_c
     if (warp < NSB) {
         const int b = warp, c = lane;
@@ -261,6 +279,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         }
     }
     __syncthreads();
+    LS_STAMP(20);
     // ---- off-diagonal blocks of X = L^-1, sub-diagonal by sub-diagonal:
     //      X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj ;  X_ij (i > j) is kept TRANSPOSED in the upper block (j, i) of As
     auto Lblk = [&](int i, int k) { return As + (i * SB) * LDA_S + k * SB; };        // L_ik[r][q]   stride LDA_S
@@ -296,13 +315,23 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         run_tasks(tasks, ntask);
         __syncthreads();
     }
+    LS_STAMP(21);
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
         double v = 0.0;
         if (j <= i) v = ((i >> 5) == (j >> 5)) ? Xd[((i >> 5) * SB + (i & 31)) * LDX_S + (j & 31)] : As[j * LDA_S + i];
         Linv[e] = v;
     }
+    LS_STAMP(22);
 }
+
+#ifdef CP_TIMING
+}  // namespace
+extern "C" int cp_debug_ls_times(long long *host_out) {  // clock64 stamps of the first panel of the last factorisation
+    return (int)cudaMemcpyFromSymbol(host_out, cp_ls_times, sizeof(long long) * 32);
+}
+namespace {
+#endif
 
 __global__ void __launch_bounds__(256)
 ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ sx, const double *__restrict__ sy,

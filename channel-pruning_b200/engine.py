@@ -342,14 +342,14 @@ class Engine:
         """C[m, nn] = alpha * sum_r a(m, r) b(nn, r) + beta * C   (cp_gemm_f64; fp64 device tensors, unit inner stride)
         a_mc: A is (R, M) else (M, R);  b_nc: B is (R, Nn) else (Nn, R)."""
         assert A.dtype == torch.float64 and B.dtype == torch.float64 and A.dim() == 2 and B.dim() == 2
-        assert A.stride(1) == 1 and B.stride(1) == 1
+        assert (A.stride(1) == 1 or A.shape[1] == 1) and (B.stride(1) == 1 or B.shape[1] == 1)
         R, M = (A.shape[0], A.shape[1]) if a_mc else (A.shape[1], A.shape[0])
         Rb, Nn = (B.shape[0], B.shape[1]) if b_nc else (B.shape[1], B.shape[0])
         assert R == Rb, "inner dimensions differ: %d vs %d" % (R, Rb)
         if out is None:
             assert beta == 0.0
             out = self.empty(M, Nn)
-        assert out.shape == (M, Nn) and out.dtype == torch.float64 and out.stride(1) == 1
+        assert out.shape == (M, Nn) and out.dtype == torch.float64 and (out.stride(1) == 1 or Nn == 1)
         self._call(self.lib.cp_gemm_f64(self.h, int(a_mc), int(b_nc), M, Nn, R, float(alpha), self._p(A, "const double*"),
                                         A.stride(0), self._p(B, "const double*"), B.stride(0), float(beta),
                                         self._p(out, "double*"), out.stride(0), self._s()))

@@ -2,21 +2,29 @@
 
 The reference's ``Net`` wraps a pycaffe handle; the hot path only needs (a) the blobs of a
 forward pass, (b) conv hyper-parameters, (c) weights.  Here a ``Net`` is built from a plain
-list of conv specs + a weight dict + a *feature provider* ``forward(net, batch) -> {blob:
+list of layer specs + a weight dict + a *feature provider* ``forward(net, data) -> {blob:
 CUDA tensor (B, C, H, W)}`` (``ConvStackForward`` below runs a sequential conv/ReLU/pool stack
 with torch.nn.functional, standing in for Caffe's GPU forward, which is also library code in
 the reference).  Methods keep the reference's names, arguments and return conventions:
 
   extract_features(names, nBatches=None, points_dict=None, save=False)   lib/net.py:368-532
   extract_XY(X, Y, DEBUG=False, w1=None)                                 lib/net.py:534-684
+  freeze_images(check_exist=False, convs=None)                           lib/net.py:749-800
   load_frozen(DEBUG=False, feats_dict=None, points_dict=None)            lib/net.py:839-876
   dictionary_kernel(X_name, weights, d_prime, Y_name, Y, DEBUG=0)        lib/net.py:1685-1735
-  R3() -> (WPQ, new_pt)    channel-pruning block only                     lib/net.py:1292-1471
+  R3() -> (WPQ, new_pt)    spatial + channel decomposition + pruning     lib/net.py:1292-1471
 
 The gathers run on the device (cp_point_gather / cp_patch_gather); sampled points come from the
 numpy global RNG with the reference's call sequence, so a seeded run draws the same points.
+Data types follow the reference: ``feats_dict{layer: float64 (N, n)}``,
+``points_dict{'nPointsPerLayer', 'nBatches', 'data', 'label', (batch, 0): images, (batch, 1): labels,
+(batch, layer, 'randx'|'randy'): int[P]}``, the frozen pickle ``[feats_dict, points_dict]`` (protocol 4),
+``WPQ{layer or (layer, 0|1): ndarray}``, ``selection{conv: bool[c]}``.
 """
 from __future__ import annotations
+
+import os
+import pickle
 
 import numpy as np
 import torch
@@ -24,8 +32,13 @@ import torch.nn.functional as F
 
 from . import cfgs
 from .cfgs import c as dcfgs
-from .decompose import _dictionary_device, rel_error
+from .decompose import ITQ_decompose, VH_decompose, _dictionary_device
 from ..engine import get_engine
+
+
+def underline(*parts):
+    """lib/utils.py:52-54"""
+    return '_'.join(str(p) for p in parts)
 
 
 class ConvSpec:
@@ -41,13 +54,20 @@ class ConvSpec:
 class ConvStackForward:
     """Feature provider for a sequential conv -> ReLU (-> pool) stack.  Blob names follow the
     reference after ``seperateConvReLU`` (net.py:1228): blob ``<conv>`` holds the PRE-ReLU conv
-    output; the next conv's bottom is ``<conv>_relu`` or ``pool<k>`` (post-ReLU)."""
+    output; the next conv's bottom is ``<conv>_relu`` or ``pool<k>`` (post-ReLU).
+    ``images_by_batch(batch) -> (B, 3, H, W)`` supplies the un-frozen batches (Caffe's data layer);
+    frozen runs pass the stored images in (net.py:446-447)."""
 
-    def __init__(self, images_by_batch):
-        self.images_by_batch = images_by_batch  # callable batch -> (B,3,H,W) CUDA fp32 tensor
+    def __init__(self, images_by_batch=None):
+        self.images_by_batch = images_by_batch
 
-    def __call__(self, net, batch, upto=None):
-        x = self.images_by_batch(batch)
+    def data(self, batch):
+        return self.images_by_batch(batch)
+
+    def __call__(self, net, data, upto=None):
+        dev = net.eng.device
+        x = data if isinstance(data, torch.Tensor) else torch.as_tensor(np.asarray(data, dtype=np.float32))
+        x = x.to(dev, torch.float32)
         blobs = {"data": x}
         for spec in net._specs:
             w = net._w[spec.name]
@@ -63,10 +83,15 @@ class ConvStackForward:
         return blobs
 
 
+# net.py:1309-1321
+RANKDIC = {'conv1_1': 17, 'conv1_2': 17, 'conv2_1': 37, 'conv2_2': 47, 'conv3_1': 83, 'conv3_2': 89, 'conv3_3': 106,
+           'conv4_1': 175, 'conv4_2': 192, 'conv4_3': 227, 'conv5_1': 398, 'conv5_2': 390, 'conv5_3': 379}
+
+
 class Net:
-    def __init__(self, specs, weights, biases, forward, pool_names=None):
+    def __init__(self, specs, weights, biases, forward, pool_names=None, frozen=None):
         """specs: ordered list of ConvSpec; weights/biases: {name: array (n,c,k,k) / (n,)};
-        forward: callable (net, batch) -> {blob name: CUDA tensor (B,C,H,W) fp32}."""
+        forward: feature provider (see ConvStackForward); frozen: path of the frozen-points pickle."""
         self.eng = get_engine()
         dev = self.eng.device
         self._specs = list(specs)
@@ -80,12 +105,15 @@ class Net:
         self._pool_name = pool_names or {}
         self.bottom_names = {s.name: [s.bottom] for s in self._specs}
         self._mem = True
+        self._protocol = 4  # net.py:94
+        self._frozen = frozen
         self.WPQ = {}
         self.selection = {}
         self._feats_dict = None
         self._points_dict = None
         self._feats_dev = {}
         self.num = None
+        self._batch_iter = 0
 
     # ---- accessors with the reference's names (net.py:174-286)
     def param_data(self, name):
@@ -112,8 +140,18 @@ class Net:
     def conv_param_stride(self, name):
         return self._spec[name].stride
 
-    def forward(self, batch):
-        return self._forward(self, batch)
+    def forward(self, data=None, upto=None):
+        """One forward pass: of the provider's next batch (data=None, like Caffe's data layer) or of given images
+        (the frozen path, net.set_input_arrays at net.py:447).  Returns the blob dict."""
+        if data is None:
+            data = self._forward.data(self._batch_iter)
+            self._batch_iter += 1
+        self._data = data
+        return self._forward(self, data, upto=upto)
+
+    def _frozen_blobs(self, batch, upto=None):
+        pd = self._points_dict
+        return self.forward(pd[(batch, 0)], upto=upto)
 
     # ---- extract_features, net.py:368-532 (conv blobs)
     def extract_features(self, names=[], nBatches=None, points_dict=None, save=False):
@@ -136,8 +174,22 @@ class Net:
         eng = self.eng
         feats_dev = {}
         P = nPointsPerLayer
+        last = names[-1] if all(n in self.convs for n in names) else None
+        upto = None
+        if last is not None:  # the deepest requested blob bounds the forward pass
+            upto = max(names, key=self.convs.index)
         for batch in range(nBatches):
-            blobs = self.forward(batch)
+            if save and frozen_points and (batch, 0) in points_dict:
+                blobs = self.forward(points_dict[(batch, 0)], upto=upto)  # net.py:446-447
+            else:
+                blobs = self.forward(upto=upto)
+                if save and not frozen_points:
+                    data = blobs["data"]
+                    if batch == 0:
+                        points_dict["data"] = tuple(data.shape)       # net.py:432-433
+                        points_dict["label"] = (data.shape[0], 1, 1, 1)
+                    points_dict[(batch, 0)] = data.cpu().numpy().copy()  # net.py:441-442
+                    points_dict[(batch, 1)] = np.zeros((data.shape[0], 1, 1, 1), dtype=np.float32)
             for name in names:
                 feat = blobs[name]
                 B, n, H, W = feat.shape
@@ -163,9 +215,25 @@ class Net:
             return feats_dict, points_dict
         return feats_dict
 
-    # ---- load_frozen, net.py:839-876 (in-memory branch)
+    # ---- freeze_images / load_frozen, net.py:749-800, 839-876
+    def freeze_images(self, check_exist=False, convs=None, **kwargs):
+        """Samples points + features of every conv once and pickles ``[feats_dict, points_dict]`` (protocol 4) to
+        ``self._frozen`` exactly like the reference (net.py:799-800).  Returns the path."""
+        frozen = self._frozen
+        assert frozen is not None, "construct the Net with frozen=<path> to use the pickle round trip"
+        if check_exist and os.path.exists(frozen):
+            return frozen
+        if convs is None:
+            convs = self.convs
+        feats_dict, points_dict = self.extract_features(names=convs, save=1, **kwargs)
+        with open(frozen, 'wb') as f:
+            pickle.dump([feats_dict, points_dict], f, protocol=self._protocol)
+        return frozen
+
     def load_frozen(self, DEBUG=False, feats_dict=None, points_dict=None):
-        assert feats_dict is not None, "only the in-memory branch (net.py:840-844) exists without Caffe/pickles"
+        if feats_dict is None:  # net.py:862-864
+            with open(self._frozen, 'rb') as f:
+                feats_dict, points_dict = pickle.load(f)
         self._feats_dict = feats_dict
         self._points_dict = points_dict
         dev = self.eng.device
@@ -174,9 +242,13 @@ class Net:
             v32 = np.asarray(v, dtype=np.float32)
             self._feats_dev[k] = torch.as_tensor(v32 if np.array_equal(v32.astype(np.float64), v) else np.asarray(v),
                                                  device=dev)
+        if DEBUG:  # net.py:866-875: re-extraction at the frozen points reproduces the frozen features exactly
+            again, _ = self.extract_features(list(feats_dict), points_dict=points_dict, save=1)
+            for i in again:
+                assert np.array_equal(again[i], feats_dict[i]), i
 
     def freeze(self, names=None):
-        """freeze_images (net.py:749-800) without the pickle: sample points + features once."""
+        """freeze_images + load_frozen without touching the disk."""
         names = names or self.convs
         feats_dict, points_dict = self.extract_features(names, save=1)
         self.load_frozen(feats_dict=feats_dict, points_dict=points_dict)
@@ -188,9 +260,15 @@ class Net:
         pd = self._points_dict
         P, nBatches = pd["nPointsPerLayer"], pd["nBatches"]
         eng = self.eng
+        # the producing layer bounds the forward pass: blobs after X are not needed
+        upto = None
+        for s in self._specs:
+            if X in (s.name, s.name + "_relu", self._pool_name.get(s.name)):
+                upto = s.name
         out = None
         for batch in range(nBatches):
-            blob = self.forward(batch)[X].contiguous()
+            blob = self._frozen_blobs(batch, upto=upto)[X].contiguous() if (batch, 0) in pd else \
+                self.forward(upto=upto)[X].contiguous()
             B, c = blob.shape[0], blob.shape[1]
             if out is None:
                 out = eng.empty(nBatches * P * B, c * spec.kernel_size ** 2, dtype=torch.float32)
@@ -225,34 +303,91 @@ class Net:
         rank = int(idxs.sum())
         return idxs, Wd.cpu().numpy().reshape(n, rank, h, h), bd.cpu().numpy()
 
-    # ---- R3, net.py:1292-1471 -- channel-pruning block (:1406-1459)
-    def R3(self, alldic=None, pooldic=None, c_ratio=1.15):
-        """Walks (conv, convnext) pairs like the reference; for conv in alldic|pooldic prunes
-        convnext's input channels.  The VH / ITQ stages of the reference loop (:1351-1404) are 3C
-        companions outside this path.  Returns (WPQ, new_pt) with new_pt a dict of pruned widths."""
+    # ---- R3, net.py:1292-1471
+    def R3(self):
+        """The 3C walk of the reference: for every conv after the first, spatial decomposition (VH_decompose, refitted
+        on data), channel decomposition (ITQ_decompose on re-extracted features), then -- for the layers of alldic /
+        pooldic -- channel pruning of the NEXT conv's input (dictionary_kernel), each stage compensating the error of
+        the ones before it because features are re-extracted through the already rewritten weights.
+        Returns (WPQ, new_pt): WPQ with the reference's keys (<conv>_V, (<conv>_H, 0|1), (<conv>_P, 0|1)); new_pt
+        describes the rewritten topology (the reference writes a prototxt, net.py:1470)."""
+        speed_ratio = dcfgs.dic.keep
+        prefix = ('3C' if dcfgs.dic.vh else '2C') + str(int(speed_ratio) + 1) + 'x'  # :1296-1300
         convs = self.convs
         self.WPQ = dict()
         self.selection = dict()
+        self._mem = True
         end = 5
-        if alldic is None:  # net.py:1307-1308 (VGG-16)
-            alldic = ['conv%d_1' % i for i in range(1, end)] + ['conv%d_2' % i for i in range(3, end)]
-        if pooldic is None:
-            pooldic = ['conv1_2', 'conv2_2']
-        new_pt = {}
-        for conv, convnext in zip(convs[1:], convs[2:] + ['pool5']):
-            if not (dcfgs.dic.vh and (conv in alldic or conv in pooldic) and (convnext in self.convs)):
+        alldic = ['conv%d_1' % i for i in range(1, end)] + ['conv%d_2' % i for i in range(3, end)]  # :1307
+        pooldic = ['conv1_2', 'conv2_2']
+        rankdic = dict(RANKDIC)
+        for i in rankdic:
+            if 'conv5' in i:
                 continue
-            d_c = int(self.param_shape(conv)[0] / c_ratio)  # :1346
-            X_name = self.bottom_names[convnext][0] if conv in pooldic else conv  # :1411-1414
-            idxs, W2, B2 = self.dictionary_kernel(X_name, None, d_c, convnext, None)
-            self.selection[convnext] = idxs
-            it = torch.as_tensor(idxs, device=self.eng.device)
-            self._w[convnext][:, ~it, ...] = 0  # :1446
-            self._w[convnext][:, it, ...] = torch.as_tensor(W2, device=self.eng.device, dtype=torch.float32)
-            self.set_param_b(convnext, B2)
-            self.WPQ[(conv, 0)] = self._w[conv][it].cpu().numpy()  # producer rows, :1455-1456
-            self.WPQ[(conv, 1)] = self._b[conv][it].cpu().numpy()
-            self.WPQ[(convnext, 0)] = W2
-            self.WPQ[(convnext, 1)] = B2
-            new_pt[conv] = int(idxs.sum())
+            rankdic[i] = int(rankdic[i] * 4. / speed_ratio)  # :1323-1326
+        c_ratio = 1.15
+        dev = self.eng.device
+
+        def getX(name):  # :1329-1331
+            x = self.extract_XY(self.bottom_names[name][0], name)
+            return np.rollaxis(x.reshape((-1, 3, 3, x.shape[1])), 3, 1).copy()
+
+        def setConv(c, d):  # :1333-1337
+            d = torch.as_tensor(np.asarray(d), device=dev, dtype=torch.float32)
+            if c in self.selection:
+                self._w[c][:, torch.as_tensor(self.selection[c], device=dev), :, :] = d
+            else:
+                self._w[c].copy_(d)
+
+        topology = []
+        for conv, convnext in zip(convs[1:], convs[2:] + ['pool5']):
+            conv_V = underline(conv, 'V')
+            conv_H = underline(conv, 'H')
+            conv_P = underline(conv, 'P')
+            W_shape = self.param_shape(conv)
+            d_c = int(W_shape[0] / c_ratio)
+            rank = rankdic[conv]
+            d_prime = rank
+            if d_c < rank:
+                d_c = rank  # :1349
+            # ---- spatial decomposition (:1351-1380)
+            weights = self._w[conv]
+            if conv in self.selection:
+                weights = weights[:, torch.as_tensor(self.selection[conv], device=dev), :, :]
+            Y = self._feats_dict[conv] - self._b[conv].cpu().numpy()
+            X = getX(conv)
+            if conv in self.selection:
+                X = X[:, self.selection[conv], :, :]
+            V, H, VHr, b = VH_decompose(weights.cpu().numpy().astype(np.float64), rank=rank, DEBUG=True, X=X, Y=Y)
+            self.set_param_b(conv, b)
+            self.WPQ[conv_V] = V
+            setConv(conv, VHr)
+            self.WPQ[(conv_H, 0)] = H
+            self.WPQ[(conv_H, 1)] = self._b[conv].cpu().numpy()
+            # ---- channel decomposition (:1384-1404)
+            feats_dict, _ = self.extract_features(names=conv, points_dict=self._points_dict, save=1)
+            Yf = feats_dict[conv]
+            W1, W2, B, W12 = ITQ_decompose(Yf, self._feats_dict[conv], H, d_prime, bias=self._b[conv].cpu().numpy(),
+                                           DEBUG=0, Wr=VHr)
+            setConv(conv, W12.copy())
+            self.set_param_b(conv, B.copy())
+            self.WPQ[(conv_H, 0)] = W1.reshape([d_prime, H.shape[1], H.shape[2], H.shape[3]])
+            self.WPQ[(conv_H, 1)] = np.zeros(d_prime)
+            self.WPQ[(conv_P, 0)] = W2.reshape([W2.shape[0], W2.shape[1], 1, 1])
+            self.WPQ[(conv_P, 1)] = B
+            # ---- channel pruning (:1406-1459)
+            if dcfgs.dic.vh and (conv in alldic or conv in pooldic) and (convnext in self.convs):
+                X_name = self.bottom_names[convnext][0] if conv in pooldic else conv  # :1411-1414
+                idxs, W2n, B2n = self.dictionary_kernel(X_name, None, d_c, convnext, None)
+                self.selection[convnext] = idxs
+                it = torch.as_tensor(idxs, device=dev)
+                self._w[convnext][:, ~it, ...] = 0  # :1446
+                self._w[convnext][:, it, ...] = torch.as_tensor(W2n, device=dev, dtype=torch.float32)
+                self.set_param_b(convnext, B2n)
+                key = conv_P if (conv_P, 0) in self.WPQ else conv_H  # :1450-1456
+                self.WPQ[(key, 0)] = self.WPQ[(key, 0)][idxs]
+                self.WPQ[(key, 1)] = self.WPQ[(key, 1)][idxs]
+            topology.append({"V": conv_V, "H": conv_H, "P": conv_P, "rank": int(rank),
+                             "num_output": int(self.WPQ[(conv_P, 0)].shape[0])})
+        new_pt = {"prefix": prefix, "layers": topology}
         return self.WPQ, new_pt

@@ -23,6 +23,7 @@ restatement of the reference's algorithm, function by function:
   nonlinear_fc                 lib/decompose.py:671-685
   VH_decompose                 lib/decompose.py:85-147
   ITQ_decompose                lib/decompose.py:163-319
+  NumpyNet + R3                lib/net.py:1292-1471 (the whole 3C walk: VH -> ITQ -> pruning, sequential)
   ===========================  ==========================================
 
 Third-party arithmetic (absent from /root/reference; the reference pins no
@@ -600,3 +601,132 @@ def prune_block_R3(forward, conv_specs, weights, biases, feats_dict, points_dict
         if infos is not None:
             infos[convnext] = info
     return weights, biases, selection, WPQ
+
+
+# --------------------------------------------------------------------------- the whole R3 walk on a numpy net
+RANKDIC = {'conv1_1': 17, 'conv1_2': 17, 'conv2_1': 37, 'conv2_2': 47, 'conv3_1': 83, 'conv3_2': 89, 'conv3_3': 106,
+           'conv4_1': 175, 'conv4_2': 192, 'conv4_3': 227, 'conv5_1': 398, 'conv5_2': 390, 'conv5_3': 379}  # net.py:1309-1321
+
+
+def conv2d_numpy(x, w, b, pad, stride):
+    """fp32 direct convolution standing in for Caffe's forward."""
+    B, c, H, W = x.shape
+    n, _, k, _ = w.shape
+    xp = np.zeros((B, c, H + 2 * pad, W + 2 * pad), dtype=np.float32)
+    xp[:, :, pad:H + pad, pad:W + pad] = x
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = np.zeros((B, n, Ho, Wo), dtype=np.float32)
+    for i in range(Ho):
+        for j in range(Wo):
+            patch = xp[:, :, i * stride:i * stride + k, j * stride:j * stride + k].reshape(B, -1)
+            out[:, :, i, j] = patch @ w.reshape(n, -1).T + b
+    return out
+
+
+class NumpyNet:
+    """What the reference's Net is on this path, without Caffe: conv / 2x2 max-pool specs (dicts: name, bottom, k, pad,
+    stride | type='pool'), fp32 weights / biases (mutated by R3 like the live Caffe net), frozen images."""
+
+    def __init__(self, specs, weights, biases):
+        self.specs = specs
+        self.convs = [s["name"] for s in specs if s.get("type") != "pool"]
+        self.bottom_names = {s["name"]: [s["bottom"]] for s in specs}
+        self.weights = {k: np.array(v, dtype=np.float32) for k, v in weights.items()}
+        self.biases = {k: np.array(v, dtype=np.float32) for k, v in biases.items()}
+        self.WPQ, self.selection = {}, {}
+        self._feats_dict = self._points_dict = None
+
+    def forward_blobs(self, data):
+        blobs = {"data": data}
+        for s in self.specs:
+            if s.get("type") == "pool":
+                x = blobs[s["bottom"]]
+                B, c, H, W = x.shape
+                blobs[s["name"]] = x[:, :, :H // 2 * 2, :W // 2 * 2].reshape(B, c, H // 2, 2, W // 2, 2).max((3, 5))
+                continue
+            y = conv2d_numpy(blobs[s["bottom"]], self.weights[s["name"]], self.biases[s["name"]], s["pad"], s["stride"])
+            blobs[s["name"]] = y
+            blobs[s["name"] + "_relu"] = np.maximum(y, 0)
+        return blobs
+
+    def spec(self, name):
+        s = [q for q in self.specs if q["name"] == name][0]
+        return ConvSpec(name, s["bottom"], s["k"], s["pad"], s["stride"])
+
+    def frozen_forward(self):
+        pd = self._points_dict
+        return lambda batch: self.forward_blobs(pd[(batch, 0)])
+
+
+def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None):
+    """lib/net.py:1292-1471 on a NumpyNet whose frozen ``_feats_dict`` / ``_points_dict`` are set (points_dict carries
+    the images under (batch, 0) like the reference's, net.py:441).  Mutates net.weights / net.biases; returns WPQ."""
+    state = state if state is not None else DictState()
+    convs = net.convs
+    net.WPQ, net.selection = {}, {}
+    end = 5
+    alldic = ['conv%d_1' % i for i in range(1, end)] + ['conv%d_2' % i for i in range(3, end)]  # :1307
+    pooldic = ['conv1_2', 'conv2_2']
+    rankdic = dict(RANKDIC)
+    for i in rankdic:
+        if 'conv5' in i:
+            continue
+        rankdic[i] = int(rankdic[i] * 4. / keep)  # :1323-1326
+
+    def getX(name):  # :1329-1331
+        x = extract_XY(net.frozen_forward(), net.bottom_names[name][0], net.spec(name), net._points_dict)
+        return np.rollaxis(x.reshape((-1, 3, 3, x.shape[1])), 3, 1).copy()
+
+    def setConv(c, d):  # :1333-1337
+        if c in net.selection:
+            net.weights[c][:, net.selection[c], :, :] = d
+        else:
+            net.weights[c][...] = d
+
+    for conv, convnext in zip(convs[1:], convs[2:] + ['pool5']):
+        conv_V, conv_H, conv_P = conv + '_V', conv + '_H', conv + '_P'
+        d_c = int(net.weights[conv].shape[0] / c_ratio)
+        rank = rankdic[conv]
+        d_prime = rank
+        if d_c < rank:
+            d_c = rank  # :1349
+        # ---- spatial decomposition (:1351-1380)
+        weights = net.weights[conv]
+        if conv in net.selection:
+            weights = weights[:, net.selection[conv], :, :]
+        Y = net._feats_dict[conv] - net.biases[conv]
+        X = getX(conv)
+        if conv in net.selection:
+            X = X[:, net.selection[conv], :, :]
+        V, H, VHr, b = VH_decompose(weights, rank=rank, X=X, Y=Y)
+        net.biases[conv][...] = b
+        net.WPQ[conv_V] = V
+        setConv(conv, VHr)
+        net.WPQ[(conv_H, 0)] = H
+        net.WPQ[(conv_H, 1)] = net.biases[conv]
+        # ---- channel decomposition (:1384-1404)
+        feats_new, _ = extract_features(net.frozen_forward(), [conv], None, None, points_dict=net._points_dict)
+        W1, W2, B, W12 = ITQ_decompose(feats_new[conv], net._feats_dict[conv], H, d_prime, bias=net.biases[conv], Wr=VHr)
+        setConv(conv, W12.copy())
+        net.biases[conv][...] = B
+        net.WPQ[(conv_H, 0)] = W1.reshape([d_prime, H.shape[1], H.shape[2], H.shape[3]])
+        net.WPQ[(conv_H, 1)] = np.zeros(d_prime)
+        net.WPQ[(conv_P, 0)] = W2.reshape([W2.shape[0], W2.shape[1], 1, 1])
+        net.WPQ[(conv_P, 1)] = B
+        # ---- channel pruning (:1406-1459)
+        if (conv in alldic or conv in pooldic) and (convnext in net.convs):
+            X_name = net.bottom_names[convnext][0] if conv in pooldic else conv
+            info = {} if infos is not None else None
+            idxs, W2n, B2n = dictionary_kernel(net.frozen_forward(), X_name, net.spec(convnext), net.weights[convnext],
+                                               net.biases[convnext], net._feats_dict[convnext], net._points_dict, d_c,
+                                               state=state, form=form, info=info)
+            net.selection[convnext] = idxs
+            net.weights[convnext][:, ~idxs, ...] = 0
+            net.weights[convnext][:, idxs, ...] = W2n.copy()
+            net.biases[convnext][...] = B2n
+            key = conv_P if (conv_P, 0) in net.WPQ else conv_H
+            net.WPQ[(key, 0)] = net.WPQ[(key, 0)][idxs]
+            net.WPQ[(key, 1)] = net.WPQ[(key, 1)][idxs]
+            if infos is not None:
+                infos[convnext] = info
+    return net.WPQ

@@ -78,7 +78,7 @@ def make_fake_net(NET, CF, images, specs, weights, biases):
             self._batch_iter = 0
             self._cur = None
             self._blobs = {}
-            self.convs = [s["name"] for s in specs]
+            self.convs = [s["name"] for s in specs if s.get("type") != "pool"]
             self.innerproduct, self.sums, self.bns = [], [], []
             self._bottom_names = {s["name"]: [s["bottom"]] for s in specs}  # backs the bottom_names property
             self.num = images[0].shape[0]
@@ -97,6 +97,11 @@ def make_fake_net(NET, CF, images, specs, weights, biases):
             self._data, self._label = data, label
             blobs = {"data": data}
             for s in specs:
+                if s.get("type") == "pool":  # 2x2 / stride 2 max pooling (VGG)
+                    x = blobs[s["bottom"]]
+                    Bq, cq, Hq, Wq = x.shape
+                    blobs[s["name"]] = x[:, :, :Hq // 2 * 2, :Wq // 2 * 2].reshape(Bq, cq, Hq // 2, 2, Wq // 2, 2).max((3, 5))
+                    continue
                 y = conv2d_numpy(blobs[s["bottom"]], weights[s["name"]], biases[s["name"]], s["pad"], s["stride"])
                 blobs[s["name"]] = y
                 blobs[s["name"] + "_relu"] = np.maximum(y, 0)
@@ -131,7 +136,14 @@ def make_fake_net(NET, CF, images, specs, weights, biases):
         def param_shape(self, name): return weights[name].shape
         def param_data(self, name): return weights[name]
         def param_b_data(self, name): return biases[name]
+        def set_param_data(self, name, data): weights[name][...] = data.copy()   # net.py:213-217
+        def set_param_b(self, name, data): biases[name][...] = data.copy()       # net.py:219-220
         def appresb(self, name): return 0  # dcfgs.res.short == 0 (net.py:1648)
+        # prototxt surgery of R3 (net.py:884-966, 321-366, 161-164): no numerical effect, nothing to edit here
+        def insert(self, *a, **k): pass
+        def set_conv(self, *a, **k): pass
+        def infer_pad_kernel(self, W, origin_name): return {}
+        def save_pt(self, *a, **k): return "pt"
 
     return FakeNet()
 
@@ -169,6 +181,40 @@ def run_net_cases(NET, CF, D):
         print(name, "XY", XY.shape, {k: v.shape for k, v in feats_dict.items()})
 
 
+def run_r3_cases(NET, CF, D):
+    """The reference's own Net.R3 (VH -> ITQ -> channel pruning per layer, sequential, error compensating) on a tiny
+    VGG-named stack.  Outputs: every WPQ entry, the selections, the final weights / biases of the live net."""
+    for name, spec in cases.R3_CASES.items():
+        images, specs, weights, biases = cases.r3_inputs(**spec["gen"])
+        CF.c.nBatches = spec["nBatches"]
+        CF.c.nPointsPerLayer = spec["P"]
+        CF.c.dic.option = 0
+        CF.c.dic.fitfc = 0
+        CF.c.dic.vh = 1
+        CF.c.dic.keep = 3.
+        CF.c.model = ''
+        CF.alpha = 1e-3
+        net = make_fake_net(NET, CF, images, specs, weights, biases)
+        np.random.seed(spec["np_seed"])
+        feats_dict, points_dict = net.extract_features(net.convs, save=1)
+        net.load_frozen(feats_dict=feats_dict, points_dict=points_dict)
+        WPQ, new_pt = net.R3()
+        out = {}
+        for k, v in WPQ.items():
+            out["WPQ__" + ("%s__%d" % k if isinstance(k, tuple) else k)] = np.asarray(v)
+        for k, v in net.selection.items():
+            out["sel__" + k] = v
+        for nm in net.convs:
+            out["w__" + nm] = weights[nm]
+            out["b__" + nm] = biases[nm]
+            out["feats__" + nm] = feats_dict[nm]
+        out["alpha_final"] = CF.alpha
+        out["rng_after"] = np.random.randint(0, 1 << 30)
+        np.savez_compressed(os.path.join(OUT, "%s.npz" % name), **out)
+        print(name, "WPQ keys", sorted(str(k) for k in WPQ), "kept", {k: int(v.sum()) for k, v in net.selection.items()},
+              "alpha", CF.alpha)
+
+
 def run_3c_cases(D, CF):
     """VH_decompose (with its nonlinear_fc refit) and ITQ_decompose of the reference on small seeded inputs."""
     for name, spec in cases.VH_CASES.items():
@@ -191,6 +237,7 @@ def main():
     run_dictionary_cases(D, CF)
     run_net_cases(NET, CF, D)
     run_3c_cases(D, CF)
+    run_r3_cases(NET, CF, D)
 
 
 if __name__ == "__main__":

@@ -136,3 +136,33 @@ ITQ_CASES = {
     "itq_small": dict(gen=dict(n=20, rvh=9, c=8, N=700, seed=51), rank=11),
     "itq_mid": dict(gen=dict(n=48, rvh=20, c=16, N=1600, seed=52), rank=30),
 }
+
+
+def r3_inputs(B, H, widths, nimgbatches, seed):
+    """A small VGG-named stack for Net.R3 (lib/net.py:1292-1471 hard-codes the VGG-16 layer names in alldic / pooldic
+    / rankdic): data (B,3,H,H) -> conv1_1 -> ReLU -> conv1_2 -> ReLU -> pool1 (2x2/2 max) -> conv2_1 -> ReLU -> conv2_2.
+    widths = output channels of the four convs."""
+    r = np.random.RandomState(seed)
+    images = [r.standard_normal((B, 3, H, H)).astype(np.float32) for _ in range(nimgbatches)]
+    names = ["conv1_1", "conv1_2", "conv2_1", "conv2_2"]
+    bottoms = ["data", "conv1_1_relu", "pool1", "conv2_1_relu"]
+    specs = []
+    for nm, bt in zip(names, bottoms):
+        specs.append(dict(name=nm, bottom=bt, k=3, pad=1, stride=1))
+        if nm == "conv1_2":
+            specs.append(dict(name="pool1", bottom="conv1_2_relu", type="pool"))
+    weights, biases = {}, {}
+    cin = 3
+    for nm, co in zip(names, widths):
+        weights[nm] = (r.standard_normal((co, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float32)
+        biases[nm] = (0.1 * r.standard_normal(co)).astype(np.float32)
+        cin = co
+    return images, specs, weights, biases
+
+
+R3_CASES = {
+    # rankdic x 4/3 (keep = 3): conv1_2 22, conv2_1 49, conv2_2 62 -- widths chosen so that rank <= n and that the
+    # `if d_c < rank: d_c = rank` floor (net.py:1349) is exercised at conv2_1 (int(56/1.15) = 48 < 49)
+    "r3_small": dict(gen=dict(B=4, H=12, widths=(12, 28, 56, 64), nimgbatches=20, seed=61), nBatches=20, P=10,
+                     np_seed=71),
+}

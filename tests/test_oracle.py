@@ -193,3 +193,60 @@ def test_itq_decompose_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(B, g["B"], rtol=0, atol=1e-8)
     np.testing.assert_allclose(_sign_align(W1, g["W1"], 0), g["W1"], rtol=0, atol=1e-7 * np.abs(g["W1"]).max())
     np.testing.assert_allclose(_sign_align(W2, g["W2"], 1), g["W2"], rtol=0, atol=1e-7 * np.abs(g["W2"]).max())
+
+
+def r3_compare(golden, WPQ, selection, weights, biases, tol_inv=1e-6, tol_fac=1e-5):
+    """Compares an R3 outcome with the reference's golden: selections exactly; sign-invariant quantities (live
+    weights/biases, the P-layer biases) tightly; the individual V / H / P factors up to the sign of each component."""
+    for k in [k for k in golden.files if k.startswith("sel__")]:
+        assert np.array_equal(selection[k[5:]], golden[k]), k
+    worst = 0.0
+    for k in [k for k in golden.files if k.startswith("w__")]:
+        nm = k[3:]
+        e = np.linalg.norm(weights[nm] - golden[k]) / np.linalg.norm(golden[k])
+        eb = np.abs(biases[nm] - golden["b__" + nm]).max() / max(1.0, np.abs(golden["b__" + nm]).max())
+        worst = max(worst, e, eb)
+        assert e <= tol_inv and eb <= tol_inv, (nm, e, eb)
+    for k in [k for k in golden.files if k.startswith("WPQ__")]:
+        parts = k[5:].split("__")
+        key = (parts[0], int(parts[1])) if len(parts) == 2 else parts[0]
+        got, ref = np.asarray(WPQ[key]), golden[k]
+        assert got.shape == ref.shape, (key, got.shape, ref.shape)
+        if isinstance(key, tuple) and key[1] == 1:     # biases: sign invariant (H bias is zeros, P bias = B)
+            assert np.abs(got - ref).max() <= tol_inv * max(1.0, np.abs(ref).max()), key
+            continue
+        name = key if isinstance(key, str) else key[0]
+        # V: (rank, c, h, 1) components along axis 0; H after ITQ = W1 (d', r, 1, w) components along axis 0 AND axis 1;
+        # P = W2 (n', d', 1, 1) components along axis 1: compare through sign-insensitive Gram matrices
+        a, b = got.reshape(got.shape[0], -1), ref.reshape(ref.shape[0], -1)
+        if name.endswith("_V"):
+            inv_a, inv_b = a.T @ a, b.T @ b            # projector onto the kept spatial components
+        elif name.endswith("_P"):
+            inv_a, inv_b = a @ a.T, b @ b.T
+        else:
+            inv_a, inv_b = np.abs(a), np.abs(b)        # |entries| are invariant to both sign families
+        assert np.linalg.norm(inv_a - inv_b) <= tol_fac * np.linalg.norm(inv_b), key
+    return worst
+
+
+@pytest.mark.parametrize("name", list(cases.R3_CASES))
+def test_r3_walk_matches_reference_golden(golden_dir, name):
+    spec = cases.R3_CASES[name]
+    g = np.load(os.path.join(golden_dir, "%s.npz" % name))
+    images, specs, weights, biases = cases.r3_inputs(**spec["gen"])
+    net = O.NumpyNet(specs, weights, biases)
+    np.random.seed(spec["np_seed"])
+    # freeze: sample points + features once (net.py:749-800), images kept under (batch, 0)
+    pd0 = {}
+    fwd = lambda b: net.forward_blobs(images[b % len(images)])  # noqa: E731
+    feats, pd = O.extract_features(fwd, net.convs, spec["nBatches"], spec["P"])
+    for b in range(spec["nBatches"]):
+        pd[(b, 0)] = images[b % len(images)]
+    for nm in net.convs:
+        np.testing.assert_array_equal(feats[nm], g["feats__" + nm])
+    net._feats_dict, net._points_dict = feats, pd
+    st = O.DictState(alpha=1e-3)
+    WPQ = O.R3(net, state=st)
+    assert st.alpha == float(g["alpha_final"])
+    assert np.random.randint(0, 1 << 30) == int(g["rng_after"])
+    r3_compare(g, WPQ, net.selection, net.weights, net.biases)
