@@ -202,12 +202,15 @@ solve_relu_kernel(const double *__restrict__ RUraw, int64_t ldr, const double *_
     if (j < n) {
         const double bj = bias ? bias[j] : 0.0;
         for (int64_t r = r0 + rg; r < r0 + 64 && r < N; r += 8) {
-            const double ru = RUraw[r * ldr + j] + bj;
+            // every operation rounded separately, in numpy's evaluation order (decompose.py:52-58): no FMA contraction
+            const double ru = bias ? __dadd_rn(RUraw[r * ldr + j], bj) : RUraw[r * ldr + j];
             const double z = Z[r * ldz + j];
             const double u0 = fmin(ru, 0.0);
-            const double cost0 = z * z + lambda * (u0 - ru) * (u0 - ru);
-            const double u1 = fmax((lambda * ru + z) / (lambda + 1.0), 0.0);
-            const double cost1 = (u1 - z) * (u1 - z) + lambda * (u1 - ru) * (u1 - ru);
+            const double d0 = __dadd_rn(u0, -ru);
+            const double cost0 = __dadd_rn(__dmul_rn(z, z), __dmul_rn(lambda, __dmul_rn(d0, d0)));
+            const double u1 = fmax(__ddiv_rn(__dadd_rn(__dmul_rn(lambda, ru), z), __dadd_rn(lambda, 1.0)), 0.0);
+            const double d1 = __dadd_rn(u1, -z), d2 = __dadd_rn(u1, -ru);
+            const double cost1 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(lambda, __dmul_rn(d2, d2)));
             const double u = (cost0 <= cost1) ? u0 : u1;
             U[r * ldu + j] = u;
             acc += u;

@@ -205,23 +205,61 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
         buf ^= 1;
     }
 
-    // ---- epilogue
+    // ---- epilogue: two tile rows at a time, all their C values LOADED before any is stored (beta != 0): the
+    // read-modify-write of a 128 x 128 tile is 64 values per thread, and one load -> fma -> store chain per value
+    // would expose the memory latency 64 times (rank-128 trailing updates spent as long here as in the k loop)
     double *C = g.C + (g.nsplit > 1 ? (int64_t)split * g.c_split_stride : 0);
     const bool partial = g.nsplit > 1;
+    const bool rmw = !partial && g.beta != 0.0;
+    const bool cvec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (g.ldc % 2 == 0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
-        if (m >= g.M) continue;
+    for (int ip = 0; ip < 4; ++ip) {
+        double old[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int nn = n0 + (j >> 1) * 32 + tx * 2 + (j & 1);
-            if (nn >= g.Nn) continue;
-            double v = acc[i][j];
-            if (!partial) {
-                v *= g.alpha;
-                if (g.beta != 0.0) v = fma(g.beta, C[(int64_t)m * g.ldc + nn], v);
+        for (int e = 0; e < 2; ++e) {
+            const int m = m0 + ip * 32 + ty * 2 + e;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nn = n0 + q * 32 + tx * 2;
+                old[e][2 * q] = old[e][2 * q + 1] = 0.0;
+                if (rmw && m < g.M) {
+                    const double *p = C + (int64_t)m * g.ldc + nn;
+                    if (cvec && nn + 1 < g.Nn) {
+                        const double2 v = *reinterpret_cast<const double2 *>(p);
+                        old[e][2 * q] = v.x;
+                        old[e][2 * q + 1] = v.y;
+                    } else {
+                        if (nn < g.Nn) old[e][2 * q] = p[0];
+                        if (nn + 1 < g.Nn) old[e][2 * q + 1] = p[1];
+                    }
+                }
             }
-            C[(int64_t)m * g.ldc + nn] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = 2 * ip + e;
+            const int m = m0 + ip * 32 + ty * 2 + e;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nn = n0 + q * 32 + tx * 2;
+                double v0 = acc[i][2 * q], v1 = acc[i][2 * q + 1];
+                if (!partial) {
+                    v0 *= g.alpha;
+                    v1 *= g.alpha;
+                    if (rmw) {
+                        v0 = fma(g.beta, old[e][2 * q], v0);
+                        v1 = fma(g.beta, old[e][2 * q + 1], v1);
+                    }
+                }
+                double *p = C + (int64_t)m * g.ldc + nn;
+                if (cvec && nn + 1 < g.Nn) {
+                    *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+                } else {
+                    if (nn < g.Nn) p[0] = v0;
+                    if (nn + 1 < g.Nn) p[1] = v1;
+                }
+            }
         }
     }
 }

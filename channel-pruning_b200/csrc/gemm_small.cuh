@@ -149,17 +149,49 @@ __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
         __syncthreads();
         buf ^= 1;
     }
+    // epilogue: every C value of the thread is loaded before any is stored (one memory latency, not sixteen)
+    const bool rmw = g.beta != 0.0;
+    const bool cvec = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 2 == 0);
+    double old[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int nn = n0 + q * 32 + tx * 2;
+            old[i][2 * q] = old[i][2 * q + 1] = 0.0;
+            if (rmw && m < g.M) {
+                const double *p = g.C + (int64_t)m * g.ldc + nn;
+                if (cvec && nn + 1 < g.Nn) {
+                    const double2 v = *reinterpret_cast<const double2 *>(p);
+                    old[i][2 * q] = v.x;
+                    old[i][2 * q + 1] = v.y;
+                } else {
+                    if (nn < g.Nn) old[i][2 * q] = p[0];
+                    if (nn + 1 < g.Nn) old[i][2 * q + 1] = p[1];
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
         if (m >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int nn = n0 + (j >> 1) * 32 + tx * 2 + (j & 1);
-            if (nn >= g.Nn) continue;
-            double v = acc[i][j] * g.alpha;
-            if (g.beta != 0.0) v = fma(g.beta, g.C[(int64_t)m * g.ldc + nn], v);
-            g.C[(int64_t)m * g.ldc + nn] = v;
+        for (int q = 0; q < 2; ++q) {
+            const int nn = n0 + q * 32 + tx * 2;
+            double v0 = acc[i][2 * q] * g.alpha, v1 = acc[i][2 * q + 1] * g.alpha;
+            if (rmw) {
+                v0 = fma(g.beta, old[i][2 * q], v0);
+                v1 = fma(g.beta, old[i][2 * q + 1], v1);
+            }
+            double *p = g.C + (int64_t)m * g.ldc + nn;
+            if (cvec && nn + 1 < g.Nn) {
+                *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+            } else {
+                if (nn < g.Nn) p[0] = v0;
+                if (nn + 1 < g.Nn) p[1] = v1;
+            }
         }
     }
 }

@@ -109,8 +109,27 @@ constexpr int MAXC = 2048;   // largest channel count (shared-memory bound)
 constexpr int LAG = CP_LASSO_LAG;  // deltas the chain warp applies itself (slack of the update warps), 1..5
 static_assert(LAG >= 1 && LAG <= 5, "the packaged record holds at most 5 lag entries");
 constexpr int NBULK = 4;     // pair-update warps
-constexpr int PK_WARP = 1 + NBULK, SEQ_WARP = 2 + NBULK;
+// Role of a warp inside a sweep.  The chain warp sits on warp CHAIN_W: with 7 warps on 4 scheduler partitions, warp 3
+// is the only one that has a partition to itself (0/4, 1/5, 2/6 share), so the serial recurrence never competes for
+// issue slots with a polling warp.  Roles of the others, in warp order: NBULK update warps, packager, sequencer.
+#ifndef CP_LASSO_CHAIN_WARP
+#define CP_LASSO_CHAIN_WARP 3
+#endif
+// Polling back-off (ns) of the warps that wait for the chain: a tight LDS polling loop of five warps keeps the
+// shared-memory pipe busy and lengthens every shared-memory access of the chain warp.
+#ifndef CP_LASSO_SLEEP
+#define CP_LASSO_SLEEP 32
+#endif
+constexpr int CHAIN_W = CP_LASSO_CHAIN_WARP;
 constexpr int WS_THREADS = 32 * (3 + NBULK);
+__device__ __forceinline__ int role_of(int warp) {  // -1 chain, 0..NBULK-1 update, NBULK packager, NBULK+1 sequencer
+    return warp == CHAIN_W ? -1 : (warp < CHAIN_W ? warp : warp - 1);
+}
+__device__ __forceinline__ void poll_backoff() {
+#if CP_LASSO_SLEEP > 0
+    __nanosleep(CP_LASSO_SLEEP);
+#endif
+}
 constexpr int QR = 64;       // rings of per-step scalars (steps in flight << QR)
 template <int NPB> struct RingDepth { static constexpr int value = NPB <= 4 ? 16 : 6; };
 
@@ -149,8 +168,10 @@ __device__ __forceinline__ void wait_ge(const int *p, int target) {
 }
 // progress hints (ring-reuse slack only; a stale value merely delays the waiter)
 __device__ __forceinline__ void wait_ge_relaxed(const int *p, int target) {
-    for (uint32_t spin = 0; *reinterpret_cast<const volatile int *>(p) < target; ++spin)
+    for (uint32_t spin = 0; *reinterpret_cast<const volatile int *>(p) < target; ++spin) {
         if (spin > (1u << 26)) __trap();
+        poll_backoff();
+    }
 }
 // Tagged 16-byte records {value, tag}: written with ONE st.shared.v2.f64 and read with ONE ld.shared.v2.f64, so
 // value and tag always travel together -- no separate flag, no fence on the serial chain.
@@ -169,6 +190,17 @@ __device__ __forceinline__ double get_tagged(uint32_t slot_saddr, uint32_t tag) 
     return v;
 }
 
+// waiting variant for the warps that trail the chain: backs off between polls
+__device__ __forceinline__ double wait_tagged(uint32_t slot_saddr, uint32_t tag) {
+    double v, t;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(slot_saddr) : "memory");
+        if ((uint32_t)__double2loint(t) == tag) break;
+        if (spin > (1u << 24)) __trap();
+        poll_backoff();
+    }
+    return v;
+}
 // the same record read WITHOUT waiting for the tag: the caller checks it later (after the latency has been hidden)
 __device__ __forceinline__ void peek_tagged(uint32_t slot_saddr, double &v, double &t) {
     asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(slot_saddr) : "memory");
@@ -347,7 +379,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
     auto sweep = [&](int n_active, bool fresh, uint32_t seed, int cur, double l1) {
         uint32_t *raw_cur = raw + cur * CP, *raw_nxt = raw + (cur ^ 1) * CP;
         if (fresh) {  // first sweep of a fit: the stream restarts from this fit's seed
-            if (tid == SEQ_WARP * 32) {
+            if (role_of(warp) == NBULK + 1 && lane == 0) {
                 uint32_t st = seed;
                 for (int f = 0; f < n_active; ++f) {
                     st = xorshift_step(st);
@@ -373,7 +405,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         const bool rec = (probe == 0 && sweep_no == 3);
 #endif
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
-        if (warp == 0) {
+        const int role = role_of(warp);
+        if (role < 0) {
             // -------- chain warp: the serial recurrence and nothing else.  Software pipelined: the operands of step
             // s+1 (coordinate, packaged scalars, w[j], the published Qw entry) are fetched BEFORE the dependent
             // arithmetic of step s, so that per step only  delta -> x -> soft threshold -> division -> delta  remains
@@ -445,10 +478,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 ctl.w_max = w_max;
                 ctl.d_w_max = d_w_max;
             }
-        } else if (warp <= NBULK) {
+        } else if (role < NBULK) {
             // -------- pair-update warps: this lane's NPB pairs of Qw live in REGISTERS for the whole sweep (loaded from /
             // written back to shared memory at its ends); the pairs of row t are in registers before delta_t arrives
-            const int b = warp - 1, bt = b * 32 + lane;
+            const int b = role, bt = b * 32 + lane;
             const double *Qmine = Q + 2 * bt;                  // this lane's first pair of any row
             double *ring_mine = ring + 2 * bt;
             double2 qw[NPB], row[NPB];
@@ -495,7 +528,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
 #ifdef CP_TIMING
                 if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 4] = clock64();
 #endif
-                const double delta = get_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
+                const double delta = wait_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
 #ifdef CP_TIMING
                 if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 5] = clock64();
 #endif
@@ -525,7 +558,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             cp_async_wait<0>();
 #pragma unroll
             for (int sp = 0; sp < NPB; ++sp) *reinterpret_cast<double2 *>(Qw + 2 * BL * sp + 2 * bt) = qw[sp];
-        } else if (warp == PK_WARP) {
+        } else if (role == NBULK) {
             // -------- packager: operands of 32 chain steps at a time
             for (int base = 0; base < n_active; base += 32) {
                 if (base >= QR) wait_ge_relaxed(&ctl.chain_pos, base - 32);  // slots of batch base-64 are free

@@ -36,7 +36,7 @@ constexpr int LDA_S = PB + 1;    // padded leading dimension of the shared-memor
 constexpr int LDX_S = SB + 1;
 constexpr int P128_T = 512;
 constexpr size_t P128_SMEM =
-    (size_t)(PB * LDA_S + 2 * NSB * SB * LDX_S + 3 * SB * LDX_S + 3 * PB) * sizeof(double);
+    (size_t)(PB * LDA_S + 2 * NSB * SB * LDX_S + 3 * SB * LDX_S + 3 * PB + 2 * SB) * sizeof(double);
 
 // ---------------------------------------------------------------- assemble
 // M rows 0..Ks-1    : G[sel_i, sel_j] - sx_i sx_j / N   (lower triangle only)
@@ -62,30 +62,38 @@ ls_assemble(const double *__restrict__ G, const double *__restrict__ Bxy, const 
 }
 
 // ---------------------------------------------------------------- 128 x 128 diagonal block: L and L^-1
-__device__ __forceinline__ double rsqrt_newton(double d) {
-    double y = (double)rsqrtf((float)d);
-    y = y * (1.5 - 0.5 * d * y * y);
-    y = y * (1.5 - 0.5 * d * y * y);
-    return y;
+// 1/sqrt(d): hardware fp64 seed (MUFU.RSQ64H, ~2^-22) + ONE third-order correction  y += y e (1/2 + 3/8 e),
+// e = 1 - d y^2: four dependent fp64 operations (32 cycles) where two Newton steps on an fp32 seed cost six plus
+// two conversions -- this sits on the serial pivot chain of the factorisation.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
 }
 
 __device__ __forceinline__ void atomic_min_pos(double *addr, double v) {  // v > 0: bit patterns order like the values
     atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-// One warp factors the 32 x 32 block at (k0, k0) of the shared-memory panel.  Lane i owns row i in
-// registers; per pivot: broadcast the pivot, 1/sqrt (fp32 seed + two fp64 Newton steps), scale the
-// column, rank-1 update of the rows to the right with the column entries fetched by shuffle.
+// One warp factors the 32 x 32 block at (k0, k0) of the shared-memory panel.  Lane i owns row i in registers.
+// Per pivot the serial chain is: pivot broadcast (one shuffle) -> 1/sqrt -> scale -> the NEXT pivot (lane k+1
+// updates its own diagonal entry from its own column entry: no communication) -> broadcast.  The rank-1 update of the
+// other entries needs column k of all lanes: published through a double-buffered shared-memory column (one store per
+// lane, broadcast LDS.128 reads) -- 32 - k shuffles per pivot had been 3/4 of this routine's time.
 __device__ __forceinline__ void potrf32_warp(double *As, int k0, const double *thr_s, double *rinv_s, int32_t *info,
-                                             int jglob, int lane, double &ratio_min, const double *inv0_s) {
+                                             int jglob, int lane, double &ratio_min, const double *inv0_s, double *cb) {
     double a[SB];
 #pragma unroll
     for (int j = 0; j < SB; ++j) a[j] = (j <= lane) ? As[(k0 + lane) * LDA_S + k0 + j] : 0.0;
     const double thr = thr_s[k0 + lane];
     double myrs = 1.0;
+    double dk = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
     for (int k = 0; k < SB; ++k) {
-        double dk = __shfl_sync(0xffffffffu, a[k], k);
         const double tk = __shfl_sync(0xffffffffu, thr, k);
         // pivot must stay above 1e-12 of the original diagonal entry: the squared form of the
         // sigma < 1e-6 sigma_max cut-off LinearRegression applies (sklearn _base.py:752-753, cond=tol=1e-6)
@@ -93,7 +101,7 @@ __device__ __forceinline__ void potrf32_warp(double *As, int k0, const double *t
             if (lane == 0) atomicCAS(info, 0, jglob + k0 + k + 1);
             dk = 1.0;
         }
-        const double rs = rsqrt_newton(dk);
+        const double rs = rsqrt_fast(dk);
         double l = (lane > k) ? a[k] * rs : 0.0;
         if (lane == k) {
             l = dk * rs;
@@ -102,10 +110,20 @@ __device__ __forceinline__ void potrf32_warp(double *As, int k0, const double *t
             if (i0 > 0.0) ratio_min = fmin(ratio_min, dk * i0);
         }
         a[k] = l;
+        if (k + 1 < SB) {
+            // the next pivot, from lane k+1's own entries (bit-identical to its general update below)
+            const double dn = fma(-l, l, a[k + 1]);
+            const double dnext = __shfl_sync(0xffffffffu, dn, k + 1);
+            double *col = cb + (k & 1) * SB;
+            col[lane] = l;
+            __syncwarp();
 #pragma unroll
-        for (int j = k + 1; j < SB; ++j) {
-            const double ljk = __shfl_sync(0xffffffffu, l, j);
-            a[j] = fma(-l, ljk, a[j]);  // entries right of the diagonal (j > lane) are never read
+            for (int jj = (k + 1) & ~1; jj < SB; jj += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(col + jj);
+                if (jj >= k + 1) a[jj] = fma(-l, v.x, a[jj]);  // entries right of the diagonal (j > lane) are never read
+                a[jj + 1] = fma(-l, v.y, a[jj + 1]);
+            }
+            dk = dnext;
         }
     }
 #pragma unroll
@@ -128,26 +146,50 @@ struct MmTask {
     int nterm;
     MmTerm t[3];
 };
+// 64 threads per task, each a 4 x 4 register micro-tile on rows tr + 8u / columns tc + 8v (interleaved: the eight
+// distinct B rows of a warp fall into distinct banks, the A rows are broadcasts): 8 shared-memory loads per 16 FMAs
+// instead of 2 per FMA -- the block inversion used to be LSU bound (1/3 of the whole panel kernel).
 __device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
-    for (int e = threadIdx.x; e < ntask * SB * SB; e += P128_T) {
-        const MmTask &tk = tasks[e >> 10];
-        const int r = (e >> 5) & 31, c = e & 31;
-        double s = 0.0;
-        for (int u = 0; u < tk.nterm; ++u) {
-            const double *ap = tk.t[u].A + r * tk.t[u].sa;
-            const double *bp = tk.t[u].B + c * tk.t[u].sb;
-#pragma unroll 8
-            for (int q = 0; q < SB; ++q) s = fma(ap[q], bp[q], s);
+    const int t = threadIdx.x;
+    if (t >= ntask * 64) return;
+    const MmTask &tk = tasks[t >> 6];
+    const int tr = (t >> 3) & 7, tc = t & 7;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int w = 0; w < tk.nterm; ++w) {
+        const double *ap = tk.t[w].A + tr * tk.t[w].sa;
+        const double *bp = tk.t[w].B + tc * tk.t[w].sb;
+        const int sa8 = 8 * tk.t[w].sa, sb8 = 8 * tk.t[w].sb;
+#pragma unroll 4
+        for (int q = 0; q < SB; ++q) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                av[u] = ap[u * sa8 + q];
+                bv[u] = bp[u * sb8 + q];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
         }
-        tk.dst[r * tk.dr + c * tk.dc] = tk.sign * s;
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) tk.dst[(tr + 8 * u) * tk.dr + (tc + 8 * v) * tk.dc] = tk.sign * acc[u][v];
 }
 
 #ifdef CP_TIMING
 __device__ long long cp_ls_times[32];
+// every lane of warp 0 stores the same stamp (no divergence before the warp-synchronous pivot routine)
 #define LS_STAMP(i)                                            \
     do {                                                       \
-        if (threadIdx.x == 0 && j0 == 0) cp_ls_times[i] = clock64(); \
+        if (threadIdx.x < 32 && j0 == 0) cp_ls_times[i] = clock64(); \
+        __syncwarp();                                          \
     } while (0)
 #else
 #define LS_STAMP(i)
@@ -167,6 +209,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
     double *rinv = Tt + 3 * SB * LDX_S;           // [128] 1 / L[k][k]
     double *thr = rinv + PB;                      // [128] pivot thresholds
     double *inv0 = thr + PB;                      // [128] 1 / original diagonal
+    double *cb = inv0 + PB;                       // [2][32] column of the pivot step, published to the whole warp
     __shared__ MmTask tasks[3];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -190,7 +233,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
     for (int sp = 0; sp < NSB; ++sp) {
         const int k0 = sp * SB;
         LS_STAMP(2 + 4 * sp);
-        if (warp == 0) potrf32_warp(As, k0, thr, rinv, info, j0, lane, ratio_min, inv0);
+        if (warp == 0) potrf32_warp(As, k0, thr, rinv, info, j0, lane, ratio_min, inv0, cb);
         __syncthreads();
         LS_STAMP(3 + 4 * sp);
         const int r0 = k0 + SB, T = PB - r0;
@@ -266,11 +309,13 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         const double *Lb = As + (b * SB) * LDA_S + b * SB;
         double x[SB];
 #pragma unroll
-        for (int i = 0; i < SB; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
+        for (int i = 0; i < SB; ++i) x[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-            for (int j = 0; j < i; ++j) s = fma(-Lb[i * LDA_S + j], x[j], s);
-            x[i] = s * rinv[b * SB + i];
+        for (int j = 0; j < SB; ++j) {  // right-looking: the updates of one step are independent of each other
+            const double xj = x[j] * rinv[b * SB + j];
+            x[j] = xj;
+#pragma unroll
+            for (int i = j + 1; i < SB; ++i) x[i] = fma(-Lb[i * LDA_S + j], xj, x[i]);
         }
 #pragma unroll
         for (int i = 0; i < SB; ++i) {
@@ -423,8 +468,17 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
     if (rc) return rc;
     rc = configure_potrf(h);
     if (rc) return rc;
+    // Trailing updates.  Panels are paired (e, o = e + 1).  What the chain needs next stays small and immediate:
+    //   crit(p)  : block column p+1, inner dimension 128, on the caller's stream, 64 x 64 tiles
+    //   far_a(e) : block column e+2 (needed by crit(o)), side stream
+    // everything else is applied once per PAIR with inner dimension 256 -- half the read-modify-write traffic of
+    // the trailing matrix per flop (a rank-128 update moves 8 bytes per 8 flop: memory bound on a 37 TF/s pipe):
+    //   near(e,o): block columns e+3, e+4 (the next pair's crit / far_a targets), side stream, then an event
+    //   rest(e,o): block columns >= e+5, side stream
+    // Every update of a block column by different panels is ordered: same stream, or through ev_side / ev_panel.
     bool side_pending = false;
-    for (int j0 = 0; j0 < Kd; j0 += PB) {
+    int ip = 0;
+    for (int j0 = 0; j0 < Kd; j0 += PB, ++ip) {
         const int nb = Kd - j0 < PB ? Kd - j0 : PB;
         const int j1 = j0 + nb;
         double *Lp = Linv + (size_t)(j0 / PB) * PB * PB;
@@ -439,10 +493,11 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
         if (rc) return rc;
         const int ncols = Kd - j1;
         if (ncols <= 0) continue;
-        const int w2 = ncols < PB ? ncols : PB;
-        const bool fork = ncols > w2;
-        if (fork) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // block column j0..j1 of L is final
-        if (side_pending) {  // the previous panel's far update also wrote the columns updated next
+        const bool odd = (ip & 1) != 0;
+        const int w2 = ncols < PB ? ncols : PB;            // block column p+1
+        const bool more = ncols > w2;                      // block columns beyond p+1 exist
+        if (more) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // block column j0..j1 of L is final
+        if (side_pending) {  // far_a(e) before crit(o); near(e-2, e-1) before crit(e)
             CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
             side_pending = false;
         }
@@ -450,19 +505,31 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
         rc = dgemm_small<false>(Pn, ld, Pn, ld, M + (int64_t)j1 * ld + j1, ld, Ktot - j1, w2, nb, -1.0, 1.0,
                                 cpsmall::TILES_LOWER, stream);
         if (rc) return rc;
-        if (fork) {
-            const int j2 = j1 + w2;
+        if (!more) continue;
+        const int j2 = j1 + w2;
+        CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
+        if (!odd) {
+            const bool has_partner = true;  // more => panel o = e + 1 exists (block column p+1 is non-empty)
+            (void)has_partner;
             const int w3 = Kd - j2 < PB ? Kd - j2 : PB;
             const double *Pf = L + (int64_t)j2 * ld + j0;
-            CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
             rc = dgemm_big(Pf, ld, Pf, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, w3, nb, -1.0, 1.0, TILES_LOWER, h->side);
             if (rc) return rc;
             CP_CUDA(cudaEventRecord(h->ev_side, h->side));
             side_pending = true;
-            const int j3 = j2 + w3;
-            if (Kd - j3 > 0) {
-                const double *Pg = L + (int64_t)j3 * ld + j0;
-                rc = dgemm_big(Pg, ld, Pg, ld, M + (int64_t)j3 * ld + j3, ld, Ktot - j3, Kd - j3, nb, -1.0, 1.0, TILES_LOWER,
+        } else {
+            // pair (e, o): columns [j0 - PB, j1) of L, inner dimension PB + nb; targets: block columns >= o + 2 = j2
+            const int je = j0 - PB, R2 = PB + nb;
+            const int wn = Kd - j2 < 2 * PB ? Kd - j2 : 2 * PB;  // near: the next pair's two block columns
+            const double *Pq = L + (int64_t)j2 * ld + je;
+            rc = dgemm_big(Pq, ld, Pq, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, wn, R2, -1.0, 1.0, TILES_LOWER, h->side);
+            if (rc) return rc;
+            CP_CUDA(cudaEventRecord(h->ev_side, h->side));
+            side_pending = true;
+            const int j4 = j2 + wn;
+            if (Kd - j4 > 0) {
+                const double *Pr = L + (int64_t)j4 * ld + je;
+                rc = dgemm_big(Pr, ld, Pr, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, Kd - j4, R2, -1.0, 1.0, TILES_LOWER,
                                h->side);
                 if (rc) return rc;
             }

@@ -448,6 +448,28 @@ class Engine:
         g = self.gram(X, Y, y_bias=y_bias, mode=GRAM_FP64)
         return self.reconstruct_async(g, X, Y, y_bias, idxs_host, k2)
 
+    def reconstruct_truncated(self, X, Y, y_bias, idxs_host, k2):
+        """Minimum-norm least squares with the reference's rank cut-off, for systems the Cholesky flags as numerically
+        rank deficient: LinearRegression.fit -> scipy.linalg.lstsq(Xc, Yc, cond=1e-6) (gelsd, sklearn _base.py:752)
+        drops singular values below 1e-6 sigma_max.  Here: one-sided Jacobi SVD of the centred selected columns
+        (cp_svd_jacobi works on X itself, so small singular values are resolved like gelsd resolves them), then
+        W = V diag(1/s) U' Yc over the kept ones.  Slow path (O(10) sweeps over N x K'), rare."""
+        cols = self._cols_device(idxs_host, k2, X.shape[1]).long()
+        N = X.shape[0]
+        Xs = X[:, cols].to(torch.float64).contiguous()
+        xm, Xc = self.colstats(Xs, 1.0 / N, centre=True)
+        Yd = Y.to(torch.float64)
+        if y_bias is not None:
+            Yd = Yd - y_bias.to(torch.float64)[None, :]
+        ym, Yc = self.colstats(Yd.contiguous(), 1.0 / N, centre=True)
+        U, s, Vh = self.svd(Xc)
+        keep = s > 1e-6 * s[0]
+        inv = torch.where(keep, 1.0 / torch.where(keep, s, torch.ones_like(s)), torch.zeros_like(s))
+        UtY = self.mm_tn(U, Yc)                                   # (r, n)
+        W = self.mm_tn((inv[:, None] * UtY).contiguous(), Vh)    # (n, K') = (V diag(1/s) U' Yc)'
+        b = ym - self.mm(W, xm[:, None].contiguous())[:, 0]
+        return W, b, int(keep.sum().item())
+
     @staticmethod
     def ls_verdict(info, stat, mode, dual=False):
         """'ok' | 'redo' (tensor-core statistics too inaccurate for this conditioning: re-solve in fp64) |

@@ -145,7 +145,8 @@ def _dictionary_device(eng, Xd, W2m, Yd, y_bias, c, h, rank, alpha=1e-4):
 def _solve_ls(eng, g_full, Xd, Yd, y_bias, idxs, k2, info=None):
     """LS on the surviving channels with the conditioning policy of engine.LS_RATIO_MIN: statistics from the
     tensor-core Gram are used while the Cholesky stays well conditioned, otherwise the layer is re-solved from
-    exact-product fp64 statistics; a pivot below sklearn's rank cut-off (cond=1e-6, _base.py:752) raises."""
+    exact-product fp64 statistics; a pivot below sklearn's rank cut-off (cond=1e-6, _base.py:752) switches to the
+    truncated minimum-norm solve gelsd would return."""
     Wd, bd, info_d, stat_d = eng.reconstruct_async(g_full, Xd, Yd, y_bias, idxs, k2)
     dual = not (g_full["N"] - 1 >= int(np.count_nonzero(idxs)) * k2)
     fail, ratio = int(info_d.cpu()[0]), float(stat_d.cpu()[0])
@@ -159,9 +160,11 @@ def _solve_ls(eng, g_full, Xd, Yd, y_bias, idxs, k2, info=None):
         if info is not None:
             info["ls"].update(pivot_ratio_exact=ratio, verdict="redo->" + verdict)
     if verdict == "singular":
-        raise np.linalg.LinAlgError(
-            "least-squares system is numerically rank deficient (pivot %d below 1e-12 of its diagonal: the "
-            "reference's gelsd would truncate here)" % fail)
+        # numerically rank deficient (a pivot below 1e-12 of its diagonal): the reference's gelsd truncates singular
+        # values below 1e-6 sigma_max and returns the minimum-norm solution -- same rule, through the SVD of the data
+        Wd, bd, kept = eng.reconstruct_truncated(Xd, Yd, y_bias, idxs, k2)
+        if info is not None:
+            info["ls"].update(verdict="truncated", rank=kept)
     return Wd, bd
 
 

@@ -255,7 +255,7 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
     # ---- every reconstruction is CHECKED before it is handed out: Cholesky status + conditioning signal.
     # Tensor-core statistics are accepted only for well-conditioned systems (engine.LS_RATIO_MIN); otherwise the
     # layer is re-solved from exact-product fp64 statistics; a system that is rank deficient by sklearn's cut-off
-    # raises (the reference's gelsd would silently truncate there).
+    # gets the truncated minimum-norm solution the reference's gelsd returns.
     for i, chk, ev_ls in checks:
         ev_ls.synchronize()
         s, d, r = shapes[i], datas[i], out[i]
@@ -272,9 +272,13 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
                 r.W, r.b = _maybe_to_host(eng, i, W, b, to_host)
             verdict = "singular" if fail else "ok"
             r.info.update(pivot_ratio_exact=ratio, verdict="redo->" + verdict)
-        if verdict == "singular":
-            raise np.linalg.LinAlgError("layer %s: least-squares system numerically rank deficient (pivot %d)"
-                                        % (s.name, fail))
+        if verdict == "singular":  # gelsd's truncated minimum-norm solution (slow path, see Engine.reconstruct_truncated)
+            stream = eng.use_slot(i)
+            ctx = torch.cuda.stream(stream) if stream is not None else _null()
+            with ctx:
+                W, b, kept = eng.reconstruct_truncated(phase1[i][0], d["feats"], d["b2"], r.idxs, s.k * s.k)
+                r.W, r.b = _maybe_to_host(eng, i, W, b, to_host)
+            r.info.update(verdict="truncated", rank=kept)
     for st in eng.streams:
         if st is not None:
             main.wait_stream(st)

@@ -258,3 +258,22 @@ def test_ls_solve_flags_singular_system(engine):
     g = engine.gram(_dev(X, engine), _dev(Y, engine), mode=0)
     W, b, info, _ = engine.ls_solve(g, _dev(np.arange(20, dtype=np.int32), engine))
     assert int(info.cpu()[0]) != 0
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["fp64", "3xtf32"])
+def test_rank_deficient_system_gets_gelsd_truncated_solution(engine, mode):
+    """Exactly collinear columns: the Cholesky flags the system, and fc_kernel returns what the reference's
+    LinearRegression returns there -- gelsd's minimum-norm solution with singular values below 1e-6 sigma_max
+    dropped (sklearn _base.py:752), the weight shared between the duplicates."""
+    from cpb200.lib import decompose
+
+    r = np.random.RandomState(4)
+    X = np.maximum(r.standard_normal((900, 120)), 0).astype(np.float32)
+    X[:, 70] = X[:, 30]          # exact duplicate
+    X[:, 100] = 0.0              # dead column
+    Y = (X @ r.standard_normal((120, 8)) + 0.1 * r.standard_normal((900, 8))).astype(np.float32)
+    engine.gram_mode = mode
+    coef, icpt = decompose.fc_kernel(X.astype(np.float64), Y.astype(np.float64))
+    rc, ri = O.linear_regression(X.astype(np.float64), Y.astype(np.float64))
+    assert np.linalg.norm(coef - rc) <= 1e-7 * np.linalg.norm(rc) and np.abs(icpt - ri).max() <= 1e-7
+    assert np.abs(coef[:, 100]).max() <= 1e-9 and np.abs(coef[:, 70] - coef[:, 30]).max() <= 1e-9
