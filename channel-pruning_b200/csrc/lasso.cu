@@ -30,6 +30,8 @@
 //   sequencer warp the xorshift stream of the NEXT sweep (it does not depend on the active set)
 // Hand-offs are release/acquire counters in shared memory (bounded spins: a protocol bug traps
 // instead of hanging); CTA barriers only at sweep boundaries.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -104,10 +106,11 @@ struct SelectParams {
 
 constexpr int MAXC = 2048;   // largest channel count (shared-memory bound)
 #ifndef CP_LASSO_LAG
-#define CP_LASSO_LAG 5
+#define CP_LASSO_LAG 4
 #endif
 constexpr int LAG = CP_LASSO_LAG;  // deltas the chain warp applies itself (slack of the update warps), 1..5
-static_assert(LAG >= 1 && LAG <= 5, "the packaged record holds at most 5 lag entries");
+static_assert(LAG == 4, "the unrolled chain / update blocks are laid out for LAG = 4 (delta ring static across 16-step "
+                        "blocks, publish targets inside two 16-byte index loads)");
 constexpr int NBULK = 4;     // pair-update warps
 // Role of a warp inside a sweep.  The chain warp sits on warp CHAIN_W: with 7 warps on 4 scheduler partitions, warp 3
 // is the only one that has a partition to itself (0/4, 1/5, 2/6 share), so the serial recurrence never competes for
@@ -131,7 +134,7 @@ __device__ __forceinline__ void poll_backoff() {
 #endif
 }
 constexpr int QR = 64;       // rings of per-step scalars (steps in flight << QR)
-template <int NPB> struct RingDepth { static constexpr int value = NPB <= 4 ? 16 : 6; };
+template <int NPB> struct RingDepth { static constexpr int value = NPB <= 4 ? 16 : 4; };  // multiple of 4 (update-warp blocks)
 
 __device__ __forceinline__ uint32_t xorshift_step(uint32_t s) {  // sklearn/utils/_random.pxd:20-34 (state update)
     if (s == 0) s = 1;
@@ -407,72 +410,84 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
         const uint32_t dq_s = (uint32_t)__cvta_generic_to_shared(dq), xq_s = (uint32_t)__cvta_generic_to_shared(xq);
         const int role = role_of(warp);
         if (role < 0) {
-            // -------- chain warp: the serial recurrence and nothing else.  Software pipelined: the operands of step
-            // s+1 (coordinate, packaged scalars, w[j], the published Qw entry) are fetched BEFORE the dependent
-            // arithmetic of step s, so that per step only  delta -> x -> soft threshold -> division -> delta  remains
-            // on the chain (8 dependent fp64 operations), not the shared-memory round trips.
-            double dl[LAG];  // dl[i-1] = delta of step s-i
+            // -------- chain warp: the serial recurrence and nothing else.  One warp alone hides no latency (every
+            // dependent instruction costs its full pipeline depth), so the loop is organised for the fewest
+            // instructions per step: blocks of 16 steps fully unrolled, two operand sets used alternately (no
+            // register rotation), ring addresses and tags that are compile-time offsets from a per-block base, the
+            // last LAG deltas in a ring indexed by the step number (LAG divides 16), hand-shake bookkeeping once
+            // per block.  The operands of step s+1 (coordinate, packaged scalars, w[j], the published Qw entry) are
+            // fetched BEFORE the dependent arithmetic of step s.
+            double D[LAG];  // D[s % LAG] = delta of step s
 #pragma unroll
-            for (int i = 0; i < LAG; ++i) dl[i] = 0.0;
+            for (int i = 0; i < LAG; ++i) D[i] = 0.0;
             double w_max = 0.0, d_w_max = 0.0;
-            auto fetch = [&](int s, uint32_t &j_, double (&p)[8], double &wj_, double &xv_, double &xt_) {
-                if ((s & 31) == 0) wait_ge(&ctl.pk_pos, s + 32 < n_active ? s + 32 : n_active);
-                if ((s & 15) == 0) {
-                    // operands of steps < s are in registers: their slots may be reused
-                    if (lane == 0) *reinterpret_cast<volatile int *>(&ctl.chain_pos) = s;
-                    if (s >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
-#pragma unroll
-                        for (int b = 0; b < NBULK; ++b) wait_ge_relaxed(&ctl.bulk_pos[b], s - 24);
-                    }
-                }
-                j_ = jz[s];
-                const double2 *rec = reinterpret_cast<const double2 *>(pk + (s & (QR - 1)) * 8);
+            uint32_t J[2];
+            double P[2][8];  // q, Qjj, 1/Qjj, r1..r5
+            double WJ[2], XV[2], XT[2];
+            const uint32_t w_s = (uint32_t)__cvta_generic_to_shared(w);
+            auto fetch = [&](int set, int s, int slot) {  // slot = s & (QR - 1)
+                const uint32_t jv = jz[s];
+                J[set] = jv;
+                const double2 *rec = reinterpret_cast<const double2 *>(pk + slot * 8);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const double2 v = rec[q];
-                    p[2 * q] = v.x;
-                    p[2 * q + 1] = v.y;
+                    P[set][2 * q] = v.x;
+                    P[set][2 * q + 1] = v.y;
                 }
-                wj_ = w[j_];
+                WJ[set] = w[jv];
                 // Qw[j] as of update s-LAG-1, published by the owning update lane (tag checked at use)
-                peek_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, xv_, xt_);
+                peek_tagged(xq_s + (uint32_t)slot * 16u, XV[set], XT[set]);
             };
-            uint32_t j = 0;
-            double pc[8];  // q, Qjj, 1/Qjj, r1..r5
-            double w_j = 0.0, xv = 0.0, xt = 0.0;
-            fetch(0, j, pc, w_j, xv, xt);
-            for (int s = 0; s < n_active; ++s) {
-                CH_STAMP(s, 0);
-                const bool has_next = s + 1 < n_active;
-                uint32_t jn = 0;
-                double pn[8];
-                double wjn = 0.0, xvn = 0.0, xtn = 0.0;
-                if (has_next) fetch(s + 1, jn, pn, wjn, xvn, xtn);
-                asm volatile("" ::: "memory");  // the loads above stay above the arithmetic below
-                CH_STAMP(s, 1);
-                const uint32_t tag = tag0 | (uint32_t)(s + 1);
-                if ((uint32_t)__double2loint(xt) != tag) xv = get_tagged(xq_s + (uint32_t)(s & (QR - 1)) * 16u, tag);
-                CH_STAMP(s, 2);
-                double x = xv;
+            auto block_sync = [&](int s0) {  // before any step of s0 .. s0+15 or the fetch of s0+16
+                wait_ge(&ctl.pk_pos, s0 + 17 < n_active ? s0 + 17 : n_active);
+                // operands of steps <= s0 are in registers: their slots may be reused
+                if (lane == 0) *reinterpret_cast<volatile int *>(&ctl.chain_pos) = s0;
+                if (s0 >= 32) {  // nobody may fall more than ~32 steps behind (ring reuse)
 #pragma unroll
-                for (int i = LAG; i >= 1; --i) x = __dadd_rn(x, __dmul_rn(dl[i - 1], pc[2 + i]));  // oldest delta first
-                double delta, aw, w_new;
-                cd_update(pc[0], pc[1], pc[2], x, w_j, l1, delta, aw, w_new);
-                w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
-                if (lane == 0) put_tagged(dq_s + (uint32_t)(s & (QR - 1)) * 16u, delta, tag);
-                CH_STAMP(s, 3);
-                d_w_max = fmax(d_w_max, fabs(delta));
-                w_max = fmax(w_max, aw);
-#pragma unroll
-                for (int i = LAG - 1; i >= 1; --i) dl[i] = dl[i - 1];
-                dl[0] = delta;
-                if (has_next) {
-                    if (jn == j) wjn = w_new;  // the same coordinate twice in a row: the prefetched w[j] was stale
-                    j = jn;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) pc[q] = pn[q];
-                    w_j = wjn; xv = xvn; xt = xtn;
+                    for (int b = 0; b < NBULK; ++b) wait_ge_relaxed(&ctl.bulk_pos[b], s0 - 24);
                 }
+            };
+            auto run_block = [&](auto guarded, int s0) {
+                constexpr bool GUARD = decltype(guarded)::value;
+                const int sb = s0 & (QR - 1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int s = s0 + i;
+                    if (GUARD && s >= n_active) break;
+                    const int cur = i & 1, nxt = cur ^ 1;
+                    CH_STAMP(s, 0);
+                    const bool has_next = (GUARD || i == 15) ? (s + 1 < n_active) : true;
+                    if (has_next) fetch(nxt, s + 1, i == 15 ? ((sb + 16) & (QR - 1)) : sb + i + 1);
+                    asm volatile("" ::: "memory");  // the loads above stay above the arithmetic below
+                    CH_STAMP(s, 1);
+                    const uint32_t tag = tag0 + (uint32_t)(s + 1);
+                    const uint32_t j = J[cur];
+                    double xv = XV[cur];
+                    if ((uint32_t)__double2loint(XT[cur]) != tag) xv = get_tagged(xq_s + (uint32_t)(sb + i) * 16u, tag);
+                    CH_STAMP(s, 2);
+                    double x = xv;
+#pragma unroll
+                    for (int k = LAG; k >= 1; --k)  // oldest delta first: delta_{s-k} * Q[j_s][j_{s-k}]
+                        x = __dadd_rn(x, __dmul_rn(D[(i + 16 * LAG - k) % LAG], P[cur][2 + k]));
+                    double delta, aw, w_new;
+                    cd_update(P[cur][0], P[cur][1], P[cur][2], x, WJ[cur], l1, delta, aw, w_new);
+                    w[j] = w_new;  // every lane stores the same value: no intra-warp ordering needed
+                    if (lane == 0) put_tagged(dq_s + (uint32_t)(sb + i) * 16u, delta, tag);
+                    CH_STAMP(s, 3);
+                    d_w_max = fmax(d_w_max, fabs(delta));
+                    w_max = fmax(w_max, aw);
+                    D[i % LAG] = delta;
+                    if (has_next && J[nxt] == j) WJ[nxt] = w_new;  // same coordinate twice in a row: prefetched w[j] stale
+                }
+            };
+            (void)w_s;
+            block_sync(0);
+            fetch(0, 0, 0);
+            for (int s0 = 0; s0 < n_active; s0 += 16) {
+                if (s0) block_sync(s0);
+                if (s0 + 16 <= n_active) run_block(std::false_type{}, s0);
+                else run_block(std::true_type{}, s0);
             }
             if (lane == 0) {
                 ctl.w_max = w_max;
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             const int b = role, bt = b * 32 + lane;
             const double *Qmine = Q + 2 * bt;                  // this lane's first pair of any row
             double *ring_mine = ring + 2 * bt;
-            double2 qw[NPB], row[NPB];
+            double2 qw[NPB], rw[2][NPB];  // rw: pairs of the current / next row of Q (alternating)
 #pragma unroll
             for (int sp = 0; sp < NPB; ++sp) qw[sp] = *reinterpret_cast<const double2 *>(Qw + 2 * BL * sp + 2 * bt);
             auto prefetch_row = [&](uint32_t j, int slot) {
@@ -495,14 +510,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                     if (2 * BL * sp + 2 * bt < c) cp_async16(dst + 2 * BL * sp, src + 2 * BL * sp);
                 }
             };
-            auto load_row = [&](int slot) {
+            auto load_row = [&](int buf, int slot) {
                 const double *r = ring_mine + (uint32_t)(slot * CP);
 #pragma unroll
-                for (int sp = 0; sp < NPB; ++sp) row[sp] = *reinterpret_cast<const double2 *>(r + 2 * BL * sp);
+                for (int sp = 0; sp < NPB; ++sp) rw[buf][sp] = *reinterpret_cast<const double2 *>(r + 2 * BL * sp);
             };
             // entry js of Qw if this lane owns it (element 2*BL*sp + 2*bt + h)
-            auto publish = [&](int step) {
-                const uint32_t js = jz[step];
+            auto publish = [&](uint32_t js, int step) {
                 const int ob = (int)((js >> 1) & (BL - 1));
                 if ((ob >> 5) == b) {  // warp-uniform: only the owning warp looks for the owning lane
                     if ((ob & 31) == lane) {
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
 #pragma unroll
                         for (int sp = 0; sp < NPB; ++sp)
                             if (sp == spj) v = (js & 1) ? qw[sp].y : qw[sp].x;
-                        put_tagged(xq_s + (uint32_t)(step & (QR - 1)) * 16u, v, tag0 | (uint32_t)(step + 1));
+                        put_tagged(xq_s + (uint32_t)(step & (QR - 1)) * 16u, v, tag0 + (uint32_t)(step + 1));
                     }
                 }
             };
@@ -520,40 +534,59 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 if (d < n_active) prefetch_row(jz[d], d);
                 cp_async_commit();
             }
-            for (int s = 0; s <= LAG && s < n_active; ++s) publish(s);  // entries the chain needs before any update
+            for (int s = 0; s <= LAG && s < n_active; ++s) publish(jz[s], s);  // entries the chain needs before any update
             cp_async_wait<RING - 1>();  // this lane's pairs of row 0 have landed
-            load_row(0);
-            for (int t = 0; t < n_active; ++t) {
-                const int slot = t % RING;
-#ifdef CP_TIMING
-                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 4] = clock64();
-#endif
-                const double delta = wait_tagged(dq_s + (uint32_t)(t & (QR - 1)) * 16u, tag0 | (uint32_t)(t + 1));
-#ifdef CP_TIMING
-                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 5] = clock64();
-#endif
-                if (delta != 0.0) {
+            load_row(0, 0);
+            // Four steps per block, fully unrolled: the coordinates a block needs (rows to prefetch, Qw entries to
+            // publish) come in as three 16-byte loads, ring slots / row buffers / record slots are static offsets.
+            static_assert(RING % 4 == 0 && QR % 4 == 0, "block layout of the update warps");
+            auto run_block = [&](auto guarded, int t0) {
+                constexpr bool GUARD = decltype(guarded)::value;
+                const int sb = t0 & (QR - 1), rb = t0 % RING;
+                const uint4 jr4 = *reinterpret_cast<const uint4 *>(jz + t0 + RING);  // rows t0+RING .. +3 (padding beyond
+                const uint4 ja4 = *reinterpret_cast<const uint4 *>(jz + t0 + 4);     // n_active is never used)
+                const uint4 jb4 = *reinterpret_cast<const uint4 *>(jz + t0 + 8);
+                const uint32_t jr[4] = {jr4.x, jr4.y, jr4.z, jr4.w};
+                const uint32_t jp[8] = {ja4.x, ja4.y, ja4.z, ja4.w, jb4.x, jb4.y, jb4.z, jb4.w};  // jz[t0+4 .. t0+11]
 #pragma unroll
-                    for (int sp = 0; sp < NPB; ++sp) {
-                        qw[sp].x = __dadd_rn(qw[sp].x, __dmul_rn(delta, row[sp].x));
-                        qw[sp].y = __dadd_rn(qw[sp].y, __dmul_rn(delta, row[sp].y));
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u;
+                    if (GUARD && t >= n_active) break;
+                    const int cur = u & 1, nxt = cur ^ 1;
+#ifdef CP_TIMING
+                    if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 4] = clock64();
+#endif
+                    const double delta = wait_tagged(dq_s + (uint32_t)(sb + u) * 16u, tag0 + (uint32_t)(t + 1));
+#ifdef CP_TIMING
+                    if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 5] = clock64();
+#endif
+                    if (delta != 0.0) {
+#pragma unroll
+                        for (int sp = 0; sp < NPB; ++sp) {
+                            qw[sp].x = __dadd_rn(qw[sp].x, __dmul_rn(delta, rw[cur][sp].x));
+                            qw[sp].y = __dadd_rn(qw[sp].y, __dmul_rn(delta, rw[cur][sp].y));
+                        }
                     }
-                }
-                const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
-                if (sp1 < n_active) publish(sp1);
+                    const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
+                    if (sp1 < n_active) publish(jp[LAG - 3 + u], sp1);
 #ifdef CP_TIMING
-                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 6] = clock64();
+                    if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 6] = clock64();
 #endif
-                if (t + RING < n_active) prefetch_row(jz[t + RING], slot);  // row t is in registers: its slot is free
-                cp_async_commit();
-                if (t + 1 < n_active) {
-                    cp_async_wait<RING - 1>();  // row t+1 has landed
-                    load_row((t + 1) % RING);
-                }
-                if ((t & 7) == 7 && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t + 1;
+                    if (t + RING < n_active) prefetch_row(jr[u], rb + u);  // row t is in registers: its slot is free
+                    cp_async_commit();
+                    if (t + 1 < n_active) {
+                        cp_async_wait<RING - 1>();  // row t+1 has landed
+                        load_row(nxt, u == 3 ? (rb + 4) % RING : rb + u + 1);
+                    }
 #ifdef CP_TIMING
-                if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 7] = clock64();
+                    if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 7] = clock64();
 #endif
+                }
+                if ((t0 & 4) && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t0 + 4;
+            };
+            for (int t0 = 0; t0 < n_active; t0 += 4) {
+                if (t0 + 4 <= n_active) run_block(std::false_type{}, t0);
+                else run_block(std::true_type{}, t0);
             }
             cp_async_wait<0>();
 #pragma unroll

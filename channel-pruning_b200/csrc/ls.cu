@@ -30,6 +30,7 @@
 namespace {
 
 constexpr int PB = 128;          // panel width
+constexpr int GB = 512;          // group of four panels: the substitutions run on inverted GB x GB diagonal blocks
 constexpr int SB = 32;           // sub-block factored by one warp
 constexpr int NSB = PB / SB;     // 4
 constexpr int LDA_S = PB + 1;    // padded leading dimension of the shared-memory panel
@@ -196,10 +197,10 @@ __device__ long long cp_ls_times[32];
 #endif
 
 // A: the (updated) diagonal block in the trailing matrix; Lout: where the factor goes; Linv: 128 x 128
-// row-major (zero above the diagonal).  nb < 128 (last panel) is padded with the identity.
+// row-major with leading dimension ldi (zero above the diagonal).  nb < 128 (last panel) is padded with the identity.
 __global__ void __launch_bounds__(P128_T, 1)
 potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__ Lout, int64_t ldl,
-         double *__restrict__ Linv, int32_t *__restrict__ info, double *__restrict__ ratio_out, int j0,
+         double *__restrict__ Linv, int64_t ldi, int32_t *__restrict__ info, double *__restrict__ ratio_out, int j0,
          const double *__restrict__ diag0) {
     extern __shared__ __align__(16) double psm[];
     double *As = psm;                             // [128][129]  lower: L ; strictly-upper blocks: (L^-1)^T
@@ -365,7 +366,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         const int i = e >> 7, j = e & (PB - 1);
         double v = 0.0;
         if (j <= i) v = ((i >> 5) == (j >> 5)) ? Xd[((i >> 5) * SB + (i & 31)) * LDX_S + (j & 31)] : As[j * LDA_S + i];
-        Linv[e] = v;
+        Linv[(int64_t)i * ldi + j] = v;
     }
     LS_STAMP(22);
 }
@@ -457,10 +458,45 @@ int configure_potrf(cp_handle_t h) {
 
 }  // namespace
 
+// dense product on 128 x 128 tiles with the (m, r) x (r, nn) operand layout of the substitutions
+static int dgemm_big_nc(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
+                        int64_t R, double alpha, double beta, cudaStream_t stream) {
+    using namespace cpgemm;
+    Args g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.M = M; g.Nn = Nn; g.R = R;
+    g.nsplit = 1; g.r_per_split = R;
+    g.alpha = alpha; g.beta = beta; g.tile_mode = TILES_ALL;
+    g.a_vec = al16(A) && (lda % 2 == 0);
+    g.b_vec = al16(B) && (ldb % 2 == 0);
+    if (M <= 0 || Nn <= 0) return CP_OK;
+    CP_GEMM_LAUNCH((launch<double, double, false, true>(g, stream)));
+    return CP_OK;
+}
+
+static inline int ngroups(int Kd) { return (Kd + GB - 1) / GB; }
+static inline size_t xinv_elems(int Kd) { return (size_t)ngroups(Kd) * GB * GB; }
+
+// X21 = -X22 * L21 * X11 inside one group block X (GB x GB, leading dimension GB): rows/cols [a0, a1) and [a1, a2)
+// of the group hold the already inverted diagonal parts X11 and X22; L21 = the factor's rows a1..a2, columns a0..a1.
+static int merge_inverse(double *X, const double *L21, int64_t ld, int a0, int a1, int a2, double *T, cudaStream_t stream) {
+    const int h1 = a1 - a0, h2 = a2 - a1;
+    if (h1 <= 0 || h2 <= 0) return CP_OK;
+    // T = L21 * X11        (h2 x h1, inner h1)
+    int rc = dgemm_small<true>(L21, ld, X + (int64_t)a0 * GB + a0, GB, T, GB, h2, h1, h1, 1.0, 0.0, cpsmall::TILES_ALL, stream);
+    if (rc) return rc;
+    // X21 = -X22 * T       (h2 x h1, inner h2)
+    return dgemm_small<true>(X + (int64_t)a1 * GB + a1, GB, T, GB, X + (int64_t)a1 * GB + a0, GB, h2, h1, h2, -1.0, 0.0,
+                             cpsmall::TILES_ALL, stream);
+}
+
 // Factorisation.  M: (Kd + nrhs) x Kd (leading dimension ld): rows 0..Kd-1 an SPD matrix (lower part used, destroyed),
 // rows Kd.. transposed right-hand sides (destroyed).  L (same shape, same ld) receives the factor in rows 0..Kd-1
-// and the forward-substituted right-hand sides  (L^-1 Rhs)'  in rows Kd.. .  Linv: ceil(Kd/128) blocks of 128 x 128.
-static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, int nrhs, double *Linv,
+// and the forward-substituted right-hand sides  (L^-1 Rhs)'  in rows Kd.. .  Xinv: ceil(Kd/512) blocks of 512 x 512
+// that end up holding the INVERSES of the 512-wide diagonal blocks of L (the 128-wide ones come out of potrf128; they
+// are merged pairwise, X21 = -X22 L21 X11, on the side stream while the factorisation proceeds); Tm: scratch of the
+// same size.  The substitutions then take ceil(Kd/512) steps instead of ceil(Kd/128).
+static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, int nrhs, double *Xinv, double *Tm,
                        const double *diag0, int32_t *info, double *ratio, cudaStream_t stream) {
     using namespace cpgemm;
     const int Ktot = Kd + nrhs;
@@ -468,6 +504,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
     if (rc) return rc;
     rc = configure_potrf(h);
     if (rc) return rc;
+    CP_CUDA(cudaMemsetAsync(Xinv, 0, xinv_elems(Kd) * sizeof(double), stream));
     // Trailing updates.  Panels are paired (e, o = e + 1).  What the chain needs next stays small and immediate:
     //   crit(p)  : block column p+1, inner dimension 128, on the caller's stream, 64 x 64 tiles
     //   far_a(e) : block column e+2 (needed by crit(o)), side stream
@@ -481,22 +518,43 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
     for (int j0 = 0; j0 < Kd; j0 += PB, ++ip) {
         const int nb = Kd - j0 < PB ? Kd - j0 : PB;
         const int j1 = j0 + nb;
-        double *Lp = Linv + (size_t)(j0 / PB) * PB * PB;
-        potrf128<<<1, P128_T, P128_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, L + (int64_t)j0 * ld + j0, ld, Lp, info,
-                                                   ratio, j0, diag0);
+        const int g0 = j0 / GB * GB, og = (j0 - g0) / PB;   // group origin, panel index inside the group
+        double *Xg = Xinv + (size_t)(j0 / GB) * GB * GB;
+        double *Lp = Xg + (int64_t)(j0 - g0) * GB + (j0 - g0);
+        potrf128<<<1, P128_T, P128_SMEM, stream>>>(M + (int64_t)j0 * ld + j0, ld, nb, L + (int64_t)j0 * ld + j0, ld, Lp, GB,
+                                                   info, ratio, j0, diag0);
         CP_CHECK_LAUNCH();
         const int below = Ktot - j1;
-        if (below <= 0) break;
-        // block column of the factor: rows below * L_d^-T  (right-hand-side rows included)
-        rc = dgemm_small<false>(M + (int64_t)j1 * ld + j0, ld, Lp, PB, L + (int64_t)j1 * ld + j0, ld, below, nb, nb, 1.0, 0.0,
-                                cpsmall::TILES_ALL, stream);
-        if (rc) return rc;
+        if (below > 0) {
+            // block column of the factor: rows below * L_d^-T  (right-hand-side rows included)
+            rc = dgemm_small<false>(M + (int64_t)j1 * ld + j0, ld, Lp, GB, L + (int64_t)j1 * ld + j0, ld, below, nb, nb, 1.0,
+                                    0.0, cpsmall::TILES_ALL, stream);
+            if (rc) return rc;
+        }
         const int ncols = Kd - j1;
-        if (ncols <= 0) continue;
-        const bool odd = (ip & 1) != 0;
         const int w2 = ncols < PB ? ncols : PB;            // block column p+1
         const bool more = ncols > w2;                      // block columns beyond p+1 exist
-        if (more) CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // block column j0..j1 of L is final
+        const bool last_in_group = (og == GB / PB - 1) || j1 >= Kd;
+        const bool merges = (og & 1) || last_in_group;     // this panel completes a pair and / or its group
+        if (more || merges) {
+            CP_CUDA(cudaEventRecord(h->ev_panel, stream));  // block column j0..j1 of L and its inverse are final
+            CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
+        }
+        if (merges) {  // inverse blocks of the group, off the critical path
+            double *Tg = Tm + (size_t)(j0 / GB) * GB * GB;
+            const int ge = (j1 - g0);  // columns of the group factored so far
+            if (og & 1) {              // pair (og-1, og): [a0, a0+128) and [a0+128, ge)
+                const int a0 = (og - 1) * PB;
+                rc = merge_inverse(Xg, L + (int64_t)(g0 + a0 + PB) * ld + g0 + a0, ld, a0, a0 + PB, ge, Tg, h->side);
+                if (rc) return rc;
+            }
+            if (last_in_group && ge > 2 * PB) {  // halves [0, 256) and [256, ge)
+                rc = merge_inverse(Xg, L + (int64_t)(g0 + 2 * PB) * ld + g0, ld, 0, 2 * PB, ge, Tg, h->side);
+                if (rc) return rc;
+            }
+        }
+        if (ncols <= 0) break;
+        const bool odd = (ip & 1) != 0;
         if (side_pending) {  // far_a(e) before crit(o); near(e-2, e-1) before crit(e)
             CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
             side_pending = false;
@@ -507,10 +565,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
         if (rc) return rc;
         if (!more) continue;
         const int j2 = j1 + w2;
-        CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_panel, 0));
         if (!odd) {
-            const bool has_partner = true;  // more => panel o = e + 1 exists (block column p+1 is non-empty)
-            (void)has_partner;
             const int w3 = Kd - j2 < PB ? Kd - j2 : PB;
             const double *Pf = L + (int64_t)j2 * ld + j0;
             rc = dgemm_big(Pf, ld, Pf, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, w3, nb, -1.0, 1.0, TILES_LOWER, h->side);
@@ -535,24 +590,25 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
             }
         }
     }
-    // whatever the side stream still holds must be ordered before the next user of this workspace
+    // whatever the side stream still holds (last merges) must be ordered before the substitutions / the next user
     CP_CUDA(cudaEventRecord(h->ev_side, h->side));
     CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
     return CP_OK;
 }
 
 // Forward substitution of further right-hand sides: Zt (n x Kd, ld) is destroyed, F (n x Kd, ld) receives (L^-1 Rhs)'.
-static int chol_forward(const double *L, int64_t ld, int Kd, const double *Linv, double *Zt, double *F, int64_t ldz, int n,
+static int chol_forward(const double *L, int64_t ld, int Kd, const double *Xinv, double *Zt, double *F, int64_t ldz, int n,
                         cudaStream_t stream) {
-    for (int j0 = 0; j0 < Kd; j0 += PB) {
-        const int nb = Kd - j0 < PB ? Kd - j0 : PB;
-        const int j1 = j0 + nb;
-        const double *Lp = Linv + (size_t)(j0 / PB) * PB * PB;
-        int rc = dgemm_small<false>(Zt + j0, ldz, Lp, PB, F + j0, ldz, n, nb, nb, 1.0, 0.0, cpsmall::TILES_ALL, stream);
+    for (int g0 = 0; g0 < Kd; g0 += GB) {
+        const int gs = Kd - g0 < GB ? Kd - g0 : GB;
+        const int g1 = g0 + gs;
+        const double *Xg = Xinv + (size_t)(g0 / GB) * GB * GB;
+        // F_g = Zt_g * Xinv_g'   (C[t, i] = sum_r Zt[t, g0 + r] * Xinv_g[i, r])
+        int rc = dgemm_small<false>(Zt + g0, ldz, Xg, GB, F + g0, ldz, n, gs, gs, 1.0, 0.0, cpsmall::TILES_ALL, stream);
         if (rc) return rc;
-        if (Kd - j1 > 0) {  // Zt[:, j1:] -= F_b * L[j1:, j0:j1]'
-            rc = dgemm_small<false>(F + j0, ldz, L + (int64_t)j1 * ld + j0, ld, Zt + j1, ldz, n, Kd - j1, nb, -1.0, 1.0,
-                                    cpsmall::TILES_ALL, stream);
+        if (Kd - g1 > 0) {  // Zt[:, g1:] -= F_g * L[g1:, g0:g1]'
+            rc = dgemm_big(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
+                           cpgemm::TILES_ALL, stream);
             if (rc) return rc;
         }
     }
@@ -560,19 +616,17 @@ static int chol_forward(const double *L, int64_t ld, int Kd, const double *Linv,
 }
 
 // Backward substitution: F (n x Kd, ldf; destroyed) holds (L^-1 Rhs)'; Wt (n x Kd, ldw) receives (SPD^-1 Rhs)'.
-static int chol_backward(const double *L, int64_t ld, int Kd, const double *Linv, double *F, int64_t ldf, double *Wt,
+static int chol_backward(const double *L, int64_t ld, int Kd, const double *Xinv, double *F, int64_t ldf, double *Wt,
                          int64_t ldw, int n, cudaStream_t stream) {
-    const int npanel = (Kd + PB - 1) / PB;
-    for (int p = npanel - 1; p >= 0; --p) {
-        const int j0 = p * PB;
-        const int nb = Kd - j0 < PB ? Kd - j0 : PB;
-        const double *Lp = Linv + (size_t)p * PB * PB;
-        // Wt_b = F_b * Linv_b   (C[t, i] = sum_r F[t, j0 + r] * Linv[r, i])
-        int rc = dgemm_small<true>(F + j0, ldf, Lp, PB, Wt + j0, ldw, n, nb, nb, 1.0, 0.0, cpsmall::TILES_ALL, stream);
+    for (int g = ngroups(Kd) - 1; g >= 0; --g) {
+        const int g0 = g * GB;
+        const int gs = Kd - g0 < GB ? Kd - g0 : GB;
+        const double *Xg = Xinv + (size_t)g * GB * GB;
+        // Wt_g = F_g * Xinv_g   (C[t, i] = sum_r F[t, g0 + r] * Xinv_g[r, i])
+        int rc = dgemm_small<true>(F + g0, ldf, Xg, GB, Wt + g0, ldw, n, gs, gs, 1.0, 0.0, cpsmall::TILES_ALL, stream);
         if (rc) return rc;
-        if (j0 > 0) {  // F[:, 0:j0] -= Wt_b * L[j0:j0+nb, 0:j0]
-            rc = dgemm_small<true>(Wt + j0, ldw, L + (int64_t)j0 * ld, ld, F, ldf, n, j0, nb, -1.0, 1.0, cpsmall::TILES_ALL,
-                                   stream);
+        if (g0 > 0) {  // F[:, 0:g0] -= Wt_g * L[g0:g0+gs, 0:g0]
+            rc = dgemm_big_nc(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0, stream);
             if (rc) return rc;
         }
     }
@@ -584,8 +638,9 @@ static inline int64_t ld_for(int K) { return (K + 7) / 8 * 8; }
 // The factor (L: rows x ld, then the inverted 128 x 128 diagonal blocks, then the pivot-ratio scalar) lives in the
 // handle's own allocation, not in the shared scratch: it must survive the calls that follow a solve (refinement
 // against the same factor, cp_ls_resolve) and every other entry point reuses the scratch.
-static int fac_reserve(cp_handle_t h, size_t rows, int64_t ld, int npanel, double **L, double **Linv, double **ratio) {
-    const size_t need = cp_carver::need(rows * (size_t)ld, 8) + cp_carver::need((size_t)npanel * PB * PB, 8) +
+static int fac_reserve(cp_handle_t h, size_t rows, int64_t ld, int Kd, double **L, double **Linv, double **Tm,
+                       double **ratio) {
+    const size_t need = cp_carver::need(rows * (size_t)ld, 8) + 2 * cp_carver::need(xinv_elems(Kd), 8) +
                         cp_carver::need(1, 8);
     if (need > h->fac_bytes) {
         if (h->fac) CP_CUDA(cudaFree(h->fac));  // synchronises: nothing in flight still reads the old block
@@ -602,7 +657,8 @@ static int fac_reserve(cp_handle_t h, size_t rows, int64_t ld, int npanel, doubl
     h->fac_K = 0;
     cp_carver fc(h->fac);
     *L = fc.take<double>(rows * (size_t)ld);
-    *Linv = fc.take<double>((size_t)npanel * PB * PB);
+    *Linv = fc.take<double>(xinv_elems(Kd));
+    *Tm = fc.take<double>(xinv_elems(Kd));
     *ratio = fc.take<double>(1);
     return CP_OK;
 }
@@ -620,8 +676,8 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     const int64_t ld = ld_for(Ksel);
     const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)(Ksel + n) * ld;
-    double *L = nullptr, *Linv = nullptr, *ratio = nullptr;
-    int rc = fac_reserve(h, (size_t)(Ksel + n), ld, npanel, &L, &Linv, &ratio);
+    double *L = nullptr, *Linv = nullptr, *Tm = nullptr, *ratio = nullptr;
+    int rc = fac_reserve(h, (size_t)(Ksel + n), ld, Ksel, &L, &Linv, &Tm, &ratio);
     if (rc) return rc;
     const size_t need = cp_carver::need(nM, 8) + cp_carver::need((size_t)n * ld, 8) + cp_carver::need(Ksel, 8);
     void *ws = nullptr;
@@ -637,7 +693,7 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     dim3 grid(cp_cdiv(Ksel, 256), Ksel + n);
     ls_assemble<<<grid, 256, 0, stream>>>(G, Bxy, sx, sy, invN, K, n, sel_cols, Ksel, M, ld, diag0);
     CP_CHECK_LAUNCH();
-    rc = chol_factor(h, M, L, ld, Ksel, n, Linv, diag0, info_out, ratio, stream);
+    rc = chol_factor(h, M, L, ld, Ksel, n, Linv, Tm, diag0, info_out, ratio, stream);
     if (rc) return rc;
     rc = chol_backward(L, ld, Ksel, Linv, L + (int64_t)Ksel * ld, ld, Wt, ld, n, stream);
     if (rc) return rc;
@@ -664,8 +720,8 @@ extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, in
     const int64_t ld = ld_for(Ksel);
     const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)Ksel * ld;
-    double *L = nullptr, *Linv = nullptr, *ratio = nullptr;
-    int rc = fac_reserve(h, (size_t)Ksel, ld, npanel, &L, &Linv, &ratio);
+    double *L = nullptr, *Linv = nullptr, *Tm = nullptr, *ratio = nullptr;
+    int rc = fac_reserve(h, (size_t)Ksel, ld, Ksel, &L, &Linv, &Tm, &ratio);
     if (rc) return rc;
     void *ws = nullptr;
     rc = cp_ws_reserve(h, cp_carver::need(nM, 8) + cp_carver::need(Ksel, 8), &ws);
@@ -678,7 +734,7 @@ extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, in
     dim3 grid(cp_cdiv(Ksel, 256), Ksel);
     ls_assemble<<<grid, 256, 0, stream>>>(G, nullptr, sx, nullptr, 1.0 / (double)N, K, 0, sel_cols, Ksel, M, ld, diag0);
     CP_CHECK_LAUNCH();
-    rc = chol_factor(h, M, L, ld, Ksel, 0, Linv, diag0, info_out, ratio, stream);
+    rc = chol_factor(h, M, L, ld, Ksel, 0, Linv, Tm, diag0, info_out, ratio, stream);
     if (rc) return rc;
     if (stat_out) CP_CUDA(cudaMemcpyAsync(stat_out, ratio, sizeof(double), cudaMemcpyDeviceToDevice, stream));
     h->fac_K = Ksel;
@@ -715,7 +771,7 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     const int npanel = (Ksel + PB - 1) / PB;
     cp_carver fc(h->fac);
     const double *L = fc.take<double>((size_t)h->fac_rows * ld);
-    const double *Linv = fc.take<double>((size_t)npanel * PB * PB);
+    const double *Linv = fc.take<double>(xinv_elems(Ksel));
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, 3 * cp_carver::need((size_t)n * ld, 8), &ws);
     if (rc) return rc;
@@ -897,7 +953,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     const int npanel = (Ni + PB - 1) / PB;
     const size_t nM = (size_t)(Ni + n) * ldm;
     const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + 2 * cp_carver::need(nM, 8) +
-                        cp_carver::need((size_t)npanel * PB * PB, 8) + cp_carver::need((size_t)n * ldm, 8) +
+                        2 * cp_carver::need(xinv_elems(Ni), 8) + cp_carver::need((size_t)n * ldm, 8) +
                         cp_carver::need((size_t)n * ldc, 8) + cp_carver::need(Ksel, 8) + cp_carver::need(n, 8) +
                         cp_carver::need(Ni, 8) + cp_carver::need(1, 8);
     void *ws = nullptr;
@@ -907,7 +963,8 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     double *Xc = cv.take<double>((size_t)Ni * ldc);
     double *M = cv.take<double>(nM);
     double *L = cv.take<double>(nM);
-    double *Linv = cv.take<double>((size_t)npanel * PB * PB);
+    double *Linv = cv.take<double>(xinv_elems(Ni));
+    double *Tm = cv.take<double>(xinv_elems(Ni));
     double *At = cv.take<double>((size_t)n * ldm);
     double *Wt = cv.take<double>((size_t)n * ldc);
     double *xmean = cv.take<double>(Ksel);
@@ -935,7 +992,7 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     else
         dual_rhs<double><<<dim3(cp_cdiv(Ni, 256), n), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, ymean, N, n, M, ldm);
     CP_CHECK_LAUNCH();
-    rc = chol_factor(h, M, L, ldm, Ni, n, Linv, diag0, info_out, ratio, stream);
+    rc = chol_factor(h, M, L, ldm, Ni, n, Linv, Tm, diag0, info_out, ratio, stream);
     if (rc) return rc;
     rc = chol_backward(L, ldm, Ni, Linv, L + (int64_t)Ni * ldm, ldm, At, ldm, n, stream);
     if (rc) return rc;

@@ -143,6 +143,12 @@ class Net:
     def forward(self, data=None, upto=None):
         """One forward pass: of the provider's next batch (data=None, like Caffe's data layer) or of given images
         (the frozen path, net.set_input_arrays at net.py:447).  Returns the blob dict."""
+        if not hasattr(self._forward, "data"):
+            # plain provider ``forward(net, batch) -> blobs`` (a batch index stands in for the frozen images)
+            if data is None:
+                data = self._batch_iter
+                self._batch_iter += 1
+            return self._forward(self, data)
         if data is None:
             data = self._forward.data(self._batch_iter)
             self._batch_iter += 1
@@ -182,8 +188,10 @@ class Net:
             if save and frozen_points and (batch, 0) in points_dict:
                 blobs = self.forward(points_dict[(batch, 0)], upto=upto)  # net.py:446-447
             else:
-                blobs = self.forward(upto=upto)
-                if save and not frozen_points:
+                blobs = self.forward(upto=upto) if hasattr(self._forward, "data") else self.forward(batch)
+                if save and not frozen_points and not hasattr(self._forward, "data"):
+                    points_dict[(batch, 0)] = batch  # plain provider: the batch index identifies the images
+                elif save and not frozen_points:
                     data = blobs["data"]
                     if batch == 0:
                         points_dict["data"] = tuple(data.shape)       # net.py:432-433
