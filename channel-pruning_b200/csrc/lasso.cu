@@ -21,9 +21,8 @@
 //                  LAG steps ago) + the last LAG deltas applied locally, soft threshold,
 //                  correctly rounded division (pre-computed reciprocal + one Markstein step),
 //                  publish delta
-//   4 update warps own interleaved pairs of Qw in shared memory, apply  Qw += delta * Q[j,:]
-//                  (LDS.128 / DMUL / DADD / STS.128), stream the rows of Q from L2 through a
-//                  cp.async ring (each lane copies exactly the pairs it reads back), and
+//   4 update warps own interleaved pairs of Qw (in registers during a sweep), apply  Qw += delta * Q[j,:]
+//                  (DMUL / DADD), stream the rows of Q from L2 into a register ring several steps ahead, and
 //                  publish the Qw entry the chain warp will need LAG+1 steps later
 //   packager warp  per-step operands of the chain (q_j, Q_jj, 1/Q_jj, the LAG entries
 //                  Q[j_s][j_{s-i}]) gathered 32 steps at a time, lane-parallel
@@ -134,7 +133,7 @@ __device__ __forceinline__ void poll_backoff() {
 #endif
 }
 constexpr int QR = 64;       // rings of per-step scalars (steps in flight << QR)
-template <int NPB> struct RingDepth { static constexpr int value = NPB <= 4 ? 16 : 4; };  // multiple of 4 (update-warp blocks)
+template <int NPB> struct RingDepth { static constexpr int value = 0; };  // no shared-memory row ring any more (register ring)
 
 __device__ __forceinline__ uint32_t xorshift_step(uint32_t s) {  // sklearn/utils/_random.pxd:20-34 (state update)
     if (s == 0) s = 1;
@@ -147,14 +146,6 @@ __device__ __forceinline__ uint32_t xorshift_step(uint32_t s) {  // sklearn/util
 __device__ __forceinline__ uint32_t fastmod(uint32_t a, uint64_t M, uint32_t d) {
     return (uint32_t)__umul64hi(M * (uint64_t)a, (uint64_t)d);
 }
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
@@ -498,22 +489,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
             // written back to shared memory at its ends); the pairs of row t are in registers before delta_t arrives
             const int b = role, bt = b * 32 + lane;
             const double *Qmine = Q + 2 * bt;                  // this lane's first pair of any row
-            double *ring_mine = ring + 2 * bt;
-            double2 qw[NPB], rw[2][NPB];  // rw: pairs of the current / next row of Q (alternating)
+            // The rows of Q go straight from L2 into a REGISTER ring, DEPTH steps ahead (ld.global.nc, no shared-memory
+            // staging: a cp.async ring cost a commit, a wait and a shared-memory read per step on a warp that hides no
+            // latency).  Blocks of DEPTH steps are fully unrolled, so ring slots, record slots and the publish targets
+            // are compile-time offsets; the coordinates a block needs arrive in 16-byte index loads.
+            constexpr int DEPTH = NPB <= 2 ? 8 : 4;
+            double2 qw[NPB], rr[DEPTH][NPB];
 #pragma unroll
             for (int sp = 0; sp < NPB; ++sp) qw[sp] = *reinterpret_cast<const double2 *>(Qw + 2 * BL * sp + 2 * bt);
-            auto prefetch_row = [&](uint32_t j, int slot) {
+            auto fetch_row = [&](uint32_t j, int slot) {
                 const double *src = Qmine + (uint32_t)(j * (uint32_t)ldq);  // c * ldq < 2^31
-                double *dst = ring_mine + (uint32_t)(slot * CP);
 #pragma unroll
                 for (int sp = 0; sp < NPB; ++sp) {
-                    if (2 * BL * sp + 2 * bt < c) cp_async16(dst + 2 * BL * sp, src + 2 * BL * sp);
+                    double2 v = make_double2(0.0, 0.0);
+                    if (2 * BL * sp + 2 * bt < c) v = __ldg(reinterpret_cast<const double2 *>(src + 2 * BL * sp));
+                    rr[slot][sp] = v;
                 }
-            };
-            auto load_row = [&](int buf, int slot) {
-                const double *r = ring_mine + (uint32_t)(slot * CP);
-#pragma unroll
-                for (int sp = 0; sp < NPB; ++sp) rw[buf][sp] = *reinterpret_cast<const double2 *>(r + 2 * BL * sp);
             };
             // entry js of Qw if this lane owns it (element 2*BL*sp + 2*bt + h)
             auto publish = [&](uint32_t js, int step) {
@@ -530,29 +521,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                 }
             };
 #pragma unroll
-            for (int d = 0; d < RING; ++d) {
-                if (d < n_active) prefetch_row(jz[d], d);
-                cp_async_commit();
-            }
+            for (int d = 0; d < DEPTH; ++d)
+                if (d < n_active) fetch_row(jz[d], d);
             for (int s = 0; s <= LAG && s < n_active; ++s) publish(jz[s], s);  // entries the chain needs before any update
-            cp_async_wait<RING - 1>();  // this lane's pairs of row 0 have landed
-            load_row(0, 0);
-            // Four steps per block, fully unrolled: the coordinates a block needs (rows to prefetch, Qw entries to
-            // publish) come in as three 16-byte loads, ring slots / row buffers / record slots are static offsets.
-            static_assert(RING % 4 == 0 && QR % 4 == 0, "block layout of the update warps");
+            static_assert(QR % DEPTH == 0 && LAG + 1 <= 8, "block layout of the update warps");
             auto run_block = [&](auto guarded, int t0) {
                 constexpr bool GUARD = decltype(guarded)::value;
-                const int sb = t0 & (QR - 1), rb = t0 % RING;
-                const uint4 jr4 = *reinterpret_cast<const uint4 *>(jz + t0 + RING);  // rows t0+RING .. +3 (padding beyond
-                const uint4 ja4 = *reinterpret_cast<const uint4 *>(jz + t0 + 4);     // n_active is never used)
-                const uint4 jb4 = *reinterpret_cast<const uint4 *>(jz + t0 + 8);
-                const uint32_t jr[4] = {jr4.x, jr4.y, jr4.z, jr4.w};
-                const uint32_t jp[8] = {ja4.x, ja4.y, ja4.z, ja4.w, jb4.x, jb4.y, jb4.z, jb4.w};  // jz[t0+4 .. t0+11]
+                const int sb = t0 & (QR - 1);
+                // coordinates: rows t0+DEPTH .. t0+2*DEPTH-1 to fetch, entries t0+LAG+1 .. t0+LAG+DEPTH to publish
+                uint32_t jr[DEPTH], jp[DEPTH + 8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int q = 0; q < DEPTH / 4; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(jz + t0 + DEPTH + 4 * q);  // (beyond n_active: unused)
+                    jr[4 * q] = v.x; jr[4 * q + 1] = v.y; jr[4 * q + 2] = v.z; jr[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < (DEPTH + 8) / 4; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(jz + t0 + 4 * q);  // jz[t0 .. t0+DEPTH+7]
+                    jp[4 * q] = v.x; jp[4 * q + 1] = v.y; jp[4 * q + 2] = v.z; jp[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) {
                     const int t = t0 + u;
                     if (GUARD && t >= n_active) break;
-                    const int cur = u & 1, nxt = cur ^ 1;
 #ifdef CP_TIMING
                     if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 4] = clock64();
 #endif
@@ -563,32 +554,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lasso_select_kernel(const Selec
                     if (delta != 0.0) {
 #pragma unroll
                         for (int sp = 0; sp < NPB; ++sp) {
-                            qw[sp].x = __dadd_rn(qw[sp].x, __dmul_rn(delta, rw[cur][sp].x));
-                            qw[sp].y = __dadd_rn(qw[sp].y, __dmul_rn(delta, rw[cur][sp].y));
+                            qw[sp].x = __dadd_rn(qw[sp].x, __dmul_rn(delta, rr[u][sp].x));
+                            qw[sp].y = __dadd_rn(qw[sp].y, __dmul_rn(delta, rr[u][sp].y));
                         }
                     }
                     const int sp1 = t + LAG + 1;  // the chain step that starts from Qw after THIS update
-                    if (sp1 < n_active) publish(jp[LAG - 3 + u], sp1);
+                    if (sp1 < n_active) publish(jp[u + LAG + 1], sp1);
 #ifdef CP_TIMING
                     if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 6] = clock64();
 #endif
-                    if (t + RING < n_active) prefetch_row(jr[u], rb + u);  // row t is in registers: its slot is free
-                    cp_async_commit();
-                    if (t + 1 < n_active) {
-                        cp_async_wait<RING - 1>();  // row t+1 has landed
-                        load_row(nxt, u == 3 ? (rb + 4) % RING : rb + u + 1);
-                    }
+                    if (t + DEPTH < n_active) fetch_row(jr[u], u);  // row t is consumed: its ring slot takes row t+DEPTH
 #ifdef CP_TIMING
                     if (rec && b == 0 && lane == 0 && t < TSTEPS) cp_lasso_times[t * 8 + 7] = clock64();
 #endif
                 }
-                if ((t0 & 4) && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t0 + 4;
+                if ((DEPTH == 8 || (t0 & 4)) && lane == 0) *reinterpret_cast<volatile int *>(&ctl.bulk_pos[b]) = t0 + DEPTH;
             };
-            for (int t0 = 0; t0 < n_active; t0 += 4) {
-                if (t0 + 4 <= n_active) run_block(std::false_type{}, t0);
+            for (int t0 = 0; t0 < n_active; t0 += DEPTH) {
+                if (t0 + DEPTH <= n_active) run_block(std::false_type{}, t0);
                 else run_block(std::true_type{}, t0);
             }
-            cp_async_wait<0>();
 #pragma unroll
             for (int sp = 0; sp < NPB; ++sp) *reinterpret_cast<double2 *>(Qw + 2 * BL * sp + 2 * bt) = qw[sp];
         } else if (role == NBULK) {

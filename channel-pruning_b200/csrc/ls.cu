@@ -147,41 +147,40 @@ struct MmTask {
     int nterm;
     MmTerm t[3];
 };
-// 64 threads per task, each a 4 x 4 register micro-tile on rows tr + 8u / columns tc + 8v (interleaved: the eight
-// distinct B rows of a warp fall into distinct banks, the A rows are broadcasts): 8 shared-memory loads per 16 FMAs
-// instead of 2 per FMA -- the block inversion used to be LSU bound (1/3 of the whole panel kernel).
+// 128 threads per task, each a 2 x 4 register micro-tile on rows tr + 16u / columns tc + 8v (interleaved: the eight
+// distinct B rows of a warp fall into distinct banks, the A rows are broadcasts): 6 shared-memory loads per 8 FMAs
+// instead of 2 per FMA (the block inversion used to be LSU bound), and 12 of the 16 warps busy.
 __device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
     const int t = threadIdx.x;
-    if (t >= ntask * 64) return;
-    const MmTask &tk = tasks[t >> 6];
-    const int tr = (t >> 3) & 7, tc = t & 7;
-    double acc[4][4];
+    if (t >= ntask * 128) return;
+    const MmTask &tk = tasks[t >> 7];
+    const int tr = (t >> 3) & 15, tc = t & 7;
+    double acc[2][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
     for (int w = 0; w < tk.nterm; ++w) {
         const double *ap = tk.t[w].A + tr * tk.t[w].sa;
         const double *bp = tk.t[w].B + tc * tk.t[w].sb;
-        const int sa8 = 8 * tk.t[w].sa, sb8 = 8 * tk.t[w].sb;
-#pragma unroll 4
+        const int sa16 = 16 * tk.t[w].sa, sb8 = 8 * tk.t[w].sb;
+#pragma unroll 8
         for (int q = 0; q < SB; ++q) {
-            double av[4], bv[4];
+            double av[2], bv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                av[u] = ap[u * sa8 + q];
-                bv[u] = bp[u * sb8 + q];
-            }
+            for (int u = 0; u < 2; ++u) av[u] = ap[u * sa16 + q];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int v = 0; v < 4; ++v) bv[v] = bp[v * sb8 + q];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
                 for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
         }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) tk.dst[(tr + 8 * u) * tk.dr + (tc + 8 * v) * tk.dc] = tk.sign * acc[u][v];
+        for (int v = 0; v < 4; ++v) tk.dst[(tr + 16 * u) * tk.dr + (tc + 8 * v) * tk.dc] = tk.sign * acc[u][v];
 }
 
 #ifdef CP_TIMING
@@ -800,20 +799,20 @@ scatter_cols(const double *__restrict__ W, int Ks, const int32_t *__restrict__ s
     const int t = blockIdx.y;
     if (j < Ks) Wf[(int64_t)t * K + (sel ? sel[j] : j)] = W[(int64_t)t * Ks + j];
 }
-// C[r, t] = Y[r, t] - y_bias[t] - b[t]
+// R[r, t] = float( (Y[r, t] - y_bias[t] - b[t]) - sum_k part_k[r, t] )
 template <typename T>
 __global__ void __launch_bounds__(256)
-residual_init(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ y_bias, const double *__restrict__ b,
-              int64_t N, int n, double *__restrict__ C) {
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= n) return;
-    const double off = (y_bias ? (double)y_bias[t] : 0.0) + b[t];
-    for (int64_t r = blockIdx.y; r < N; r += gridDim.y) C[r * n + t] = (double)Y[r * ldy + t] - off;
-}
-__global__ void __launch_bounds__(256)
-to_float(const double *__restrict__ C, int64_t count, int n, float *__restrict__ R, int64_t ldr) {
+residual_finish(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ y_bias, const double *__restrict__ b,
+                const double *__restrict__ part, int64_t split_stride, int nsplit, int64_t N, int n, float *__restrict__ R,
+                int64_t ldr) {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (e < count) R[(e / n) * ldr + (e % n)] = (float)C[e];
+    if (e >= N * n) return;
+    const int64_t r = e / n;
+    const int t = (int)(e - r * n);
+    double acc = 0.0;
+    for (int k = 0; k < nsplit; ++k) acc += part[(int64_t)k * split_stride + e];
+    const double y0 = (double)Y[r * ldy + t] - ((y_bias ? (double)y_bias[t] : 0.0) + b[t]);
+    R[r * ldr + t] = (float)(y0 - acc);
 }
 }  // namespace
 
@@ -828,32 +827,49 @@ extern "C" int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, i
     CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t ldw = ld_for(K);
+    // X Wf' in fp64 (exact products of fp32 data with the fp64 weights): 128 x 128 tiles, reduction split so that the
+    // tile count fills whole waves of the SMs (5000 x 512 is 160 tiles on 148 SMs: two waves for 1.08 waves of work)
+    const int tiles = num_tiles((int)N, n, TILES_ALL);
+    int nsplit = 1;
+    double best = 1e30;
+    for (int ns = 1; ns <= 6; ++ns) {
+        if (K / ns < 8 * BK) break;
+        const double cost = (double)cp_cdiv((int64_t)tiles * ns, h->num_sms) / ns + 0.02 * ns;  // waves of 1/ns length
+        if (cost < best) {
+            best = cost;
+            nsplit = ns;
+        }
+    }
+    int64_t rps = (K + nsplit - 1) / nsplit;
+    rps = (rps + BK - 1) / BK * BK;
+    nsplit = (int)((K + rps - 1) / rps);
     void *ws = nullptr;
-    int rc = cp_ws_reserve(h, cp_carver::need((size_t)n * ldw, 8) + cp_carver::need((size_t)N * n, 8), &ws);
+    int rc = cp_ws_reserve(h, cp_carver::need((size_t)n * ldw, 8) + cp_carver::need((size_t)nsplit * N * n, 8), &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     double *Wf = cv.take<double>((size_t)n * ldw);
-    double *C = cv.take<double>((size_t)N * n);
+    double *part = cv.take<double>((size_t)nsplit * N * n);
     CP_CUDA(cudaMemsetAsync(Wf, 0, (size_t)n * ldw * sizeof(double), stream));
     scatter_cols<<<dim3(cp_cdiv(Ksel, 256), n), 256, 0, stream>>>(W, Ksel, sel_cols, Wf, (int)ldw);
     CP_CHECK_LAUNCH();
-    const unsigned gy = (unsigned)(N < 4096 ? N : 4096);
-    if (y_dtype == CP_F32)
-        residual_init<float><<<dim3(cp_cdiv(n, 256), gy), 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, b, N, n, C);
-    else
-        residual_init<double><<<dim3(cp_cdiv(n, 256), gy), 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, b, N, n, C);
-    CP_CHECK_LAUNCH();
-    // C -= X Wf'   (exact products of fp32 data with the fp64 weights, fp64 accumulation)
     Args g{};
-    g.A = X; g.lda = ldx; g.B = Wf; g.ldb = ldw; g.C = C; g.ldc = n;
+    g.A = X; g.lda = ldx; g.B = Wf; g.ldb = ldw; g.C = part; g.ldc = n;
+    g.c_split_stride = N * (int64_t)n;
     g.M = (int)N; g.Nn = n; g.R = K;
-    g.nsplit = 1; g.r_per_split = K;
-    g.alpha = -1.0; g.beta = 1.0; g.tile_mode = TILES_ALL;
+    g.nsplit = nsplit > 1 ? nsplit : 1;
+    g.r_per_split = nsplit > 1 ? rps : K;
+    g.alpha = 1.0; g.beta = 0.0; g.tile_mode = TILES_ALL;
     g.a_vec = al16(X) && (ldx % 4 == 0);
     g.b_vec = al16(Wf) && (ldw % 2 == 0);
     CP_GEMM_LAUNCH((launch<float, double, false, false>(g, stream)));
     const int64_t count = N * (int64_t)n;
-    to_float<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(C, count, n, R_out, ldr);
+    const unsigned nblk = (unsigned)((count + 255) / 256);
+    if (y_dtype == CP_F32)
+        residual_finish<float><<<nblk, 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, b, part, g.c_split_stride, g.nsplit,
+                                                        N, n, R_out, ldr);
+    else
+        residual_finish<double><<<nblk, 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, b, part, g.c_split_stride,
+                                                         g.nsplit, N, n, R_out, ldr);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }

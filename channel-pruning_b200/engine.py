@@ -337,6 +337,53 @@ class Engine:
         self.ls_resolve(gr["B"], g["sx"], gr["sy"], sel_cols, accumulate_into=(W, b))
         return W, b
 
+    # ------------------------------------------------------------------ data-form LASSO (benchmark kernel)
+    def lasso_dataform_build(self, X, W2m, Y, y_bias, samples, c, k2):
+        """Materialises the reference's design matrix Z ((S*n) x c, column major fp32) and target y (lib/decompose.py:
+        428-437).  Returns (Z as a (c, m) tensor whose rows are the columns of Z, y (m,) fp64)."""
+        N, K = X.shape
+        n = W2m.shape[0]
+        S = samples.numel()
+        m = S * n
+        Z = self.empty(c, m, dtype=torch.float32)
+        y = self.empty(m)
+        self._call(self.lib.cp_lasso_dataform_build(self.h, self._p(X, "const float*"), N, K, X.stride(0),
+                                                    self._p(W2m, "const float*"), n, c, k2,
+                                                    self._p(samples, "const int32_t*"), S, self._p(Y, "const void*"),
+                                                    0 if Y.dtype == torch.float32 else 1, Y.stride(0),
+                                                    self._p(y_bias, "const float*"), self._p(Z, "float*"), Z.stride(0),
+                                                    self._p(y, "double*"), self._s()))
+        return Z, y
+
+    def lasso_cd_dataform(self, Z, y, alpha, seed, w=None, tol=1e-4, max_iter=1000):
+        """One Lasso.fit in data form (cp_lasso_cd_dataform).  Returns (w (c,), scalars [n_iter, gap, tol, sweeps, checks])."""
+        c, m = Z.shape
+        if w is None:
+            w = torch.zeros(c, dtype=torch.float64, device=self.device)
+        out = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._call(self.lib.cp_lasso_cd_dataform(self.h, self._p(Z, "const float*"), Z.stride(0), self._p(y, "const double*"),
+                                                 m, c, float(alpha), float(tol), int(max_iter), int(seed) & 0xffffffff,
+                                                 self._p(w, "double*"), self._p(out, "double*"), self._s()))
+        return w, out
+
+    def dataform_benchmark(self, X, W2m, Y, y_bias, samples, shape, alpha, seed=12345):
+        """Times one cold-start data-form fit at ``alpha`` (profiles/sweep_config5.py): bytes of Z streamed per second."""
+        Z, y = self.lasso_dataform_build(X, W2m, Y, y_bias, samples, shape.c, shape.k * shape.k)
+        self.lasso_cd_dataform(Z, y, alpha, seed)  # warm-up
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        w, out = self.lasso_cd_dataform(Z, y, alpha, seed)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        o = out.cpu().numpy()
+        sweeps, checks = int(o[3]), int(o[4])
+        nbytes = 4.0 * Z.shape[0] * Z.shape[1] * (sweeps + checks)  # SURVEY 8(d): 4 m c per sweep (+ per gap check)
+        return {"m": int(Z.shape[1]), "c": int(Z.shape[0]), "alpha": alpha, "n_iter": int(o[0]), "sweeps": sweeps,
+                "gap_checks": checks, "ms": ms, "stream_gbs": nbytes / (ms / 1e3) / 1e9, "nnz": int((w != 0).sum().item()),
+                "algorithmic_bytes": nbytes}
+
     # ------------------------------------------------------------------ dense fp64 blocks (3C companions)
     def gemm(self, A, B, a_mc=False, b_nc=False, alpha=1.0, beta=0.0, out=None):
         """C[m, nn] = alpha * sum_r a(m, r) b(nn, r) + beta * C   (cp_gemm_f64; fp64 device tensors, unit inner stride)

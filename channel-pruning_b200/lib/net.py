@@ -348,6 +348,7 @@ class Net:
                 self._w[c].copy_(d)
 
         topology = []
+        trace = getattr(self, "_trace", None)  # optional list: (conv, stage, {name: array}) per stage (debugging aid)
         for conv, convnext in zip(convs[1:], convs[2:] + ['pool5']):
             conv_V = underline(conv, 'V')
             conv_H = underline(conv, 'H')
@@ -372,6 +373,8 @@ class Net:
             setConv(conv, VHr)
             self.WPQ[(conv_H, 0)] = H
             self.WPQ[(conv_H, 1)] = self._b[conv].cpu().numpy()
+            if trace is not None:
+                trace.append((conv, "vh", dict(VHr=VHr.copy(), b=np.asarray(b).copy(), X=X.copy(), Y=Y.copy())))
             # ---- channel decomposition (:1384-1404)
             feats_dict, _ = self.extract_features(names=conv, points_dict=self._points_dict, save=1)
             Yf = feats_dict[conv]
@@ -383,6 +386,8 @@ class Net:
             self.WPQ[(conv_H, 1)] = np.zeros(d_prime)
             self.WPQ[(conv_P, 0)] = W2.reshape([W2.shape[0], W2.shape[1], 1, 1])
             self.WPQ[(conv_P, 1)] = B
+            if trace is not None:
+                trace.append((conv, "itq", dict(W12=W12.copy(), B=np.asarray(B).copy(), Yf=Yf.copy())))
             # ---- channel pruning (:1406-1459)
             if dcfgs.dic.vh and (conv in alldic or conv in pooldic) and (convnext in self.convs):
                 X_name = self.bottom_names[convnext][0] if conv in pooldic else conv  # :1411-1414
@@ -395,6 +400,10 @@ class Net:
                 key = conv_P if (conv_P, 0) in self.WPQ else conv_H  # :1450-1456
                 self.WPQ[(key, 0)] = self.WPQ[(key, 0)][idxs]
                 self.WPQ[(key, 1)] = self.WPQ[(key, 1)][idxs]
+                if trace is not None:
+                    from .decompose import DictionaryInfo
+                    trace.append((conv, "prune", dict(idxs=idxs.copy(), W2=W2n.copy(), B2=np.asarray(B2n).copy(),
+                                                      ls=dict(DictionaryInfo.last.get("ls", {})))))
             topology.append({"V": conv_V, "H": conv_H, "P": conv_P, "rank": int(rank),
                              "num_output": int(self.WPQ[(conv_P, 0)].shape[0])})
         new_pt = {"prefix": prefix, "layers": topology}

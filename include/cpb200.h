@@ -151,6 +151,27 @@ int cp_lasso_select(cp_handle_t h, const double *Q, int ldq, const double *qv, c
                     double *out_scalars, double *out_probe_log, cp_stream_t stream);
 
 /*
+ * Data-form coordinate descent (benchmark kernel; SURVEY.md 8b/8d "LASSO data-form CD: 4 m c bytes per sweep") --
+ * the algorithm sklearn runs for the reference's Lasso.fit(Z, reY) (lib/decompose.py:428-457), on the MATERIALISED
+ * design matrix instead of its Gram matrix.  The product path never forms Z (cp_lasso_build + cp_lasso_select).
+ *
+ * cp_lasso_dataform_build: Z (m = S*n rows, c columns, fp32, COLUMN major, leading dimension ldz) and y (m, fp64):
+ *   Z[a*ldz + s*n + t] = sum_p X[samples[s], a*k2 + p] * W2[t, a*k2 + p],   y[s*n + t] = Y[samples[s], t] - y_bias[t]
+ *   (lib/decompose.py:428-437).
+ * cp_lasso_cd_dataform: ONE Lasso.fit at `alpha` (l1_reg = alpha*m), warm start from / result in w (c, fp64):
+ *   enet_coordinate_descent with selection='random' (32-bit xorshift from `seed`), tol / duality-gap stopping rule,
+ *   no screening; centring of Z and y implicit.  Coordinates are processed 8 at a time with exact sequential
+ *   semantics (see csrc/lasso_df.cu); Z is streamed from HBM once per sweep.
+ *   out_scalars: [n_iter, gap, tol*|yc|^2, sweeps, gap checks].  Cooperative launch: synchronises `stream` once
+ *   before the launch (one scalar read-back).
+ */
+int cp_lasso_dataform_build(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const float *W2, int n, int c,
+                            int k2, const int32_t *samples, int S, const void *Yraw, int y_dtype, int64_t ldy,
+                            const float *y_bias, float *Z_out, int64_t ldz, double *y_out, cp_stream_t stream);
+int cp_lasso_cd_dataform(cp_handle_t h, const float *Z, int64_t ldz, const double *y, int m, int c, double alpha,
+                         double tol, int max_iter, uint32_t seed, double *w, double *out_scalars, cp_stream_t stream);
+
+/*
  * Least-squares reconstruction on the surviving channels -- replaces fc_kernel /
  * LinearRegression(fit_intercept=True).fit (lib/decompose.py:622-623, 665-669) by
  * the centred normal equations on the principal sub-block of G:

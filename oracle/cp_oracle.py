@@ -658,7 +658,7 @@ class NumpyNet:
         return lambda batch: self.forward_blobs(pd[(batch, 0)])
 
 
-def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None):
+def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=None):
     """lib/net.py:1292-1471 on a NumpyNet whose frozen ``_feats_dict`` / ``_points_dict`` are set (points_dict carries
     the images under (batch, 0) like the reference's, net.py:441).  Mutates net.weights / net.biases; returns WPQ."""
     state = state if state is not None else DictState()
@@ -704,6 +704,8 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None):
         setConv(conv, VHr)
         net.WPQ[(conv_H, 0)] = H
         net.WPQ[(conv_H, 1)] = net.biases[conv]
+        if trace is not None:
+            trace.append((conv, "vh", dict(VHr=VHr.copy(), b=np.asarray(b).copy(), X=X.copy(), Y=Y.copy())))
         # ---- channel decomposition (:1384-1404)
         feats_new, _ = extract_features(net.frozen_forward(), [conv], None, None, points_dict=net._points_dict)
         W1, W2, B, W12 = ITQ_decompose(feats_new[conv], net._feats_dict[conv], H, d_prime, bias=net.biases[conv], Wr=VHr)
@@ -713,6 +715,8 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None):
         net.WPQ[(conv_H, 1)] = np.zeros(d_prime)
         net.WPQ[(conv_P, 0)] = W2.reshape([W2.shape[0], W2.shape[1], 1, 1])
         net.WPQ[(conv_P, 1)] = B
+        if trace is not None:
+            trace.append((conv, "itq", dict(W12=W12.copy(), B=np.asarray(B).copy(), Yf=feats_new[conv].copy())))
         # ---- channel pruning (:1406-1459)
         if (conv in alldic or conv in pooldic) and (convnext in net.convs):
             X_name = net.bottom_names[convnext][0] if conv in pooldic else conv
@@ -727,6 +731,8 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None):
             key = conv_P if (conv_P, 0) in net.WPQ else conv_H
             net.WPQ[(key, 0)] = net.WPQ[(key, 0)][idxs]
             net.WPQ[(key, 1)] = net.WPQ[(key, 1)][idxs]
+            if trace is not None:
+                trace.append((conv, "prune", dict(idxs=idxs.copy(), W2=W2n.copy(), B2=np.asarray(B2n).copy())))
             if infos is not None:
                 infos[convnext] = info
     return net.WPQ
