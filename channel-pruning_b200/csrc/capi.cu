@@ -35,18 +35,21 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->fac_K = h->fac_Kfull = 0;
     h->fac_N = 0;
     h->fac_rows = 0;
+    h->aux = nullptr;
+    h->aux_bytes = 0;
     *out = h;
     return CP_OK;
 }
 
 extern "C" int cp_destroy(cp_handle_t h) {
     if (!h) return CP_OK;
-    if (h->ws || h->side || h->fac) {
+    if (h->ws || h->side || h->fac || h->aux) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(h->device);
         if (h->ws) cudaFree(h->ws);
         if (h->fac) cudaFree(h->fac);
+        if (h->aux) cudaFree(h->aux);
         if (h->side) {
             cudaStreamDestroy(h->side);
             cudaEventDestroy(h->ev_panel);
@@ -75,5 +78,22 @@ int cp_ws_reserve(cp_handle_t h, size_t bytes, void **out) {
         h->ws_bytes = want;
     }
     *out = h->ws;
+    return CP_OK;
+}
+
+int cp_aux_reserve(cp_handle_t h, size_t bytes, void **out) {
+    if (bytes > h->aux_bytes) {
+        if (h->aux) CP_CUDA(cudaFree(h->aux));
+        h->aux = nullptr;
+        h->aux_bytes = 0;
+        size_t want = cp_align_up(bytes + bytes / 8, (size_t)1 << 20);
+        cudaError_t e = cudaMalloc(&h->aux, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            CP_FAIL(CP_ERR_WORKSPACE, "auxiliary workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        h->aux_bytes = want;
+    }
+    *out = h->aux;
     return CP_OK;
 }

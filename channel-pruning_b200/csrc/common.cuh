@@ -23,6 +23,10 @@ struct cp_handle_s {
     int fac_K, fac_Kfull;
     int64_t fac_N;
     int fac_rows;  // rows of L stored in `fac` (Ksel, or Ksel + n when right-hand sides rode along)
+    // second scratch: temporaries of an entry point that calls another one (cp_ls_residual -> cp_gram), which
+    // carves its own scratch out of `ws`
+    void *aux;
+    size_t aux_bytes;
 };
 
 // Entry points run on the handle's device whatever the caller's current device is (restored on return).
@@ -92,6 +96,7 @@ extern std::atomic<unsigned long long> cp_launch_counter;
 
 // Returns scratch of at least `bytes` (256-byte aligned); grows (synchronising) if needed.
 int cp_ws_reserve(cp_handle_t h, size_t bytes, void **out);
+int cp_aux_reserve(cp_handle_t h, size_t bytes, void **out);
 
 static inline size_t cp_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cp_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(DF_T, 1) df_kernel(const DfParams P) {
     double *scratch = ws + P.c;                // [8][DF_NV]
     double *red = scratch + 8 * DF_NV;         // [DF_NV]
     double *tot = red + DF_NV;                 // [DF_NV]
-    double *dl = tot + DF_NV;                  // [DF_B] deltas of the block, then the block's column means
-    double *mk = dl + DF_B;                    // [DF_B]
+    double *dl = tot + DF_NV;                  // [DF_B] deltas of the block
+    double *zm_s = dl + DF_B;                  // [c] column means   (shared copies: the per-block scalar work of thread 0
+    double *n2_s = zm_s + P.c;                 // [c] centred norms   must not wait on global loads)
     __shared__ int js[2][DF_B];
     __shared__ double ctl_gap, ctl_wmax, ctl_dwmax;
     const int tid = threadIdx.x, cta = blockIdx.x, G = P.G;
@@ -103,7 +104,11 @@ __global__ void __launch_bounds__(DF_T, 1) df_kernel(const DfParams P) {
     const int nrows = max(0, min(P.rows_per_cta, P.m - r0));
     unsigned long long epoch = 0;
     for (int i = tid; i < nrows; i += DF_T) Rs[i] = P.R[r0 + i];
-    for (int j = tid; j < P.c; j += DF_T) ws[j] = P.w[j];
+    for (int j = tid; j < P.c; j += DF_T) {
+        ws[j] = P.w[j];
+        zm_s[j] = P.zmean[j];
+        n2_s[j] = P.norm2[j];
+    }
     __syncthreads();
 
     // ---- duality gap (gap_enet + dual_gap_formulation_A, beta = 0): one pass over all columns
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(DF_T, 1) df_kernel(const DfParams P) {
                 const double r = Rs[i];
 #pragma unroll
                 for (int k = 0; k < DF_B; ++k)
-                    if (j0 + k < P.c) acc[k] = fma((double)P.Z[(int64_t)(j0 + k) * P.ldz + r0 + i] - P.zmean[j0 + k], r, acc[k]);
+                    if (j0 + k < P.c) acc[k] = fma((double)P.Z[(int64_t)(j0 + k) * P.ldz + r0 + i] - zm_s[j0 + k], r, acc[k]);
             }
             block_reduce<DF_B>(acc, scratch, red);
             if (tid < DF_B && j0 + tid < P.c) mine[j0 + tid] = red[tid];
@@ -196,8 +201,8 @@ __global__ void __launch_bounds__(DF_T, 1) df_kernel(const DfParams P) {
                 for (int k = 0; k < DF_B; ++k) {
                     jc[k] = have_cur ? js[par][k] : -1;
                     jp[k] = have_prev ? js[par ^ 1][k] : -1;
-                    mc[k] = jc[k] >= 0 ? P.zmean[jc[k]] : 0.0;
-                    mp[k] = jp[k] >= 0 ? P.zmean[jp[k]] : 0.0;
+                    mc[k] = jc[k] >= 0 ? zm_s[jc[k]] : 0.0;
+                    mp[k] = jp[k] >= 0 ? zm_s[jp[k]] : 0.0;
                     dp[k] = have_prev ? dl[k] : 0.0;
                 }
                 double acc[DF_NV];
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(DF_T, 1) df_kernel(const DfParams P) {
                         d[k] = 0.0;
                         const int j = js[par][k];
                         if (j < 0) continue;
-                        const double nj = P.norm2[j];
+                        const double nj = n2_s[j];
                         if (nj == 0.0) continue;
                         double dot = tot[k];
                         for (int i2 = 0; i2 < k; ++i2) dot -= d[i2] * tot[DF_B + k * (k + 1) / 2 + i2];
@@ -439,7 +444,7 @@ extern "C" int cp_lasso_cd_dataform(cp_handle_t h, const float *Z, int64_t ldz, 
     int rows = (m + G - 1) / G;
     rows = (rows + 3) / 4 * 4;
     G = (m + rows - 1) / rows;
-    const size_t smem = (size_t)(rows + c + 8 * DF_NV + 2 * DF_NV + 2 * DF_B) * sizeof(double);
+    const size_t smem = (size_t)(rows + 3 * c + 8 * DF_NV + 2 * DF_NV + DF_B) * sizeof(double);
     CP_REQUIRE(smem <= 200 * 1024, "cp_lasso_cd_dataform: m = %d rows / c = %d columns do not fit the per-CTA residual slice", m, c);
     static cp_per_device_flag configured;
     if (bool *done = configured.slot(); !*done) {

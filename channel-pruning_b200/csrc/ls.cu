@@ -606,8 +606,13 @@ static int chol_forward(const double *L, int64_t ld, int Kd, const double *Xinv,
         int rc = dgemm_small<false>(Zt + g0, ldz, Xg, GB, F + g0, ldz, n, gs, gs, 1.0, 0.0, cpsmall::TILES_ALL, stream);
         if (rc) return rc;
         if (Kd - g1 > 0) {  // Zt[:, g1:] -= F_g * L[g1:, g0:g1]'
-            rc = dgemm_big(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
-                           cpgemm::TILES_ALL, stream);
+            // few right-hand sides: 128 x 128 tiles would leave most SMs idle on a 512-deep product, 64 x 64 tiles fill them
+            if (cpgemm::num_tiles(n, Kd - g1, cpgemm::TILES_ALL) >= 2 * 148)
+                rc = dgemm_big(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
+                               cpgemm::TILES_ALL, stream);
+            else
+                rc = dgemm_small<false>(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
+                                        cpsmall::TILES_ALL, stream);
             if (rc) return rc;
         }
     }
@@ -625,7 +630,11 @@ static int chol_backward(const double *L, int64_t ld, int Kd, const double *Xinv
         int rc = dgemm_small<true>(F + g0, ldf, Xg, GB, Wt + g0, ldw, n, gs, gs, 1.0, 0.0, cpsmall::TILES_ALL, stream);
         if (rc) return rc;
         if (g0 > 0) {  // F[:, 0:g0] -= Wt_g * L[g0:g0+gs, 0:g0]
-            rc = dgemm_big_nc(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0, stream);
+            if (cpgemm::num_tiles(n, g0, cpgemm::TILES_ALL) >= 2 * 148)
+                rc = dgemm_big_nc(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0, stream);
+            else
+                rc = dgemm_small<true>(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0,
+                                       cpsmall::TILES_ALL, stream);
             if (rc) return rc;
         }
     }
@@ -799,6 +808,26 @@ scatter_cols(const double *__restrict__ W, int Ks, const int32_t *__restrict__ s
     const int t = blockIdx.y;
     if (j < Ks) Wf[(int64_t)t * K + (sel ? sel[j] : j)] = W[(int64_t)t * Ks + j];
 }
+// Xt[k, r] = X[r, k]   (fp32, 32 x 32 tiles through shared memory: both sides coalesced)
+__global__ void __launch_bounds__(256)
+transpose_f32(const float *__restrict__ X, int64_t ldx, int64_t N, int K, float *__restrict__ Xt, int64_t ldt) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    for (int q = ty; q < 32; q += 8)
+        if (r0 + q < N && k0 + tx < K) tile[q][tx] = X[(r0 + q) * ldx + k0 + tx];
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8)
+        if (k0 + q < K && r0 + tx < N) Xt[(int64_t)(k0 + q) * ldt + r0 + tx] = tile[tx][q];
+}
+// WfT[sel_j, t] = (float) W[t, j]   (K x n fp32, zero rows for unselected columns)
+__global__ void __launch_bounds__(256)
+scatter_cols_t(const double *__restrict__ W, int Ks, const int32_t *__restrict__ sel, float *__restrict__ WfT, int n) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int j = blockIdx.y;
+    if (t < n) WfT[(int64_t)(sel ? sel[j] : j) * n + t] = (float)W[(int64_t)t * Ks + j];
+}
 // R[r, t] = float( (Y[r, t] - y_bias[t] - b[t]) - sum_k part_k[r, t] )
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -818,14 +847,46 @@ residual_finish(const T *__restrict__ Y, int64_t ldy, const float *__restrict__ 
 
 extern "C" int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
                               int n, int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, const double *W,
-                              const double *b, float *R_out, int64_t ldr, cp_stream_t stream_) {
+                              const double *b, float *R_out, int64_t ldr, int mode, cp_stream_t stream_) {
     using namespace cpgemm;
     CP_REQUIRE(h && X && Yraw && W && b && R_out, "cp_ls_residual: NULL argument");
     CP_REQUIRE(N > 0 && K > 0 && n > 0 && Ksel > 0 && Ksel <= K && ldx >= K && ldy >= n && ldr >= n, "cp_ls_residual: bad shape");
     CP_REQUIRE(sel_cols || Ksel == K, "cp_ls_residual: sel_cols may be NULL only when every column is used");
     CP_REQUIRE(y_dtype == CP_F32 || y_dtype == CP_F64, "cp_ls_residual: unknown y_dtype %d", y_dtype);
+    CP_REQUIRE(mode == CP_GRAM_FP64 || mode == CP_GRAM_3XTF32, "cp_ls_residual: unknown mode %d", mode);
     CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (mode == CP_GRAM_3XTF32 && N % 4 == 0 && N >= 128 && K >= 64 && n % 4 == 0) {
+        // Tensor-core variant: X Wf' = (X')'(Wf') is a product of the cp_gram shape (reduction over the ROWS of both
+        // operands) once X is transposed: 3xTF32 on the tcgen05 pipe instead of 2 N K n flops on the FP64 pipe.  Its
+        // ~4e-7 relative error in the prediction perturbs the correction ~sqrt(N) times less than the same relative
+        // error in the Gram matrix did (the residual error is uncorrelated noise, not a structured change of G).
+        const int64_t ldt = N;
+        void *aux = nullptr;
+        int rc = cp_aux_reserve(h, cp_carver::need((size_t)K * ldt, 4) + cp_carver::need((size_t)K * n, 4) +
+                                       cp_carver::need((size_t)N * n, 8), &aux);
+        if (rc) return rc;
+        cp_carver cv(aux);
+        float *Xt = cv.take<float>((size_t)K * ldt);
+        float *WfT = cv.take<float>((size_t)K * n);
+        double *P = cv.take<double>((size_t)N * n);
+        transpose_f32<<<dim3(cp_cdiv(N, 32), cp_cdiv(K, 32)), 256, 0, stream>>>(X, ldx, N, K, Xt, ldt);
+        CP_CHECK_LAUNCH();
+        CP_CUDA(cudaMemsetAsync(WfT, 0, (size_t)K * n * sizeof(float), stream));
+        scatter_cols_t<<<dim3(cp_cdiv(n, 256), Ksel), 256, 0, stream>>>(W, Ksel, sel_cols, WfT, n);
+        CP_CHECK_LAUNCH();
+        rc = cp_gram(h, Xt, K, (int)N, ldt, WfT, CP_F32, n, n, nullptr, nullptr, 0, nullptr, P, nullptr, nullptr, nullptr,
+                     CP_GRAM_3XTF32, stream_);
+        if (rc) return rc;
+        const int64_t count = N * (int64_t)n;
+        const unsigned nblk = (unsigned)((count + 255) / 256);
+        if (y_dtype == CP_F32)
+            residual_finish<float><<<nblk, 256, 0, stream>>>((const float *)Yraw, ldy, y_bias, b, P, 0, 1, N, n, R_out, ldr);
+        else
+            residual_finish<double><<<nblk, 256, 0, stream>>>((const double *)Yraw, ldy, y_bias, b, P, 0, 1, N, n, R_out, ldr);
+        CP_CHECK_LAUNCH();
+        return CP_OK;
+    }
     const int64_t ldw = ld_for(K);
     // X Wf' in fp64 (exact products of fp32 data with the fp64 weights): 128 x 128 tiles, reduction split so that the
     // tile count fills whole waves of the SMs (5000 x 512 is 160 tiles on 148 SMs: two waves for 1.08 waves of work)

@@ -315,8 +315,9 @@ class Engine:
                                           self._p(W, "double*"), self._p(b, "double*"), acc, self._s()))
         return W, b
 
-    def ls_residual(self, X, Y, y_bias, sel_cols, W, b):
-        """fp32 residual (N, n) of the fit (W, b) on columns sel_cols, computed from the data in fp64 (cp_ls_residual)."""
+    def ls_residual(self, X, Y, y_bias, sel_cols, W, b, mode=None):
+        """fp32 residual (N, n) of the fit (W, b) on columns sel_cols, computed from the data (cp_ls_residual): prediction
+        in fp64 (mode 0) or on the tensor cores (mode 1, default = the engine's Gram mode)."""
         N, K = X.shape
         n = Y.shape[1]
         Ks = sel_cols.numel() if sel_cols is not None else K
@@ -325,14 +326,14 @@ class Engine:
                                            0 if Y.dtype == torch.float32 else 1, n, Y.stride(0),
                                            self._p(y_bias, "const float*"), self._p(sel_cols, "const int32_t*"), Ks,
                                            self._p(W, "const double*"), self._p(b, "const double*"), self._p(R, "float*"),
-                                           R.stride(0), self._s()))
+                                           R.stride(0), self.gram_mode if mode is None else mode, self._s()))
         return R
 
     def ls_refine(self, g, X, Y, y_bias, sel_cols, W, b):
         """One step of iterative refinement of (W, b) against the factor the last ls_solve left on this handle:
         residual from the data (exact fp64), its cross products with X on the tensor cores, forward/backward
         substitution, correction added in place.  Removes the error tensor-core statistics put into the solution."""
-        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b)
+        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b, mode=g["mode"])
         gr = self.gram(X, R, want_G=False, mode=g["mode"])
         self.ls_resolve(gr["B"], g["sx"], gr["sy"], sel_cols, accumulate_into=(W, b))
         return W, b

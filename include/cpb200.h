@@ -215,8 +215,9 @@ int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const doub
                   const int32_t *sel_cols, double *W_out, double *b_out, int accumulate, cp_stream_t stream);
 
 /*
- * Residual of a least-squares solve, from the DATA (not from the Gram statistics): exact products of the fp32 features
- * with the fp64 weights, fp64 accumulation, rounded to fp32 on output --
+ * Residual of a least-squares solve, from the DATA (not from the Gram statistics).  mode CP_GRAM_FP64: exact products
+ * of the fp32 features with the fp64 weights, fp64 accumulation; mode CP_GRAM_3XTF32: the prediction X W' on the
+ * tensor cores (X transposed once, then a product of the cp_gram shape).  Rounded to fp32 on output --
  *   R_out[r, t] = (Y[r, t] - y_bias[t]) - sum_j X[r, sel_j] W[t, j] - b[t]           (N x n, leading dimension ldr)
  * With statistics from the tensor-core Gram (~4e-7 relative), refitting this residual against the same factor
  * (cp_gram of (X, R) + cp_ls_resolve(accumulate = 1)) removes the error the statistics put into W and b: one step of
@@ -224,7 +225,7 @@ int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const doub
  */
 int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
                    int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, const double *W, const double *b,
-                   float *R_out, int64_t ldr, cp_stream_t stream);
+                   float *R_out, int64_t ldr, int mode, cp_stream_t stream);
 
 /*
  * ---- dense fp64 building blocks of the 3C companions (VH_decompose, nonlinear_fc, ITQ_decompose) ----

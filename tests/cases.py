@@ -163,6 +163,8 @@ def r3_inputs(B, H, widths, nimgbatches, seed):
 R3_CASES = {
     # rankdic x 4/3 (keep = 3): conv1_2 22, conv2_1 49, conv2_2 62 -- widths chosen so that rank <= n and that the
     # `if d_c < rank: d_c = rank` floor (net.py:1349) is exercised at conv2_1 (int(56/1.15) = 48 < 49)
-    "r3_small": dict(gen=dict(B=4, H=12, widths=(12, 28, 56, 64), nimgbatches=20, seed=61), nBatches=20, P=10,
+    # conv2_2 is kept wide (96, like VGG's 2:1 ratio of width to rank): truncating 64 channels to rank 62 sits on a
+    # near-degenerate pair of singular values, where the reference's own result moves with LAPACK's rounding
+    "r3_small": dict(gen=dict(B=4, H=12, widths=(12, 28, 56, 96), nimgbatches=20, seed=61), nBatches=20, P=10,
                      np_seed=71),
 }
