@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=13)
     ap.add_argument("--gram", default="tc", choices=["tc", "fp64"],
                     help="arithmetic of the big Gram products: tc = tcgen05 3xTF32 (default), fp64 = DFMA")
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
+                    help="HBM layout of the bottom blobs for the device-resident arm (nhwc: TMA gather; the host copies of "
+                         "the e2e arm keep the reference's NCHW blob order)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -354,7 +357,7 @@ def parity_check(shapes, datas, results, names):
         if s.name not in names or s.name in out["layers_checked"]:
             continue
         t0 = time.perf_counter()
-        oi, oW, oB, info = oracle_on_arrays(s, d["fmap"].cpu().numpy(), d["randx"].cpu().numpy(), d["randy"].cpu().numpy(),
+        oi, oW, oB, info = oracle_on_arrays(s, cpb200.synth.fmap_nchw(d).contiguous().cpu().numpy(), d["randx"].cpu().numpy(), d["randy"].cpu().numpy(),
                                             d["W2"].cpu().numpy(), d["b2"].cpu().numpy(), d["feats"].cpu().numpy(),
                                             d["samples"].cpu().numpy(), d["seeds"])
         W = (r.W if not r.W.is_cuda else r.W.cpu()).numpy().reshape(-1)
@@ -419,7 +422,8 @@ def run_gpu(args):
             want_e2e = False
             e2e_skip = "host has %.0f GB available, the pinned feature maps of %d ranks need %.0f GB" % (
                 avail / 1e9, world, need / 1e9)
-    datas = [cpb200.synth.make_problem_device(shapes[i], 1000 + i, eng, pinned_host=want_e2e) for i in mine]
+    datas = [cpb200.synth.make_problem_device(shapes[i], 1000 + i, eng, pinned_host=want_e2e, layout=args.layout)
+             for i in mine]
     sizes = [pruner.slot_size(s.c, s.n, s.k * s.k, s.rank, .1) for s in shapes]
     per_rank = [sum(sizes[i] for i in range(len(shapes)) if owner[i] == r) for r in range(world)]
     gbuf = torch.zeros(max(per_rank), dtype=torch.float64, device=dev)
@@ -513,7 +517,8 @@ def run_gpu(args):
         s_mine = [i for i, o in enumerate(s_owner) if o == rank]
         s_shapes = [base[i] for i in s_mine]
         have = {i: d for i, d in zip(mine, datas)}
-        s_datas = [have[i] if i in have else cpb200.synth.make_problem_device(base[i], 1000 + i, eng) for i in s_mine]
+        s_datas = [have[i] if i in have else cpb200.synth.make_problem_device(base[i], 1000 + i, eng, layout=args.layout)
+                   for i in s_mine]
         s_sizes = [pruner.slot_size(s.c, s.n, s.k * s.k, s.rank, .1) for s in base]
 
         def sstep():
@@ -538,8 +543,9 @@ def run_gpu(args):
         traffic = ncu_traffic()
         s = max(base, key=lambda q: q.K)
         names = [shapes[i].name for i in mine]
-        d = datas[names.index(s.name)] if s.name in names else cpb200.synth.make_problem_device(s, 5, eng)
-        X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+        d = datas[names.index(s.name)] if s.name in names else cpb200.synth.make_problem_device(s, 5, eng, layout=args.layout)
+        lay = d.get("layout", "nchw")
+        X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True, layout=lay)
         t_ms = timed_alone(torch, dev, lambda: eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False))
         flops = float(s.N) * s.K * (s.K + 1) + 2.0 * s.N * s.K * s.n  # symmetric half + X'Y
         achieved = flops / (t_ms / 1e3) / 1e12
@@ -557,10 +563,20 @@ def run_gpu(args):
                 "ms": t_ms, "algorithmic_flops": flops, "peak_source": peak_note,
                 "mode": "fp64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "3xtf32"}
         t_g = timed_alone(torch, dev, lambda: eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad,
-                                                               s.stride, relu=True, out=X))
+                                                               s.stride, relu=True, out=X, layout=lay))
         gbytes = 8.0 * s.N * s.K  # unique patch elements read + X written
-        trg = traffic.get("patch_gather")
-        roof_g = {"kernel": "cp_patch_gather (sparse-point im2col, NCHW) on %s: N=%d K=%d" % (s.name, s.N, s.K),
+        trg = traffic.get("patch_gather_nhwc_tma" if lay == "nhwc" else "patch_gather")
+        # the other layout, for the record (same values, same X)
+        fm_other = cpb200.synth.fmap_nchw(d).contiguous() if lay == "nhwc" else d["fmap"].permute(0, 2, 3, 1).contiguous()
+        other = "nchw" if lay == "nhwc" else "nhwc"
+        X2 = torch.empty_like(X)
+        t_o = timed_alone(torch, dev, lambda: eng.patch_gather(fm_other, d["randx"], d["randy"], s.B, s.P, s.k, s.pad,
+                                                               s.stride, relu=True, out=X2, layout=other))
+        same_X = bool(torch.equal(X, X2))
+        del fm_other, X2
+        roof_g = {"kernel": "cp_patch_gather (sparse-point im2col, %s%s) on %s: N=%d K=%d" % (
+                      lay.upper(), ", TMA window loads + bulk row stores" if lay == "nhwc" else "", s.name, s.N, s.K),
+                  "other_layout": {"layout": other, "ms": t_o, "GB/s": gbytes / (t_o / 1e3) / 1e9, "X_bit_identical": same_X},
                   "bound": "hbm", "achieved": gbytes / (t_g / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": gbytes / (t_g / 1e3) / 1e9 / peaks["hbm_gbs"],
                   "traffic": trg["bytes"] if trg else None, "traffic_source": trg["source"] if trg else None,
@@ -580,7 +596,7 @@ def run_gpu(args):
     if rank == 0:
         kept = [int(r.idxs.sum()) for r in res]
         cfg = config_dict(args, base, world)
-        cfg.update(streams=args.streams, kept_channels_rank0=kept)
+        cfg.update(streams=args.streams, kept_channels_rank0=kept, hbm_layout=args.layout)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

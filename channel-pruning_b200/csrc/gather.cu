@@ -113,6 +113,19 @@ point_gather(const float *__restrict__ fmap, const int32_t *__restrict__ randx,
 
 }  // namespace
 
+// gather_tma.cu
+bool cp_gather_tma_eligible(const float *fmap, int c, int k, float *X_out, int64_t ldx);
+int cp_patch_gather_tma(cp_handle_t h, const float *fmap, int nbatch, int B, int c, int H, int W, const int32_t *randx,
+                        const int32_t *randy, int P, int k, int pad, int stride, int relu, float *X_out, int64_t ldx,
+                        cudaStream_t stream);
+static bool tma_enabled() {  // CPB200_GATHER_TMA=0 keeps the SIMT kernel (A/B measurements)
+    static const bool on = [] {
+        const char *e = getenv("CPB200_GATHER_TMA");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 extern "C" int cp_patch_gather(cp_handle_t h, const float *fmap, int nbatch, int B, int c, int H, int W,
                                int layout, const int32_t *randx, const int32_t *randy, int P, int k, int pad,
                                int stride, int relu, float *X_out, int64_t ldx, cp_stream_t stream_) {
@@ -144,6 +157,9 @@ extern "C" int cp_patch_gather(cp_handle_t h, const float *fmap, int nbatch, int
             patch_gather_nchw<1><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, rows, B, c, H, W, P, k, pad, stride, relu);
         else
             patch_gather_nchw<0><<<grid, 256, 0, stream>>>(fmap, randx, randy, X_out, ldx, rows, B, c, H, W, P, k, pad, stride, relu);
+    } else if (tma_enabled() && cp_gather_tma_eligible(fmap, c, k, X_out, ldx)) {
+        // NHWC map in HBM: whole windows by TMA, rows out by bulk store (gather_tma.cu)
+        return cp_patch_gather_tma(h, fmap, nbatch, B, c, H, W, randx, randy, P, k, pad, stride, relu, X_out, ldx, stream);
     } else {
         const size_t smem = (size_t)k * k * (NHWC_CT + 1) * sizeof(float);
         CP_REQUIRE(smem <= 48 * 1024, "cp_patch_gather: kernel_size %d too large for the NHWC tile", k);

@@ -29,6 +29,8 @@ MAX_PROBES = 64
 # most collinear column); below that the layer is re-solved from exact-product fp64 statistics.
 LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.005"))
 LS_REFINE = os.environ.get("CPB200_LS_REFINE", "1") == "1"
+# prediction X W' of the refinement residual: "tc" (tensor cores, 3xTF32) or "fp64" (SIMT fp64 GEMM); A/B knob
+LS_RESID = os.environ.get("CPB200_LS_RESID", "tc")
 
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
 GRAM_FP64, GRAM_3XTF32 = 0, 1
@@ -333,7 +335,7 @@ class Engine:
         """One step of iterative refinement of (W, b) against the factor the last ls_solve left on this handle:
         residual from the data (exact fp64), its cross products with X on the tensor cores, forward/backward
         substitution, correction added in place.  Removes the error tensor-core statistics put into the solution."""
-        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b, mode=g["mode"])
+        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b, mode=g["mode"] if LS_RESID == "tc" else GRAM_FP64)
         gr = self.gram(X, R, want_G=False, mode=g["mode"])
         self.ls_resolve(gr["B"], g["sx"], gr["sy"], sel_cols, accumulate_into=(W, b))
         return W, b

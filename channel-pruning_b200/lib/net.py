@@ -349,6 +349,9 @@ class Net:
 
         topology = []
         trace = getattr(self, "_trace", None)  # optional list: (conv, stage, {name: array}) per stage (debugging aid)
+        # optional test hook, called where the reference enters VH_decompose / ITQ_decompose / dictionary_kernel and
+        # at the end ('vh' | 'itq' | 'prune' | 'final'); it may inspect and overwrite the live parameters
+        checkpoint = getattr(self, "_checkpoint", None) or (lambda stage: None)
         for conv, convnext in zip(convs[1:], convs[2:] + ['pool5']):
             conv_V = underline(conv, 'V')
             conv_H = underline(conv, 'H')
@@ -360,6 +363,7 @@ class Net:
             if d_c < rank:
                 d_c = rank  # :1349
             # ---- spatial decomposition (:1351-1380)
+            checkpoint("vh")
             weights = self._w[conv]
             if conv in self.selection:
                 weights = weights[:, torch.as_tensor(self.selection[conv], device=dev), :, :]
@@ -376,6 +380,7 @@ class Net:
             if trace is not None:
                 trace.append((conv, "vh", dict(VHr=VHr.copy(), b=np.asarray(b).copy(), X=X.copy(), Y=Y.copy())))
             # ---- channel decomposition (:1384-1404)
+            checkpoint("itq")
             feats_dict, _ = self.extract_features(names=conv, points_dict=self._points_dict, save=1)
             Yf = feats_dict[conv]
             W1, W2, B, W12 = ITQ_decompose(Yf, self._feats_dict[conv], H, d_prime, bias=self._b[conv].cpu().numpy(),
@@ -391,6 +396,7 @@ class Net:
             # ---- channel pruning (:1406-1459)
             if dcfgs.dic.vh and (conv in alldic or conv in pooldic) and (convnext in self.convs):
                 X_name = self.bottom_names[convnext][0] if conv in pooldic else conv  # :1411-1414
+                checkpoint("prune")
                 idxs, W2n, B2n = self.dictionary_kernel(X_name, None, d_c, convnext, None)
                 self.selection[convnext] = idxs
                 it = torch.as_tensor(idxs, device=dev)
@@ -406,5 +412,6 @@ class Net:
                                                       ls=dict(DictionaryInfo.last.get("ls", {})))))
             topology.append({"V": conv_V, "H": conv_H, "P": conv_P, "rank": int(rank),
                              "num_output": int(self.WPQ[(conv_P, 0)].shape[0])})
+        checkpoint("final")
         new_pt = {"prefix": prefix, "layers": topology}
         return self.WPQ, new_pt

@@ -180,6 +180,7 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             if stream is not None:
                 stream.wait_stream(main)
             X = None
+            layout = "nchw"
             if pre[i] is not None:
                 kind, obj, ev = pre[i]
                 stream.wait_event(ev)
@@ -196,8 +197,10 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
                 fmap = d["fmap_host"]
             else:
                 fmap = d["fmap"]
+                layout = d.get("layout", "nchw")  # host copies keep the reference's NCHW blob order
             if X is None:
-                X = eng.patch_gather(fmap, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True)
+                X = eng.patch_gather(fmap, d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True,
+                                     layout=layout)
             W2m = d["W2"].reshape(s.n, s.K)
             if s.rank == s.c:
                 g_full = eng.gram(X, d["feats"], y_bias=d["b2"])

@@ -128,10 +128,18 @@ def gather_patches_numpy(fmap, randx, randy, B, k, pad, stride, relu):
     return out
 
 
-def make_problem_device(shape: LayerShape, seed: int, eng, noise=0.01, pinned_host=False):
+def fmap_nchw(d):
+    """The feature map of a problem dict in the reference's blob order (nimg, c, H, W), whatever its HBM layout."""
+    return d["fmap"].permute(0, 3, 1, 2) if d.get("layout", "nchw") == "nhwc" else d["fmap"]
+
+
+def make_problem_device(shape: LayerShape, seed: int, eng, noise=0.01, pinned_host=False, layout="nchw"):
     """Device instance (torch CUDA generator), sized for BASELINE configs (GBs of feature maps).
     feats are produced with the library's own gather + a torch fp64 matmul: this is data
-    generation, outside any timed region."""
+    generation, outside any timed region.
+    layout: how the bottom blob sits in HBM.  'nhwc' (channels last, what a device-side forward provider hands over)
+    takes the TMA gather; the VALUES are those of the 'nchw' instance of the same seed.  The pinned host copy
+    (fmap_host) always keeps the reference's NCHW blob order."""
     import torch
 
     s = shape
@@ -151,9 +159,13 @@ def make_problem_device(shape: LayerShape, seed: int, eng, noise=0.01, pinned_ho
     feats = Y.to(torch.float32)
     samples = torch.as_tensor(r.randint(0, s.N, s.S).astype(np.int32), device=dev)
     seeds = r.randint(0, 2147483647, size=64)
-    out = dict(fmap=fmap, randx=randx, randy=randy, W2=W2, b2=b2, feats=feats, samples=samples, seeds=seeds)
+    out = dict(fmap=fmap, randx=randx, randy=randy, W2=W2, b2=b2, feats=feats, samples=samples, seeds=seeds,
+               layout=layout)
     del X, Y
     if pinned_host:
         out["fmap_host"] = torch.empty(fmap.shape, dtype=torch.float32, pin_memory=True)
         out["fmap_host"].copy_(fmap)
+    if layout == "nhwc":
+        out["fmap"] = fmap.permute(0, 2, 3, 1).contiguous()
+        del fmap
     return out

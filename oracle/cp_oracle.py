@@ -658,10 +658,14 @@ class NumpyNet:
         return lambda batch: self.forward_blobs(pd[(batch, 0)])
 
 
-def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=None):
+def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=None, checkpoint=None):
     """lib/net.py:1292-1471 on a NumpyNet whose frozen ``_feats_dict`` / ``_points_dict`` are set (points_dict carries
-    the images under (batch, 0) like the reference's, net.py:441).  Mutates net.weights / net.biases; returns WPQ."""
+    the images under (batch, 0) like the reference's, net.py:441).  Mutates net.weights / net.biases; returns WPQ.
+    checkpoint(stage): test hook called where the reference enters VH_decompose / ITQ_decompose / dictionary_kernel and
+    at the end ('vh', 'itq', 'prune', 'final'); it may inspect and overwrite net.weights / net.biases (make_golden.py
+    stores the reference's live state at exactly those points)."""
     state = state if state is not None else DictState()
+    checkpoint = checkpoint or (lambda stage: None)
     convs = net.convs
     net.WPQ, net.selection = {}, {}
     end = 5
@@ -691,6 +695,7 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=N
         if d_c < rank:
             d_c = rank  # :1349
         # ---- spatial decomposition (:1351-1380)
+        checkpoint("vh")
         weights = net.weights[conv]
         if conv in net.selection:
             weights = weights[:, net.selection[conv], :, :]
@@ -707,6 +712,7 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=N
         if trace is not None:
             trace.append((conv, "vh", dict(VHr=VHr.copy(), b=np.asarray(b).copy(), X=X.copy(), Y=Y.copy())))
         # ---- channel decomposition (:1384-1404)
+        checkpoint("itq")
         feats_new, _ = extract_features(net.frozen_forward(), [conv], None, None, points_dict=net._points_dict)
         W1, W2, B, W12 = ITQ_decompose(feats_new[conv], net._feats_dict[conv], H, d_prime, bias=net.biases[conv], Wr=VHr)
         setConv(conv, W12.copy())
@@ -721,6 +727,7 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=N
         if (conv in alldic or conv in pooldic) and (convnext in net.convs):
             X_name = net.bottom_names[convnext][0] if conv in pooldic else conv
             info = {} if infos is not None else None
+            checkpoint("prune")
             idxs, W2n, B2n = dictionary_kernel(net.frozen_forward(), X_name, net.spec(convnext), net.weights[convnext],
                                                net.biases[convnext], net._feats_dict[convnext], net._points_dict, d_c,
                                                state=state, form=form, info=info)
@@ -735,4 +742,5 @@ def R3(net, keep=3., c_ratio=1.15, state=None, form="dense", infos=None, trace=N
                 trace.append((conv, "prune", dict(idxs=idxs.copy(), W2=W2n.copy(), B2=np.asarray(B2n).copy())))
             if infos is not None:
                 infos[convnext] = info
+    checkpoint("final")
     return net.WPQ

@@ -198,8 +198,38 @@ def run_r3_cases(NET, CF, D):
         np.random.seed(spec["np_seed"])
         feats_dict, points_dict = net.extract_features(net.convs, save=1)
         net.load_frozen(feats_dict=feats_dict, points_dict=points_dict)
-        WPQ, new_pt = net.R3()
-        out = {}
+        # Stage snapshots: the live weights / biases on ENTRY of each of the three per-layer solvers (and at the end).
+        # The walk is error compensating, so a deviation in one stage feeds the next through features of nearly
+        # rank-deficient blobs; the snapshots let a test re-synchronise an implementation stage by stage
+        # (tests/test_gpu_r3.py: teacher-forced walk) instead of comparing only the compounded end result.
+        snaps = []
+
+        def snap(stage):
+            snaps.append((stage, {nm: weights[nm].copy() for nm in net.convs}, {nm: biases[nm].copy() for nm in net.convs}))
+
+        def wrap(fn, stage):
+            def inner(*a, **k):
+                snap(stage)
+                return fn(*a, **k)
+            return inner
+
+        orig_vh, orig_itq = NET.VH_decompose, NET.ITQ_decompose
+        NET.VH_decompose, NET.ITQ_decompose = wrap(orig_vh, "vh"), wrap(orig_itq, "itq")
+        net.dictionary_kernel = wrap(net.dictionary_kernel, "prune")
+        try:
+            WPQ, new_pt = net.R3()
+        finally:
+            NET.VH_decompose, NET.ITQ_decompose = orig_vh, orig_itq
+        snap("final")
+        out = {"snap_stages": np.array([st for st, _, _ in snaps])}
+        prev_w, prev_b = {}, {}
+        for i, (st, w_, b_) in enumerate(snaps):  # only what changed since the previous snapshot
+            for nm in net.convs:
+                if nm not in prev_w or not np.array_equal(prev_w[nm], w_[nm]):
+                    out["snap__%d__w__%s" % (i, nm)] = w_[nm]
+                if nm not in prev_b or not np.array_equal(prev_b[nm], b_[nm]):
+                    out["snap__%d__b__%s" % (i, nm)] = b_[nm]
+            prev_w, prev_b = w_, b_
         for k, v in WPQ.items():
             out["WPQ__" + ("%s__%d" % k if isinstance(k, tuple) else k)] = np.asarray(v)
         for k, v in net.selection.items():

@@ -69,6 +69,33 @@ def test_gathers_bit_exact_vs_reference_golden(engine, golden_dir, name, layout)
     np.testing.assert_array_equal(Yf.cpu().numpy().astype(np.float64), g["feats_conv2"])
 
 
+@pytest.mark.parametrize("c,k,pad,stride,H", [(16, 3, 1, 1, 9), (64, 3, 1, 1, 14), (384, 3, 1, 2, 13), (512, 3, 1, 1, 7),
+                                              (1024, 1, 0, 1, 6), (96, 5, 2, 1, 8), (2048, 1, 0, 2, 7), (256, 3, 0, 1, 10)])
+def test_tma_gather_is_bit_identical_to_the_nchw_kernel(engine, c, k, pad, stride, H):
+    """The NHWC TMA path (whole windows by cp.async.bulk.tensor, zero fill for the padding taps, bulk row stores)
+    against the SIMT NCHW kernel that the reference goldens pin: every corner and border point is sampled."""
+    g = torch.Generator(device=engine.device)
+    g.manual_seed(c * 7 + k)
+    B, nb = 3, 4
+    fm = torch.randn((nb * B, c, H, H), generator=g, device=engine.device)
+    Ho = (H + 2 * pad - k) // stride + 1
+    pts = [(0, 0), (0, Ho - 1), (Ho - 1, 0), (Ho - 1, Ho - 1), (Ho // 2, Ho // 2), (1 % Ho, Ho - 1), (Ho - 1, 1 % Ho)]
+    P = len(pts)
+    rx = torch.tensor([[p[0] for p in pts]] * nb, dtype=torch.int32, device=engine.device)
+    ry = torch.tensor([[p[1] for p in pts]] * nb, dtype=torch.int32, device=engine.device)
+    rx[1] = rx[1].flip(0)
+    fm_l = fm.permute(0, 2, 3, 1).contiguous()
+    for relu in (False, True):
+        want = engine.patch_gather(fm, rx, ry, B, P, k, pad, stride, relu=relu, layout="nchw")
+        got = engine.patch_gather(fm_l, rx, ry, B, P, k, pad, stride, relu=relu, layout="nhwc")
+        assert torch.equal(want, got)
+    # rows with a leading dimension larger than K (X riding in a wider buffer)
+    K = c * k * k
+    wide = torch.full((nb * P * B, K + 8), -7.0, device=engine.device)
+    engine.patch_gather(fm_l, rx, ry, B, P, k, pad, stride, relu=True, layout="nhwc", out=wide[:, :K])
+    assert torch.equal(wide[:, :K], want) and bool((wide[:, K:] == -7.0).all())
+
+
 def test_gather_rejects_bad_arguments(engine):
     import cpb200
 

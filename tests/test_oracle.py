@@ -195,6 +195,40 @@ def test_itq_decompose_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(_sign_align(W2, g["W2"], 1), g["W2"], rtol=0, atol=1e-7 * np.abs(g["W2"]).max())
 
 
+class StageSync:
+    """R3 checkpoint hook (cp_oracle.R3 / cpb200 Net.R3): at every point where the reference enters one of its three
+    per-layer solvers -- and at the end -- compares the live parameters with the snapshot the reference run left in the
+    golden (oracle/make_golden.py: run_r3_cases) and, when ``put`` is given, replaces them with the reference's
+    (teacher forcing: every stage then starts from the reference's exact state, so its own deviation is measured
+    instead of the compounded one)."""
+
+    def __init__(self, golden, get, put, tol):
+        self.g, self.get, self.put, self.tol = golden, get, put, tol
+        self.i, self.worst, self.log = 0, 0.0, []
+
+    def __call__(self, stage):
+        stages = [str(x) for x in self.g["snap_stages"]]
+        assert self.i < len(stages) and stage == stages[self.i], (self.i, stage, stages)
+        pre = "snap__%d__" % self.i
+        for key in [k for k in self.g.files if k.startswith(pre)]:
+            kind, nm = key[len(pre):].split("__")
+            ref = self.g[key]
+            live = np.asarray(self.get(kind, nm), dtype=np.float64)
+            if kind == "w":
+                e = float(np.linalg.norm(live - ref) / max(np.linalg.norm(ref), 1e-30))
+            else:
+                e = float(np.abs(live - ref).max() / max(1.0, np.abs(ref).max()))
+            self.log.append((self.i, stage, kind, nm, e))
+            self.worst = max(self.worst, e)
+            assert e <= self.tol, (self.i, stage, kind, nm, e)
+            if self.put is not None:
+                self.put(kind, nm, ref)
+        self.i += 1
+
+    def done(self):
+        return self.i == len(self.g["snap_stages"])
+
+
 def r3_compare(golden, WPQ, selection, weights, biases, tol_inv=1e-6, tol_fac=1e-5):
     """Compares an R3 outcome with the reference's golden: selections exactly; sign-invariant quantities (live
     weights/biases, the P-layer biases) tightly; the individual V / H / P factors up to the sign of each component."""
@@ -246,7 +280,9 @@ def test_r3_walk_matches_reference_golden(golden_dir, name):
         np.testing.assert_array_equal(feats[nm], g["feats__" + nm])
     net._feats_dict, net._points_dict = feats, pd
     st = O.DictState(alpha=1e-3)
-    WPQ = O.R3(net, state=st)
+    sync = StageSync(g, lambda kind, nm: (net.weights if kind == "w" else net.biases)[nm], None, tol=1e-6)
+    WPQ = O.R3(net, state=st, checkpoint=sync)
+    assert sync.done()
     assert st.alpha == float(g["alpha_final"])
     assert np.random.randint(0, 1 << 30) == int(g["rng_after"])
     r3_compare(g, WPQ, net.selection, net.weights, net.biases)
