@@ -350,6 +350,8 @@ def parity_check(shapes, datas, results, names):
     """Re-solves the named layer problems with the CPU oracle on the SAME arrays the GPU just used and compares."""
     import numpy as np
 
+    import cpb200
+
     out = {"layers_checked": [], "mask_equal": True, "probes_equal": True, "rel_W_max": 0.0, "rel_b_max": 0.0,
            "oracle": "cp_oracle.dictionary_kernel (sklearn data-form coordinate descent restated in C, LAPACK gelsd)",
            "tolerance": {"rel_W": 1e-4, "rel_b": 1e-4}}

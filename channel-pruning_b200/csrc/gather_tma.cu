@@ -5,20 +5,24 @@
 // contiguous floats (6 KB at c = 512): a 4-D tensor map over (c, W, H, image) with box (c_box, k, k, 1) lets ONE
 // cp.async.bulk.tensor request fetch it, zero-filling the taps that fall into the padding (out-of-range coordinates,
 // net.py:631-632), and the finished patch row (K = c k k contiguous floats of X) leaves through a bulk shared->global
-// copy.  A persistent CTA per SM keeps a ring of windows in flight:
-//     producer thread   mbarrier expect_tx + TMA loads of the next windows (ring of NS stages)
-//     256 consumers     [tap][channel] -> [channel][tap] (the reference's column order a*k*k + p) with the ReLU folded in,
+// copy.  Persistent CTAs (as many per SM as shared memory allows: the latency of one row -- TMA flight, two CTA-wide
+// hand-offs, the transposition -- is hidden by the other CTAs of the SM) each keep a ring of windows in flight:
+//     producer warp     the 32 lanes prefetch the sampled coordinates of the next 32 rows (one global-load latency per
+//                       32 rows instead of per row); one lane arms the mbarrier and issues the TMA loads (ring of NS stages)
+//     128 consumers     [tap][channel] -> [channel][tap] (the reference's column order a*k*k + p) with the ReLU folded in,
 //                       conflict-free both ways (lanes walk channels; the tap stride k*k is odd)
 //     one consumer      bulk store of the row, two rows in flight
 // Bytes: the window is read once and the row written once -- 8 N K bytes, the algorithmic figure of SURVEY.md 8(d).
 // Bound: HBM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int GT_CONS = 256;             // consumer threads
+constexpr int GT_CONS = 128;             // consumer threads
 constexpr int GT_THREADS = GT_CONS + 32; // + producer warp
 constexpr int GT_OUT = 2;                // output rows in flight
 
@@ -64,10 +68,11 @@ __device__ __forceinline__ void g_bulk_store(void *gdst, uint32_t ssrc, uint32_t
 }
 __device__ __forceinline__ void g_cons_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GT_CONS) : "memory"); }
 
-__global__ void __launch_bounds__(GT_THREADS, 1)
+template <int K2>  // k*k known at compile time (1, 9, 25) or 0
+__global__ void __launch_bounds__(GT_THREADS)
 patch_gather_nhwc_tma(const __grid_constant__ CUtensorMap map, const GtParams P) {
     extern __shared__ __align__(128) unsigned char gsm_raw[];
-    const int k2 = P.k * P.k, K = P.c * k2;
+    const int k2 = K2 > 0 ? K2 : P.k * P.k, K = P.c * k2;
     const uint32_t stage_bytes = (uint32_t)K * 4u;
     // layout: [nstage][K] input windows ([box][tap][c_box]), [GT_OUT][K] output rows, mbarriers
     unsigned char *base = (unsigned char *)(((uintptr_t)gsm_raw + 127) & ~(uintptr_t)127);
@@ -88,23 +93,36 @@ patch_gather_nhwc_tma(const __grid_constant__ CUtensorMap map, const GtParams P)
     __syncthreads();
     const int64_t first = blockIdx.x, step = gridDim.x;
     if (tid >= GT_CONS) {
-        // ---------------- producer: one thread
-        if (tid == GT_CONS) {
-            int it = 0;
-            for (int64_t r = first; r < P.rows; r += step, ++it) {
-                const int s = it % P.nstage;
-                const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
-                if (it >= P.nstage) g_mbar_wait(empty(s), ph ^ 1);  // the consumers have released the stage
+        // ---------------- producer warp
+        const int lane = tid & 31;
+        int it = 0;
+        for (int64_t rb = first; rb < P.rows; rb += 32 * step) {
+            // lane l looks up the window of row rb + l * step
+            const int64_t r = rb + (int64_t)lane * step;
+            int x0 = 0, y0 = 0, img = 0;
+            if (r < P.rows) {
                 const int img_in_batch = (int)(r % P.B);
                 const int64_t bp = r / P.B;  // batch * P + point
                 const int batch = (int)(bp / P.P);
-                const int y0 = P.stride * P.randx[bp] - P.pad;  // window origin, rows  (feat[:,:,x,y]: x indexes H)
-                const int x0 = P.stride * P.randy[bp] - P.pad;
-                g_mbar_expect_tx(full(s), stage_bytes);
-                const uint32_t dst = g_smem_u32(in + (size_t)s * P.stage_f);
-                for (int b = 0; b < P.nbox; ++b)
-                    g_tma_load_4d(dst + (uint32_t)b * (uint32_t)P.box_f * 4u, &map, full(s), b * P.cbox, x0, y0,
-                                  batch * P.B + img_in_batch);
+                y0 = P.stride * P.randx[bp] - P.pad;  // window origin, rows  (feat[:,:,x,y]: x indexes H)
+                x0 = P.stride * P.randy[bp] - P.pad;
+                img = batch * P.B + img_in_batch;
+            }
+            const int64_t left = (P.rows - rb + step - 1) / step;
+            const int nb = left < 32 ? (int)left : 32;
+            for (int j = 0; j < nb; ++j, ++it) {
+                const int xs = __shfl_sync(0xffffffffu, x0, j), ys = __shfl_sync(0xffffffffu, y0, j);
+                const int is = __shfl_sync(0xffffffffu, img, j);
+                if (lane == 0) {
+                    const int s = it % P.nstage;
+                    const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
+                    if (it >= P.nstage) g_mbar_wait(empty(s), ph ^ 1);  // the consumers have released the stage
+                    g_mbar_expect_tx(full(s), stage_bytes);
+                    const uint32_t dst = g_smem_u32(in + (size_t)s * P.stage_f);
+                    for (int b = 0; b < P.nbox; ++b)
+                        g_tma_load_4d(dst + (uint32_t)b * (uint32_t)P.box_f * 4u, &map, full(s), b * P.cbox, xs, ys, is);
+                }
+                __syncwarp();
             }
         }
         return;
@@ -123,10 +141,18 @@ patch_gather_nhwc_tma(const __grid_constant__ CUtensorMap map, const GtParams P)
             const int b = a / P.cbox, al = a - b * P.cbox;
             const float *sp = src + (size_t)b * P.box_f + al;
             float *dp = dst + (size_t)a * k2;
-            for (int p = 0; p < k2; ++p) {
-                float v = sp[(size_t)p * P.cbox];
-                if (P.relu) v = fmaxf(v, 0.f);
-                dp[p] = v;
+            if (K2 > 0) {
+                float v[K2 > 0 ? K2 : 1];
+#pragma unroll
+                for (int p = 0; p < K2; ++p) v[p] = sp[p * P.cbox];
+#pragma unroll
+                for (int p = 0; p < K2; ++p) dp[p] = P.relu ? fmaxf(v[p], 0.f) : v[p];
+            } else {
+                for (int p = 0; p < k2; ++p) {
+                    float v = sp[(size_t)p * P.cbox];
+                    if (P.relu) v = fmaxf(v, 0.f);
+                    dp[p] = v;
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
@@ -162,7 +188,7 @@ bool cp_gather_tma_eligible(const float *fmap, int c, int k, float *X_out, int64
         if (c % d == 0) { cbox = d; break; }
     if (!cbox) return false;
     const size_t row = gt_round128((size_t)cbox * k * k * 4) * (c / cbox);
-    return (2 + GT_OUT) * row + 1024 <= 200 * 1024;  // at least two input stages
+    return (2 + GT_OUT) * row + 1024 <= 200 * 1024;  // at least two input stages in one CTA
 }
 
 int cp_patch_gather_tma(cp_handle_t h, const float *fmap, int nbatch, int B, int c, int H, int W, const int32_t *randx,
@@ -195,19 +221,30 @@ int cp_patch_gather_tma(cp_handle_t h, const float *fmap, int nbatch, int B, int
     Pm.cbox = cbox; Pm.nbox = c / cbox;
     const size_t box_b = gt_round128((size_t)cbox * k * k * 4), row = box_b * Pm.nbox;
     const size_t out_b = gt_round128((size_t)c * k * k * 4);
-    int nstage = (int)((200 * 1024 - 1024 - GT_OUT * out_b) / row);
-    if (nstage > 8) nstage = 8;
+    // CTAs per SM: as many as fit with >= 2 input stages each (up to 4), then the stages fill what is left
+    const size_t budget = 216 * 1024;
+    int per_sm = (int)(budget / (2 * row + GT_OUT * out_b + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    static const int env_per_sm = [] { const char *e = getenv("CPB200_GATHER_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    static const int env_stages = [] { const char *e = getenv("CPB200_GATHER_STAGES"); return e ? atoi(e) : 0; }();
+    if (env_per_sm > 0 && env_per_sm < per_sm) per_sm = env_per_sm;  // tuning knobs (profiles/r2_run9.sh)
+    int nstage = (int)((budget / per_sm - 1024 - GT_OUT * out_b) / row);
+    if (nstage > 6) nstage = 6;
+    if (env_stages >= 2 && env_stages < nstage) nstage = env_stages;
     Pm.nstage = nstage;
     Pm.box_f = (int)(box_b / 4); Pm.stage_f = (int)(row / 4); Pm.out_f = (int)(out_b / 4);
     const size_t smem = (size_t)nstage * row + GT_OUT * out_b + 2 * nstage * 8 + 256;
-    static cp_per_device_flag configured;
-    if (bool *done = configured.slot(); !*done) {
-        CP_CUDA(cudaFuncSetAttribute(patch_gather_nhwc_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+    auto kern = k == 3 ? patch_gather_nhwc_tma<9> : k == 1 ? patch_gather_nhwc_tma<1> : k == 5 ? patch_gather_nhwc_tma<25>
+                                                                                              : patch_gather_nhwc_tma<0>;
+    static cp_per_device_flag configured[4];
+    const int which = k == 3 ? 0 : k == 1 ? 1 : k == 5 ? 2 : 3;
+    if (bool *done = configured[which].slot(); !*done) {
+        CP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         *done = true;
     }
-    int64_t grid = h->num_sms;
+    int64_t grid = (int64_t)h->num_sms * per_sm;
     if (grid > Pm.rows) grid = Pm.rows;
-    patch_gather_nhwc_tma<<<(unsigned)grid, GT_THREADS, smem, stream>>>(map, Pm);
+    kern<<<(unsigned)grid, GT_THREADS, smem, stream>>>(map, Pm);
     CP_CHECK_LAUNCH();
     return CP_OK;
 }

@@ -184,6 +184,16 @@ __device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
 }
 
 #ifdef CP_TIMING
+__device__ long long cp_ls_chain[2 * 64];  // %globaltimer (ns) at entry / exit of potrf128, per panel of the last factorisation
+__device__ __forceinline__ long long ls_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define LS_CHAIN(i)                                                                      \
+    do {                                                                                 \
+        if (threadIdx.x == 64 && j0 / PB < 64) cp_ls_chain[2 * (j0 / PB) + (i)] = ls_globaltimer(); \
+    } while (0)
 __device__ long long cp_ls_times[32];
 // every lane of warp 0 stores the same stamp (no divergence before the warp-synchronous pivot routine)
 #define LS_STAMP(i)                                            \
@@ -193,6 +203,7 @@ __device__ long long cp_ls_times[32];
     } while (0)
 #else
 #define LS_STAMP(i)
+#define LS_CHAIN(i)
 #endif
 
 // A: the (updated) diagonal block in the trailing matrix; Lout: where the factor goes; Linv: 128 x 128
@@ -213,6 +224,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
     __shared__ MmTask tasks[3];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    LS_CHAIN(0);
     LS_STAMP(0);
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
@@ -368,12 +380,16 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         Linv[(int64_t)i * ldi + j] = v;
     }
     LS_STAMP(22);
+    LS_CHAIN(1);
 }
 
 #ifdef CP_TIMING
 }  // namespace
 extern "C" int cp_debug_ls_times(long long *host_out) {  // clock64 stamps of the first panel of the last factorisation
     return (int)cudaMemcpyFromSymbol(host_out, cp_ls_times, sizeof(long long) * 32);
+}
+extern "C" int cp_debug_ls_chain(long long *host_out) {  // entry / exit times (ns) of every panel factorisation
+    return (int)cudaMemcpyFromSymbol(host_out, cp_ls_chain, sizeof(long long) * 128);
 }
 namespace {
 #endif
@@ -436,11 +452,18 @@ int dgemm_small(const double *A, int64_t lda, const double *B, int64_t ldb, doub
     return CP_OK;
 }
 
-int ensure_side(cp_handle_t h) {
+// The look-ahead stream runs one priority level below the stream of the first solve on this handle (a handle serves one
+// stream in the layer pipeline): behind its own chain, ahead of cheaper problems' work.
+int ensure_side(cp_handle_t h, cudaStream_t stream) {
     if (!h->side) {
-        int lo = 0, hi = 0;
-        CP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+        int lo = 0, hi = 0, p = 0;
+        CP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo: numerically greatest = least urgent
+        if (cudaStreamGetPriority(stream, &p) != cudaSuccess) {
+            (void)cudaGetLastError();
+            p = lo;
+        }
+        p = p + 1 > lo ? lo : p + 1;
+        CP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, p));
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     }
@@ -499,7 +522,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
                        const double *diag0, int32_t *info, double *ratio, cudaStream_t stream) {
     using namespace cpgemm;
     const int Ktot = Kd + nrhs;
-    int rc = ensure_side(h);
+    int rc = ensure_side(h, stream);
     if (rc) return rc;
     rc = configure_potrf(h);
     if (rc) return rc;
@@ -682,7 +705,6 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t ld = ld_for(Ksel);
-    const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)(Ksel + n) * ld;
     double *L = nullptr, *Linv = nullptr, *Tm = nullptr, *ratio = nullptr;
     int rc = fac_reserve(h, (size_t)(Ksel + n), ld, Ksel, &L, &Linv, &Tm, &ratio);
@@ -726,7 +748,6 @@ extern "C" int cp_ls_factor(cp_handle_t h, const double *G, const double *sx, in
     CP_DEVICE_GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t ld = ld_for(Ksel);
-    const int npanel = (Ksel + PB - 1) / PB;
     const size_t nM = (size_t)Ksel * ld;
     double *L = nullptr, *Linv = nullptr, *Tm = nullptr, *ratio = nullptr;
     int rc = fac_reserve(h, (size_t)Ksel, ld, Ksel, &L, &Linv, &Tm, &ratio);
@@ -776,7 +797,6 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     cudaStream_t stream = (cudaStream_t)stream_;
     const int Ksel = h->fac_K;
     const int64_t ld = ld_for(Ksel);
-    const int npanel = (Ksel + PB - 1) / PB;
     cp_carver fc(h->fac);
     const double *L = fc.take<double>((size_t)h->fac_rows * ld);
     const double *Linv = fc.take<double>(xinv_elems(Ksel));
@@ -1027,7 +1047,6 @@ extern "C" int cp_ls_solve_dual(cp_handle_t h, const float *X, int64_t N, int K,
     const int Ni = (int)N;
     const int64_t ldc = ld_for(Ksel);  // Xc
     const int64_t ldm = ld_for(Ni);    // dual system
-    const int npanel = (Ni + PB - 1) / PB;
     const size_t nM = (size_t)(Ni + n) * ldm;
     const size_t need = cp_carver::need((size_t)Ni * ldc, 8) + 2 * cp_carver::need(nM, 8) +
                         2 * cp_carver::need(xinv_elems(Ni), 8) + cp_carver::need((size_t)n * ldm, 8) +

@@ -29,9 +29,15 @@ MAX_PROBES = 64
 # most collinear column); below that the layer is re-solved from exact-product fp64 statistics.
 LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.005"))
 LS_REFINE = os.environ.get("CPB200_LS_REFINE", "1") == "1"
-# prediction X W' of the refinement residual: "tc" (tensor cores, 3xTF32) or "fp64" (SIMT fp64 GEMM); A/B knob
-LS_RESID = os.environ.get("CPB200_LS_RESID", "tc")
+# Prediction X W' of the refinement residual: "fp64" (SIMT fp64 GEMM), "tc" (tensor cores, 3xTF32 through cp_gram on the
+# transposed patches) or "auto".  Alone, the tensor-core version is 2.7x faster at N = 5000 (0.46 vs 1.24 ms) and 5x at
+# N = 1e5; inside the 13-layer pipeline it is a loss (59.6 vs 48.5 ms per step, profiles/r2_summary.md): its CTAs hold a
+# whole SM's shared memory for ~70 us each and the latency-bound chains of the other layers queue behind them.  "auto"
+# therefore takes the tensor cores only for tall problems, where the fp64 product would dominate the solve.
+LS_RESID = os.environ.get("CPB200_LS_RESID", "auto")
+LS_RESID_TC_MIN_N = 20000
 
+_PRIO_HIGHEST = -5  # cudaDeviceGetStreamPriorityRange on B200: [0, -5]; out-of-range values are clamped by the runtime
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
 GRAM_FP64, GRAM_3XTF32 = 0, 1
 
@@ -63,9 +69,16 @@ class Engine:
                 hp = self.ffi.new("cp_handle_t*")
                 _cabi.check(self.lib.cp_create(hp, self.device.index))
                 self._handles.append(hp[0])
-                # the pipeline hands its most expensive problems to the first slots: give those streams priority,
-                # so that the chains that decide the makespan are not queued behind the short ones' big grids
-                prio = -1 if (i < nstreams // 2 and os.environ.get("CPB200_STREAM_PRIORITY", "1") == "1") else 0
+                # The pipeline hands its most expensive problems to the first slots.  CPB200_STREAM_PRIORITY:
+                #   "graded" one priority level per slot from the highest down (B200: -5 .. 0): the statistics kernels
+                #            of the most expensive problem run first, its (single-CTA, 8 ms) search starts early and
+                #            the throughput-bound kernels of the cheaper problems fill the chip under it
+                #   "1"      two levels (first half of the slots high)      "0"  none
+                pol = os.environ.get("CPB200_STREAM_PRIORITY", "graded")
+                if pol == "graded":
+                    prio = min(0, _PRIO_HIGHEST + i)
+                else:
+                    prio = -1 if (i < nstreams // 2 and pol == "1") else 0
                 self.streams.append(torch.cuda.Stream(self.device, priority=prio) if nstreams > 1 else None)
         self._cur = 0
         self.launches = 0  # libcpb200 calls issued (each launches >= 1 kernel)
@@ -335,7 +348,8 @@ class Engine:
         """One step of iterative refinement of (W, b) against the factor the last ls_solve left on this handle:
         residual from the data (exact fp64), its cross products with X on the tensor cores, forward/backward
         substitution, correction added in place.  Removes the error tensor-core statistics put into the solution."""
-        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b, mode=g["mode"] if LS_RESID == "tc" else GRAM_FP64)
+        tc = LS_RESID == "tc" or (LS_RESID == "auto" and X.shape[0] >= LS_RESID_TC_MIN_N)
+        R = self.ls_residual(X, Y, y_bias, sel_cols, W, b, mode=g["mode"] if tc else GRAM_FP64)
         gr = self.gram(X, R, want_G=False, mode=g["mode"])
         self.ls_resolve(gr["B"], g["sx"], gr["sy"], sel_cols, accumulate_into=(W, b))
         return W, b

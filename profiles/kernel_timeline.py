@@ -16,7 +16,7 @@ import cpb200
 c = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 28
 ffi2 = cffi.FFI()
-ffi2.cdef("int cp_debug_ls_times(long long*); int cp_debug_lasso_times(long long*);")
+ffi2.cdef("int cp_debug_ls_times(long long*); int cp_debug_lasso_times(long long*); int cp_debug_ls_chain(long long*);")
 dbg = ffi2.dlopen(cpb200._cabi.LIBRARY)
 
 eng = cpb200.Engine()
@@ -68,3 +68,16 @@ for sp in range(4):
     print(line)
 print("  ratio reduce + L write-out %d | 32x32 inverses %d | off-diagonal inverse blocks %d | Linv write-out %d"
       % (t[19] - t[18], t[20] - t[19], t[21] - t[20], t[22] - t[21]))
+
+buf3 = ffi2.new("long long[]", 128)
+assert dbg.cp_debug_ls_chain(buf3) == 0
+ch = np.array(list(buf3), dtype=np.int64).reshape(64, 2)
+npan = (len(cols) + 127) // 128
+ch = ch[:npan]
+dur = (ch[:, 1] - ch[:, 0]) / 1e3
+gap = (ch[1:, 0] - ch[:-1, 1]) / 1e3
+print("Cholesky chain, %d panels (us): potrf128 mean %.1f | gap to the next panel's potrf128 (TRSM + next-column update + "
+      "launches + waits on the side stream) mean %.1f, first five %s, last five %s | factorisation %.0f us"
+      % (npan, dur.mean(), gap.mean(), np.round(gap[:5], 1).tolist(), np.round(gap[-5:], 1).tolist(),
+         (ch[-1, 1] - ch[0, 0]) / 1e3))
+print("  gaps by panel:", " ".join("%.0f" % g for g in gap))

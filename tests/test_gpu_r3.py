@@ -108,9 +108,11 @@ def test_r3_stage_by_stage_against_reference_golden(engine, golden_dir, name, mo
 @pytest.mark.parametrize("name", list(cases.R3_CASES))
 def test_r3_free_running_walk(engine, golden_dir, name, mode):
     """The same walk left alone.  The blobs behind an approximated layer are nearly rank deficient (sigma_min/sigma_max
-    of the conv2_2 patches here: 1e-3), so the pseudo-inverses of the next stage amplify the 1e-6 differences of the
-    previous one by that ratio: individual weights are compared loosely, what must hold tightly is what the reference
-    guarantees -- the discrete outcome (selections, alpha schedule, RNG draws) and the function the network computes."""
+    of the conv2_2 patches here: 1e-3), so the pseudo-inverses of the next stage amplify the differences of the
+    previous one by about that ratio (measured: 1e-7 -> 3.5e-5 with exact-product statistics, 3e-6 -> 1e-2 with the
+    tensor-core ones; the stage-by-stage test above bounds each stage's own deviation at 3e-6 in both).  Individual
+    weights are therefore compared loosely; what must hold is what the reference guarantees -- the discrete outcome
+    (selections, alpha schedule, RNG draws) and the function the network computes."""
     from cpb200.lib import cfgs
 
     spec, g, net, images = _frozen_net(engine, golden_dir, name, mode)
@@ -138,7 +140,7 @@ def test_r3_free_running_walk(engine, golden_dir, name, mode):
     for k in [k for k in g.files if k.startswith("w__")]:
         worst = max(worst, float(np.linalg.norm(net._w[k[3:]].cpu().numpy() - g[k]) / np.linalg.norm(g[k])))
     print("R3 %s mode %d free running: network output deviates %.2e, worst weight tensor %.2e" % (name, mode, e_out, worst))
-    assert e_out <= 1e-3 and worst <= 5e-2
+    assert e_out <= (1e-3 if mode == 0 else 2e-2) and worst <= (1e-3 if mode == 0 else 5e-2)
 
 
 def test_frozen_pickle_round_trip(engine, tmp_path):
