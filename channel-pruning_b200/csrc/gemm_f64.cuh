@@ -7,18 +7,22 @@
 //   a(m, r) = A_MC ? A[rowidx(r) * lda + m] : A[m * lda + r]      (TA = float | double)
 //   b(nn,r) = B_NC ? B[rowidx(r) * ldb + nn] - bias[nn] : B[nn * ldb + r]
 //
-// CTA tile 128 x 128, 256 threads, 8 x 8 register micro-tile per thread (interleaved
-// 2-wide so that every shared-memory read is a conflict-free LDS.128), reduction
-// staged 16 deep through double-buffered shared memory with register prefetch of the
-// next stage.  Bound: FP64 FMA pipe (64 DFMA / clk / SM).
+// CTA tile 128 x 128, 256 threads, reduction staged 16 deep through double-buffered shared
+// memory with register prefetch of the next stage.  Two inner loops over the same staged tiles:
+//   DMMA (default)  mma.sync.m8n8k4.f64: warp tile 64 x 32 (8 x 4 MMA tiles, 64 accumulators per lane),
+//                   12 conflict-free LDS.64 per 32 MMAs (the staged leading dimension is 4 mod 16 doubles)
+//   DFMA            8 x 8 register micro-tile per thread (interleaved 2-wide, LDS.128)
+// CPB200_GEMM=dfma selects the second (A/B measurements: profiles/gemm_bench.py).  Bound: FP64 pipe.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace cpgemm {
 
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
-constexpr int LDS_ = BM + 2;  // padded leading dimension of a staged tile (doubles)
+constexpr int LDS_ = BM + 4;  // padded leading dimension of a staged tile (doubles): 4 mod 16 (DMMA fragment loads)
 constexpr size_t SMEM_BYTES = 2ull /*buffers*/ * 2 /*A,B*/ * BK * LDS_ * sizeof(double);
 
 enum TileMode { TILES_ALL = 0, TILES_UPPER_SYM = 1, TILES_LOWER = 2 };
@@ -40,6 +44,8 @@ struct Args {
     double alpha, beta;     // nsplit == 1: C = alpha*acc + beta*C ; nsplit > 1: partial = acc
     int tile_mode;
     int a_vec, b_vec;       // 16-byte vector loads allowed (alignment checked by the host)
+    int max_ctas;           // > 0: at most that many CTAs walk the tiles (leaves SMs free for latency-bound kernels of
+                            // other streams: a resident 128 x 128 x 256 tile holds its SM for ~60 us)
 };
 
 template <typename T>
@@ -123,16 +129,34 @@ __device__ __forceinline__ void stage_rcontig(double *S, const double v[8]) {
     for (int i = 0; i < 8; ++i) d[i * LDS_] = v[i];
 }
 
-template <typename TA, typename TB, bool A_MC, bool B_NC>
+__device__ __forceinline__ int num_tiles_dev(int tm, int tn, int mode) {
+    if (mode == 1) return tn * (tn + 1) / 2;
+    if (mode == 2) return tn * tm - tn * (tn - 1) / 2;
+    return tm * tn;
+}
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename TA, typename TB, bool A_MC, bool B_NC, bool DMMA>
 __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
     extern __shared__ __align__(16) double smem[];
     // stage buffer b: A tile at smem + b*2*BK*LDS_, B tile right after it
     auto As = [&](int b) { return smem + (size_t)b * 2 * BK * LDS_; };
     auto Bs = [&](int b) { return smem + (size_t)b * 2 * BK * LDS_ + BK * LDS_; };
 
-    // ---- tile decode
+    // ---- tile decode (a capped grid walks the tiles with a stride)
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.Nn + BN - 1) / BN;
-    int l = blockIdx.x, ti, tj;
+    const int ntiles = num_tiles_dev(tiles_m, tiles_n, g.tile_mode);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, wm = threadIdx.x >> 7, wn = (threadIdx.x >> 5) & 3;  // DMMA: 2 x 4 warps
+    const TA *A = reinterpret_cast<const TA *>(g.A);
+    const TB *B = reinterpret_cast<const TB *>(g.B);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int l = tile, ti, tj;
     if (g.tile_mode == TILES_UPPER_SYM) {
         ti = 0;
         while (l >= tiles_n - ti) { l -= tiles_n - ti; ++ti; }
@@ -152,16 +176,12 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
     int64_t r_end = r_begin + g.r_per_split;
     if (r_end > g.R) r_end = g.R;
 
-    const TA *A = reinterpret_cast<const TA *>(g.A);
-    const TB *B = reinterpret_cast<const TB *>(g.B);
-
     double acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double ra[8], rb[8];
 
     auto fetch = [&](int64_t r0) {
@@ -185,20 +205,38 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
         const bool has_next = r0 + BK < r_end;
         if (has_next) fetch(r0 + BK);
         const double *a_s = As(buf), *b_s = Bs(buf);
+        if constexpr (DMMA) {
+            // acc[i][2j + e]: rows wm*64 + 8i + (lane >> 2), columns wn*32 + 8j + 2 (lane & 3) + e
+            const double *ap = a_s + (lane & 3) * LDS_ + wm * 64 + (lane >> 2);
+            const double *bp = b_s + (lane & 3) * LDS_ + wn * 32 + (lane >> 2);
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double a[8], b[8];
+            for (int k4 = 0; k4 < BK; k4 += 4) {
+                double af[8], bf[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double2 av = *reinterpret_cast<const double2 *>(a_s + kk * LDS_ + q * 32 + ty * 2);
-                const double2 bv = *reinterpret_cast<const double2 *>(b_s + kk * LDS_ + q * 32 + tx * 2);
-                a[2 * q] = av.x; a[2 * q + 1] = av.y;
-                b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+                for (int i = 0; i < 8; ++i) af[i] = ap[k4 * LDS_ + 8 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = bp[k4 * LDS_ + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][2 * j], acc[i][2 * j + 1], af[i], bf[j]);
             }
+        } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int kk = 0; kk < BK; ++kk) {
+                double a[8], b[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int q = 0; q < 4; ++q) {
+                    const double2 av = *reinterpret_cast<const double2 *>(a_s + kk * LDS_ + q * 32 + ty * 2);
+                    const double2 bv = *reinterpret_cast<const double2 *>(b_s + kk * LDS_ + q * 32 + tx * 2);
+                    a[2 * q] = av.x; a[2 * q + 1] = av.y;
+                    b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
         }
         if (has_next) stage(buf ^ 1);
         __syncthreads();
@@ -212,15 +250,18 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
     const bool partial = g.nsplit > 1;
     const bool rmw = !partial && g.beta != 0.0;
     const bool cvec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (g.ldc % 2 == 0);
+    // element (i, 2q + e') of the thread's accumulators sits at tile row erow(i), tile column ecol(q) + e'
+    auto erow = [&](int i) { return DMMA ? wm * 64 + 8 * i + (lane >> 2) : (i >> 1) * 32 + ty * 2 + (i & 1); };
+    auto ecol = [&](int q) { return DMMA ? wn * 32 + 8 * q + 2 * (lane & 3) : q * 32 + tx * 2; };
 #pragma unroll
     for (int ip = 0; ip < 4; ++ip) {
         double old[2][8];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int m = m0 + ip * 32 + ty * 2 + e;
+            const int m = m0 + erow(2 * ip + e);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int nn = n0 + q * 32 + tx * 2;
+                const int nn = n0 + ecol(q);
                 old[e][2 * q] = old[e][2 * q + 1] = 0.0;
                 if (rmw && m < g.M) {
                     const double *p = C + (int64_t)m * g.ldc + nn;
@@ -238,11 +279,11 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = 2 * ip + e;
-            const int m = m0 + ip * 32 + ty * 2 + e;
+            const int m = m0 + erow(i);
             if (m >= g.M) continue;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int nn = n0 + q * 32 + tx * 2;
+                const int nn = n0 + ecol(q);
                 double v0 = acc[i][2 * q], v1 = acc[i][2 * q + 1];
                 if (!partial) {
                     v0 *= g.alpha;
@@ -262,6 +303,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const Args g) {
             }
         }
     }
+    }  // tile loop (the k loop ends with a __syncthreads: the staging buffers are free again)
 }
 
 inline int num_tiles(int M, int Nn, int mode) {
@@ -271,9 +313,17 @@ inline int num_tiles(int M, int Nn, int mode) {
     return tm * tn;
 }
 
-template <typename TA, typename TB, bool A_MC, bool B_NC>
-inline cudaError_t launch(const Args &g, cudaStream_t stream) {
-    auto kern = gemm_kernel<TA, TB, A_MC, B_NC>;
+inline bool use_dmma() {
+    static const bool on = [] {
+        const char *e = getenv("CPB200_GEMM");
+        return !(e && (e[0] == 'd' || e[0] == 'D') && (e[1] == 'f' || e[1] == 'F'));  // "dfma" switches the MMA loop off
+    }();
+    return on;
+}
+
+template <typename TA, typename TB, bool A_MC, bool B_NC, bool DMMA>
+inline cudaError_t launch_impl(const Args &g, cudaStream_t stream) {
+    auto kern = gemm_kernel<TA, TB, A_MC, B_NC, DMMA>;
     static bool configured[64] = {};  // per instantiation and per device (the attribute is per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -285,8 +335,14 @@ inline cudaError_t launch(const Args &g, cudaStream_t stream) {
     }
     dim3 grid((unsigned)num_tiles(g.M, g.Nn, g.tile_mode), (unsigned)(g.nsplit > 1 ? g.nsplit : 1));
     if (grid.x == 0) return cudaSuccess;
+    if (g.max_ctas > 0 && grid.x > (unsigned)g.max_ctas) grid.x = (unsigned)g.max_ctas;
     kern<<<grid, NT, SMEM_BYTES, stream>>>(g);
     return cudaGetLastError();
+}
+
+template <typename TA, typename TB, bool A_MC, bool B_NC>
+inline cudaError_t launch(const Args &g, cudaStream_t stream) {
+    return use_dmma() ? launch_impl<TA, TB, A_MC, B_NC, true>(g, stream) : launch_impl<TA, TB, A_MC, B_NC, false>(g, stream);
 }
 
 }  // namespace cpgemm

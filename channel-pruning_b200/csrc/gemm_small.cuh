@@ -9,17 +9,19 @@
 //   a(m, r)  = A[m * lda + r]                               (reduction index contiguous)
 //   b(nn, r) = B_NC ? B[r * ldb + nn] : B[nn * ldb + r]
 //
-// 256 threads, 4 x 4 register micro-tile per thread (interleaved 2-wide so that every
-// shared-memory read is a conflict-free LDS.128), reduction staged 16 deep through
-// double-buffered shared memory with register prefetch.  Bound: FP64 FMA pipe.
+// 256 threads, reduction staged 16 deep through double-buffered shared memory with register prefetch; inner loop
+// on mma.sync.m8n8k4.f64 (warp tile 32 x 16: 4 x 2 MMA tiles, 6 conflict-free LDS.64 per 8 MMAs) or, with
+// CPB200_GEMM=dfma, a 4 x 4 register micro-tile per thread.  Bound: FP64 pipe.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace cpsmall {
 
 constexpr int TM = 64, TN = 64, BK = 16, NT = 256;
-constexpr int LDS_ = TM + 2;  // padded leading dimension of a staged tile (doubles), even
+constexpr int LDS_ = TM + 4;  // padded leading dimension of a staged tile (doubles): 4 mod 16 (MMA fragment loads)
 
 enum TileMode { TILES_ALL = 0, TILES_LOWER = 2 };
 
@@ -89,7 +91,13 @@ __device__ __forceinline__ void stage_xc(double *S, const double v[4]) {
     *reinterpret_cast<double2 *>(d + 2) = make_double2(v[2], v[3]);
 }
 
-template <bool B_NC>
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool B_NC, bool DMMA>
 __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
     __shared__ __align__(16) double As[2][BK * LDS_];
     __shared__ __align__(16) double Bs[2][BK * LDS_];
@@ -110,6 +118,7 @@ __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, wm = threadIdx.x >> 7, wn = (threadIdx.x >> 5) & 3;  // MMA: 2 x 4 warps
     double ra[4], rb[4];
     auto fetch = [&](int r0) {
         fetch_rc(g.A, g.lda, m0, g.M, r0, g.R, g.a_vec, ra);
@@ -130,20 +139,38 @@ __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
         const bool has_next = r0 + BK < g.R;
         if (has_next) fetch(r0 + BK);
         const double *a_s = As[buf], *b_s = Bs[buf];
+        if constexpr (DMMA) {
+            // acc[i][2j + e]: rows wm*32 + 8i + (lane >> 2), columns wn*16 + 8j + 2 (lane & 3) + e   (j < 2)
+            const double *ap = a_s + (lane & 3) * LDS_ + wm * 32 + (lane >> 2);
+            const double *bp = b_s + (lane & 3) * LDS_ + wn * 16 + (lane >> 2);
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            double a[4], b[4];
+            for (int k4 = 0; k4 < BK; k4 += 4) {
+                double af[4], bf[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const double2 av = *reinterpret_cast<const double2 *>(a_s + kk * LDS_ + q * 32 + ty * 2);
-                const double2 bv = *reinterpret_cast<const double2 *>(b_s + kk * LDS_ + q * 32 + tx * 2);
-                a[2 * q] = av.x; a[2 * q + 1] = av.y;
-                b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+                for (int i = 0; i < 4; ++i) af[i] = ap[k4 * LDS_ + 8 * i];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bf[j] = bp[k4 * LDS_ + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma884(acc[i][2 * j], acc[i][2 * j + 1], af[i], bf[j]);
             }
+        } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int kk = 0; kk < BK; ++kk) {
+                double a[4], b[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int q = 0; q < 2; ++q) {
+                    const double2 av = *reinterpret_cast<const double2 *>(a_s + kk * LDS_ + q * 32 + ty * 2);
+                    const double2 bv = *reinterpret_cast<const double2 *>(b_s + kk * LDS_ + q * 32 + tx * 2);
+                    a[2 * q] = av.x; a[2 * q + 1] = av.y;
+                    b[2 * q] = bv.x; b[2 * q + 1] = bv.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
         }
         if (has_next) stage(buf ^ 1);
         __syncthreads();
@@ -152,13 +179,15 @@ __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
     // epilogue: every C value of the thread is loaded before any is stored (one memory latency, not sixteen)
     const bool rmw = g.beta != 0.0;
     const bool cvec = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 2 == 0);
+    auto erow = [&](int i) { return DMMA ? wm * 32 + 8 * i + (lane >> 2) : (i >> 1) * 32 + ty * 2 + (i & 1); };
+    auto ecol = [&](int q) { return DMMA ? wn * 16 + 8 * q + 2 * (lane & 3) : q * 32 + tx * 2; };
     double old[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
+        const int m = m0 + erow(i);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const int nn = n0 + q * 32 + tx * 2;
+            const int nn = n0 + ecol(q);
             old[i][2 * q] = old[i][2 * q + 1] = 0.0;
             if (rmw && m < g.M) {
                 const double *p = g.C + (int64_t)m * g.ldc + nn;
@@ -175,11 +204,11 @@ __global__ void __launch_bounds__(NT) gemm_small_kernel(const Args g) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int m = m0 + (i >> 1) * 32 + ty * 2 + (i & 1);
+        const int m = m0 + erow(i);
         if (m >= g.M) continue;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const int nn = n0 + q * 32 + tx * 2;
+            const int nn = n0 + ecol(q);
             double v0 = acc[i][2 * q] * g.alpha, v1 = acc[i][2 * q + 1] * g.alpha;
             if (rmw) {
                 v0 = fma(g.beta, old[i][2 * q], v0);
@@ -206,7 +235,12 @@ template <bool B_NC>
 inline cudaError_t launch(const Args &g, cudaStream_t stream) {
     if (g.M <= 0 || g.Nn <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)num_tiles(g.M, g.Nn, g.tile_mode);
-    gemm_small_kernel<B_NC><<<grid, NT, 0, stream>>>(g);
+    static const bool dmma = [] {
+        const char *e = getenv("CPB200_GEMM");
+        return !(e && (e[0] == 'd' || e[0] == 'D') && (e[1] == 'f' || e[1] == 'F'));
+    }();
+    if (dmma) gemm_small_kernel<B_NC, true><<<grid, NT, 0, stream>>>(g);
+    else gemm_small_kernel<B_NC, false><<<grid, NT, 0, stream>>>(g);
     return cudaGetLastError();
 }
 

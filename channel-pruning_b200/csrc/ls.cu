@@ -23,6 +23,8 @@
 // reads and writes the same tile, whatever the tile shape.
 // Bound: the dependency chain of ~K'/128 x (potrf128 + 2 small GEMMs) for the factorisation,
 // the FP64 pipe for the far updates (K'^3/3 flop).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "gemm_small.cuh"
@@ -423,7 +425,7 @@ inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 // 128 x 128 tiles (throughput: the far trailing updates)
 int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
-              int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
+              int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream, int max_ctas = 0) {
     using namespace cpgemm;
     Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
@@ -432,6 +434,7 @@ int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double
     g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode;
     g.a_vec = al16(A) && (lda % 2 == 0);
     g.b_vec = al16(B) && (ldb % 2 == 0);
+    g.max_ctas = max_ctas;
     if (M <= 0 || Nn <= 0) return CP_OK;
     CP_GEMM_LAUNCH((launch<double, double, false, false>(g, stream)));
     return CP_OK;
@@ -454,6 +457,12 @@ int dgemm_small(const double *A, int64_t lda, const double *B, int64_t ldb, doub
 
 // The look-ahead stream runs one priority level below the stream of the first solve on this handle (a handle serves one
 // stream in the layer pipeline): behind its own chain, ahead of cheaper problems' work.
+// grid cap of the bulk trailing updates: two thirds of the SMs (CPB200_LS_REST_CTAS overrides; 0 = uncapped)
+int rest_ctas(cp_handle_t h) {
+    static const int env = [] { const char *e = getenv("CPB200_LS_REST_CTAS"); return e ? atoi(e) : -1; }();
+    return env >= 0 ? env : h->num_sms * 2 / 3;
+}
+
 int ensure_side(cp_handle_t h, cudaStream_t stream) {
     if (!h->side) {
         int lo = 0, hi = 0, p = 0;
@@ -606,8 +615,10 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
             const int j4 = j2 + wn;
             if (Kd - j4 > 0) {
                 const double *Pr = L + (int64_t)j4 * ld + je;
+                // the bulk of the trailing update has slack; its long-running tiles must not take every SM, or the
+                // chain's small kernels queue behind them (measured: 240 us instead of 33 us between two panels)
                 rc = dgemm_big(Pr, ld, Pr, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, Kd - j4, R2, -1.0, 1.0, TILES_LOWER,
-                               h->side);
+                               h->side, rest_ctas(h));
                 if (rc) return rc;
             }
         }

@@ -70,11 +70,11 @@ class Engine:
                 _cabi.check(self.lib.cp_create(hp, self.device.index))
                 self._handles.append(hp[0])
                 # The pipeline hands its most expensive problems to the first slots.  CPB200_STREAM_PRIORITY:
-                #   "graded" one priority level per slot from the highest down (B200: -5 .. 0): the statistics kernels
-                #            of the most expensive problem run first, its (single-CTA, 8 ms) search starts early and
-                #            the throughput-bound kernels of the cheaper problems fill the chip under it
-                #   "1"      two levels (first half of the slots high)      "0"  none
-                pol = os.environ.get("CPB200_STREAM_PRIORITY", "graded")
+                #   "1"      (default) two levels: the first half of the slots high
+                #   "graded" one level per slot from the highest down (B200: -5 .. 0)        "0"  none
+                # measured on the 13-layer step (profiles/r2_summary.md): 48.3 / 48.9 / 49.0 ms -- priorities only order
+                # CTAs that are not yet resident, and the step is bound by FP64 throughput, not by the order
+                pol = os.environ.get("CPB200_STREAM_PRIORITY", "1")
                 if pol == "graded":
                     prio = min(0, _PRIO_HIGHEST + i)
                 else:
