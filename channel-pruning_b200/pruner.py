@@ -94,6 +94,14 @@ def prune_layers(eng: Engine, shapes, datas, right0=1e-3, rank_tol=.1, from_host
     and copied in the pipeline; to_host: results are copied back to pinned host memory.
     trace: optional dict; filled with {layer name: [(label, timing event), ...]} plus '_t0' (device timeline
     of the step: profiles/e2e_breakdown.py prints it).
+    Batch mode: the problems are INDEPENDENT -- every alpha search starts from ``right0`` and the seeds come with the
+    problem (datas[i]['seeds']), so the call neither reads nor writes ``cfgs.alpha`` and draws nothing from numpy's
+    global RNG.  The reference's sequential walk carries alpha from layer to layer (lib/decompose.py:491,627) and draws
+    one seed per probe; that behaviour lives in lib.decompose.dictionary / Net.R3, which run the layers one after the
+    other.  Masks and alphas of the two modes are therefore not comparable layer by layer.
+    Every reconstruction is verified before it is returned (Cholesky status + pivot ratio, see the end of
+    _prune_layers_ordered): r.info['verdict'] is 'ok', 'redo->ok' (re-solved from exact-product statistics) or
+    'truncated' (rank deficient: gelsd's minimum-norm solution).
     Returns a list of LayerResult (W, b as device fp64 tensors unless to_host)."""
     nslots = len(eng.streams)
     main = torch.cuda.current_stream(eng.device)

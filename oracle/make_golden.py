@@ -260,6 +260,17 @@ def run_3c_cases(D, CF):
         print(name, "W1", W1.shape, "W2", W2.shape, "W12", W12.shape)
 
 
+def write_versions():
+    """The reference pins no versions of its third-party solvers (README.md:46); the goldens -- and the control flow the
+    LASSO kernel reproduces bit for bit (gap-safe screening, stopping rule) -- are those of the versions recorded here."""
+    import json
+
+    import scipy
+    import sklearn
+    with open(os.path.join(OUT, "VERSIONS.json"), "w") as f:
+        json.dump({"scikit-learn": sklearn.__version__, "scipy": scipy.__version__, "numpy": np.__version__}, f, indent=1)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     D, NET, CF = ref_shims.load_reference()
@@ -268,6 +279,7 @@ def main():
     run_net_cases(NET, CF, D)
     run_3c_cases(D, CF)
     run_r3_cases(NET, CF, D)
+    write_versions()
 
 
 if __name__ == "__main__":

@@ -34,6 +34,19 @@ def test_dictionary_matches_reference_golden(golden_dir, name, form):
     assert np.abs(B - g["B"]).max() <= 1e-9 * max(1.0, np.abs(g["B"]).max())
 
 
+def test_golden_versions_recorded(golden_dir):
+    """The goldens and the coordinate-descent control flow are those of the third-party versions recorded next to
+    them; a different installed scikit-learn is reported (the sklearn cross-checks below may then differ, the goldens
+    stay authoritative)."""
+    import json
+
+    import sklearn
+    v = json.load(open(os.path.join(golden_dir, "VERSIONS.json")))
+    assert set(v) == {"scikit-learn", "scipy", "numpy"}
+    if sklearn.__version__ != v["scikit-learn"]:
+        pytest.skip("installed scikit-learn %s differs from the goldens' %s" % (sklearn.__version__, v["scikit-learn"]))
+
+
 def test_lasso_cd_matches_sklearn():
     from sklearn.linear_model import Lasso
 
