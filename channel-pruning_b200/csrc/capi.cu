@@ -27,8 +27,10 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->ws_bytes = 0;
     h->tmap_encode = nullptr;
     h->side = nullptr;
+    h->bulk = nullptr;
     h->ev_panel = nullptr;
     h->ev_side = nullptr;
+    h->ev_bulk = nullptr;
     h->potrf_configured = false;
     h->fac = nullptr;
     h->fac_bytes = 0;
@@ -52,8 +54,10 @@ extern "C" int cp_destroy(cp_handle_t h) {
         if (h->aux) cudaFree(h->aux);
         if (h->side) {
             cudaStreamDestroy(h->side);
+            cudaStreamDestroy(h->bulk);
             cudaEventDestroy(h->ev_panel);
             cudaEventDestroy(h->ev_side);
+            cudaEventDestroy(h->ev_bulk);
         }
         cudaSetDevice(cur);
     }

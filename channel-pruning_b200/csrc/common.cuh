@@ -14,8 +14,9 @@ struct cp_handle_s {
     size_t ws_bytes;
     void *tmap_encode; // cuTensorMapEncodeTiled entry point (resolved lazily)
     // look-ahead of the blocked Cholesky (ls.cu): low-priority side stream + fork/join events, created lazily
-    cudaStream_t side;
-    cudaEvent_t ev_panel, ev_side;
+    cudaStream_t side;   // urgent look-ahead: the updates the chain will need within the next few panels
+    cudaStream_t bulk;   // the rest of every pair's trailing update (long kernels with slack): never ahead of `side` work
+    cudaEvent_t ev_panel, ev_side, ev_bulk;
     bool potrf_configured;  // opt-in shared memory of potrf128 set on this handle's device
     // factor kept between cp_ls_factor and cp_ls_resolve (own allocation: the scratch above is reused by every call)
     void *fac;

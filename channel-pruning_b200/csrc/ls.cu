@@ -473,6 +473,8 @@ int ensure_side(cp_handle_t h, cudaStream_t stream) {
         }
         p = p + 1 > lo ? lo : p + 1;
         CP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, p));
+        CP_CUDA(cudaStreamCreateWithPriority(&h->bulk, cudaStreamNonBlocking, lo));
+        CP_CUDA(cudaEventCreateWithFlags(&h->ev_bulk, cudaEventDisableTiming));
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
         CP_CUDA(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     }
@@ -537,14 +539,19 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
     if (rc) return rc;
     CP_CUDA(cudaMemsetAsync(Xinv, 0, xinv_elems(Kd) * sizeof(double), stream));
     // Trailing updates.  Panels are paired (e, o = e + 1).  What the chain needs next stays small and immediate:
-    //   crit(p)  : block column p+1, inner dimension 128, on the caller's stream, 64 x 64 tiles
-    //   far_a(e) : block column e+2 (needed by crit(o)), side stream
+    //   crit(p)   : block column p+1, inner dimension 128, on the caller's stream, 64 x 64 tiles
+    //   far_a(e)  : block column e+2 (needed by crit(o)), side stream
     // everything else is applied once per PAIR with inner dimension 256 -- half the read-modify-write traffic of
     // the trailing matrix per flop (a rank-128 update moves 8 bytes per 8 flop: memory bound on a 37 TF/s pipe):
-    //   near(e,o): block columns e+3, e+4 (the next pair's crit / far_a targets), side stream, then an event
-    //   rest(e,o): block columns >= e+5, side stream
-    // Every update of a block column by different panels is ordered: same stream, or through ev_side / ev_panel.
-    bool side_pending = false;
+    //   near(e,o) : block columns e+3, e+4 (the next pair's crit / far_a targets), side stream, then an event
+    //   near2(e,o): block columns e+5, e+6 (the next pair's near targets), side stream
+    //   rest(e,o) : block columns >= e+7, BULK stream, capped grid
+    // The side stream is a FIFO the chain waits on: with the bulk update in it, far_a of the next pair queued behind a
+    // ~250 us kernel and every second panel stalled (in-kernel chain timeline: 219 us instead of 30 us between panels).
+    // Every update of a block column by different panels is ordered (same stream, or through ev_side / ev_panel /
+    // ev_bulk): near2(e,o) and rest(e-2,o-2) touch the same columns, so the side stream waits for the previous pair's
+    // bulk update there -- five panels after that update was issued.
+    bool side_pending = false, bulk_pending = false;
     int ip = 0;
     for (int j0 = 0; j0 < Kd; j0 += PB, ++ip) {
         const int nb = Kd - j0 < PB ? Kd - j0 : PB;
@@ -614,18 +621,35 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
             side_pending = true;
             const int j4 = j2 + wn;
             if (Kd - j4 > 0) {
-                const double *Pr = L + (int64_t)j4 * ld + je;
-                // the bulk of the trailing update has slack; its long-running tiles must not take every SM, or the
-                // chain's small kernels queue behind them (measured: 240 us instead of 33 us between two panels)
-                rc = dgemm_big(Pr, ld, Pr, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, Kd - j4, R2, -1.0, 1.0, TILES_LOWER,
-                               h->side, rest_ctas(h));
+                if (bulk_pending) {  // rest(e-2, o-2) updates these columns too
+                    CP_CUDA(cudaStreamWaitEvent(h->side, h->ev_bulk, 0));
+                    bulk_pending = false;
+                }
+                const int wm = Kd - j4 < 2 * PB ? Kd - j4 : 2 * PB;
+                const double *P4 = L + (int64_t)j4 * ld + je;
+                rc = dgemm_big(P4, ld, P4, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, wm, R2, -1.0, 1.0, TILES_LOWER, h->side);
                 if (rc) return rc;
+                const int j6 = j4 + wm;
+                if (Kd - j6 > 0) {
+                    // the bulk of the trailing update has slack; its long-running tiles must not take every SM either,
+                    // or the chain's small kernels queue behind them
+                    CP_CUDA(cudaStreamWaitEvent(h->bulk, h->ev_panel, 0));
+                    const double *Pr = L + (int64_t)j6 * ld + je;
+                    rc = dgemm_big(Pr, ld, Pr, ld, M + (int64_t)j6 * ld + j6, ld, Ktot - j6, Kd - j6, R2, -1.0, 1.0,
+                                   TILES_LOWER, h->bulk, rest_ctas(h));
+                    if (rc) return rc;
+                    CP_CUDA(cudaEventRecord(h->ev_bulk, h->bulk));
+                    bulk_pending = true;
+                }
             }
         }
     }
-    // whatever the side stream still holds (last merges) must be ordered before the substitutions / the next user
+    // whatever the side streams still hold (last merges, last bulk update: its targets were all consumed by later
+    // updates on the side stream, but the scratch must not be reused under it) is ordered before the next user
     CP_CUDA(cudaEventRecord(h->ev_side, h->side));
     CP_CUDA(cudaStreamWaitEvent(stream, h->ev_side, 0));
+    CP_CUDA(cudaEventRecord(h->ev_bulk, h->bulk));
+    CP_CUDA(cudaStreamWaitEvent(stream, h->ev_bulk, 0));
     return CP_OK;
 }
 
