@@ -13,8 +13,11 @@
 // reference takes SVDs of on this path is small (VH: (c k) x (n k) <= 1536 x 1536; ITQ: reduced to n x n, n <= 512,
 // because X = G M has the right singular vectors of the n x n matrix L_S' M with G'G = L_S L_S') so the kernel keeps
 // both columns of a pair in shared memory.  Jacobi is also the most accurate dense SVD (high relative accuracy).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include "gemm_async.cuh"
 
 namespace {
 
@@ -57,6 +60,18 @@ int gemm_any(cp_handle_t h, const double *A, int64_t lda, const double *B, int64
     rps = (rps + BK - 1) / BK * BK;
     nsplit = (int)((R + rps - 1) / rps);
     if (nsplit <= 1) {
+        if constexpr (!A_MC) {  // plain fp64 operands: the cp.async-staged kernel (gemm_async.cuh)
+            cpasync::Args a{};
+            a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+            a.M = M; a.Nn = Nn; a.R = (int)R;
+            a.alpha = alpha; a.beta = beta; a.tile_mode = cpasync::TILES_ALL;
+            static const bool on = [] { const char *e = getenv("CPB200_GEMM"); return !e || e[0] == 'a' || e[0] == 'A'; }();
+            if (on && R > 0 && R <= 0x7fffffff && cpasync::eligible(a)) {
+                if (tiles >= h->num_sms) CP_GEMM_LAUNCH((cpasync::launch<128, B_NC>(a, stream)));
+                else CP_GEMM_LAUNCH((cpasync::launch<64, B_NC>(a, stream)));
+                return CP_OK;
+            }
+        }
         g.nsplit = 1;
         g.r_per_split = R > 0 ? R : 1;
         g.C = C; g.ldc = ldc;

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "gemm_small.cuh"
+#include "gemm_async.cuh"
 
 namespace {
 
@@ -423,10 +424,37 @@ ls_output(const double *__restrict__ Wt, int64_t ld, const double *__restrict__ 
 
 inline bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
+// CPB200_GEMM: "async" (default: cp.async-staged DMMA kernels of gemm_async.cuh for the solver's fp64 products),
+// "dmma" / "dfma" (register-staged kernels of gemm_f64.cuh / gemm_small.cuh with the MMA or the FMA inner loop)
+bool use_async_gemm() {
+    static const bool on = [] {
+        const char *e = getenv("CPB200_GEMM");
+        return !e || e[0] == 'a' || e[0] == 'A';
+    }();
+    return on;
+}
+template <int T, bool B_NC>
+int dgemm_async(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn, int64_t R,
+                double alpha, double beta, int tile_mode, cudaStream_t stream, int max_ctas, bool *done) {
+    cpasync::Args g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.M = M; g.Nn = Nn; g.R = (int)R;
+    g.alpha = alpha; g.beta = beta; g.tile_mode = tile_mode; g.max_ctas = max_ctas;
+    *done = false;
+    if (!use_async_gemm() || !cpasync::eligible(g) || R > 0x7fffffff) return CP_OK;
+    *done = true;
+    if (M <= 0 || Nn <= 0) return CP_OK;
+    CP_GEMM_LAUNCH((cpasync::launch<T, B_NC>(g, stream)));
+    return CP_OK;
+}
+
 // 128 x 128 tiles (throughput: the far trailing updates)
 int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
               int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream, int max_ctas = 0) {
     using namespace cpgemm;
+    bool done = false;
+    int rca = dgemm_async<128, false>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, tile_mode, stream, max_ctas, &done);
+    if (rca || done) return rca;
     Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.M = M; g.Nn = Nn; g.R = R;
@@ -444,6 +472,9 @@ template <bool B_NC>
 int dgemm_small(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
                 int R, double alpha, double beta, int tile_mode, cudaStream_t stream) {
     using namespace cpsmall;
+    bool done = false;
+    int rca = dgemm_async<64, B_NC>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, tile_mode, stream, 0, &done);
+    if (rca || done) return rca;
     Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.M = M; g.Nn = Nn; g.R = R;
@@ -495,6 +526,9 @@ int configure_potrf(cp_handle_t h) {
 static int dgemm_big_nc(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
                         int64_t R, double alpha, double beta, cudaStream_t stream) {
     using namespace cpgemm;
+    bool done = false;
+    int rca = dgemm_async<128, true>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, cpasync::TILES_ALL, stream, 0, &done);
+    if (rca || done) return rca;
     Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.M = M; g.Nn = Nn; g.R = R;
