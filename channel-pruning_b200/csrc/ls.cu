@@ -150,40 +150,45 @@ struct MmTask {
     int nterm;
     MmTerm t[3];
 };
-// 128 threads per task, each a 2 x 4 register micro-tile on rows tr + 16u / columns tc + 8v (interleaved: the eight
-// distinct B rows of a warp fall into distinct banks, the A rows are broadcasts): 6 shared-memory loads per 8 FMAs
-// instead of 2 per FMA (the block inversion used to be LSU bound), and 12 of the 16 warps busy.
-__device__ __forceinline__ void run_tasks(const MmTask *tasks, int ntask) {
-    const int t = threadIdx.x;
-    if (t >= ntask * 128) return;
-    const MmTask &tk = tasks[t >> 7];
-    const int tr = (t >> 3) & 15, tc = t & 7;
-    double acc[2][4];
+// Block products on the FP64 tensor path: four warps per task, one 16 x 16 quadrant each (2 x 2 m8n8k4 tiles), so the
+// twelve warps of a three-task phase sit on all four schedulers (a 2 x 4 register micro-tile per thread on 128
+// threads per task took 40k cycles for the block inversion of a panel; profiles/r2_summary.md has the new figure).
+// Fragment loads: A[r][q], B[c][q] with q contiguous (the MmTerm convention).
+__device__ __forceinline__ void run_tasks_mma(const MmTask *tasks, int ntask) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= ntask * 4) return;
+    const MmTask &tk = tasks[warp >> 2];
+    const int r0 = ((warp >> 1) & 1) * 16, c0 = (warp & 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[2][2][2];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+        for (int v = 0; v < 2; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
     for (int w = 0; w < tk.nterm; ++w) {
-        const double *ap = tk.t[w].A + tr * tk.t[w].sa;
-        const double *bp = tk.t[w].B + tc * tk.t[w].sb;
-        const int sa16 = 16 * tk.t[w].sa, sb8 = 8 * tk.t[w].sb;
-#pragma unroll 8
-        for (int q = 0; q < SB; ++q) {
-            double av[2], bv[4];
+        const double *ap = tk.t[w].A + (r0 + fr) * tk.t[w].sa + fk;
+        const double *bp = tk.t[w].B + (c0 + fr) * tk.t[w].sb + fk;
+        const int sa8 = 8 * tk.t[w].sa, sb8 = 8 * tk.t[w].sb;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) av[u] = ap[u * sa16 + q];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) bv[v] = bp[v * sb8 + q];
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        for (int q = 0; q < SB; q += 4) {
+            const double a0 = ap[q], a1 = ap[sa8 + q], b0 = bp[q], b1 = bp[sb8 + q];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[0][0][0]), "+d"(acc[0][0][1]) : "d"(a0), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[0][1][0]), "+d"(acc[0][1][1]) : "d"(a0), "d"(b1));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[1][0][0]), "+d"(acc[1][0][1]) : "d"(a1), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(acc[1][1][0]), "+d"(acc[1][1][1]) : "d"(a1), "d"(b1));
         }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) tk.dst[(tr + 16 * u) * tk.dr + (tc + 8 * v) * tk.dc] = tk.sign * acc[u][v];
+        for (int v = 0; v < 2; ++v)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                tk.dst[(r0 + 8 * u + fr) * tk.dr + (c0 + 8 * v + 2 * fk + e) * tk.dc] = tk.sign * acc[u][v][e];
 }
 
 #ifdef CP_TIMING
@@ -229,10 +234,12 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
 
     LS_CHAIN(0);
     LS_STAMP(0);
+    // (eight loads in flight per thread: this CTA is alone on the chain, nothing else hides the memory latency)
+#pragma unroll 8
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
         double v = 0.0;
-        if (i < nb && j <= i) v = A[(int64_t)i * lda + j];
+        if (i < nb && j <= i) v = __ldg(A + (int64_t)i * lda + j);
         else if (i >= nb && i == j) v = 1.0;
         As[i * LDA_S + j] = v;
     }
@@ -271,37 +278,43 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         }
         __syncthreads();
         LS_STAMP(4 + 4 * sp);
-        // trailing block -= P P'   (4 x 4 micro-tiles on interleaved rows: conflict-free shared-memory reads)
-        const int nt = T >> 2;
-        for (int idx = tid; idx < nt * nt; idx += P128_T) {
-            const int ti = idx / nt, tj = idx - ti * nt;
-            double acc[4][4];
+        // trailing block -= P P'  on the FP64 tensor path: one warp per 16 x 16 block of the lower triangle
+        {
+            const int nb16 = T >> 4, nblk = nb16 * (nb16 + 1) / 2;
+            const int fr = lane >> 2, fk = lane & 3;
+            for (int blk = warp; blk < nblk; blk += P128_T / 32) {
+                int bj = 0, l = blk;
+                while (l >= nb16 - bj) { l -= nb16 - bj; ++bj; }
+                const int bi = bj + l;
+                const double *pa = As + (r0 + 16 * bi + fr) * LDA_S + k0 + fk;
+                const double *pb = As + (r0 + 16 * bj + fr) * LDA_S + k0 + fk;
+                double acc[2][2][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-            const double *pa = As + (r0 + ti) * LDA_S + k0;
-            const double *pb = As + (r0 + tj) * LDA_S + k0;
-#pragma unroll 4
-            for (int k = 0; k < SB; ++k) {
-                double av[4], bv[4];
+                    for (int v = 0; v < 2; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    av[u] = pa[u * nt * LDA_S + k];
-                    bv[u] = pb[u * nt * LDA_S + k];
+                for (int q = 0; q < SB; q += 4) {
+                    const double a0 = pa[q], a1 = pa[8 * LDA_S + q], b0 = pb[q], b1 = pb[8 * LDA_S + q];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[0][0][0]), "+d"(acc[0][0][1]) : "d"(a0), "d"(b0));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[0][1][0]), "+d"(acc[0][1][1]) : "d"(a0), "d"(b1));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[1][0][0]), "+d"(acc[1][0][1]) : "d"(a1), "d"(b0));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[1][1][0]), "+d"(acc[1][1][1]) : "d"(a1), "d"(b1));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+                    for (int v = 0; v < 2; ++v)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int ri = r0 + 16 * bi + 8 * u + fr, cj = r0 + 16 * bj + 8 * v + 2 * fk + e;
+                            if (ri >= cj) As[ri * LDA_S + cj] -= acc[u][v][e];
+                        }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int ri = r0 + ti + nt * u, cj = r0 + tj + nt * v;
-                    if (ri >= cj) As[ri * LDA_S + cj] -= acc[u][v];
-                }
         }
         __syncthreads();
         LS_STAMP(5 + 4 * sp);
@@ -313,6 +326,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
         if (lane == 0 && ratio_min < 1e299 && ratio_out) atomic_min_pos(ratio_out, ratio_min > 0.0 ? ratio_min : 1e-300);
     }
     // ---- the factor leaves now (coalesced rows); the shared copy stays for the inversion
+#pragma unroll 8
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
         if (i < nb && j <= i) Lout[(int64_t)i * ldl + j] = As[i * LDA_S + j];
@@ -360,7 +374,7 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
             tasks[tid] = t;
         }
         __syncthreads();
-        run_tasks(tasks, ntask);
+        run_tasks_mma(tasks, ntask);
         __syncthreads();
         if (tid < ntask) {
             const int j = tid, i = j + d;
@@ -372,10 +386,11 @@ potrf128(const double *__restrict__ A, int64_t lda, int nb, double *__restrict__
             tasks[tid] = t;
         }
         __syncthreads();
-        run_tasks(tasks, ntask);
+        run_tasks_mma(tasks, ntask);
         __syncthreads();
     }
     LS_STAMP(21);
+#pragma unroll 8
     for (int e = tid; e < PB * PB; e += P128_T) {
         const int i = e >> 7, j = e & (PB - 1);
         double v = 0.0;
