@@ -125,73 +125,25 @@ def _zero_copy_seconds(s):
     return s.N * s.c * lines / 4.5e8
 
 
-# Measured constants of the two transfer paths when they run CONCURRENTLY (profiles/r2_summary.md, e2e timelines):
-# the copy engine alone moves 54 GB/s, 31 GB/s next to the in-place reader; the reader loses ~20 % next to a DMA.
-_DMA_GBS_ALONE, _DMA_GBS_SHARED, _ZC_SLOWDOWN_SHARED = 54.0, 31.0, 1.2
-
-
-def _compute_ms(s):
-    """What follows the arrival of a layer's patches (statistics, search, reconstruction), alone on the GPU; calibrated
-    on conv4_x (c = n = 512: ~20 ms).  Only the ORDER of magnitude matters: it ranks the tails of candidate plans."""
-    return 2.0 + 18.0 * s.cost() / 1.7e11
-
-
-def _simulate_transfers(plan, shapes, datas):
-    """Makespan (ms) of one step for a transfer plan: two queues (in-place gathers on the SMs, whole-map copies on the
-    copy engine) served concurrently in the given (longest-problem-first) order, each layer's compute starting when
-    its transfer ends."""
-    zc = [(i, 1e3 * _zero_copy_seconds(shapes[i])) for i in range(len(shapes)) if plan[i] == "zc"]
-    dma = [(i, 1e3 * datas[i]["fmap_host"].numel() * 4 / (_DMA_GBS_ALONE * 1e9) + 0.1) for i in range(len(shapes))
-           if plan[i] == "dma"]
-    t, zi, di, end = 0.0, 0, 0, 0.0
-    zrem = zc[0][1] if zc else 0.0
-    drem = dma[0][1] if dma else 0.0
-    while zi < len(zc) or di < len(dma):
-        both = zi < len(zc) and di < len(dma)
-        zs = 1.0 / _ZC_SLOWDOWN_SHARED if both else 1.0
-        ds = _DMA_GBS_SHARED / _DMA_GBS_ALONE if both else 1.0
-        tz = zrem / zs if zi < len(zc) else float("inf")
-        td = drem / ds if di < len(dma) else float("inf")
-        dt = min(tz, td)
-        t += dt
-        if zi < len(zc):
-            zrem -= dt * zs
-        if di < len(dma):
-            drem -= dt * ds
-        if zi < len(zc) and zrem <= 1e-9:
-            end = max(end, t + _compute_ms(shapes[zc[zi][0]]))
-            zi += 1
-            zrem = zc[zi][1] if zi < len(zc) else 0.0
-        if di < len(dma) and drem <= 1e-9:
-            end = max(end, t + _compute_ms(shapes[dma[di][0]]))
-            di += 1
-            drem = dma[di][1] if di < len(dma) else 0.0
-    return end
-
-
 def h2d_plan(shapes, datas, from_host):
     """Per layer: 'zc' (gather kernel reads the windows in place from pinned host memory) or 'dma' (copy engine
-    moves the whole map, gather from HBM).  The two paths run concurrently (the reader is bound by PCIe read requests,
-    the copy engine by bytes), so the plan is the subset of stageable maps (<= CPB200_DMA_MAX_MB each) that minimises
-    the simulated makespan of the step -- whole-map copies pay off where the windows cover most of the map (conv5_x)
-    and for as many mid-size maps (conv4_x) as keep the copy queue no longer than the reader's."""
+    moves the whole map at full PCIe bandwidth, gather from HBM).  DMA pays off when the windows cover most of
+    the map (small spatial maps: conv5_x).  CPB200_DMA_MAX_MB caps the size of a map that may be staged.
+    Tried and measured worse (profiles/r2_summary.md): also staging one conv4_x map (802 MB) on the copy engine next to
+    the reader -- 86.1 instead of 78.7 ms per step; the two paths share the link (the reader slows down 1.7x while a
+    copy is in flight), so moving work between them buys nothing unless it removes bytes."""
     if from_host == "zc":
         return ["zc"] * len(shapes)
     if from_host == "copy":
         return ["dma"] * len(shapes)
-    cap = float(os.environ.get("CPB200_DMA_MAX_MB", "1000")) * 1e6
-    cand = [i for i, d in enumerate(datas) if d["fmap_host"].numel() * 4 <= cap]
-    cand = sorted(cand, key=lambda i: datas[i]["fmap_host"].numel())[:10]  # 2^10 plans at most
-    best, best_t = None, float("inf")
-    for mask in range(1 << len(cand)):
-        plan = ["zc"] * len(shapes)
-        for b, i in enumerate(cand):
-            if mask >> b & 1:
-                plan[i] = "dma"
-        t = _simulate_transfers(plan, shapes, datas)
-        if t < best_t - 1e-9:
-            best, best_t = plan, t
-    return best
+    cap = float(os.environ.get("CPB200_DMA_MAX_MB", "300")) * 1e6
+    ratio = float(os.environ.get("CPB200_DMA_RATIO", "0.8"))
+    plan = []
+    for s, d in zip(shapes, datas):
+        nbytes = d["fmap_host"].numel() * 4
+        t_dma = nbytes / 50e9 + 1e-4
+        plan.append("dma" if (nbytes <= cap and t_dma < ratio * _zero_copy_seconds(s)) else "zc")
+    return plan
 
 
 def _mark(trace, name, label):
@@ -211,7 +163,8 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
         zc_stream, dma_stream = eng.xfer_streams()
         zc_stream.wait_stream(main)
         dma_stream.wait_stream(main)
-        dma_order = [i for i in range(len(shapes)) if plan[i] == "dma"]  # longest problem first, like the reader's queue
+        dma_order = sorted((i for i in range(len(shapes)) if plan[i] == "dma"),
+                           key=lambda i: (datas[i]["fmap_host"].numel(), i))
         for i in dma_order:
             with torch.cuda.stream(dma_stream):
                 st = eng.staging(("fmap", i), datas[i]["fmap_host"].shape)

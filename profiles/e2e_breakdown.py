@@ -29,14 +29,12 @@ def run(fh, th, reps=3):
 
 for fh, th in [(False, False), (False, True), ("zc", True)]:
     print("from_host=%-5s to_host=%-5s : %7.2f ms/step (wall)" % (fh, th, run(fh, th)))
-order = sorted(range(len(shapes)), key=lambda i: (-shapes[i].cost(), i))
-for cap in (250, 1000):
+for cap, ratio in ((300, 0.8),):
     os.environ["CPB200_DMA_MAX_MB"] = str(cap)
-    plan = pruner.h2d_plan([shapes[i] for i in order], [datas[i] for i in order], True)
-    print("from_host=auto (DMA maps <= %4d MB: %s) to_host=True : %7.2f ms/step (wall), simulated %.1f" % (
-        cap, " ".join(shapes[i].name for i, p in zip(order, plan) if p == "dma"), run(True, True),
-        pruner._simulate_transfers(plan, [shapes[i] for i in order], [datas[i] for i in order])))
-os.environ["CPB200_DMA_MAX_MB"] = "1000"
+    os.environ["CPB200_DMA_RATIO"] = str(ratio)
+    print("from_host=auto (DMA maps <= %4d MB: %s) to_host=True : %7.2f ms/step (wall)" % (
+        cap, "".join("D" if p == "dma" else "z" for p in pruner.h2d_plan(shapes, datas, True)), run(True, True)))
+os.environ["CPB200_DMA_MAX_MB"], os.environ["CPB200_DMA_RATIO"] = "300", "0.8"
 for fh in (False, True):
     tr = {}
     pruner.prune_layers(eng, shapes, datas, from_host=fh, to_host=True, trace=tr)

@@ -171,9 +171,7 @@ def test_two_rank_allgather_reassembles_every_layer(tmp_path):
 
 def test_h2d_plan_stages_small_maps_and_reads_large_ones_in_place(monkeypatch):
     """Transfer plan of the host-resident input path: maps that the sampled windows mostly cover (conv5_x: 14x14)
-    are DMA'd whole, the large ones are read in place, and of the mid-size conv4_x maps only as many go to the copy
-    engine as keep its queue shorter than the reader's (the plan minimises a simulated makespan of the two concurrent
-    queues); explicit policies override."""
+    are DMA'd whole, the others are read in place; explicit policies override."""
     import torch
 
     import cpb200
@@ -191,16 +189,10 @@ def test_h2d_plan_stages_small_maps_and_reads_large_ones_in_place(monkeypatch):
             return self._n
 
     datas = [dict(fmap_host=FakeMap(s.nbatch * s.B * s.c * s.H * s.W)) for s in shapes]
-    order = sorted(range(len(shapes)), key=lambda i: (-shapes[i].cost(), i))  # the order prune_layers issues them in
-    shapes, datas = [shapes[i] for i in order], [datas[i] for i in order]
     plan = pruner.h2d_plan(shapes, datas, True)
     by_name = {s.name: p for s, p in zip(shapes, plan)}
     assert all(by_name[n] == "dma" for n in ("conv5_1", "conv5_2", "conv5_3"))
-    assert all(by_name[n] == "zc" for n in ("conv1_2", "conv2_2", "conv3_2", "conv3_3"))
-    assert sum(by_name[n] == "dma" for n in ("conv4_1", "conv4_2", "conv4_3")) in (1, 2)
-    old = ["dma" if s.name.startswith("conv5") else "zc" for s in shapes]
-    assert pruner._simulate_transfers(plan, shapes, datas) < pruner._simulate_transfers(old, shapes, datas)
-    assert 70 < pruner._simulate_transfers(old, shapes, datas) < 90  # the round-1 plan measured 78 ms per step
+    assert all(by_name[n] == "zc" for n in ("conv1_2", "conv2_2", "conv3_2", "conv4_2"))
     assert pruner.h2d_plan(shapes, datas, "zc") == ["zc"] * len(shapes)
     assert pruner.h2d_plan(shapes, datas, "copy") == ["dma"] * len(shapes)
     monkeypatch.setenv("CPB200_DMA_MAX_MB", "1")
