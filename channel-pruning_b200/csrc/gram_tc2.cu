@@ -1,0 +1,715 @@
+// cp_gram, tensor-core mode (CP_GRAM_3XTF32 in the header), second generation: split-fp16 operands prepared once,
+// a persistent TMA -> tcgen05 pipeline with no conversion work on the critical path.
+//
+//   G = X'X (K x K),  Bxy = X'(Y - b) (K x n)      X: N x K fp32 row-major, N ~ 5e3..1e5, K = c*k*k
+//
+// The reference does this arithmetic in float64 on the CPU (numpy matmul / LAPACK inside LinearRegression.fit,
+// lib/decompose.py:665-666, and the LASSO design products lib/decompose.py:428-457).  tcgen05 has no fp32/fp64
+// MMA; the first-generation kernel (gram_tc.cu) used three kind::tf32 products of a hi/lo split made by converter
+// warps inside the GEMM -- 46 % tensor-pipe utilisation, bound by the per-k-block hand-shake of those warps
+// (profiles/r1c_summary.md).  This version removes them:
+//
+//   prep   xs = fl32(x - s_col)             s = fp32 column mean (removes the rank-one mean component)
+//          v  = xs * 2^e_col                power-of-two column scale (exact): max|v| in [2^9, 2^10)
+//          v  = hi + lo                     hi = fp16_rn(v), lo = fp16_rn(v - hi): 22 mantissa bits kept -- the
+//                                           same split precision as tf32 (10 explicit bits each), but kind::f16
+//                                           runs at twice the tf32 rate and the operands are half as wide
+//          written TRANSPOSED (operand row = column of X, reduction index contiguous, zero padded) so that the
+//          GEMM reads plain K-major SWIZZLE_128B tiles with TMA; the same pass produces the fp64 column sums
+//          and sums of squares of xs (fixed summation order)
+//   gemm   P += hi'hi + hi'lo + lo'hi       three kind::f16 MMAs (128 x 256 x 16) per k-step, fp32 accumulation
+//          in TMEM, both operands from shared memory; the tensor core truncates when it adds into its fp32
+//          accumulator, so an accumulator takes 128 rows (24 additions), then the drain warps add it into fp32
+//          registers with round-to-nearest while the MMAs continue on the second accumulator
+//   reduce fp64 sum of the row splits, exact rescale by 2^-(e_i + e_j), shift undone exactly
+//          (G = P + s T' + T s' + N s s',  T = column sums of xs in fp64), diagonal from the fp64 squares,
+//          lower triangle written in the same pass.
+//
+// GEMM anatomy: persistent grid (one CTA per SM), static round-robin over (output tile, row split) items.
+//   warp 8   TMA producer: per 64-row stage four boxes (A hi/lo 64 x 128, B hi/lo 64 x 256; diagonal tiles take
+//            the A operand out of the B tile), 2 stages of 96 KB
+//   warp 9   TMEM allocator + single-thread MMA issuer; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 0-7  drain: thread = accumulator row x 128 columns, tcgen05.ld, fp32 adds, one fp32 partial tile per item
+// Bound: L2 -> SM operand traffic (96 KB per 1536 tensor-pipe cycles = 62 B/clk/SM against ~42 B/clk/SM of L2
+// slice throughput), then the tensor pipe.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+int cp_gram_fp64_products(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype,
+                          int n, int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G,
+                          double *Bxy, double *sx, double *sy, double *yy, cudaStream_t stream);
+bool cp_gram_tc_eligible(const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n, int64_t ldy,
+                         const int32_t *rows, bool wantB);
+
+namespace {
+
+constexpr int TM = 128, TN = 256, KS = 64;  // output tile (rows of A x rows of B), reduction rows per stage
+constexpr int A_TILE = TM * 128;            // bytes of one A operand tile (hi or lo): 128 rows x 128 B
+constexpr int B_TILE = TN * 128;
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // 96 KB
+constexpr int STAGES = 2;
+constexpr int SUB_STAGES = 2;               // stages per accumulator run (128 rows)
+constexpr int NDRAIN_WARPS = 8;
+constexpr int NTHREADS = 32 * (NDRAIN_WARPS + 2);
+constexpr int W_TMA = NDRAIN_WARPS, W_MMA = NDRAIN_WARPS + 1;  // single-thread roles on the highest warp ids
+constexpr int T_TMA = 32 * W_TMA, T_MMA = 32 * W_MMA;
+constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+constexpr int NBAR = 2 * STAGES + 4;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
+constexpr int RS = 32;                      // row splits of the statistics passes (partials combined in fixed order)
+constexpr int PT = 64;                      // prep tile: 64 rows x 64 columns
+
+struct Tc2Params {
+    float *partial;      // [nsplit][ntiles][128][256]
+    int64_t Np;          // padded row count (multiple of 64) = inner extent of the operand matrix
+    int rows_per_split;  // multiple of 128
+    int nsplit;
+    int tiles_sym;       // number of 128 x 256 tiles covering the upper triangle of G (0 when G is not requested)
+    int tk;              // ceil(K / 128): A tiles
+    int tjx;             // ceil(K / 256): B tiles inside X
+    int tjy0;            // first B tile of the Y region (= Kp / 256)
+    int tnb;             // B tiles of the Y region
+    int ntiles;
+    int mtot;            // operand rows of one half (hi); the lo half starts at row mtot
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (the hardware descriptor format
+// documented as cute::UMMA::SmemDescriptor: start >> 4 | LBO | SBO >> 4 at 32 | version 1 at 46 | layout 2 at 61)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// item -> (tile, split) -> (ti, tJ); the tiles of the upper triangle first (row ti: tJ = ti/2 .. tjx-1), then X'Y
+struct Item {
+    int tile, split, ti, tj, nst;
+    int64_t r_begin;
+    bool diag;  // the A rows are part of the B tile (ti / 2 == tJ inside X)
+};
+__device__ __forceinline__ Item decode_item(const Tc2Params &P, int w) {
+    Item it;
+    it.split = w / P.ntiles;
+    it.tile = w - it.split * P.ntiles;
+    int l = it.tile;
+    if (l < P.tiles_sym) {
+        int ti = 0;
+        while (l >= P.tjx - (ti >> 1)) { l -= P.tjx - (ti >> 1); ++ti; }
+        it.ti = ti;
+        it.tj = (ti >> 1) + l;
+        it.diag = (l == 0);
+    } else {
+        l -= P.tiles_sym;
+        it.ti = l / P.tnb;
+        it.tj = P.tjy0 + (l - it.ti * P.tnb);
+        it.diag = false;
+    }
+    it.r_begin = (int64_t)it.split * P.rows_per_split;
+    int64_t r_end = it.r_begin + P.rows_per_split;
+    if (r_end > P.Np) r_end = P.Np;
+    it.nst = (int)((r_end - it.r_begin) / KS);
+    return it;
+}
+
+// ------------------------------------------------------------------ the GEMM
+__global__ void __launch_bounds__(NTHREADS, 1)
+gram_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Tc2Params P) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = P.ntiles * P.nsplit;
+
+    auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
+    constexpr int FULL = 0, EMPTY = STAGES, ACC_FULL = 2 * STAGES, ACC_EMPTY = 2 * STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
+
+    if (threadIdx.x == T_TMA) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar(FULL + s), 1);
+            mbar_init(bar(EMPTY + s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar(ACC_FULL + a), 1);
+            mbar_init(bar(ACC_EMPTY + a), NDRAIN_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {  // all 512 TMEM columns: two fp32 accumulators of 256 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == W_TMA) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t g = 0;  // stages issued so far
+            for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+                const Item it = decode_item(P, w);
+                const int rowA = it.ti * TM, rowB = it.tj * TN;
+                for (int st = 0; st < it.nst; ++st, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    mbar_wait(bar(EMPTY + s), ph ^ 1);
+                    const uint32_t dst = sbase + s * STAGE_BYTES;
+                    const int r0 = (int)(it.r_begin + (int64_t)st * KS);
+                    mbar_arrive_expect_tx(bar(FULL + s), it.diag ? 2 * B_TILE : STAGE_BYTES);
+                    if (!it.diag) {
+                        tma_load_2d(dst, &mapA, bar(FULL + s), r0, rowA);
+                        tma_load_2d(dst + A_TILE, &mapA, bar(FULL + s), r0, P.mtot + rowA);
+                    }
+                    tma_load_2d(dst + 2 * A_TILE, &mapB, bar(FULL + s), r0, rowB);
+                    tma_load_2d(dst + 2 * A_TILE + B_TILE, &mapB, bar(FULL + s), r0, P.mtot + rowB);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D fp32 (1 << 4), A and B fp16 (format 0), both K-major, N >> 3 at 17, M >> 4 at 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            uint32_t g = 0, gc = 0;  // stages / accumulator runs so far
+            for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+                const Item it = decode_item(P, w);
+                for (int st = 0; st < it.nst; ++st, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t ph = (g / STAGES) & 1;
+                    const int kk = st % SUB_STAGES;
+                    const uint32_t ab = gc & 1;
+                    if (kk == 0) mbar_wait(bar(ACC_EMPTY + ab), ((gc >> 1) & 1) ^ 1);  // accumulator drained
+                    mbar_wait(bar(FULL + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t stage = sbase + s * STAGE_BYTES;
+                    const uint32_t b_hi = stage + 2 * A_TILE, b_lo = b_hi + B_TILE;
+                    const uint32_t a_hi = it.diag ? b_hi + (uint32_t)(it.ti & 1) * A_TILE : stage;
+                    const uint32_t a_lo = it.diag ? b_lo + (uint32_t)(it.ti & 1) * A_TILE : stage + A_TILE;
+                    const uint32_t acc = tmem_base + ab * TN;
+#pragma unroll
+                    for (int ks = 0; ks < KS / 16; ++ks) {
+                        const uint32_t off = ks * 32;  // 16 fp16 = 32 bytes along K inside the 128-byte swizzled row
+                        const uint32_t first = (kk == 0 && ks == 0) ? 0u : 1u;
+                        umma_f16_ss(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
+                        umma_f16_ss(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
+                        umma_f16_ss(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
+                    }
+                    umma_commit(bar(EMPTY + s));  // stage free once these MMAs have read it
+                    if (kk == SUB_STAGES - 1 || st == it.nst - 1) {
+                        umma_commit(bar(ACC_FULL + ab));
+                        ++gc;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== drain warps =====================
+        // thread -> accumulator row m (TMEM lane; a warp reaches the lanes of its quadrant, warp % 4) x 128 columns
+        const int quad = warp & 3, half = warp >> 2;
+        const int m = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
+        uint32_t gc = 0;
+        for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+            const Item it = decode_item(P, w);
+            const int nsub = (it.nst + SUB_STAGES - 1) / SUB_STAGES;
+            float accv[128];
+#pragma unroll
+            for (int e = 0; e < 128; ++e) accv[e] = 0.f;
+            for (int c = 0; c < nsub; ++c, ++gc) {
+                const uint32_t ab = gc & 1;
+                mbar_wait(bar(ACC_FULL + ab), (gc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int gq = 0; gq < 2; ++gq) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(lane_addr + ab * TN + (uint32_t)(gq * 64), r0);
+                    tmem_ld32(lane_addr + ab * TN + (uint32_t)(gq * 64 + 32), r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        accv[gq * 64 + e] = __fadd_rn(accv[gq * 64 + e], __uint_as_float(r0[e]));
+                        accv[gq * 64 + 32 + e] = __fadd_rn(accv[gq * 64 + 32 + e], __uint_as_float(r1[e]));
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(ACC_EMPTY + ab));
+            }
+            float *dst = P.partial + ((size_t)it.split * P.ntiles + it.tile) * (size_t)(TM * TN) + (size_t)m * TN + half * 128;
+#pragma unroll
+            for (int e = 0; e < 128; e += 4)
+                *reinterpret_cast<float4 *>(dst + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------ statistics pass 1: column sums and max |x|
+__global__ void __launch_bounds__(256)
+colstat_part(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, double *__restrict__ part,
+             float *__restrict__ part_max) {
+    __shared__ double s1[8][33];
+    __shared__ float s2[8][33];
+    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    const int64_t per = (nrows + RS - 1) / RS;
+    const int64_t r0 = (int64_t)blockIdx.y * per;
+    const int64_t r1 = r0 + per < nrows ? r0 + per : nrows;
+    double a = 0.0;
+    float mx = 0.f;
+    if (col < ncols) {
+        for (int64_t r = r0 + rg; r < r1; r += 8) {
+            const float v = __ldg(X + r * ld + col);
+            a += (double)v;
+            mx = fmaxf(mx, fabsf(v));
+        }
+    }
+    s1[rg][cx] = a;
+    s2[rg][cx] = mx;
+    __syncthreads();
+    if (rg == 0 && col < ncols) {
+        double t = 0.0;
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t += s1[k][cx]; m2 = fmaxf(m2, s2[k][cx]); }
+        part[(size_t)blockIdx.y * ncols + col] = t;
+        part_max[(size_t)blockIdx.y * ncols + col] = m2;
+    }
+}
+
+// shift[j] = fl32(mean), scale[j] = 2^e with 2 * max|x| * 2^e in [2^9, 2^10), inv[j] = 2^-e (fp64)
+__global__ void colstat_finish(const double *__restrict__ part, const float *__restrict__ part_max, int ncols, double invN,
+                               float *__restrict__ shift, float *__restrict__ scale, double *__restrict__ inv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    double t = 0.0;
+    float mx = 0.f;
+    for (int r = 0; r < RS; ++r) {
+        t += part[(size_t)r * ncols + j];
+        mx = fmaxf(mx, part_max[(size_t)r * ncols + j]);
+    }
+    shift[j] = (float)(t * invN);
+    int e = 0;
+    const float b = 2.f * mx;  // |x - mean| <= 2 max|x|
+    if (b > 0.f && isfinite(b)) {
+        e = 9 - ilogbf(b);
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    scale[j] = ldexpf(1.f, e);
+    inv[j] = ldexp(1.0, -e);
+}
+
+// ------------------------------------------------------------------ operand preparation (+ statistics pass 2)
+// One CTA = a strip of 64 columns x the 64-row tiles of one row split.  Reads X once (coalesced along the columns),
+// writes the hi and lo operand rows (coalesced along the reduction index) through a swizzled shared-memory tile,
+// and accumulates the fp64 column sums / sums of squares of xs in a fixed order.
+__global__ void __launch_bounds__(256)
+tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int64_t Np, int tiles_per_split,
+         const float *__restrict__ shift, const float *__restrict__ scale, __half *__restrict__ Ohi,
+         __half *__restrict__ Olo, double *__restrict__ part, double *__restrict__ part_sq, int part_ld) {
+    __shared__ __align__(16) unsigned char tile_hi[PT * 128], tile_lo[PT * 128];
+    __shared__ double red[16][PT + 1];
+    const int t = threadIdx.x, jq = t & 15, rg = t >> 4;
+    const int col0 = blockIdx.x * PT;     // first column of the strip = first operand row
+    const int cj = col0 + jq * 4;
+    const bool vec = (cj + 3 < ncols);
+    float sh[4], sc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        sh[c] = cj + c < ncols ? shift[cj + c] : 0.f;
+        sc[c] = cj + c < ncols ? scale[cj + c] : 0.f;
+    }
+    double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    const int64_t ntile = Np / PT;
+    const int64_t tb = (int64_t)blockIdx.y * tiles_per_split;
+    int64_t te = tb + tiles_per_split;
+    if (te > ntile) te = ntile;
+
+    float4 cur[4], nxt[4];
+    auto load = [&](int64_t tile, float4(&v)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = tile * PT + rg * 4 + i;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) {
+                const float *p = X + r * ld + cj;
+                if (vec) x = __ldg(reinterpret_cast<const float4 *>(p));
+                else {
+                    if (cj + 0 < ncols) x.x = __ldg(p + 0);
+                    if (cj + 1 < ncols) x.y = __ldg(p + 1);
+                    if (cj + 2 < ncols) x.z = __ldg(p + 2);
+                }
+            }
+            v[i] = x;
+        }
+    };
+    if (tb < te) load(tb, cur);
+    for (int64_t tile = tb; tile < te; ++tile) {
+        if (tile + 1 < te) load(tile + 1, nxt);
+        // split: thread owns rows rg*4 .. rg*4+3 of the tile and 4 columns
+        __half hi[4][4], lo[4][4];  // [column][row]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool live = tile * PT + rg * 4 + i < nrows;
+            const float xv[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float xs = (live && cj + c < ncols) ? __fsub_rn(xv[c], sh[c]) : 0.f;
+                const double x64 = (double)xs;
+                a[c] += x64;
+                q[c] = fma(x64, x64, q[c]);
+                const float v = __fmul_rn(xs, sc[c]);
+                const __half h = __float2half_rn(v);
+                hi[c][i] = h;
+                lo[c][i] = __float2half_rn(__fsub_rn(v, __half2float(h)));
+            }
+        }
+        // operand row j (= column of the strip): 64 reduction values = 8 chunks of 16 B; chunk index swizzled by j >> 2
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = jq * 4 + c;
+            const uint32_t off = (uint32_t)j * 128u + (uint32_t)(((rg >> 1) ^ (jq & 7)) << 4) + (uint32_t)((rg & 1) << 3);
+            uint2 ph, pl;
+            ph.x = (uint32_t)__half_as_ushort(hi[c][0]) | ((uint32_t)__half_as_ushort(hi[c][1]) << 16);
+            ph.y = (uint32_t)__half_as_ushort(hi[c][2]) | ((uint32_t)__half_as_ushort(hi[c][3]) << 16);
+            pl.x = (uint32_t)__half_as_ushort(lo[c][0]) | ((uint32_t)__half_as_ushort(lo[c][1]) << 16);
+            pl.y = (uint32_t)__half_as_ushort(lo[c][2]) | ((uint32_t)__half_as_ushort(lo[c][3]) << 16);
+            *reinterpret_cast<uint2 *>(tile_hi + off) = ph;
+            *reinterpret_cast<uint2 *>(tile_lo + off) = pl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int j = (t >> 3) + 32 * it, ch = t & 7;
+            const uint32_t off = (uint32_t)j * 128u + (uint32_t)((ch ^ ((j >> 2) & 7)) << 4);
+            const size_t o = (size_t)(col0 + j) * (size_t)Np + (size_t)tile * PT + (size_t)ch * 8;
+            *reinterpret_cast<uint4 *>(Ohi + o) = *reinterpret_cast<const uint4 *>(tile_hi + off);
+            *reinterpret_cast<uint4 *>(Olo + o) = *reinterpret_cast<const uint4 *>(tile_lo + off);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+    }
+    // column statistics of the strip: 16 row groups summed in a fixed order
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[rg][jq * 4 + c] = pass ? q[c] : a[c];
+        __syncthreads();
+        if (t < PT && col0 + t < ncols) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s += red[k][t];
+            (pass ? part_sq : part)[(size_t)blockIdx.y * part_ld + col0 + t] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void tc2_stat_finish(const double *__restrict__ part, const double *__restrict__ part_sq, int nsplit_used,
+                                int part_ld, int ncols, double *__restrict__ T, double *__restrict__ SQ) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    double t = 0.0, t2 = 0.0;
+    for (int r = 0; r < nsplit_used; ++r) {
+        t += part[(size_t)r * part_ld + j];
+        t2 += part_sq[(size_t)r * part_ld + j];
+    }
+    T[j] = t;
+    if (SQ) SQ[j] = t2;
+}
+
+// ------------------------------------------------------------------ reduction of the row splits
+// One CTA = one 32 x 32 block of a tile.  C[i,j] = inv_i inv_j sum_s P_s[i,j] + uA_i TB_j + TA_i uB_j + N uA_i uB_j,
+// u = (double)shift32 - bias.  Symmetric mode: blocks below the diagonal 128-block are skipped, the diagonal
+// 128-block reads the upper element for both (i,j) and (j,i) (the tensor core produced them with different
+// rounding; G must be bitwise symmetric), strictly-upper blocks are also written transposed.
+__global__ void __launch_bounds__(256)
+reduce_tc2(const float *__restrict__ partial, int nsplit, int ntiles, int tile0, int sym, int tjx, int tjy0, int tnb,
+           const float *__restrict__ shiftA, const double *__restrict__ invA, const double *__restrict__ TA,
+           const float *__restrict__ shiftB, const double *__restrict__ invB, const float *__restrict__ biasB,
+           const double *__restrict__ TB, const double *__restrict__ diag_sq, double Nd, int M, int Nn,
+           double *__restrict__ C, int64_t ldc) {
+    __shared__ double tr[32][33];
+    int l = blockIdx.x, ti, tj, colbase;  // colbase: first column of C covered by the tile
+    if (sym) {
+        ti = 0;
+        while (l >= tjx - (ti >> 1)) { l -= tjx - (ti >> 1); ++ti; }
+        tj = (ti >> 1) + l;
+        colbase = tj * TN;
+    } else {
+        ti = l / tnb;
+        tj = l - ti * tnb;
+        colbase = tj * TN;
+    }
+    const int sr = blockIdx.y >> 3, sc = blockIdx.y & 7;  // 4 x 8 blocks of 32 x 32
+    const int i0 = ti * TM + sr * 32, j0 = colbase + sc * 32;
+    if (i0 >= M || j0 >= Nn) return;
+    const int cb128 = j0 / 128;
+    if (sym && cb128 < ti) return;
+    const bool dblock = sym && cb128 == ti;
+    const size_t tile_elems = (size_t)TM * TN;
+    const float *p0 = partial + (size_t)(tile0 + blockIdx.x) * tile_elems;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int lr = ty * 4 + rr;                 // row inside the block
+        const int i = i0 + lr, j = j0 + tx;
+        double s = 0.0;
+        if (i < M && j < Nn) {
+            int er = sr * 32 + lr, ec = sc * 32 + tx;  // element inside the tile
+            if (dblock && i > j) {                      // mirror inside the diagonal 128-block
+                const int cb = (ti & 1) * 128;
+                const int nr = ec - cb, nc = cb + er;
+                er = nr;
+                ec = nc;
+            }
+            const size_t e = (size_t)er * TN + ec;
+            for (int c = 0; c < nsplit; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
+            s *= invA[i] * invB[j];
+            if (sym && i == j) s = diag_sq[i];
+            const double ua = (double)shiftA[i];
+            const double ub = (double)shiftB[j] - (biasB ? (double)biasB[j] : 0.0);
+            s += ua * TB[j] + TA[i] * ub + Nd * ua * ub;
+            C[(int64_t)i * ldc + j] = s;
+        }
+        tr[lr][tx] = s;
+    }
+    if (sym && cb128 > ti) {  // strictly above the diagonal blocks: the transposed copy
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int lc = ty * 4 + rr;
+            const int j = j0 + lc, i = i0 + tx;
+            if (i < M && j < Nn) C[(int64_t)j * ldc + i] = tr[tx][lc];
+        }
+    }
+}
+
+// out[j] = T[j] + N * ((double)shift[j] - bias[j])
+__global__ void finish_sums2(const double *__restrict__ T, const float *__restrict__ shift, const float *__restrict__ bias,
+                             double Nd, int ncols, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncols) out[j] = T[j] + Nd * ((double)shift[j] - (bias ? (double)bias[j] : 0.0));
+}
+
+typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map16(cp_handle_t h, CUtensorMap *map, const __half *base, int64_t inner, int64_t rows, int box_rows) {
+    if (!h->tmap_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) CP_FAIL(CP_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        h->tmap_encode = fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((encode_fn_t)h->tmap_encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box,
+                                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CP_FAIL(CP_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed (%d)", (int)r);
+    return CP_OK;
+}
+
+}  // namespace
+
+int cp_gram_tc2(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
+                int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy, double *sx,
+                double *sy, double *yy, cudaStream_t stream) {
+    const bool wantB = Bxy != nullptr;
+    if (yy != nullptr || !cp_gram_tc_eligible(X, N, K, ldx, Yraw, y_dtype, n, ldy, rows, wantB || sy != nullptr))
+        return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
+    if (sy != nullptr && !wantB)  // column sums of Y alone: nothing for the tensor cores to do
+        return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
+    const float *Y = (const float *)Yraw;
+    const bool haveY = wantB;
+    const int tk = cp_cdiv(K, TM), tjx = cp_cdiv(K, TN);
+    const int Kp = tjx * TN;
+    const int tnb = wantB ? cp_cdiv(n, TN) : 0;
+    const int np_ = tnb * TN;
+    const int mtot = Kp + np_;
+    int tiles_sym = 0;
+    if (G)
+        for (int ti = 0; ti < tk; ++ti) tiles_sym += tjx - (ti >> 1);
+    const int ntiles = tiles_sym + tk * tnb;
+    const int64_t Np = cp_cdiv(N, KS) * (int64_t)KS;
+
+    // Row splits.  An item (tile x split) costs its stages (~1.2 us each: the L2 -> SM operand stream) plus a small
+    // hand-over; items run round-robin on the persistent grid; every split adds one fp32 partial per tile (written,
+    // then read by the reduction).  A split is a multiple of the 128-row accumulator run and at most 32 runs
+    // (the fp32 register sums stay below 4e-7 of the partial sum whatever N is).
+    constexpr int64_t SUB = SUB_STAGES * KS, MAX_SPLIT_ROWS = 32 * SUB;
+    const int ns_min = (int)cp_cdiv(N, MAX_SPLIT_ROWS);
+    int nsplit = ns_min, rps = (int)(cp_cdiv(cp_cdiv(N, ns_min), SUB) * SUB);
+    if (ntiles > 0) {
+        double best = 1e300;
+        const int max_ns = (int)cp_cdiv(N, SUB);
+        for (int ns = ns_min; ns <= max_ns && ns < ns_min + 32; ++ns) {
+            const int64_t r = cp_cdiv(cp_cdiv(N, ns), SUB) * SUB;
+            const int ns_eff = (int)cp_cdiv(N, r);
+            const double rounds = (double)cp_cdiv((int64_t)ntiles * ns_eff, h->num_sms);
+            const double cost = rounds * (1.2 * (double)(r / KS) + 1.0) +
+                                (double)ns_eff * (2.0 * ntiles * TM * TN * 4.0 / 5.0e6);
+            if (cost < best * 0.98) {
+                best = cost;
+                nsplit = ns_eff;
+                rps = (int)r;
+            }
+        }
+    }
+
+    const size_t part_elems = (size_t)nsplit * ntiles * TM * TN;
+    const size_t op_elems = 2 * (size_t)mtot * (size_t)Np;  // hi rows, then lo rows
+    const int wmax = Kp > np_ ? Kp : (np_ > 0 ? np_ : 1);
+    const int nY = n > 0 ? n : 1;
+    const size_t need = cp_carver::need(part_elems, 4) + cp_carver::need(op_elems, 2) + 2 * cp_carver::need(K, 8) +
+                        cp_carver::need(nY, 8) + 2 * cp_carver::need((size_t)RS * wmax, 8) +
+                        cp_carver::need((size_t)RS * wmax, 4) + 2 * cp_carver::need(K, 4) + 2 * cp_carver::need(nY, 4) +
+                        cp_carver::need(K, 8) + cp_carver::need(nY, 8);
+    void *ws = nullptr;
+    int rc = cp_ws_reserve(h, need, &ws);
+    if (rc) return rc;
+    cp_carver cv(ws);
+    float *partial = cv.take<float>(part_elems);
+    __half *ops = cv.take<__half>(op_elems);
+    double *TX = cv.take<double>(K), *SQX = cv.take<double>(K);
+    double *TY = cv.take<double>(nY);
+    double *cpart = cv.take<double>((size_t)RS * wmax), *cpart_sq = cv.take<double>((size_t)RS * wmax);
+    float *cpart_max = cv.take<float>((size_t)RS * wmax);
+    float *shX = cv.take<float>(K), *scX = cv.take<float>(K);
+    float *shY = cv.take<float>(nY), *scY = cv.take<float>(nY);
+    double *invX = cv.take<double>(K), *invY = cv.take<double>(nY);
+    const double invN = 1.0 / (double)N, Nd = (double)N;
+    __half *Ohi = ops, *Olo = ops + (size_t)mtot * (size_t)Np;
+    const int64_t ntile_rows = Np / PT;
+    const int tiles_per_split = cp_cdiv(ntile_rows, RS);
+    const int splits_used = cp_cdiv(ntile_rows, tiles_per_split);
+
+    colstat_part<<<dim3(cp_cdiv(K, 32), RS), 256, 0, stream>>>(X, ldx, K, N, cpart, cpart_max);
+    CP_CHECK_LAUNCH();
+    colstat_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, cpart_max, K, invN, shX, scX, invX);
+    CP_CHECK_LAUNCH();
+    // operand rows 0..Kp-1 (columns >= K give zero rows) + statistics of xs
+    tc2_prep<<<dim3(Kp / PT, splits_used), 256, 0, stream>>>(X, ldx, K, N, Np, tiles_per_split, shX, scX, Ohi, Olo, cpart,
+                                                             cpart_sq, wmax);
+    CP_CHECK_LAUNCH();
+    tc2_stat_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, cpart_sq, splits_used, wmax, K, TX, SQX);
+    CP_CHECK_LAUNCH();
+    if (haveY) {
+        colstat_part<<<dim3(cp_cdiv(n, 32), RS), 256, 0, stream>>>(Y, ldy, n, N, cpart, cpart_max);
+        CP_CHECK_LAUNCH();
+        colstat_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, cpart_max, n, invN, shY, scY, invY);
+        CP_CHECK_LAUNCH();
+        tc2_prep<<<dim3(np_ / PT, splits_used), 256, 0, stream>>>(Y, ldy, n, N, Np, tiles_per_split, shY, scY,
+                                                                  Ohi + (size_t)Kp * Np, Olo + (size_t)Kp * Np, cpart,
+                                                                  cpart_sq, wmax);
+        CP_CHECK_LAUNCH();
+        tc2_stat_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, cpart_sq, splits_used, wmax, n, TY, nullptr);
+        CP_CHECK_LAUNCH();
+    }
+    if (ntiles > 0) {
+        CUtensorMap mapA, mapB;
+        rc = make_map16(h, &mapA, ops, Np, 2 * (int64_t)mtot, TM);
+        if (rc) return rc;
+        rc = make_map16(h, &mapB, ops, Np, 2 * (int64_t)mtot, TN);
+        if (rc) return rc;
+        Tc2Params P{};
+        P.partial = partial; P.Np = Np; P.rows_per_split = rps; P.nsplit = nsplit; P.tiles_sym = tiles_sym; P.tk = tk;
+        P.tjx = tjx; P.tjy0 = Kp / TN; P.tnb = tnb; P.ntiles = ntiles; P.mtot = mtot;
+        static cp_per_device_flag configured;
+        if (bool *done = configured.slot(); !*done) {
+            CP_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            *done = true;
+        }
+        const int nitems = ntiles * nsplit;
+        const int grid = nitems < h->num_sms ? nitems : h->num_sms;
+        gram_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, P);
+        CP_CHECK_LAUNCH();
+        if (tiles_sym > 0) {
+            reduce_tc2<<<dim3(tiles_sym, 32), 256, 0, stream>>>(partial, nsplit, ntiles, 0, 1, tjx, 0, 0, shX, invX, TX, shX,
+                                                               invX, nullptr, TX, SQX, Nd, K, K, G, K);
+            CP_CHECK_LAUNCH();
+        }
+        if (wantB) {
+            reduce_tc2<<<dim3(tk * tnb, 32), 256, 0, stream>>>(partial, nsplit, ntiles, tiles_sym, 0, tjx, P.tjy0, tnb, shX,
+                                                              invX, TX, shY, invY, y_bias, TY, nullptr, Nd, K, n, Bxy, n);
+            CP_CHECK_LAUNCH();
+        }
+    }
+    if (sx) {
+        finish_sums2<<<cp_cdiv(K, 256), 256, 0, stream>>>(TX, shX, nullptr, Nd, K, sx);
+        CP_CHECK_LAUNCH();
+    }
+    if (sy) {
+        finish_sums2<<<cp_cdiv(n, 256), 256, 0, stream>>>(TY, shY, y_bias, Nd, n, sy);
+        CP_CHECK_LAUNCH();
+    }
+    return CP_OK;
+}
