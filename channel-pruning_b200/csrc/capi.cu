@@ -39,19 +39,25 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->fac_rows = 0;
     h->aux = nullptr;
     h->aux_bytes = 0;
+    h->gram_profile = false;
+    h->ev_gram0 = h->ev_gram1 = nullptr;
     *out = h;
     return CP_OK;
 }
 
 extern "C" int cp_destroy(cp_handle_t h) {
     if (!h) return CP_OK;
-    if (h->ws || h->side || h->fac || h->aux) {
+    if (h->ws || h->side || h->fac || h->aux || h->ev_gram0) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(h->device);
         if (h->ws) cudaFree(h->ws);
         if (h->fac) cudaFree(h->fac);
         if (h->aux) cudaFree(h->aux);
+        if (h->ev_gram0) {
+            cudaEventDestroy(h->ev_gram0);
+            cudaEventDestroy(h->ev_gram1);
+        }
         if (h->side) {
             cudaStreamDestroy(h->side);
             cudaStreamDestroy(h->bulk);
@@ -62,6 +68,26 @@ extern "C" int cp_destroy(cp_handle_t h) {
         cudaSetDevice(cur);
     }
     delete h;
+    return CP_OK;
+}
+
+extern "C" int cp_gram_profile(cp_handle_t h, int enable) {
+    CP_REQUIRE(h != nullptr, "cp_gram_profile: NULL handle");
+    CP_DEVICE_GUARD(h);
+    if (enable && !h->ev_gram0) {
+        CP_CUDA(cudaEventCreate(&h->ev_gram0));
+        CP_CUDA(cudaEventCreate(&h->ev_gram1));
+    }
+    h->gram_profile = enable != 0;
+    return CP_OK;
+}
+
+extern "C" int cp_gram_kernel_ms(cp_handle_t h, float *ms) {
+    CP_REQUIRE(h != nullptr && ms != nullptr, "cp_gram_kernel_ms: NULL argument");
+    CP_REQUIRE(h->gram_profile && h->ev_gram0, "cp_gram_kernel_ms: profiling is off (cp_gram_profile)");
+    CP_DEVICE_GUARD(h);
+    CP_CUDA(cudaEventSynchronize(h->ev_gram1));
+    CP_CUDA(cudaEventElapsedTime(ms, h->ev_gram0, h->ev_gram1));
     return CP_OK;
 }
 

@@ -28,6 +28,9 @@ struct cp_handle_s {
     // carves its own scratch out of `ws`
     void *aux;
     size_t aux_bytes;
+    // cp_gram_profile: CUDA events around the tensor-core GEMM kernel of cp_gram (bench.py's roofline of that kernel)
+    bool gram_profile;
+    cudaEvent_t ev_gram0, ev_gram1;
 };
 
 // Entry points run on the handle's device whatever the caller's current device is (restored on return).

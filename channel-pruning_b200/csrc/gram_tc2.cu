@@ -34,6 +34,7 @@
 // slice throughput), then the tensor pipe.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -87,9 +88,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+// bounded wait: a protocol bug traps (CUDA error) after ~2 s instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+    uint64_t t0 = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -98,7 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 26)) __trap();
+        if (!done && (spin & 63) == 63) {
+            uint64_t t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -142,6 +149,7 @@ struct Item {
     int64_t r_begin;
     bool diag;  // the A rows are part of the B tile (ti / 2 == tJ inside X)
 };
+template <bool PAIR>
 __device__ __forceinline__ Item decode_item(const Tc2Params &P, int w) {
     Item it;
     it.split = w / P.ntiles;
@@ -149,9 +157,14 @@ __device__ __forceinline__ Item decode_item(const Tc2Params &P, int w) {
     int l = it.tile;
     if (l < P.tiles_sym) {
         int ti = 0;
-        while (l >= P.tjx - (ti >> 1)) { l -= P.tjx - (ti >> 1); ++ti; }
+        if (PAIR) {  // 256 x 256 tiles: row ti holds tJ = ti .. tjx-1
+            while (l >= P.tjx - ti) { l -= P.tjx - ti; ++ti; }
+            it.tj = ti + l;
+        } else {     // 128 x 256 tiles: row ti holds tJ = ti/2 .. tjx-1
+            while (l >= P.tjx - (ti >> 1)) { l -= P.tjx - (ti >> 1); ++ti; }
+            it.tj = (ti >> 1) + l;
+        }
         it.ti = ti;
-        it.tj = (ti >> 1) + l;
         it.diag = (l == 0);
     } else {
         l -= P.tiles_sym;
@@ -204,7 +217,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) {
             uint32_t g = 0;  // stages issued so far
             for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
-                const Item it = decode_item(P, w);
+                const Item it = decode_item<false>(P, w);
                 const int rowA = it.ti * TM, rowB = it.tj * TN;
                 for (int st = 0; st < it.nst; ++st, ++g) {
                     const int s = g % STAGES;
@@ -229,7 +242,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t g = 0, gc = 0;  // stages / accumulator runs so far
             for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
-                const Item it = decode_item(P, w);
+                const Item it = decode_item<false>(P, w);
                 for (int st = 0; st < it.nst; ++st, ++g) {
                     const int s = g % STAGES;
                     const uint32_t ph = (g / STAGES) & 1;
@@ -267,7 +280,7 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
         uint32_t gc = 0;
         for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
-            const Item it = decode_item(P, w);
+            const Item it = decode_item<false>(P, w);
             const int nsub = (it.nst + SUB_STAGES - 1) / SUB_STAGES;
             float accv[128];
 #pragma unroll
@@ -306,80 +319,316 @@ gram_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
-// ------------------------------------------------------------------ statistics pass 1: column sums and max |x|
-__global__ void __launch_bounds__(256)
-colstat_part(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, double *__restrict__ part,
-             float *__restrict__ part_max) {
-    __shared__ double s1[8][33];
-    __shared__ float s2[8][33];
-    const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + cx;
-    const int64_t per = (nrows + RS - 1) / RS;
-    const int64_t r0 = (int64_t)blockIdx.y * per;
-    const int64_t r1 = r0 + per < nrows ? r0 + per : nrows;
-    double a = 0.0;
-    float mx = 0.f;
-    if (col < ncols) {
-        for (int64_t r = r0 + rg; r < r1; r += 8) {
-            const float v = __ldg(X + r * ld + col);
-            a += (double)v;
-            mx = fmaxf(mx, fabsf(v));
+// ------------------------------------------------------------------ the GEMM, CTA-pair version (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute one 256 x 256 tile: UMMA M = 256 (128 accumulator rows in the tensor memory
+// of each CTA), N = 256 with each CTA holding half of the B rows in ITS shared memory.  Per CTA and 64-row stage:
+// A hi/lo (own 128 rows) + B hi/lo (own 128 of the 256 B rows) = 64 KB for the same 1536 tensor-pipe cycles -- two
+// thirds of the operand traffic of the single-CTA tile -- which also makes room for a third stage.
+//   both CTAs   TMA producer (cp.async.bulk.tensor ... cta_group::2: complete_tx lands on the LEADER's full barrier),
+//               8 drain warps (own accumulator rows), arrive on the leader's accumulator-empty barrier
+//   leader      expect_tx for both CTAs' bytes, single-thread MMA issuer, commits multicast to both CTAs
+constexpr int PS_TILE = 128 * 128;                 // bytes of one 128-row operand tile (hi or lo)
+constexpr int PS_STAGE_BYTES = 4 * PS_TILE;        // A hi, A lo, B-half hi, B-half lo
+constexpr int PS_STAGES = 3;
+constexpr int PS_OFF_BAR = PS_STAGES * PS_STAGE_BYTES;
+constexpr int PS_NBAR = 2 * PS_STAGES + 4;
+constexpr int PS_OFF_TMEM = PS_OFF_BAR + PS_NBAR * 8;
+constexpr int PS_SMEM_BYTES = PS_OFF_TMEM + 16 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  // shared::cluster address of `saddr` in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t both = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(both) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gram_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA, const Tc2Params P) {
+    extern __shared__ unsigned char smem_dyn[];
+    // both CTAs of the pair must use the same shared-memory offsets: the dynamic segment starts at the same offset in
+    // every CTA of a launch, so the aligned base is the same too
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const int nitems = P.ntiles * P.nsplit;
+
+    auto bar = [&](int i) { return sbase + PS_OFF_BAR + 8 * i; };
+    constexpr int FULL = 0, EMPTY = PS_STAGES, ACC_FULL = 2 * PS_STAGES, ACC_EMPTY = 2 * PS_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + PS_OFF_TMEM);
+
+    if (threadIdx.x == T_TMA) {
+        for (int s = 0; s < PS_STAGES; ++s) {
+            mbar_init(bar(FULL + s), 1);
+            mbar_init(bar(EMPTY + s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar(ACC_FULL + a), 1);
+            mbar_init(bar(ACC_EMPTY + a), 2 * NDRAIN_WARPS);  // the drain warps of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == W_TMA) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int w = cid; w < nitems; w += ncl) {
+                const Item it = decode_item<true>(P, w);
+                const int rowA = it.ti * 256 + (int)rank * 128, rowB = it.tj * 256 + (int)rank * 128;
+                for (int st = 0; st < it.nst; ++st, ++g) {
+                    const int s = g % PS_STAGES;
+                    const uint32_t ph = (g / PS_STAGES) & 1;
+                    mbar_wait(bar(EMPTY + s), ph ^ 1);
+                    const uint32_t dst = sbase + s * PS_STAGE_BYTES;
+                    const uint32_t lbar = mapa_rank(bar(FULL + s), 0);
+                    const int r0 = (int)(it.r_begin + (int64_t)st * KS);
+                    if (leader) mbar_arrive_expect_tx(bar(FULL + s), 2 * (it.diag ? 2 * PS_TILE : PS_STAGE_BYTES));
+                    if (!it.diag) {
+                        tma_load_2d_pair(dst, &mapA, lbar, r0, rowA);
+                        tma_load_2d_pair(dst + PS_TILE, &mapA, lbar, r0, P.mtot + rowA);
+                    }
+                    tma_load_2d_pair(dst + 2 * PS_TILE, &mapA, lbar, r0, rowB);
+                    tma_load_2d_pair(dst + 3 * PS_TILE, &mapA, lbar, r0, P.mtot + rowB);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t g = 0, gc = 0;
+            for (int w = cid; w < nitems; w += ncl) {
+                const Item it = decode_item<true>(P, w);
+                for (int st = 0; st < it.nst; ++st, ++g) {
+                    const int s = g % PS_STAGES;
+                    const uint32_t ph = (g / PS_STAGES) & 1;
+                    const int kk = st % SUB_STAGES;
+                    const uint32_t ab = gc & 1;
+                    if (kk == 0) mbar_wait(bar(ACC_EMPTY + ab), ((gc >> 1) & 1) ^ 1);
+                    mbar_wait(bar(FULL + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t stage = sbase + s * PS_STAGE_BYTES;
+                    const uint32_t b_hi = stage + 2 * PS_TILE, b_lo = stage + 3 * PS_TILE;
+                    // diagonal tile: the A rows of each CTA are exactly its half of the B rows
+                    const uint32_t a_hi = it.diag ? b_hi : stage, a_lo = it.diag ? b_lo : stage + PS_TILE;
+                    const uint32_t acc = tmem_base + ab * 256;
+#pragma unroll
+                    for (int ks = 0; ks < KS / 16; ++ks) {
+                        const uint32_t off = ks * 32;
+                        const uint32_t first = (kk == 0 && ks == 0) ? 0u : 1u;
+                        umma_f16_ss_pair(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, first);
+                        umma_f16_ss_pair(acc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1u);
+                        umma_f16_ss_pair(acc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1u);
+                    }
+                    umma_commit_pair(bar(EMPTY + s));
+                    if (kk == SUB_STAGES - 1 || st == it.nst - 1) {
+                        umma_commit_pair(bar(ACC_FULL + ab));
+                        ++gc;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== drain warps (both CTAs, own 128 accumulator rows) =====================
+        const int quad = warp & 3, half = warp >> 2;
+        const int m = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
+        uint32_t gc = 0;
+        for (int w = cid; w < nitems; w += ncl) {
+            const Item it = decode_item<true>(P, w);
+            const int nsub = (it.nst + SUB_STAGES - 1) / SUB_STAGES;
+            float accv[128];
+#pragma unroll
+            for (int e = 0; e < 128; ++e) accv[e] = 0.f;
+            for (int c = 0; c < nsub; ++c, ++gc) {
+                const uint32_t ab = gc & 1;
+                mbar_wait(bar(ACC_FULL + ab), (gc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int gq = 0; gq < 2; ++gq) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(lane_addr + ab * 256 + (uint32_t)(gq * 64), r0);
+                    tmem_ld32(lane_addr + ab * 256 + (uint32_t)(gq * 64 + 32), r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        accv[gq * 64 + e] = __fadd_rn(accv[gq * 64 + e], __uint_as_float(r0[e]));
+                        accv[gq * 64 + 32 + e] = __fadd_rn(accv[gq * 64 + 32 + e], __uint_as_float(r1[e]));
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_rank(bar(ACC_EMPTY + ab), 0));
+            }
+            float *dst = P.partial + ((size_t)it.split * P.ntiles + it.tile) * (size_t)(256 * 256) +
+                         (size_t)(rank * 128 + m) * 256 + half * 128;
+#pragma unroll
+            for (int e = 0; e < 128; e += 4)
+                *reinterpret_cast<float4 *>(dst + e) = make_float4(accv[e], accv[e + 1], accv[e + 2], accv[e + 3]);
         }
     }
-    s1[rg][cx] = a;
-    s2[rg][cx] = mx;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (rg == 0 && col < ncols) {
-        double t = 0.0;
-        float m2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { t += s1[k][cx]; m2 = fmaxf(m2, s2[k][cx]); }
-        part[(size_t)blockIdx.y * ncols + col] = t;
-        part_max[(size_t)blockIdx.y * ncols + col] = m2;
+    cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the other may still touch it
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
-// shift[j] = fl32(mean), scale[j] = 2^e with 2 * max|x| * 2^e in [2^9, 2^10), inv[j] = 2^-e (fp64)
-__global__ void colstat_finish(const double *__restrict__ part, const float *__restrict__ part_max, int ncols, double invN,
-                               float *__restrict__ shift, float *__restrict__ scale, double *__restrict__ inv) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
+// ------------------------------------------------------------------ operand space
+// Operand row o of the GEMM: o < Kp -> column o of X (zero row when o >= K); o >= Kp -> column o - Kp of Y.
+// Kp and the Y extent are multiples of 256, so no strip of the kernels below straddles the two matrices.
+struct Cols {
+    const float *X, *Y;
+    int64_t ldx, ldy;
+    int K, n, Kp;
+};
+struct ColRef {
+    const float *base;
+    int64_t ld;
+    int col, ncols;
+};
+__device__ __forceinline__ ColRef col_ref(const Cols &C, int o) {
+    ColRef r;
+    if (o < C.Kp) { r.base = C.X; r.ld = C.ldx; r.col = o; r.ncols = C.K; }
+    else { r.base = C.Y; r.ld = C.ldy; r.col = o - C.Kp; r.ncols = C.n; }
+    return r;
+}
+
+// ------------------------------------------------------------------ statistics pass 1: column sums and max |x|
+// CTA = 128 operand rows (32 float4 lanes) x 8 row lanes over one row split; fixed summation order.
+__global__ void __launch_bounds__(256)
+colstat_part(const Cols C, int64_t nrows, int mtot, double *__restrict__ part, float *__restrict__ part_max) {
+    __shared__ double s1[8][132];
+    __shared__ float s2[8][132];
+    const int cq = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int o0 = blockIdx.x * 128 + cq * 4;
+    const ColRef cr = col_ref(C, o0);
+    const int64_t per = (nrows + RS - 1) / RS;
+    const int64_t r0 = (int64_t)blockIdx.y * per;
+    const int64_t r1 = r0 + per < nrows ? r0 + per : nrows;
+    double a[4] = {0, 0, 0, 0};
+    float mx[4] = {0, 0, 0, 0};
+    if (cr.col + 3 < cr.ncols) {
+#pragma unroll 4
+        for (int64_t r = r0 + rg; r < r1; r += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(cr.base + r * cr.ld + cr.col));
+            a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w;
+            mx[0] = fmaxf(mx[0], fabsf(v.x)); mx[1] = fmaxf(mx[1], fabsf(v.y));
+            mx[2] = fmaxf(mx[2], fabsf(v.z)); mx[3] = fmaxf(mx[3], fabsf(v.w));
+        }
+    } else if (cr.col < cr.ncols) {
+        for (int64_t r = r0 + rg; r < r1; r += 8)
+            for (int c = 0; c < 4 && cr.col + c < cr.ncols; ++c) {
+                const float v = __ldg(cr.base + r * cr.ld + cr.col + c);
+                a[c] += (double)v;
+                mx[c] = fmaxf(mx[c], fabsf(v));
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { s1[rg][cq * 4 + c] = a[c]; s2[rg][cq * 4 + c] = mx[c]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        double t = 0.0;
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t += s1[k][threadIdx.x]; m2 = fmaxf(m2, s2[k][threadIdx.x]); }
+        part[(size_t)blockIdx.y * mtot + blockIdx.x * 128 + threadIdx.x] = t;
+        part_max[(size_t)blockIdx.y * mtot + blockIdx.x * 128 + threadIdx.x] = m2;
+    }
+}
+
+// shift[o] = fl32(mean), scale[o] = 2^e with 2 * max|x| * 2^e in [2^9, 2^10), inv[o] = 2^-e (fp64)
+__global__ void __launch_bounds__(128)
+colstat_finish(const double *__restrict__ part, const float *__restrict__ part_max, int mtot, double invN,
+               float *__restrict__ shift, float *__restrict__ scale, double *__restrict__ inv) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= mtot) return;
+    double v[RS];
+    float m[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) { v[r] = part[(size_t)r * mtot + o]; m[r] = part_max[(size_t)r * mtot + o]; }
     double t = 0.0;
     float mx = 0.f;
-    for (int r = 0; r < RS; ++r) {
-        t += part[(size_t)r * ncols + j];
-        mx = fmaxf(mx, part_max[(size_t)r * ncols + j]);
-    }
-    shift[j] = (float)(t * invN);
+#pragma unroll
+    for (int r = 0; r < RS; ++r) { t += v[r]; mx = fmaxf(mx, m[r]); }
+    shift[o] = (float)(t * invN);
     int e = 0;
     const float b = 2.f * mx;  // |x - mean| <= 2 max|x|
     if (b > 0.f && isfinite(b)) {
         e = 9 - ilogbf(b);
         e = e > 100 ? 100 : (e < -100 ? -100 : e);
     }
-    scale[j] = ldexpf(1.f, e);
-    inv[j] = ldexp(1.0, -e);
+    scale[o] = ldexpf(1.f, e);
+    inv[o] = ldexp(1.0, -e);
 }
 
 // ------------------------------------------------------------------ operand preparation (+ statistics pass 2)
-// One CTA = a strip of 64 columns x the 64-row tiles of one row split.  Reads X once (coalesced along the columns),
-// writes the hi and lo operand rows (coalesced along the reduction index) through a swizzled shared-memory tile,
-// and accumulates the fp64 column sums / sums of squares of xs in a fixed order.
+// One CTA = a strip of 64 operand rows x the 64-row tiles of one row split.  Reads the data once (coalesced along the
+// columns), writes the hi and lo operand rows (coalesced along the reduction index) through a swizzled shared-memory
+// tile, and accumulates the fp64 column sums / sums of squares of xs in a fixed order.
 __global__ void __launch_bounds__(256)
-tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int64_t Np, int tiles_per_split,
-         const float *__restrict__ shift, const float *__restrict__ scale, __half *__restrict__ Ohi,
-         __half *__restrict__ Olo, double *__restrict__ part, double *__restrict__ part_sq, int part_ld) {
+tc2_prep(const Cols C, int64_t nrows, int64_t Np, int tiles_per_split, int mtot, const float *__restrict__ shift,
+         const float *__restrict__ scale, __half *__restrict__ Ohi, __half *__restrict__ Olo, double *__restrict__ part,
+         double *__restrict__ part_sq) {
     __shared__ __align__(16) unsigned char tile_hi[PT * 128], tile_lo[PT * 128];
     __shared__ double red[16][PT + 1];
     const int t = threadIdx.x, jq = t & 15, rg = t >> 4;
-    const int col0 = blockIdx.x * PT;     // first column of the strip = first operand row
-    const int cj = col0 + jq * 4;
+    const int o0 = blockIdx.x * PT;       // first operand row of the strip
+    const ColRef cr = col_ref(C, o0);
+    const float *__restrict__ X = cr.base;
+    const int64_t ld = cr.ld;
+    const int ncols = cr.ncols;
+    const int cj = cr.col + jq * 4;
     const bool vec = (cj + 3 < ncols);
     float sh[4], sc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        sh[c] = cj + c < ncols ? shift[cj + c] : 0.f;
-        sc[c] = cj + c < ncols ? scale[cj + c] : 0.f;
+        sh[c] = cj + c < ncols ? shift[o0 + jq * 4 + c] : 0.f;
+        sc[c] = cj + c < ncols ? scale[o0 + jq * 4 + c] : 0.f;
     }
     double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     const int64_t ntile = Np / PT;
@@ -405,6 +654,8 @@ tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int6
             v[i] = x;
         }
     };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tb < te) load(tb, cur);
     for (int64_t tile = tb; tile < te; ++tile) {
         if (tile + 1 < te) load(tile + 1, nxt);
@@ -426,7 +677,7 @@ tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int6
                 lo[c][i] = __float2half_rn(__fsub_rn(v, __half2float(h)));
             }
         }
-        // operand row j (= column of the strip): 64 reduction values = 8 chunks of 16 B; chunk index swizzled by j >> 2
+        // operand row j of the strip: 64 reduction values = 8 chunks of 16 B; chunk index swizzled by j >> 2
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int j = jq * 4 + c;
@@ -444,7 +695,7 @@ tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int6
         for (int it = 0; it < 2; ++it) {
             const int j = (t >> 3) + 32 * it, ch = t & 7;
             const uint32_t off = (uint32_t)j * 128u + (uint32_t)((ch ^ ((j >> 2) & 7)) << 4);
-            const size_t o = (size_t)(col0 + j) * (size_t)Np + (size_t)tile * PT + (size_t)ch * 8;
+            const size_t o = (size_t)(o0 + j) * (size_t)Np + (size_t)tile * PT + (size_t)ch * 8;
             *reinterpret_cast<uint4 *>(Ohi + o) = *reinterpret_cast<const uint4 *>(tile_hi + off);
             *reinterpret_cast<uint4 *>(Olo + o) = *reinterpret_cast<const uint4 *>(tile_lo + off);
         }
@@ -458,101 +709,128 @@ tc2_prep(const float *__restrict__ X, int64_t ld, int ncols, int64_t nrows, int6
 #pragma unroll
         for (int c = 0; c < 4; ++c) red[rg][jq * 4 + c] = pass ? q[c] : a[c];
         __syncthreads();
-        if (t < PT && col0 + t < ncols) {
+        if (t < PT) {
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) s += red[k][t];
-            (pass ? part_sq : part)[(size_t)blockIdx.y * part_ld + col0 + t] = s;
+            (pass ? part_sq : part)[(size_t)blockIdx.y * mtot + o0 + t] = s;
         }
         __syncthreads();
     }
 }
 
-__global__ void tc2_stat_finish(const double *__restrict__ part, const double *__restrict__ part_sq, int nsplit_used,
-                                int part_ld, int ncols, double *__restrict__ T, double *__restrict__ SQ) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
-    double t = 0.0, t2 = 0.0;
-    for (int r = 0; r < nsplit_used; ++r) {
-        t += part[(size_t)r * part_ld + j];
-        t2 += part_sq[(size_t)r * part_ld + j];
+// T[o] = sum of the split partials (fixed order), SQ likewise; the caller's column sums:
+// out[col] = T + N * ((double)shift - bias)   (sx for the X part, sy for the Y part)
+__global__ void __launch_bounds__(128)
+tc2_stat_finish(const double *__restrict__ part, const double *__restrict__ part_sq, int nsplit_used, int mtot, Cols C,
+                const float *__restrict__ shift, const float *__restrict__ y_bias, double Nd, double *__restrict__ T,
+                double *__restrict__ SQ, double *__restrict__ sx, double *__restrict__ sy) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= mtot) return;
+    double v[RS], w[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        v[r] = r < nsplit_used ? part[(size_t)r * mtot + o] : 0.0;
+        w[r] = r < nsplit_used ? part_sq[(size_t)r * mtot + o] : 0.0;
     }
-    T[j] = t;
-    if (SQ) SQ[j] = t2;
+    double t = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < RS; ++r) { t += v[r]; t2 += w[r]; }
+    T[o] = t;
+    SQ[o] = t2;
+    if (o < C.Kp) {
+        if (sx && o < C.K) sx[o] = t + Nd * (double)shift[o];
+    } else if (sy && o - C.Kp < C.n) {
+        const int j = o - C.Kp;
+        sy[j] = t + Nd * ((double)shift[o] - (y_bias ? (double)y_bias[j] : 0.0));
+    }
 }
 
 // ------------------------------------------------------------------ reduction of the row splits
-// One CTA = one 32 x 32 block of a tile.  C[i,j] = inv_i inv_j sum_s P_s[i,j] + uA_i TB_j + TA_i uB_j + N uA_i uB_j,
-// u = (double)shift32 - bias.  Symmetric mode: blocks below the diagonal 128-block are skipped, the diagonal
-// 128-block reads the upper element for both (i,j) and (j,i) (the tensor core produced them with different
-// rounding; G must be bitwise symmetric), strictly-upper blocks are also written transposed.
+// CTA = 32 rows x 128 columns of a tile (four 32 x 32 blocks).
+//   C[i,j] = inv_i inv_j sum_s P_s[i,j] + uA_i TB_j + TA_i uB_j + N uA_i uB_j,   u = (double)shift32 - bias.
+// G tiles: blocks below the diagonal 128-block are skipped, the diagonal 128-block reads the upper element for both
+// (i,j) and (j,i) (the tensor core produced them with different rounding; G must be bitwise symmetric), blocks above
+// it are also written transposed (the lower triangle of G).  TR = rows of a tile (128, or 256 for the pair kernel).
+template <int TR>
 __global__ void __launch_bounds__(256)
-reduce_tc2(const float *__restrict__ partial, int nsplit, int ntiles, int tile0, int sym, int tjx, int tjy0, int tnb,
-           const float *__restrict__ shiftA, const double *__restrict__ invA, const double *__restrict__ TA,
-           const float *__restrict__ shiftB, const double *__restrict__ invB, const float *__restrict__ biasB,
-           const double *__restrict__ TB, const double *__restrict__ diag_sq, double Nd, int M, int Nn,
-           double *__restrict__ C, int64_t ldc) {
+reduce_tc2(const float *__restrict__ partial, int nsplit, int ntiles, int tiles_sym, int tjx, int tjy0, int tnb, int Kp,
+           const float *__restrict__ shift, const double *__restrict__ inv, const double *__restrict__ T,
+           const double *__restrict__ SQ, const float *__restrict__ y_bias, double Nd, int K, int n,
+           double *__restrict__ G, double *__restrict__ Bxy) {
     __shared__ double tr[32][33];
-    int l = blockIdx.x, ti, tj, colbase;  // colbase: first column of C covered by the tile
+    int l = blockIdx.x, ti, tj;
+    const bool sym = l < tiles_sym;
     if (sym) {
         ti = 0;
-        while (l >= tjx - (ti >> 1)) { l -= tjx - (ti >> 1); ++ti; }
-        tj = (ti >> 1) + l;
-        colbase = tj * TN;
-    } else {
-        ti = l / tnb;
-        tj = l - ti * tnb;
-        colbase = tj * TN;
-    }
-    const int sr = blockIdx.y >> 3, sc = blockIdx.y & 7;  // 4 x 8 blocks of 32 x 32
-    const int i0 = ti * TM + sr * 32, j0 = colbase + sc * 32;
-    if (i0 >= M || j0 >= Nn) return;
-    const int cb128 = j0 / 128;
-    if (sym && cb128 < ti) return;
-    const bool dblock = sym && cb128 == ti;
-    const size_t tile_elems = (size_t)TM * TN;
-    const float *p0 = partial + (size_t)(tile0 + blockIdx.x) * tile_elems;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const int lr = ty * 4 + rr;                 // row inside the block
-        const int i = i0 + lr, j = j0 + tx;
-        double s = 0.0;
-        if (i < M && j < Nn) {
-            int er = sr * 32 + lr, ec = sc * 32 + tx;  // element inside the tile
-            if (dblock && i > j) {                      // mirror inside the diagonal 128-block
-                const int cb = (ti & 1) * 128;
-                const int nr = ec - cb, nc = cb + er;
-                er = nr;
-                ec = nc;
-            }
-            const size_t e = (size_t)er * TN + ec;
-            for (int c = 0; c < nsplit; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
-            s *= invA[i] * invB[j];
-            if (sym && i == j) s = diag_sq[i];
-            const double ua = (double)shiftA[i];
-            const double ub = (double)shiftB[j] - (biasB ? (double)biasB[j] : 0.0);
-            s += ua * TB[j] + TA[i] * ub + Nd * ua * ub;
-            C[(int64_t)i * ldc + j] = s;
+        if (TR == 128) {
+            while (l >= tjx - (ti >> 1)) { l -= tjx - (ti >> 1); ++ti; }
+            tj = (ti >> 1) + l;
+        } else {
+            while (l >= tjx - ti) { l -= tjx - ti; ++ti; }
+            tj = ti + l;
         }
-        tr[lr][tx] = s;
+    } else {
+        l -= tiles_sym;
+        ti = l / tnb;
+        tj = tjy0 + (l - ti * tnb);
     }
-    if (sym && cb128 > ti) {  // strictly above the diagonal blocks: the transposed copy
-        __syncthreads();
+    const int rowbase = ti * TR, colbase = tj * TN;  // colbase in operand space
+    const int sr = blockIdx.y, i0 = rowbase + sr * 32;
+    if (i0 >= K) return;
+    const size_t tile_elems = (size_t)TR * TN;
+    const float *p0 = partial + (size_t)blockIdx.x * tile_elems;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double *__restrict__ Cm = sym ? G : Bxy;
+    const int64_t ldc = sym ? K : n;
+    const int Nn = sym ? K : n;
+    const int coff = sym ? 0 : Kp;  // operand index of column 0 of C
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int sc = blockIdx.z * 4 + q;
+        const int oj0 = colbase + sc * 32, j0 = oj0 - coff;
+        if (j0 >= Nn) break;
+        const int rb128 = i0 >> 7, cb128 = j0 >> 7;
+        if (sym && cb128 < rb128) continue;
+        const bool dblock = sym && cb128 == rb128, upper = sym && cb128 > rb128;
+        double sv[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const int lc = ty * 4 + rr;
-            const int j = j0 + lc, i = i0 + tx;
-            if (i < M && j < Nn) C[(int64_t)j * ldc + i] = tr[tx][lc];
+            const int lr = ty * 4 + rr;
+            const int i = i0 + lr, j = j0 + tx;
+            double s = 0.0;
+            if (i < K && j < Nn) {
+                int er = sr * 32 + lr, ec = sc * 32 + tx;  // element inside the tile
+                if (dblock && i > j) {                      // mirror inside the diagonal 128-block
+                    const int nr = (colbase + ec) - rowbase, nc = (rowbase + er) - colbase;
+                    er = nr;
+                    ec = nc;
+                }
+                const size_t e = (size_t)er * TN + ec;
+                for (int c = 0; c < nsplit; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
+                const int oj = oj0 + tx;
+                s *= inv[i] * inv[oj];
+                if (sym && i == j) s = SQ[i];
+                const double ua = (double)shift[i];
+                const double ub = (double)shift[oj] - ((!sym && y_bias) ? (double)y_bias[j] : 0.0);
+                s += ua * T[oj] + T[i] * ub + Nd * ua * ub;
+                Cm[(int64_t)i * ldc + j] = s;
+            }
+            sv[rr] = s;
+        }
+        if (upper) {  // the transposed copy (block-uniform condition)
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) tr[ty * 4 + rr][tx] = sv[rr];
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int lc = ty * 4 + rr;
+                const int j = j0 + lc, i = i0 + tx;
+                if (i < K && j < K) G[(int64_t)j * K + i] = tr[tx][lc];
+            }
+            __syncthreads();
         }
     }
-}
-
-// out[j] = T[j] + N * ((double)shift[j] - bias[j])
-__global__ void finish_sums2(const double *__restrict__ T, const float *__restrict__ shift, const float *__restrict__ bias,
-                             double Nd, int ncols, double *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < ncols) out[j] = T[j] + Nd * ((double)shift[j] - (bias ? (double)bias[j] : 0.0));
 }
 
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -580,6 +858,12 @@ int make_map16(cp_handle_t h, CUtensorMap *map, const __half *base, int64_t inne
 
 }  // namespace
 
+// CPB200_GRAM_PAIR=0 selects the single-CTA 128 x 256 tiles (A/B measurements); default: CTA pairs, 256 x 256 tiles
+static bool tc2_use_pair() {
+    static const bool pair = [] { const char *e = getenv("CPB200_GRAM_PAIR"); return !(e && e[0] == '0'); }();
+    return pair;
+}
+
 int cp_gram_tc2(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
                 int64_t ldy, const float *y_bias, const int32_t *rows, int nrows, double *G, double *Bxy, double *sx,
                 double *sy, double *yy, cudaStream_t stream) {
@@ -588,23 +872,24 @@ int cp_gram_tc2(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, co
         return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
     if (sy != nullptr && !wantB)  // column sums of Y alone: nothing for the tensor cores to do
         return cp_gram_fp64_products(h, X, N, K, ldx, Yraw, y_dtype, n, ldy, y_bias, rows, nrows, G, Bxy, sx, sy, yy, stream);
-    const float *Y = (const float *)Yraw;
-    const bool haveY = wantB;
-    const int tk = cp_cdiv(K, TM), tjx = cp_cdiv(K, TN);
+    const bool pair = tc2_use_pair();
+    const int TR = pair ? 256 : TM;
+    const int tjx = cp_cdiv(K, TN), tk = cp_cdiv(K, TR);
     const int Kp = tjx * TN;
     const int tnb = wantB ? cp_cdiv(n, TN) : 0;
     const int np_ = tnb * TN;
     const int mtot = Kp + np_;
     int tiles_sym = 0;
     if (G)
-        for (int ti = 0; ti < tk; ++ti) tiles_sym += tjx - (ti >> 1);
+        for (int ti = 0; ti < tk; ++ti) tiles_sym += pair ? tjx - ti : tjx - (ti >> 1);
     const int ntiles = tiles_sym + tk * tnb;
     const int64_t Np = cp_cdiv(N, KS) * (int64_t)KS;
+    const int units = pair ? h->num_sms / 2 : h->num_sms;  // CTAs or CTA pairs working concurrently
 
-    // Row splits.  An item (tile x split) costs its stages (~1.2 us each: the L2 -> SM operand stream) plus a small
-    // hand-over; items run round-robin on the persistent grid; every split adds one fp32 partial per tile (written,
-    // then read by the reduction).  A split is a multiple of the 128-row accumulator run and at most 32 runs
-    // (the fp32 register sums stay below 4e-7 of the partial sum whatever N is).
+    // Row splits.  An item (tile x split) costs its stages (~1.2 us each) plus a small hand-over; items run
+    // round-robin on the persistent grid; every split adds one fp32 partial per tile (written, then read by the
+    // reduction).  A split is a multiple of the 128-row accumulator run and at most 32 runs (the fp32 register
+    // sums stay below 4e-7 of the partial sum whatever N is).
     constexpr int64_t SUB = SUB_STAGES * KS, MAX_SPLIT_ROWS = 32 * SUB;
     const int ns_min = (int)cp_cdiv(N, MAX_SPLIT_ROWS);
     int nsplit = ns_min, rps = (int)(cp_cdiv(cp_cdiv(N, ns_min), SUB) * SUB);
@@ -614,9 +899,9 @@ int cp_gram_tc2(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, co
         for (int ns = ns_min; ns <= max_ns && ns < ns_min + 32; ++ns) {
             const int64_t r = cp_cdiv(cp_cdiv(N, ns), SUB) * SUB;
             const int ns_eff = (int)cp_cdiv(N, r);
-            const double rounds = (double)cp_cdiv((int64_t)ntiles * ns_eff, h->num_sms);
+            const double rounds = (double)cp_cdiv((int64_t)ntiles * ns_eff, units);
             const double cost = rounds * (1.2 * (double)(r / KS) + 1.0) +
-                                (double)ns_eff * (2.0 * ntiles * TM * TN * 4.0 / 5.0e6);
+                                (double)ns_eff * (2.0 * ntiles * TR * TN * 4.0 / 5.0e6);
             if (cost < best * 0.98) {
                 best = cost;
                 nsplit = ns_eff;
@@ -625,90 +910,75 @@ int cp_gram_tc2(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, co
         }
     }
 
-    const size_t part_elems = (size_t)nsplit * ntiles * TM * TN;
+    const size_t part_elems = (size_t)nsplit * ntiles * TR * TN;
     const size_t op_elems = 2 * (size_t)mtot * (size_t)Np;  // hi rows, then lo rows
-    const int wmax = Kp > np_ ? Kp : (np_ > 0 ? np_ : 1);
-    const int nY = n > 0 ? n : 1;
-    const size_t need = cp_carver::need(part_elems, 4) + cp_carver::need(op_elems, 2) + 2 * cp_carver::need(K, 8) +
-                        cp_carver::need(nY, 8) + 2 * cp_carver::need((size_t)RS * wmax, 8) +
-                        cp_carver::need((size_t)RS * wmax, 4) + 2 * cp_carver::need(K, 4) + 2 * cp_carver::need(nY, 4) +
-                        cp_carver::need(K, 8) + cp_carver::need(nY, 8);
+    const size_t need = cp_carver::need(part_elems, 4) + cp_carver::need(op_elems, 2) + 3 * cp_carver::need(mtot, 8) +
+                        2 * cp_carver::need((size_t)RS * mtot, 8) + cp_carver::need((size_t)RS * mtot, 4) +
+                        2 * cp_carver::need(mtot, 4);
     void *ws = nullptr;
     int rc = cp_ws_reserve(h, need, &ws);
     if (rc) return rc;
     cp_carver cv(ws);
     float *partial = cv.take<float>(part_elems);
     __half *ops = cv.take<__half>(op_elems);
-    double *TX = cv.take<double>(K), *SQX = cv.take<double>(K);
-    double *TY = cv.take<double>(nY);
-    double *cpart = cv.take<double>((size_t)RS * wmax), *cpart_sq = cv.take<double>((size_t)RS * wmax);
-    float *cpart_max = cv.take<float>((size_t)RS * wmax);
-    float *shX = cv.take<float>(K), *scX = cv.take<float>(K);
-    float *shY = cv.take<float>(nY), *scY = cv.take<float>(nY);
-    double *invX = cv.take<double>(K), *invY = cv.take<double>(nY);
+    double *T = cv.take<double>(mtot), *SQ = cv.take<double>(mtot), *inv = cv.take<double>(mtot);
+    double *cpart = cv.take<double>((size_t)RS * mtot), *cpart_sq = cv.take<double>((size_t)RS * mtot);
+    float *cpart_max = cv.take<float>((size_t)RS * mtot);
+    float *shift = cv.take<float>(mtot), *scale = cv.take<float>(mtot);
     const double invN = 1.0 / (double)N, Nd = (double)N;
     __half *Ohi = ops, *Olo = ops + (size_t)mtot * (size_t)Np;
     const int64_t ntile_rows = Np / PT;
     const int tiles_per_split = cp_cdiv(ntile_rows, RS);
     const int splits_used = cp_cdiv(ntile_rows, tiles_per_split);
+    Cols C{X, (const float *)Yraw, ldx, ldy, K, wantB ? n : 0, Kp};
 
-    colstat_part<<<dim3(cp_cdiv(K, 32), RS), 256, 0, stream>>>(X, ldx, K, N, cpart, cpart_max);
+    colstat_part<<<dim3(mtot / 128, RS), 256, 0, stream>>>(C, N, mtot, cpart, cpart_max);
     CP_CHECK_LAUNCH();
-    colstat_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, cpart_max, K, invN, shX, scX, invX);
+    colstat_finish<<<cp_cdiv(mtot, 128), 128, 0, stream>>>(cpart, cpart_max, mtot, invN, shift, scale, inv);
     CP_CHECK_LAUNCH();
-    // operand rows 0..Kp-1 (columns >= K give zero rows) + statistics of xs
-    tc2_prep<<<dim3(Kp / PT, splits_used), 256, 0, stream>>>(X, ldx, K, N, Np, tiles_per_split, shX, scX, Ohi, Olo, cpart,
-                                                             cpart_sq, wmax);
+    tc2_prep<<<dim3(mtot / PT, splits_used), 256, 0, stream>>>(C, N, Np, tiles_per_split, mtot, shift, scale, Ohi, Olo, cpart,
+                                                               cpart_sq);
     CP_CHECK_LAUNCH();
-    tc2_stat_finish<<<cp_cdiv(K, 256), 256, 0, stream>>>(cpart, cpart_sq, splits_used, wmax, K, TX, SQX);
+    tc2_stat_finish<<<cp_cdiv(mtot, 128), 128, 0, stream>>>(cpart, cpart_sq, splits_used, mtot, C, shift, y_bias, Nd, T, SQ, sx,
+                                                            wantB ? sy : nullptr);
     CP_CHECK_LAUNCH();
-    if (haveY) {
-        colstat_part<<<dim3(cp_cdiv(n, 32), RS), 256, 0, stream>>>(Y, ldy, n, N, cpart, cpart_max);
-        CP_CHECK_LAUNCH();
-        colstat_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, cpart_max, n, invN, shY, scY, invY);
-        CP_CHECK_LAUNCH();
-        tc2_prep<<<dim3(np_ / PT, splits_used), 256, 0, stream>>>(Y, ldy, n, N, Np, tiles_per_split, shY, scY,
-                                                                  Ohi + (size_t)Kp * Np, Olo + (size_t)Kp * Np, cpart,
-                                                                  cpart_sq, wmax);
-        CP_CHECK_LAUNCH();
-        tc2_stat_finish<<<cp_cdiv(n, 256), 256, 0, stream>>>(cpart, cpart_sq, splits_used, wmax, n, TY, nullptr);
-        CP_CHECK_LAUNCH();
-    }
     if (ntiles > 0) {
         CUtensorMap mapA, mapB;
         rc = make_map16(h, &mapA, ops, Np, 2 * (int64_t)mtot, TM);
         if (rc) return rc;
-        rc = make_map16(h, &mapB, ops, Np, 2 * (int64_t)mtot, TN);
-        if (rc) return rc;
         Tc2Params P{};
         P.partial = partial; P.Np = Np; P.rows_per_split = rps; P.nsplit = nsplit; P.tiles_sym = tiles_sym; P.tk = tk;
         P.tjx = tjx; P.tjy0 = Kp / TN; P.tnb = tnb; P.ntiles = ntiles; P.mtot = mtot;
-        static cp_per_device_flag configured;
-        if (bool *done = configured.slot(); !*done) {
-            CP_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            *done = true;
-        }
         const int nitems = ntiles * nsplit;
-        const int grid = nitems < h->num_sms ? nitems : h->num_sms;
-        gram_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, P);
-        CP_CHECK_LAUNCH();
-        if (tiles_sym > 0) {
-            reduce_tc2<<<dim3(tiles_sym, 32), 256, 0, stream>>>(partial, nsplit, ntiles, 0, 1, tjx, 0, 0, shX, invX, TX, shX,
-                                                               invX, nullptr, TX, SQX, Nd, K, K, G, K);
-            CP_CHECK_LAUNCH();
+        const bool prof = h->gram_profile;
+        if (prof) CP_CUDA(cudaEventRecord(h->ev_gram0, stream));
+        if (pair) {
+            static cp_per_device_flag configured;
+            if (bool *done = configured.slot(); !*done) {
+                CP_CUDA(cudaFuncSetAttribute(gram_tc2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM_BYTES));
+                *done = true;
+            }
+            const int ncl = nitems < units ? nitems : units;
+            gram_tc2_pair_kernel<<<2 * ncl, NTHREADS, PS_SMEM_BYTES, stream>>>(mapA, P);
+        } else {
+            rc = make_map16(h, &mapB, ops, Np, 2 * (int64_t)mtot, TN);
+            if (rc) return rc;
+            static cp_per_device_flag configured;
+            if (bool *done = configured.slot(); !*done) {
+                CP_CUDA(cudaFuncSetAttribute(gram_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+                *done = true;
+            }
+            const int grid = nitems < units ? nitems : units;
+            gram_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(mapA, mapB, P);
         }
-        if (wantB) {
-            reduce_tc2<<<dim3(tk * tnb, 32), 256, 0, stream>>>(partial, nsplit, ntiles, tiles_sym, 0, tjx, P.tjy0, tnb, shX,
-                                                              invX, TX, shY, invY, y_bias, TY, nullptr, Nd, K, n, Bxy, n);
-            CP_CHECK_LAUNCH();
-        }
-    }
-    if (sx) {
-        finish_sums2<<<cp_cdiv(K, 256), 256, 0, stream>>>(TX, shX, nullptr, Nd, K, sx);
         CP_CHECK_LAUNCH();
-    }
-    if (sy) {
-        finish_sums2<<<cp_cdiv(n, 256), 256, 0, stream>>>(TY, shY, y_bias, Nd, n, sy);
+        if (prof) CP_CUDA(cudaEventRecord(h->ev_gram1, stream));
+        if (pair)
+            reduce_tc2<256><<<dim3(ntiles, 8, 2), 256, 0, stream>>>(partial, nsplit, ntiles, tiles_sym, tjx, P.tjy0, tnb, Kp, shift,
+                                                                   inv, T, SQ, y_bias, Nd, K, n, G, Bxy);
+        else
+            reduce_tc2<128><<<dim3(ntiles, 4, 2), 256, 0, stream>>>(partial, nsplit, ntiles, tiles_sym, tjx, P.tjy0, tnb, Kp, shift,
+                                                                   inv, T, SQ, y_bias, Nd, K, n, G, Bxy);
         CP_CHECK_LAUNCH();
     }
     return CP_OK;

@@ -226,6 +226,16 @@ class Engine:
         out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n, mode=self.gram_mode if mode is None else mode)
         return out
 
+    def gram_profile(self, enable=True):
+        """CUDA events around the tensor-core GEMM launch of every following gram() on this engine's handle."""
+        self._call(self.lib.cp_gram_profile(self.h, 1 if enable else 0))
+
+    def gram_kernel_ms(self):
+        """Elapsed time (ms) of the tensor-core GEMM launch of the last gram() (needs gram_profile(True))."""
+        ms = self.ffi.new("float*")
+        self._call(self.lib.cp_gram_kernel_ms(self.h, ms))
+        return float(ms[0])
+
     def lasso_build(self, gs, gw, W2m, c, k2, S):
         """gs: gram over sampled rows (with yy); gw: gram of W2 viewed (n, K); W2m: (n, K) fp32."""
         n = W2m.shape[0]

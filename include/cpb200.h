@@ -52,8 +52,12 @@ enum { CP_F32 = 0, CP_F64 = 1 };
 /* arithmetic of cp_gram */
 enum {
     CP_GRAM_FP64 = 0,  /* fp32 inputs widened to fp64, DFMA accumulate (exact products) */
-    CP_GRAM_3XTF32 = 1 /* tcgen05 kind::tf32, hi/lo split, fp32 TMEM accumulate per row chunk,
-                          fp64 reduction over chunks */
+    CP_GRAM_3XTF32 = 1 /* tensor cores (tcgen05), three products of a 22-bit hi/lo operand split, fp32 TMEM
+                          accumulation per 128-row run, fp64 reduction over the runs.  Since round 2 the split is
+                          into two fp16 halves of the shifted and power-of-two scaled data (kind::f16, the same
+                          split precision as tf32 at twice the rate; csrc/gram_tc2.cu); the name of the constant
+                          is kept for source compatibility.  CPB200_GRAM_TC=1 selects the first-generation
+                          kind::tf32 kernel (csrc/gram_tc.cu). */
 };
 
 int cp_version(void);
@@ -66,6 +70,11 @@ int cp_destroy(cp_handle_t h);
 int64_t cp_launch_count(void);
 /* bytes of scratch currently owned by the handle (diagnostics) */
 int64_t cp_workspace_bytes(cp_handle_t h);
+/* Diagnostics for the roofline of the tensor-core Gram kernel: with profiling enabled, cp_gram (mode CP_GRAM_3XTF32)
+ * records CUDA events on its stream right before and after the tcgen05 GEMM launch; cp_gram_kernel_ms waits for the
+ * second event and returns the elapsed time of that launch alone (bench.py divides the algorithmic flops by it). */
+int cp_gram_profile(cp_handle_t h, int enable);
+int cp_gram_kernel_ms(cp_handle_t h, float *ms);
 
 /*
  * Sparse-point im2col -- replaces Net.extract_XY (lib/net.py:534-684, w1=None

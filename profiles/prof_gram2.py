@@ -13,7 +13,7 @@ import cpb200
 
 eng = cpb200.Engine(gram_mode=1)
 dev = eng.device
-gen = "gen1" if os.environ.get("CPB200_GRAM_TC", "") == "1" else "gen2"
+gen = "gen1" if os.environ.get("CPB200_GRAM_TC", "") == "1" else ("gen2-single" if os.environ.get("CPB200_GRAM_PAIR", "") == "0" else "gen2-pair")
 
 
 def check(N, K, n, seed=0, scale=1.0, offset=0.0):
@@ -55,7 +55,9 @@ s = cpb200.synth.LayerShape("conv4_2", 512, 512, 28, N=int(os.environ.get("CP_N"
 d = cpb200.synth.make_problem_device(s, 5, eng, layout="nhwc")
 X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True, layout="nhwc")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-ts = []
+ts, tk = [], []
+if gen != "gen1":
+    eng.gram_profile(True)
 for it in range(8):
     flush.fill_(it)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -64,9 +66,14 @@ for it in range(8):
     b.record()
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
+    if gen != "gen1":
+        tk.append(eng.gram_kernel_ms())
 flop = s.N * s.K * (s.K + 1) + 2.0 * s.N * s.K * s.n
 print("%s cp_gram conv4_2 N=%d: %s ms -> best %.4f ms = %.1f TF/s algorithmic" %
       (gen, s.N, ["%.3f" % t for t in ts], min(ts[2:]), flop / (min(ts[2:]) / 1e3) / 1e12), flush=True)
+if tk:
+    print("%s GEMM kernel alone: %s ms -> best %.4f ms = %.1f TF/s algorithmic (x3 issued)" %
+          (gen, ["%.3f" % t for t in tk], min(tk[2:]), flop / (min(tk[2:]) / 1e3) / 1e12), flush=True)
 X64 = X.double()
 Gr = X64.T @ X64
 dx = Gr.diagonal().sqrt()
