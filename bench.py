@@ -494,8 +494,9 @@ def run_gpu(args):
     if want_e2e:
         for d in datas:  # the reference's blob order (NCHW) in page-locked host memory
             src = cpb200.synth.fmap_nchw(d)
-            d["fmap_host"] = torch.empty(src.shape, dtype=torch.float32, pin_memory=True)
-            d["fmap_host"].copy_(src)
+            with cpb200.engine.numa_local(local):  # pages on the socket this rank's GPU hangs off
+                d["fmap_host"] = torch.empty(src.shape, dtype=torch.float32, pin_memory=True)
+                d["fmap_host"].copy_(src)
         torch.cuda.synchronize()
         for _ in range(min(args.warmup, 3)):
             step(True)
@@ -554,22 +555,53 @@ def run_gpu(args):
         d = datas[names.index(s.name)] if s.name in names else cpb200.synth.make_problem_device(s, 5, eng, layout=args.layout)
         lay = d.get("layout", "nchw")
         X = eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad, s.stride, relu=True, layout=lay)
+        fp64_mode = eng.gram_mode == cpb200.engine.GRAM_FP64
+        gen1 = os.environ.get("CPB200_GRAM_TC", "") == "1"
+        kern_ms = []
         t_ms = timed_alone(torch, dev, lambda: eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False))
+        if not fp64_mode and not gen1:
+            # second pass with CUDA events around the tcgen05 GEMM launch (on its stream), read after each call
+            eng.gram_profile(True)
+
+            def one_gram():
+                eng.gram(X, d["feats"], y_bias=d["b2"], want_sums=False)
+                kern_ms.append(eng.gram_kernel_ms())
+
+            timed_alone(torch, dev, one_gram)
+            eng.gram_profile(False)
         flops = float(s.N) * s.K * (s.K + 1) + 2.0 * s.N * s.K * s.n  # symmetric half + X'Y
-        achieved = flops / (t_ms / 1e3) / 1e12
-        if eng.gram_mode == cpb200.engine.GRAM_FP64:
+        call_tflops = flops / (t_ms / 1e3) / 1e12
+        if fp64_mode:
+            kernel, k_ms = "cp_gram (fp64 products)", t_ms
             peak, peak_note = peaks_lib["fp64_tflops"], "cuBLAS FP64 GEMM 4096^3 measured in this run"
+            extra = {}
+        elif gen1:
+            kernel, k_ms = "cp_gram, first-generation gram_tc_kernel (3xTF32) + its passes", t_ms
+            peak, peak_note = peaks_lib["tf32_tflops"], "cuBLAS TF32 GEMM 8192^3 measured in this run; 3 MMAs per product: ceiling 1/3"
+            extra = {}
         else:
-            peak, peak_note = peaks_lib["tf32_tflops"], "cuBLAS TF32 GEMM 8192^3 measured in this run (bf16 burst in " \
-                "MEASURED_PEAKS.json: %.0f, %s); 3xTF32 issues 3 MMAs per product: ceiling 1/3" % (peaks["bf16_tflops"], which)
-        tr = traffic.get("gram_tc_kernel") if eng.gram_mode != cpb200.engine.GRAM_FP64 else None
-        roof = {"kernel": "cp_gram (X'X upper tiles + X'Y) on %s: N=%d K=%d n=%d" % (s.name, s.N, s.K, s.n),
-                "bound": "tensor" if eng.gram_mode != cpb200.engine.GRAM_FP64 else "fp64-pipe",
+            # the dominant kernel of the call, timed alone: gram_tc2_pair_kernel (kind::f16 tcgen05, three products of
+            # the split-fp16 operands per algorithmic product -> ceiling = 1/3 of the dense 16-bit rate)
+            k_ms = sum(kern_ms[2:]) / max(1, len(kern_ms[2:]))
+            kernel = "gram_tc2_pair_kernel (tcgen05 kind::f16, cta_group::2, 256x256 tiles; 3 MMAs per product)"
+            peak = peaks["bf16_tflops"]
+            peak_note = "dense bf16 burst of MEASURED_PEAKS.json (%s); split-precision scheme issues 3 MMAs per " \
+                        "algorithmic product: ceiling 1/3" % which
+            extra = {"issued_tflops": 3.0 * flops / (k_ms / 1e3) / 1e12, "frac_issued": 3.0 * flops / (k_ms / 1e3) / 1e12 / peak,
+                     "call": {"what": "whole cp_gram call (statistics passes, operand preparation, GEMM, fp64 reduction "
+                                      "of the splits, lower triangle)", "ms": t_ms, "achieved": call_tflops,
+                              "frac": call_tflops / peak},
+                     "cublas_tf32_tflops": peaks_lib["tf32_tflops"]}
+        achieved = flops / (k_ms / 1e3) / 1e12
+        tr = traffic.get("gram_tc2_pair_kernel" if not gen1 else "gram_tc_kernel") if not fp64_mode else None
+        roof = {"kernel": "%s on %s: N=%d K=%d n=%d (X'X upper tiles + X'Y)" % (kernel, s.name, s.N, s.K, s.n),
+                "bound": "tensor" if not fp64_mode else "fp64-pipe",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": tr["bytes"] if tr and s.name == "conv4_2" and s.N == 5000 else None,
                 "traffic_source": tr["source"] if tr else None,
-                "ms": t_ms, "algorithmic_flops": flops, "peak_source": peak_note,
-                "mode": "fp64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "3xtf32"}
+                "ms": k_ms, "algorithmic_flops": flops, "peak_source": peak_note,
+                "mode": "fp64" if fp64_mode else ("3xtf32" if gen1 else "3xfp16-split")}
+        roof.update(extra)
         t_g = timed_alone(torch, dev, lambda: eng.patch_gather(d["fmap"], d["randx"], d["randy"], s.B, s.P, s.k, s.pad,
                                                                s.stride, relu=True, out=X, layout=lay))
         gbytes = 8.0 * s.N * s.K  # unique patch elements read + X written
@@ -608,7 +640,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "tf32x3+f64", "data": "synthetic",
+            "dtype": "f64" if eng.gram_mode == cpb200.engine.GRAM_FP64 else "f16x3-split+f64", "data": "synthetic",
             "config": cfg, "clocks": clocks,
             "e2e": e2e if e2e is not None or e2e_skip is None else {"unavailable": e2e_skip},
             "gpu_launches": int(launches // max(1, args.steps)),

@@ -747,18 +747,20 @@ tc2_stat_finish(const double *__restrict__ part, const double *__restrict__ part
 }
 
 // ------------------------------------------------------------------ reduction of the row splits
-// CTA = 32 rows x 128 columns of a tile (four 32 x 32 blocks).
+// CTA = 32 rows x 128 columns (one 128-column block) of a tile; thread = 4 consecutive columns x 4 rows (float4 loads of
+// every split's partial, all issued before the first use).
 //   C[i,j] = inv_i inv_j sum_s P_s[i,j] + uA_i TB_j + TA_i uB_j + N uA_i uB_j,   u = (double)shift32 - bias.
-// G tiles: blocks below the diagonal 128-block are skipped, the diagonal 128-block reads the upper element for both
+// G tiles: 128-blocks below the diagonal block are skipped, the diagonal 128-block reads the upper element for both
 // (i,j) and (j,i) (the tensor core produced them with different rounding; G must be bitwise symmetric), blocks above
-// it are also written transposed (the lower triangle of G).  TR = rows of a tile (128, or 256 for the pair kernel).
+// it are also written transposed (the lower triangle of G) through shared memory.  TR = rows of a tile (128, or 256
+// for the pair kernel).
 template <int TR>
 __global__ void __launch_bounds__(256)
 reduce_tc2(const float *__restrict__ partial, int nsplit, int ntiles, int tiles_sym, int tjx, int tjy0, int tnb, int Kp,
            const float *__restrict__ shift, const double *__restrict__ inv, const double *__restrict__ T,
            const double *__restrict__ SQ, const float *__restrict__ y_bias, double Nd, int K, int n,
            double *__restrict__ G, double *__restrict__ Bxy) {
-    __shared__ double tr[32][33];
+    __shared__ double tr[32][129];
     int l = blockIdx.x, ti, tj;
     const bool sym = l < tiles_sym;
     if (sym) {
@@ -778,57 +780,109 @@ reduce_tc2(const float *__restrict__ partial, int nsplit, int ntiles, int tiles_
     const int rowbase = ti * TR, colbase = tj * TN;  // colbase in operand space
     const int sr = blockIdx.y, i0 = rowbase + sr * 32;
     if (i0 >= K) return;
-    const size_t tile_elems = (size_t)TR * TN;
-    const float *p0 = partial + (size_t)blockIdx.x * tile_elems;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    double *__restrict__ Cm = sym ? G : Bxy;
-    const int64_t ldc = sym ? K : n;
     const int Nn = sym ? K : n;
     const int coff = sym ? 0 : Kp;  // operand index of column 0 of C
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        const int sc = blockIdx.z * 4 + q;
-        const int oj0 = colbase + sc * 32, j0 = oj0 - coff;
-        if (j0 >= Nn) break;
-        const int rb128 = i0 >> 7, cb128 = j0 >> 7;
-        if (sym && cb128 < rb128) continue;
-        const bool dblock = sym && cb128 == rb128, upper = sym && cb128 > rb128;
-        double sv[4];
+    const int oj0 = colbase + blockIdx.z * 128, j0 = oj0 - coff;
+    if (j0 >= Nn) return;
+    const int rb128 = i0 >> 7, cb128 = j0 >> 7;
+    if (sym && cb128 < rb128) return;
+    const bool dblock = sym && cb128 == rb128, upper = sym && cb128 > rb128;
+    const size_t tile_elems = (size_t)TR * TN, split_stride = (size_t)ntiles * tile_elems;
+    const float *p0 = partial + (size_t)blockIdx.x * tile_elems;
+    double *__restrict__ Cm = sym ? G : Bxy;
+    const int64_t ldc = sym ? K : n;
+    const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int jc = j0 + cq * 4, ojc = oj0 + cq * 4;  // first of this thread's 4 columns
+    const int ec0 = blockIdx.z * 128 + cq * 4;        // ... inside the tile
+
+    double sv[4][4];
+    if (!dblock) {
+        double d[4][4];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int lr = ty * 4 + rr;
-            const int i = i0 + lr, j = j0 + tx;
-            double s = 0.0;
-            if (i < K && j < Nn) {
-                int er = sr * 32 + lr, ec = sc * 32 + tx;  // element inside the tile
-                if (dblock && i > j) {                      // mirror inside the diagonal 128-block
-                    const int nr = (colbase + ec) - rowbase, nc = (rowbase + er) - colbase;
-                    er = nr;
-                    ec = nc;
-                }
-                const size_t e = (size_t)er * TN + ec;
-                for (int c = 0; c < nsplit; ++c) s += (double)p0[(size_t)c * ntiles * tile_elems + e];
-                const int oj = oj0 + tx;
-                s *= inv[i] * inv[oj];
-                if (sym && i == j) s = SQ[i];
-                const double ua = (double)shift[i];
-                const double ub = (double)shift[oj] - ((!sym && y_bias) ? (double)y_bias[j] : 0.0);
-                s += ua * T[oj] + T[i] * ub + Nd * ua * ub;
-                Cm[(int64_t)i * ldc + j] = s;
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[p][e] = 0.0;
+        for (int c = 0; c < nsplit; ++c) {
+            float4 v[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                v[p] = __ldg(reinterpret_cast<const float4 *>(p0 + (size_t)c * split_stride +
+                                                              (size_t)(sr * 32 + rl + 8 * p) * TN + ec0));
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                d[p][0] += (double)v[p].x; d[p][1] += (double)v[p].y; d[p][2] += (double)v[p].z; d[p][3] += (double)v[p].w;
             }
-            sv[rr] = s;
         }
-        if (upper) {  // the transposed copy (block-uniform condition)
+        double invj[4], ubj[4], Tj[4];
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) tr[ty * 4 + rr][tx] = sv[rr];
-            __syncthreads();
+        for (int e = 0; e < 4; ++e) {
+            const bool ok = jc + e < Nn;
+            invj[e] = ok ? inv[ojc + e] : 0.0;
+            Tj[e] = ok ? T[ojc + e] : 0.0;
+            ubj[e] = ok ? (double)shift[ojc + e] - ((!sym && y_bias) ? (double)y_bias[jc + e] : 0.0) : 0.0;
+        }
+        const bool vec2 = ((ldc & 1) == 0) && (jc + 3 < Nn) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int lc = ty * 4 + rr;
-                const int j = j0 + lc, i = i0 + tx;
-                if (i < K && j < K) G[(int64_t)j * K + i] = tr[tx][lc];
+        for (int p = 0; p < 4; ++p) {
+            const int i = i0 + rl + 8 * p;
+            if (i < K) {
+                const double invi = inv[i], ua = (double)shift[i], Ti = T[i];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    sv[p][e] = d[p][e] * (invi * invj[e]) + (ua * Tj[e] + Ti * ubj[e] + Nd * ua * ubj[e]);
+                double *dst = Cm + (int64_t)i * ldc + jc;
+                if (vec2) {
+                    *reinterpret_cast<double2 *>(dst) = make_double2(sv[p][0], sv[p][1]);
+                    *reinterpret_cast<double2 *>(dst + 2) = make_double2(sv[p][2], sv[p][3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (jc + e < Nn) dst[e] = sv[p][e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sv[p][e] = 0.0;
             }
-            __syncthreads();
+        }
+    } else {
+        // diagonal 128-block: element-wise, (i > j) reads the mirrored element
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int lr = rl + 8 * p, i = i0 + lr;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = jc + e;
+                double s = 0.0;
+                if (i < K && j < K) {
+                    int er = sr * 32 + lr, ec = ec0 + e;
+                    if (i > j) {
+                        const int nr = (colbase + ec) - rowbase, nc = (rowbase + er) - colbase;
+                        er = nr;
+                        ec = nc;
+                    }
+                    for (int c = 0; c < nsplit; ++c) s += (double)p0[(size_t)c * split_stride + (size_t)er * TN + ec];
+                    s *= inv[i] * inv[j];
+                    if (i == j) s = SQ[i];
+                    const double ua = (double)shift[i], ub = (double)shift[j];
+                    s += ua * T[j] + T[i] * ub + Nd * ua * ub;
+                    G[(int64_t)i * K + j] = s;
+                }
+                sv[p][e] = s;
+            }
+        }
+    }
+    if (upper) {  // the transposed copy: G[j][i] for the 32 x 128 strip (CTA-uniform condition)
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tr[rl + 8 * p][cq * 4 + e] = sv[p][e];
+        __syncthreads();
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int col = w * 16 + k;
+            const int j = j0 + col, i = i0 + lane;
+            if (i < K && j < K) G[(int64_t)j * K + i] = tr[lane][col];
         }
     }
 }

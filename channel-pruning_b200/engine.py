@@ -29,12 +29,13 @@ MAX_PROBES = 64
 # most collinear column); below that the layer is re-solved from exact-product fp64 statistics.
 LS_RATIO_MIN = float(os.environ.get("CPB200_LS_RATIO_MIN", "0.005"))
 LS_REFINE = os.environ.get("CPB200_LS_REFINE", "1") == "1"
-# Prediction X W' of the refinement residual: "fp64" (SIMT fp64 GEMM), "tc" (tensor cores, 3xTF32 through cp_gram on the
-# transposed patches) or "auto".  Alone, the tensor-core version is 2.7x faster at N = 5000 (0.46 vs 1.24 ms) and 5x at
-# N = 1e5; inside the 13-layer pipeline it is a loss (59.6 vs 48.5 ms per step, profiles/r2_summary.md): its CTAs hold a
-# whole SM's shared memory for ~70 us each and the latency-bound chains of the other layers queue behind them.  "auto"
-# therefore takes the tensor cores only for tall problems, where the fp64 product would dominate the solve.
-LS_RESID = os.environ.get("CPB200_LS_RESID", "auto")
+# Prediction X W' of the refinement residual: "fp64" (SIMT fp64 GEMM), "tc" (tensor cores, through cp_gram on the
+# transposed patches) or "auto" (tensor cores for N >= 20000 only).  With the first-generation 3xTF32 kernel "tc" was
+# a loss inside the 13-layer pipeline (59.6 vs 48.5 ms per step, profiles/r2_summary.md: one CTA per tile held a whole
+# SM's shared memory for ~70 us and the latency-bound chains of the other layers queued behind them).  The second-
+# generation kernel (gram_tc2.cu) is a ~100 us persistent launch: 32.1 vs 36.1 ms per step (call 19) -- the FP64 pipe
+# is the step's scarce resource and this takes 2NK'n flop per layer off it.  Default "tc" (in the tensor-core mode).
+LS_RESID = os.environ.get("CPB200_LS_RESID", "tc")
 LS_RESID_TC_MIN_N = 20000
 
 _PRIO_HIGHEST = -5  # cudaDeviceGetStreamPriorityRange on B200: [0, -5]; out-of-range values are clamped by the runtime
@@ -49,6 +50,54 @@ class LassoResult:
 
     def __init__(self, idxs, coef, scalars, probe_log, seeds):
         self.idxs, self.coef, self.scalars, self.probe_log, self.seeds = idxs, coef, scalars, probe_log, seeds
+
+
+def gpu_numa_cpus(device_index):
+    """CPUs of the NUMA node the GPU hangs off (from sysfs), or None when the platform does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus or None
+    except Exception:
+        return None
+
+
+class numa_local:
+    """Context: page-locked host buffers allocated inside are placed on the NUMA node of ``device_index`` (first
+    touch under a temporary CPU affinity; a GPU reading host memory of the other socket pays the inter-socket
+    link on every PCIe read -- round-1 measurement: 0.75 e2e scaling efficiency at 8 GPUs from one node's memory)."""
+
+    def __init__(self, device_index):
+        self.cpus = gpu_numa_cpus(device_index)
+        self.old = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.old = os.sched_getaffinity(0)
+                allowed = self.cpus & self.old
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+                else:
+                    self.old = None
+            except Exception:
+                self.old = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except Exception:
+                pass
+        return False
 
 
 class Engine:
@@ -104,7 +153,8 @@ class Engine:
         k = (key, tuple(shape), dtype)
         t = self._pinned.get(k)
         if t is None:
-            t = self._pinned[k] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            with numa_local(self.device.index if self.device.index is not None else 0):
+                t = self._pinned[k] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         return t
 
     def _ring(self):

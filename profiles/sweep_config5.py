@@ -70,6 +70,7 @@ def main(args=None):
               "gather_frac_of_hbm": 8.0 * N * s.K / (t_g / 1e3) / 1e9 / peaks["hbm_gbs"],
               "gram_ms": t_gram, "gram_tflops": flops / (t_gram / 1e3) / 1e12,
               "gram_frac_of_tf32": flops / (t_gram / 1e3) / 1e12 / lib_peaks["tf32_tflops"],
+              "gram_frac_of_bf16_peak": flops / (t_gram / 1e3) / 1e12 / peaks["bf16_tflops"],  # 3 MMAs per product: ceiling 1/3
               "select_ms": t_sel, "probes": int(scal[1]), "cd_sweeps": sweeps,
               "select_ns_per_coordinate": 1e6 * t_sel / max(1, sweeps * s.c), "kept": int(idxs.sum()),
               "ls_ms": t_ls, "ls_path": "dual (N-1 < K')" if N - 1 < int(idxs.sum()) * 9 else "primal + refinement",
@@ -84,7 +85,7 @@ def main(args=None):
         torch.cuda.empty_cache()
     line = {"metric": "conv4_3_patch_count_sweep", "unit": "per-kernel", "n_gpus": 1, "data": "synthetic",
             "config": {"workload": bench.WORKLOADS["sweep"], "c": 512, "n": 512, "k": 3, "K": 4608},
-            "peaks": {"hbm_gbs": peaks["hbm_gbs"], "hbm_source": which, **lib_peaks}, "points": points}
+            "peaks": {"hbm_gbs": peaks["hbm_gbs"], "bf16_tflops": peaks["bf16_tflops"], "hbm_source": which, **lib_peaks}, "points": points}
     print(json.dumps(line), flush=True)
 
 

@@ -119,3 +119,43 @@ def test_gram_tc_is_bitwise_reproducible(engine):
     a = engine.gram(X, Y, mode=1)
     b = engine.gram(X, Y, mode=1)
     assert torch.equal(a["G"], b["G"]) and torch.equal(a["B"], b["B"])
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import cpb200
+eng = cpb200.Engine(gram_mode=1)
+worst = 0.0
+for (N, K, n) in [(1500, 640, 72), (333, 130, 5)]:
+    r = np.random.RandomState(N)
+    X = np.maximum(r.standard_normal((N, K)), 0).astype(np.float32)
+    Y = r.standard_normal((N, (n + 3) // 4 * 4)).astype(np.float32)
+    g = eng.gram(torch.as_tensor(X, device=eng.device), torch.as_tensor(Y, device=eng.device)[:, :n], mode=1)
+    X64, Y64 = X.astype(np.float64), Y[:, :n].astype(np.float64)
+    Gr, Br = X64.T @ X64, X64.T @ Y64
+    dx, dy = np.sqrt(np.diag(Gr)), np.sqrt((Y64 ** 2).sum(0))
+    G, B = g["G"].cpu().numpy(), g["B"].cpu().numpy()
+    assert np.array_equal(G, G.T)
+    worst = max(worst, (np.abs(G - Gr) / np.outer(dx, dx)).max(), (np.abs(B - Br) / np.outer(dx, dy)).max())
+print("WORST %%.3e" %% worst)
+"""
+
+
+@pytest.mark.parametrize("env", [{"CPB200_GRAM_PAIR": "0"}, {"CPB200_GRAM_TC": "1"}],
+                         ids=["gen2-single-cta-tiles", "gen1-3xtf32"])
+def test_gram_tc_build_variants(env):
+    """The kernel variants kept for A/B measurements (selected once per process by the environment): the
+    single-CTA 128x256 tiles of the second generation and the first-generation 3xTF32 kernel meet the same
+    tolerance as the default CTA-pair kernel."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root], env=e, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float(out.stdout.strip().split("WORST")[-1])
+    assert worst <= 1e-6, worst
