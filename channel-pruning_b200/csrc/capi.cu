@@ -41,19 +41,26 @@ extern "C" int cp_create(cp_handle_t *out, int device) {
     h->aux_bytes = 0;
     h->gram_profile = false;
     h->ev_gram0 = h->ev_gram1 = nullptr;
+    h->ls_tc = false;
+    for (int i = 0; i < 3; ++i) {
+        h->tcbuf[i] = nullptr;
+        h->tcbuf_bytes[i] = 0;
+    }
     *out = h;
     return CP_OK;
 }
 
 extern "C" int cp_destroy(cp_handle_t h) {
     if (!h) return CP_OK;
-    if (h->ws || h->side || h->fac || h->aux || h->ev_gram0) {
+    if (h->ws || h->side || h->fac || h->aux || h->ev_gram0 || h->tcbuf[0] || h->tcbuf[1] || h->tcbuf[2]) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(h->device);
         if (h->ws) cudaFree(h->ws);
         if (h->fac) cudaFree(h->fac);
         if (h->aux) cudaFree(h->aux);
+        for (int i = 0; i < 3; ++i)
+            if (h->tcbuf[i]) cudaFree(h->tcbuf[i]);
         if (h->ev_gram0) {
             cudaEventDestroy(h->ev_gram0);
             cudaEventDestroy(h->ev_gram1);
@@ -79,6 +86,12 @@ extern "C" int cp_gram_profile(cp_handle_t h, int enable) {
         CP_CUDA(cudaEventCreate(&h->ev_gram1));
     }
     h->gram_profile = enable != 0;
+    return CP_OK;
+}
+
+extern "C" int cp_ls_tensor_cores(cp_handle_t h, int enable) {
+    CP_REQUIRE(h != nullptr, "cp_ls_tensor_cores: NULL handle");
+    h->ls_tc = enable != 0;
     return CP_OK;
 }
 

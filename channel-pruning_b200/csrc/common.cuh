@@ -31,6 +31,11 @@ struct cp_handle_s {
     // cp_gram_profile: CUDA events around the tensor-core GEMM kernel of cp_gram (bench.py's roofline of that kernel)
     bool gram_profile;
     cudaEvent_t ev_gram0, ev_gram1;
+    // tensor-core (split-precision) bulk products of the least-squares solver (gemm_tc.cu): on/off per handle
+    // (cp_ls_tensor_cores) and one operand buffer per stream the solver issues work on (caller's, side, bulk)
+    bool ls_tc;
+    void *tcbuf[3];
+    size_t tcbuf_bytes[3];
 };
 
 // Entry points run on the handle's device whatever the caller's current device is (restored on return).

@@ -30,6 +30,11 @@
 #include "gemm_small.cuh"
 #include "gemm_async.cuh"
 
+bool cp_gemm_tc_enabled();
+int cp_gemm_tc_f64(cp_handle_t h, int slot, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
+                   int64_t ldc, int M, int Nn, int R, double alpha, double beta, int lower, cudaStream_t stream,
+                   int max_clusters);
+
 namespace {
 
 constexpr int PB = 128;          // panel width
@@ -465,8 +470,17 @@ int dgemm_async(const double *A, int64_t lda, const double *B, int64_t ldb, doub
 
 // 128 x 128 tiles (throughput: the far trailing updates)
 int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
-              int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream, int max_ctas = 0) {
+              int64_t R, double alpha, double beta, int tile_mode, cudaStream_t stream, int max_ctas = 0,
+              cp_handle_t tc = nullptr) {
     using namespace cpgemm;
+    // tensor-core handle given and enabled: split-precision product (gemm_tc.cu) for everything wide enough to fill
+    // 256 x 256 tiles; one operand buffer per stream of the solver
+    if (tc && tc->ls_tc && cp_gemm_tc_enabled() && R >= 128 && R <= 1024 && Nn >= 192 && M >= 256 &&
+        (tile_mode == TILES_ALL || tile_mode == TILES_LOWER)) {
+        const int slot = stream == tc->side ? 1 : (stream == tc->bulk ? 2 : 0);
+        return cp_gemm_tc_f64(tc, slot, A, lda, B, ldb, C, ldc, M, Nn, (int)R, alpha, beta, tile_mode == TILES_LOWER, stream,
+                              max_ctas > 0 ? max_ctas / 2 : 0);
+    }
     bool done = false;
     int rca = dgemm_async<128, false>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, tile_mode, stream, max_ctas, &done);
     if (rca || done) return rca;
@@ -655,7 +669,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
         if (!odd) {
             const int w3 = Kd - j2 < PB ? Kd - j2 : PB;
             const double *Pf = L + (int64_t)j2 * ld + j0;
-            rc = dgemm_big(Pf, ld, Pf, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, w3, nb, -1.0, 1.0, TILES_LOWER, h->side);
+            rc = dgemm_big(Pf, ld, Pf, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, w3, nb, -1.0, 1.0, TILES_LOWER, h->side, 0, h);
             if (rc) return rc;
             CP_CUDA(cudaEventRecord(h->ev_side, h->side));
             side_pending = true;
@@ -664,7 +678,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
             const int je = j0 - PB, R2 = PB + nb;
             const int wn = Kd - j2 < 2 * PB ? Kd - j2 : 2 * PB;  // near: the next pair's two block columns
             const double *Pq = L + (int64_t)j2 * ld + je;
-            rc = dgemm_big(Pq, ld, Pq, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, wn, R2, -1.0, 1.0, TILES_LOWER, h->side);
+            rc = dgemm_big(Pq, ld, Pq, ld, M + (int64_t)j2 * ld + j2, ld, Ktot - j2, wn, R2, -1.0, 1.0, TILES_LOWER, h->side, 0, h);
             if (rc) return rc;
             CP_CUDA(cudaEventRecord(h->ev_side, h->side));
             side_pending = true;
@@ -676,7 +690,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
                 }
                 const int wm = Kd - j4 < 2 * PB ? Kd - j4 : 2 * PB;
                 const double *P4 = L + (int64_t)j4 * ld + je;
-                rc = dgemm_big(P4, ld, P4, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, wm, R2, -1.0, 1.0, TILES_LOWER, h->side);
+                rc = dgemm_big(P4, ld, P4, ld, M + (int64_t)j4 * ld + j4, ld, Ktot - j4, wm, R2, -1.0, 1.0, TILES_LOWER, h->side, 0, h);
                 if (rc) return rc;
                 const int j6 = j4 + wm;
                 if (Kd - j6 > 0) {
@@ -685,7 +699,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
                     CP_CUDA(cudaStreamWaitEvent(h->bulk, h->ev_panel, 0));
                     const double *Pr = L + (int64_t)j6 * ld + je;
                     rc = dgemm_big(Pr, ld, Pr, ld, M + (int64_t)j6 * ld + j6, ld, Ktot - j6, Kd - j6, R2, -1.0, 1.0,
-                                   TILES_LOWER, h->bulk, rest_ctas(h));
+                                   TILES_LOWER, h->bulk, rest_ctas(h), h);
                     if (rc) return rc;
                     CP_CUDA(cudaEventRecord(h->ev_bulk, h->bulk));
                     bulk_pending = true;
@@ -704,7 +718,7 @@ static int chol_factor(cp_handle_t h, double *M, double *L, int64_t ld, int Kd, 
 
 // Forward substitution of further right-hand sides: Zt (n x Kd, ld) is destroyed, F (n x Kd, ld) receives (L^-1 Rhs)'.
 static int chol_forward(const double *L, int64_t ld, int Kd, const double *Xinv, double *Zt, double *F, int64_t ldz, int n,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, cp_handle_t tc = nullptr) {
     for (int g0 = 0; g0 < Kd; g0 += GB) {
         const int gs = Kd - g0 < GB ? Kd - g0 : GB;
         const int g1 = g0 + gs;
@@ -714,9 +728,11 @@ static int chol_forward(const double *L, int64_t ld, int Kd, const double *Xinv,
         if (rc) return rc;
         if (Kd - g1 > 0) {  // Zt[:, g1:] -= F_g * L[g1:, g0:g1]'
             // few right-hand sides: 128 x 128 tiles would leave most SMs idle on a 512-deep product, 64 x 64 tiles fill them
-            if (cpgemm::num_tiles(n, Kd - g1, cpgemm::TILES_ALL) >= 2 * 148)
+            // tensor-core mode: 256 x 256 pair tiles (n >= 256 right-hand sides, a few column tiles) beat the fp64 pipe
+            const bool use_tc = tc && tc->ls_tc && cp_gemm_tc_enabled() && n >= 256 && Kd - g1 >= 512;
+            if (use_tc || cpgemm::num_tiles(n, Kd - g1, cpgemm::TILES_ALL) >= 2 * 148)
                 rc = dgemm_big(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
-                               cpgemm::TILES_ALL, stream);
+                               cpgemm::TILES_ALL, stream, 0, use_tc ? tc : nullptr);
             else
                 rc = dgemm_small<false>(F + g0, ldz, L + (int64_t)g1 * ld + g0, ld, Zt + g1, ldz, n, Kd - g1, gs, -1.0, 1.0,
                                         cpsmall::TILES_ALL, stream);
@@ -894,7 +910,7 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     const double invN = 1.0 / (double)h->fac_N;
     rhs_assemble<<<dim3(cp_cdiv(Ksel, 256), n), 256, 0, stream>>>(Bxy, sx, sy, invN, n, sel_cols, Ksel, Zt, ld);
     CP_CHECK_LAUNCH();
-    rc = chol_forward(L, ld, Ksel, Linv, Zt, F, ld, n, stream);
+    rc = chol_forward(L, ld, Ksel, Linv, Zt, F, ld, n, stream, h);
     if (rc) return rc;
     rc = chol_backward(L, ld, Ksel, Linv, F, ld, Wt, ld, n, stream);
     if (rc) return rc;

@@ -37,6 +37,8 @@ LS_REFINE = os.environ.get("CPB200_LS_REFINE", "1") == "1"
 # is the step's scarce resource and this takes 2NK'n flop per layer off it.  Default "tc" (in the tensor-core mode).
 LS_RESID = os.environ.get("CPB200_LS_RESID", "tc")
 LS_RESID_TC_MIN_N = 20000
+# Bulk products of the Cholesky solve on the tensor cores when the statistics came from there (cp_ls_tensor_cores)
+LS_TC = os.environ.get("CPB200_LS_TC", "1") == "1"
 
 _PRIO_HIGHEST = -5  # cudaDeviceGetStreamPriorityRange on B200: [0, -5]; out-of-range values are clamped by the runtime
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
@@ -276,6 +278,25 @@ class Engine:
         out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n, mode=self.gram_mode if mode is None else mode)
         return out
 
+    def gemm_tc_split(self, A, B, C=None, alpha=1.0, beta=0.0, lower=False):
+        """C = alpha A B' + beta C on the tensor cores in 22-bit split precision (cp_gemm_tc_split): A (M, R), B (Nn, R),
+        C (M, Nn) fp64 device tensors with unit inner stride."""
+        assert A.dtype == B.dtype == torch.float64 and A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+        M, R = A.shape
+        Nn = B.shape[0]
+        if C is None:
+            assert beta == 0.0
+            C = self.empty(M, Nn)
+        assert C.shape == (M, Nn) and C.dtype == torch.float64 and C.stride(1) == 1
+        self._call(self.lib.cp_gemm_tc_split(self.h, M, Nn, R, float(alpha), self._p(A, "const double*"), A.stride(0),
+                                             self._p(B, "const double*"), B.stride(0), float(beta), self._p(C, "double*"),
+                                             C.stride(0), 1 if lower else 0, self._s()))
+        return C
+
+    def ls_tensor_cores(self, enable):
+        """Bulk products of the following ls_solve / ls_factor / ls_resolve calls on the tensor cores (cp_ls_tensor_cores)."""
+        self._call(self.lib.cp_ls_tensor_cores(self.h, 1 if enable else 0))
+
     def gram_profile(self, enable=True):
         """CUDA events around the tensor-core GEMM launch of every following gram() on this engine's handle."""
         self._call(self.lib.cp_gram_profile(self.h, 1 if enable else 0))
@@ -341,6 +362,7 @@ class Engine:
         b = self.empty(n)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         stat = self.empty(1)
+        self.ls_tensor_cores(LS_TC and g.get("mode", GRAM_FP64) != GRAM_FP64)
         self._call(self.lib.cp_ls_solve(self.h, self._p(g["G"], "const double*"), self._p(g["B"], "const double*"),
                                         self._p(g["sx"], "const double*"), self._p(g["sy"], "const double*"),
                                         g["N"], g["K"], n, self._p(sel_cols, "const int32_t*"), Ks,
@@ -370,6 +392,7 @@ class Engine:
         Ks = sel_cols.numel() if sel_cols is not None else g["K"]
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         stat = self.empty(1)
+        self.ls_tensor_cores(LS_TC and g.get("mode", GRAM_FP64) != GRAM_FP64)
         self._call(self.lib.cp_ls_factor(self.h, self._p(g["G"], "const double*"), self._p(g["sx"], "const double*"),
                                          g["N"], g["K"], self._p(sel_cols, "const int32_t*"), Ks,
                                          self._p(info, "int32_t*"), self._p(stat, "double*"), self._s()))

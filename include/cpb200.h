@@ -74,6 +74,13 @@ int64_t cp_workspace_bytes(cp_handle_t h);
  * records CUDA events on its stream right before and after the tcgen05 GEMM launch; cp_gram_kernel_ms waits for the
  * second event and returns the elapsed time of that launch alone (bench.py divides the algorithmic flops by it). */
 int cp_gram_profile(cp_handle_t h, int enable);
+/* Arithmetic of the bulk products inside the following cp_ls_solve / cp_ls_factor / cp_ls_resolve calls on this handle
+ * (the solver behind LinearRegression.fit, lib/decompose.py:665-666).  0 (default): fp64 (DMMA).  1: Cholesky
+ * trailing updates and forward substitutions with >= 256 columns run on the tensor cores in 22-bit split precision
+ * (csrc/gemm_tc.cu) -- meant for statistics that came from cp_gram's tensor-core mode and are followed by a
+ * refinement step (cp_ls_residual + cp_ls_resolve); the panel factorisations, the panel solves and the pivot-ratio
+ * statistic stay fp64. */
+int cp_ls_tensor_cores(cp_handle_t h, int enable);
 int cp_gram_kernel_ms(cp_handle_t h, float *ms);
 
 /*
@@ -239,6 +246,16 @@ int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx, const doub
 int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx, const void *Yraw, int y_dtype, int n,
                    int64_t ldy, const float *y_bias, const int32_t *sel_cols, int Ksel, const double *W, const double *b,
                    float *R_out, int64_t ldr, int mode, cp_stream_t stream);
+
+/*
+ * The split-precision tensor-core product the solver uses for its bulk updates when cp_ls_tensor_cores is on
+ * (csrc/gemm_tc.cu), exposed for tests and measurements: the fp64 matrix products inside LinearRegression.fit's
+ * solve (lib/decompose.py:665-666), evaluated with 22 mantissa bits per operand entry on tcgen05.
+ *   C[m, nn] = alpha * sum_r A[m * lda + r] * B[nn * ldb + r] + beta * C[m * ldc + nn]      (fp64 in, fp64 out)
+ * lower != 0: only the 256 x 256 tiles with row tile >= column tile are touched (M >= Nn).  R <= 1024.
+ */
+int cp_gemm_tc_split(cp_handle_t h, int M, int Nn, int R, double alpha, const double *A, int64_t lda, const double *B,
+                     int64_t ldb, double beta, double *C, int64_t ldc, int lower, cp_stream_t stream);
 
 /*
  * ---- dense fp64 building blocks of the 3C companions (VH_decompose, nonlinear_fc, ITQ_decompose) ----

@@ -65,3 +65,10 @@ torch.cuda.profiler.start()
 eng.reconstruct_async(g_full, X, d["feats"], d["b2"], idxs, 9)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+# accuracy of the tensor-core path (statistics, bulk products of the solve, residual) against the exact-product fp64 solve
+Wt, bt, _, st = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], idxs, 9)
+We, be, _, _ = eng.reconstruct_exact_async(X, d["feats"], d["b2"], idxs, 9)
+torch.cuda.synchronize()
+print("tensor-core path vs exact fp64 solve: rel W %.2e, rel b %.2e, pivot ratio %.3g (LS_TC=%s, residual %s)" % (
+    ((Wt - We).norm() / We.norm()).item(), ((bt - be).norm() / be.norm()).item(), st.item(),
+    cpb200.engine.LS_TC, cpb200.engine.LS_RESID), flush=True)

@@ -304,3 +304,33 @@ def test_rank_deficient_system_gets_gelsd_truncated_solution(engine, mode):
     rc, ri = O.linear_regression(X.astype(np.float64), Y.astype(np.float64))
     assert np.linalg.norm(coef - rc) <= 1e-7 * np.linalg.norm(rc) and np.abs(icpt - ri).max() <= 1e-7
     assert np.abs(coef[:, 100]).max() <= 1e-9 and np.abs(coef[:, 70] - coef[:, 30]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("M,Nn,R,lower", [(700, 300, 256, False), (1030, 520, 128, True), (512, 512, 384, True),
+                                          (257, 200, 130, False), (2048, 768, 512, False)])
+def test_gemm_tc_split_matches_fp64(engine, M, Nn, R, lower):
+    """cp_gemm_tc_split (the solver's tensor-core bulk product): C = beta C + alpha A B', rows of very different magnitude
+    (power-of-two row scales).  Tolerance: |err| <= 4e-6 * sum_r |a||b|.  The operand split keeps 22 bits (<= 5e-7 of
+    sum|a||b|); the rest is the tensor core's fp32 accumulator, which TRUNCATES: up to 24 (R <= 256) or 48 additions
+    per accumulator, each losing < 2^-23 of the running sum in the same direction when all terms have one sign -- the
+    diagonal of a symmetric update (measured: 1.5e-6 there, 3.5e-7 for mixed signs)."""
+    r = np.random.RandomState(M + Nn + R)
+    A = r.standard_normal((M, R)) * np.exp(3.0 * r.standard_normal((M, 1)))
+    if lower:
+        B = A[:Nn].copy()
+    else:
+        B = r.standard_normal((Nn, R)) * np.exp(3.0 * r.standard_normal((Nn, 1)))
+    C0 = r.standard_normal((M, Nn))
+    Ad, Bd, Cd = (torch.as_tensor(x, device=engine.device) for x in (A, B, C0.copy()))
+    engine.gemm_tc_split(Ad, Bd, Cd, alpha=-1.0, beta=1.0, lower=lower)
+    got = Cd.cpu().numpy()
+    ref = C0 - A @ B.T
+    bound = np.abs(A) @ np.abs(B).T
+    err = np.abs(got - ref) / bound
+    if lower:  # 256 x 256 tiles with row tile >= column tile are written; the others must be untouched
+        ti, tj = np.arange(M)[:, None] // 256, np.arange(Nn)[None, :] // 256
+        touched = ti >= tj
+        assert np.array_equal(got[~touched], C0[~touched])
+        err = err[touched]
+    print("max err / sum|a||b| = %.2e" % err.max())
+    assert err.max() <= 4e-6
