@@ -38,11 +38,13 @@ constexpr int T_TMA = 32 * W_TMA;
 constexpr int SUB_STAGES = 2;                      // stages per accumulator run (128 reduction elements)
 constexpr int PS_TILE = 128 * 128;                 // bytes of one 128-row operand tile (hi or lo)
 constexpr int PS_STAGE_BYTES = 4 * PS_TILE;        // A hi, A lo, B-half hi, B-half lo
-constexpr int PS_STAGES = 3;
+constexpr int PS_STAGES = 2;                       // short reductions (R <= 1024): two stages leave room for the epilogue tiles
 constexpr int PS_OFF_BAR = PS_STAGES * PS_STAGE_BYTES;
 constexpr int PS_NBAR = 2 * PS_STAGES + 2;
 constexpr int PS_OFF_TMEM = PS_OFF_BAR + PS_NBAR * 8;
-constexpr int PS_SMEM_BYTES = PS_OFF_TMEM + 16 + 1024;
+constexpr int EP_LD = 66;                          // floats per row of a drain warp's 32 x 64 transposition tile
+constexpr int PS_OFF_EPI = (PS_OFF_TMEM + 16 + 15) / 16 * 16;
+constexpr int PS_SMEM_BYTES = PS_OFF_EPI + NDRAIN_WARPS * 32 * EP_LD * 4 + 1024;
 
 struct GtParams {
     double *C;
@@ -169,58 +171,76 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
     } else {
-        // drain warps of both CTAs: accumulator row m of this CTA = row ti*256 + rank*128 + m of C, 128 columns each,
-        // in groups of 32 columns: tensor memory -> registers, C = beta C + alpha 2^-(eA_i + eB_j) acc in fp64
+        // drain warps of both CTAs.  A warp owns 32 accumulator rows (its TMEM lane quadrant) x 128 columns; tcgen05.ld
+        // hands every lane ONE ROW, but a read-modify-write of C with one row per lane is 32 transactions per
+        // instruction (measured: 30 us per tile).  So the accumulators pass through a per-warp shared-memory tile and
+        // leave transposed: one instruction = one row x 64 columns = 512 contiguous bytes, 16 rows in flight per lane.
         const int quad = warp & 3, half = warp >> 2;
-        const int m = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
         const bool two = P.nst > SUB_STAGES;  // the second accumulator holds the odd runs
         const bool vec = ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && ((P.ldc & 1) == 0);
+        float *tile = reinterpret_cast<float *>(smem + PS_OFF_EPI) + warp * 32 * EP_LD;
         uint32_t nt = 0;
         for (int w = cid; w < nitems; w += ncl, ++nt) {
             const GtItem it = gt_decode(P, w);
             mbar_wait(bar(ACC_FULL), nt & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int i = it.ti * 256 + (int)rank * 128 + m;
-            const int j0 = it.tj * 256 + half * 128;
-            const bool live = i < P.M && j0 < P.Nn;
-            const double ai = live ? P.alpha * P.invA[i] : 0.0;
-            double *crow = P.C + (int64_t)(live ? i : 0) * P.ldc + (live ? j0 : 0);
-            const double *ib = P.invB + (live ? j0 : 0);
-            const int nvalid = live ? (P.Nn - j0 < 128 ? P.Nn - j0 : 128) : 0;
+            const int ibase = it.ti * 256 + (int)rank * 128 + quad * 32;   // first row of this warp
+            const int jbase = it.tj * 256 + half * 128;                      // first column of this warp
 #pragma unroll 1
-            for (int gq = 0; gq < 4; ++gq) {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(lane_addr + (uint32_t)(gq * 32), r0);
-                if (two) tmem_ld32(lane_addr + 256 + (uint32_t)(gq * 32), r1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float av[32];
+            for (int p = 0; p < 2; ++p) {
+                {
+                    uint32_t r0[32], r1[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    av[e] = two ? __fadd_rn(__uint_as_float(r0[e]), __uint_as_float(r1[e])) : __uint_as_float(r0[e]);
-                const int c0 = gq * 32;
-                if (vec && nvalid - c0 >= 32) {
-                    double2 cv[16], sj[16];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tmem_ld32(lane_addr + (uint32_t)(p * 64 + hh * 32), r0);
+                        if (two) tmem_ld32(lane_addr + 256 + (uint32_t)(p * 64 + hh * 32), r1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        sj[q] = __ldg(reinterpret_cast<const double2 *>(ib + c0 + 2 * q));
-                        cv[q] = P.beta != 0.0 ? *reinterpret_cast<const double2 *>(crow + c0 + 2 * q) : make_double2(0.0, 0.0);
+                        for (int e = 0; e < 32; ++e)
+                            tile[lane * EP_LD + hh * 32 + e] =
+                                two ? __fadd_rn(__uint_as_float(r0[e]), __uint_as_float(r1[e])) : __uint_as_float(r0[e]);
                     }
+                }
+                __syncwarp();
+                const int j = jbase + p * 64 + 2 * lane;  // this lane's two columns
+                if (j < P.Nn && ibase < P.M) {
+                    const bool pairok = vec && (j + 1 < P.Nn);
+                    const double sj0 = P.invB[j], sj1 = (j + 1 < P.Nn) ? P.invB[j + 1] : 0.0;
+#pragma unroll 1
+                    for (int rb = 0; rb < 32; rb += 16) {
+                        double2 cv[16];
+                        if (P.beta != 0.0) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        cv[q].x = P.beta * cv[q].x + ai * sj[q].x * (double)av[2 * q];
-                        cv[q].y = P.beta * cv[q].y + ai * sj[q].y * (double)av[2 * q + 1];
-                        *reinterpret_cast<double2 *>(crow + c0 + 2 * q) = cv[q];
-                    }
-                } else {
+                            for (int q = 0; q < 16; ++q) {
+                                const int i = ibase + rb + q;
+                                cv[q] = make_double2(0.0, 0.0);
+                                if (i < P.M) {
+                                    const double *src = P.C + (int64_t)i * P.ldc + j;
+                                    if (pairok) cv[q] = *reinterpret_cast<const double2 *>(src);
+                                    else { cv[q].x = src[0]; if (j + 1 < P.Nn) cv[q].y = src[1]; }
+                                }
+                            }
+                        } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        if (c0 + e < nvalid) {
-                            const double old = P.beta != 0.0 ? crow[c0 + e] : 0.0;
-                            crow[c0 + e] = P.beta * old + ai * ib[c0 + e] * (double)av[e];
+                            for (int q = 0; q < 16; ++q) cv[q] = make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int i = ibase + rb + q;
+                            const float2 v = *reinterpret_cast<const float2 *>(tile + (rb + q) * EP_LD + 2 * lane);
+                            if (i < P.M) {
+                                const double ai = P.alpha * __ldg(P.invA + i);  // same address in every lane: one broadcast
+                                cv[q].x = P.beta * cv[q].x + ai * sj0 * (double)v.x;
+                                cv[q].y = P.beta * cv[q].y + ai * sj1 * (double)v.y;
+                                double *dst = P.C + (int64_t)i * P.ldc + j;
+                                if (pairok) *reinterpret_cast<double2 *>(dst) = cv[q];
+                                else { dst[0] = cv[q].x; if (j + 1 < P.Nn) dst[1] = cv[q].y; }
+                            }
                         }
                     }
                 }
+                __syncwarp();  // the tile is rewritten by the next pass
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -270,6 +290,62 @@ gemm_tc_prep(const double *__restrict__ P, int64_t ld, int rows, int R, int rows
     if (lane == 0) inv[row] = ldexp(1.0, -e);
 }
 
+// ------------------------------------------------------------------ operand preparation, transposed source
+// operand row nn, reduction index r  <-  P[r * ld + nn]   (the factor's block row in the backward substitution)
+// pass 1: per-column maximum -> power-of-two scale; pass 2: 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+gemm_tc_colmax(const double *__restrict__ P, int64_t ld, int ncols, int R, int rows_pad, double *__restrict__ scale,
+               double *__restrict__ inv) {
+    // CTA = 32 columns x 8 row lanes (the loads of a lane are independent: 8 in flight per thread)
+    __shared__ double red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nn = blockIdx.x * 32 + tx;
+    double mx = 0.0;
+    if (nn < ncols) {
+#pragma unroll 8
+        for (int r = ty; r < R; r += 8) mx = fmax(mx, fabs(P[(int64_t)r * ld + nn]));
+    }
+    red[ty][tx] = mx;
+    __syncthreads();
+    if (ty == 0 && nn < rows_pad) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) mx = fmax(mx, red[k][tx]);
+        int e = 0;
+        if (mx > 0.0 && isfinite(mx)) {
+            e = 9 - ilogb(mx);
+            e = e > 900 ? 900 : (e < -900 ? -900 : e);
+        }
+        scale[nn] = nn < ncols ? ldexp(1.0, e) : 0.0;
+        inv[nn] = nn < ncols ? ldexp(1.0, -e) : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256)
+gemm_tc_prep_t(const double *__restrict__ P, int64_t ld, int ncols, int R, int Rp, const double *__restrict__ scale,
+               __half *__restrict__ Ohi, __half *__restrict__ Olo) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nn0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int nn = nn0 + tx;
+    const double sc = scale[nn];  // 0 for padding rows
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k;
+        float v = 0.f;
+        if (r < R && nn < ncols) v = (float)(P[(int64_t)r * ld + nn] * sc);
+        tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int row = nn0 + ty + 8 * k;  // operand row
+        const float v = tile[tx][ty + 8 * k];
+        const __half h = __float2half_rn(v);
+        const size_t o = (size_t)row * Rp + r0 + tx;
+        Ohi[o] = h;
+        Olo[o] = __float2half_rn(__fsub_rn(v, __half2float(h)));
+    }
+}
+
 }  // namespace
 
 bool cp_gemm_tc_enabled() {
@@ -279,15 +355,17 @@ bool cp_gemm_tc_enabled() {
 
 // slot: which of the handle's operand buffers to use -- one per stream the solver issues work on (calls on one stream
 // are ordered, so a buffer is never rewritten under a kernel that still reads it)
+// b_nc: the B operand is stored reduction-major, b(nn, r) = B[r * ldb + nn]
 int cp_gemm_tc_f64(cp_handle_t h, int slot, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
-                   int M, int Nn, int R, double alpha, double beta, int lower, cudaStream_t stream, int max_clusters) {
+                   int M, int Nn, int R, double alpha, double beta, int lower, cudaStream_t stream, int max_clusters,
+                   int b_nc) {
     if (M <= 0 || Nn <= 0) return CP_OK;
     CP_REQUIRE(slot >= 0 && slot < 3 && R > 0, "cp_gemm_tc_f64: bad slot / R");
-    const bool same = (A == B && lda == ldb && Nn <= M);
+    const bool same = (!b_nc && A == B && lda == ldb && Nn <= M);
     const int Rp = cp_cdiv(R, KS) * KS;
     const int rowsA = cp_cdiv(M, 256) * 256, rowsB = same ? rowsA : cp_cdiv(Nn, 256) * 256;
     const size_t needA = 2 * (size_t)rowsA * Rp * sizeof(__half), needB = same ? 0 : 2 * (size_t)rowsB * Rp * sizeof(__half);
-    const size_t need = cp_align_up(needA, 256) + cp_align_up(needB, 256) + cp_align_up((size_t)(rowsA + rowsB) * 8, 256);
+    const size_t need = cp_align_up(needA, 256) + cp_align_up(needB, 256) + cp_align_up((size_t)(rowsA + 2 * rowsB) * 8, 256);
     if (need > h->tcbuf_bytes[slot]) {
         if (h->tcbuf[slot]) CP_CUDA(cudaFree(h->tcbuf[slot]));  // synchronises: nothing in flight uses the old block
         h->tcbuf[slot] = nullptr;
@@ -303,12 +381,18 @@ int cp_gemm_tc_f64(cp_handle_t h, int slot, const double *A, int64_t lda, const 
     cp_carver cv(h->tcbuf[slot]);
     __half *opA = cv.take<__half>(2 * (size_t)rowsA * Rp);
     __half *opB = same ? opA : cv.take<__half>(2 * (size_t)rowsB * Rp);
-    double *invA = cv.take<double>(rowsA + rowsB);
+    double *invA = cv.take<double>(rowsA + 2 * rowsB);
     double *invB = same ? invA : invA + rowsA;
+    double *scaleB = invA + rowsA + rowsB;  // transposed source only
 
     gemm_tc_prep<<<rowsA / 8, 256, 0, stream>>>(A, lda, M, R, rowsA, Rp, opA, opA + (size_t)rowsA * Rp, invA);
     CP_CHECK_LAUNCH();
-    if (!same) {
+    if (b_nc) {
+        gemm_tc_colmax<<<rowsB / 32, 256, 0, stream>>>(B, ldb, Nn, R, rowsB, scaleB, invB);
+        CP_CHECK_LAUNCH();
+        gemm_tc_prep_t<<<dim3(rowsB / 32, Rp / 32), 256, 0, stream>>>(B, ldb, Nn, R, Rp, scaleB, opB, opB + (size_t)rowsB * Rp);
+        CP_CHECK_LAUNCH();
+    } else if (!same) {
         gemm_tc_prep<<<rowsB / 8, 256, 0, stream>>>(B, ldb, Nn, R, rowsB, Rp, opB, opB + (size_t)rowsB * Rp, invB);
         CP_CHECK_LAUNCH();
     }
@@ -339,8 +423,9 @@ extern "C" int cp_gemm_tc_split(cp_handle_t h, int M, int Nn, int R, double alph
                                 const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int lower,
                                 cp_stream_t stream) {
     CP_REQUIRE(h && A && B && C, "cp_gemm_tc_split: NULL argument");
-    CP_REQUIRE(M >= 0 && Nn >= 0 && R > 0 && R <= 1024 && lda >= R && ldb >= R && ldc >= Nn, "cp_gemm_tc_split: bad shape");
-    CP_REQUIRE(!lower || M >= Nn, "cp_gemm_tc_split: lower tiles need M >= Nn");
+    CP_REQUIRE(M >= 0 && Nn >= 0 && R > 0 && R <= 1024 && lda >= R && ldb >= ((lower & 2) ? Nn : R) && ldc >= Nn,
+               "cp_gemm_tc_split: bad shape");
+    CP_REQUIRE(!(lower & 1) || M >= Nn, "cp_gemm_tc_split: lower tiles need M >= Nn");
     CP_DEVICE_GUARD(h);
-    return cp_gemm_tc_f64(h, 0, A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, lower, (cudaStream_t)stream, 0);
+    return cp_gemm_tc_f64(h, 0, A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, lower & 1, (cudaStream_t)stream, 0, (lower >> 1) & 1);
 }

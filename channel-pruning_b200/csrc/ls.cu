@@ -33,7 +33,7 @@
 bool cp_gemm_tc_enabled();
 int cp_gemm_tc_f64(cp_handle_t h, int slot, const double *A, int64_t lda, const double *B, int64_t ldb, double *C,
                    int64_t ldc, int M, int Nn, int R, double alpha, double beta, int lower, cudaStream_t stream,
-                   int max_clusters);
+                   int max_clusters, int b_nc);
 
 namespace {
 
@@ -479,7 +479,7 @@ int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double
         (tile_mode == TILES_ALL || tile_mode == TILES_LOWER)) {
         const int slot = stream == tc->side ? 1 : (stream == tc->bulk ? 2 : 0);
         return cp_gemm_tc_f64(tc, slot, A, lda, B, ldb, C, ldc, M, Nn, (int)R, alpha, beta, tile_mode == TILES_LOWER, stream,
-                              max_ctas > 0 ? max_ctas / 2 : 0);
+                              max_ctas > 0 ? max_ctas / 2 : 0, 0);
     }
     bool done = false;
     int rca = dgemm_async<128, false>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, tile_mode, stream, max_ctas, &done);
@@ -553,8 +553,12 @@ int configure_potrf(cp_handle_t h) {
 
 // dense product on 128 x 128 tiles with the (m, r) x (r, nn) operand layout of the substitutions
 static int dgemm_big_nc(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int M, int Nn,
-                        int64_t R, double alpha, double beta, cudaStream_t stream) {
+                        int64_t R, double alpha, double beta, cudaStream_t stream, cp_handle_t tc = nullptr) {
     using namespace cpgemm;
+    if (tc && tc->ls_tc && cp_gemm_tc_enabled() && R >= 128 && R <= 1024 && Nn >= 192 && M >= 256) {
+        const int slot = stream == tc->side ? 1 : (stream == tc->bulk ? 2 : 0);
+        return cp_gemm_tc_f64(tc, slot, A, lda, B, ldb, C, ldc, M, Nn, (int)R, alpha, beta, 0, stream, 0, 1);
+    }
     bool done = false;
     int rca = dgemm_async<128, true>(A, lda, B, ldb, C, ldc, M, Nn, R, alpha, beta, cpasync::TILES_ALL, stream, 0, &done);
     if (rca || done) return rca;
@@ -744,7 +748,7 @@ static int chol_forward(const double *L, int64_t ld, int Kd, const double *Xinv,
 
 // Backward substitution: F (n x Kd, ldf; destroyed) holds (L^-1 Rhs)'; Wt (n x Kd, ldw) receives (SPD^-1 Rhs)'.
 static int chol_backward(const double *L, int64_t ld, int Kd, const double *Xinv, double *F, int64_t ldf, double *Wt,
-                         int64_t ldw, int n, cudaStream_t stream) {
+                         int64_t ldw, int n, cudaStream_t stream, cp_handle_t tc = nullptr) {
     for (int g = ngroups(Kd) - 1; g >= 0; --g) {
         const int g0 = g * GB;
         const int gs = Kd - g0 < GB ? Kd - g0 : GB;
@@ -753,8 +757,10 @@ static int chol_backward(const double *L, int64_t ld, int Kd, const double *Xinv
         int rc = dgemm_small<true>(F + g0, ldf, Xg, GB, Wt + g0, ldw, n, gs, gs, 1.0, 0.0, cpsmall::TILES_ALL, stream);
         if (rc) return rc;
         if (g0 > 0) {  // F[:, 0:g0] -= Wt_g * L[g0:g0+gs, 0:g0]
-            if (cpgemm::num_tiles(n, g0, cpgemm::TILES_ALL) >= 2 * 148)
-                rc = dgemm_big_nc(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0, stream);
+            const bool use_tc = tc && tc->ls_tc && cp_gemm_tc_enabled() && n >= 256 && g0 >= 512;
+            if (use_tc || cpgemm::num_tiles(n, g0, cpgemm::TILES_ALL) >= 2 * 148)
+                rc = dgemm_big_nc(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0, stream,
+                                  use_tc ? tc : nullptr);
             else
                 rc = dgemm_small<true>(Wt + g0, ldw, L + (int64_t)g0 * ld, ld, F, ldf, n, g0, gs, -1.0, 1.0,
                                        cpsmall::TILES_ALL, stream);
@@ -825,7 +831,7 @@ extern "C" int cp_ls_solve(cp_handle_t h, const double *G, const double *Bxy, co
     CP_CHECK_LAUNCH();
     rc = chol_factor(h, M, L, ld, Ksel, n, Linv, Tm, diag0, info_out, ratio, stream);
     if (rc) return rc;
-    rc = chol_backward(L, ld, Ksel, Linv, L + (int64_t)Ksel * ld, ld, Wt, ld, n, stream);
+    rc = chol_backward(L, ld, Ksel, Linv, L + (int64_t)Ksel * ld, ld, Wt, ld, n, stream, h);
     if (rc) return rc;
     ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out, 0);
     CP_CHECK_LAUNCH();
@@ -912,7 +918,7 @@ extern "C" int cp_ls_resolve(cp_handle_t h, const double *Bxy, const double *sx,
     CP_CHECK_LAUNCH();
     rc = chol_forward(L, ld, Ksel, Linv, Zt, F, ld, n, stream, h);
     if (rc) return rc;
-    rc = chol_backward(L, ld, Ksel, Linv, F, ld, Wt, ld, n, stream);
+    rc = chol_backward(L, ld, Ksel, Linv, F, ld, Wt, ld, n, stream, h);
     if (rc) return rc;
     ls_output<<<n, 256, 0, stream>>>(Wt, ld, sx, sy, sel_cols, Ksel, invN, W_out, b_out, accumulate);
     CP_CHECK_LAUNCH();

@@ -278,19 +278,20 @@ class Engine:
         out.update(G=G, B=Bxy, sx=sx, sy=sy, yy=yy, N=N, K=K, n=n, mode=self.gram_mode if mode is None else mode)
         return out
 
-    def gemm_tc_split(self, A, B, C=None, alpha=1.0, beta=0.0, lower=False):
-        """C = alpha A B' + beta C on the tensor cores in 22-bit split precision (cp_gemm_tc_split): A (M, R), B (Nn, R),
-        C (M, Nn) fp64 device tensors with unit inner stride."""
-        assert A.dtype == B.dtype == torch.float64 and A.stride(1) == 1 and B.stride(1) == 1 and A.shape[1] == B.shape[1]
+    def gemm_tc_split(self, A, B, C=None, alpha=1.0, beta=0.0, lower=False, b_nc=False):
+        """C = alpha A B' + beta C on the tensor cores in 22-bit split precision (cp_gemm_tc_split): A (M, R), B (Nn, R)
+        -- or (R, Nn) with b_nc -- C (M, Nn), fp64 device tensors with unit inner stride."""
+        assert A.dtype == B.dtype == torch.float64 and A.stride(1) == 1 and B.stride(1) == 1
         M, R = A.shape
-        Nn = B.shape[0]
+        Nn = B.shape[1] if b_nc else B.shape[0]
+        assert (B.shape[0] if b_nc else B.shape[1]) == R
         if C is None:
             assert beta == 0.0
             C = self.empty(M, Nn)
         assert C.shape == (M, Nn) and C.dtype == torch.float64 and C.stride(1) == 1
         self._call(self.lib.cp_gemm_tc_split(self.h, M, Nn, R, float(alpha), self._p(A, "const double*"), A.stride(0),
                                              self._p(B, "const double*"), B.stride(0), float(beta), self._p(C, "double*"),
-                                             C.stride(0), 1 if lower else 0, self._s()))
+                                             C.stride(0), (1 if lower else 0) | (2 if b_nc else 0), self._s()))
         return C
 
     def ls_tensor_cores(self, enable):

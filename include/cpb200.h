@@ -252,7 +252,8 @@ int cp_ls_residual(cp_handle_t h, const float *X, int64_t N, int K, int64_t ldx,
  * (csrc/gemm_tc.cu), exposed for tests and measurements: the fp64 matrix products inside LinearRegression.fit's
  * solve (lib/decompose.py:665-666), evaluated with 22 mantissa bits per operand entry on tcgen05.
  *   C[m, nn] = alpha * sum_r A[m * lda + r] * B[nn * ldb + r] + beta * C[m * ldc + nn]      (fp64 in, fp64 out)
- * lower != 0: only the 256 x 256 tiles with row tile >= column tile are touched (M >= Nn).  R <= 1024.
+ * lower bit 0: only the 256 x 256 tiles with row tile >= column tile are touched (M >= Nn); bit 1: B is stored
+ * reduction-major, b(nn, r) = B[r * ldb + nn] (the factor's block row in the backward substitution).  R <= 1024.
  */
 int cp_gemm_tc_split(cp_handle_t h, int M, int Nn, int R, double alpha, const double *A, int64_t lda, const double *B,
                      int64_t ldb, double beta, double *C, int64_t ldc, int lower, cp_stream_t stream);

@@ -307,7 +307,8 @@ def test_rank_deficient_system_gets_gelsd_truncated_solution(engine, mode):
 
 
 @pytest.mark.parametrize("M,Nn,R,lower", [(700, 300, 256, False), (1030, 520, 128, True), (512, 512, 384, True),
-                                          (257, 200, 130, False), (2048, 768, 512, False)])
+                                          (257, 200, 130, False), (2048, 768, 512, False), (512, 1100, 512, "nc"),
+                                          (300, 333, 200, "nc")])
 def test_gemm_tc_split_matches_fp64(engine, M, Nn, R, lower):
     """cp_gemm_tc_split (the solver's tensor-core bulk product): C = beta C + alpha A B', rows of very different magnitude
     (power-of-two row scales).  Tolerance: |err| <= 4e-6 * sum_r |a||b|.  The operand split keeps 22 bits (<= 5e-7 of
@@ -316,13 +317,15 @@ def test_gemm_tc_split_matches_fp64(engine, M, Nn, R, lower):
     diagonal of a symmetric update (measured: 1.5e-6 there, 3.5e-7 for mixed signs)."""
     r = np.random.RandomState(M + Nn + R)
     A = r.standard_normal((M, R)) * np.exp(3.0 * r.standard_normal((M, 1)))
-    if lower:
+    if lower is True:
         B = A[:Nn].copy()
     else:
         B = r.standard_normal((Nn, R)) * np.exp(3.0 * r.standard_normal((Nn, 1)))
     C0 = r.standard_normal((M, Nn))
-    Ad, Bd, Cd = (torch.as_tensor(x, device=engine.device) for x in (A, B, C0.copy()))
-    engine.gemm_tc_split(Ad, Bd, Cd, alpha=-1.0, beta=1.0, lower=lower)
+    nc = lower == "nc"   # B handed over reduction-major (R, Nn)
+    lower = lower is True
+    Ad, Bd, Cd = (torch.as_tensor(x, device=engine.device) for x in (A, np.ascontiguousarray(B.T) if nc else B, C0.copy()))
+    engine.gemm_tc_split(Ad, Bd, Cd, alpha=-1.0, beta=1.0, lower=lower, b_nc=nc)
     got = Cd.cpu().numpy()
     ref = C0 - A @ B.T
     bound = np.abs(A) @ np.abs(B).T
