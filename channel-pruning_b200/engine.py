@@ -13,6 +13,7 @@ libcpb200.so construction fails.
 from __future__ import annotations
 
 import os
+import threading
 
 import numpy as np
 import torch
@@ -131,7 +132,8 @@ class Engine:
                 else:
                     prio = -1 if (i < nstreams // 2 and pol == "1") else 0
                 self.streams.append(torch.cuda.Stream(self.device, priority=prio) if nstreams > 1 else None)
-        self._cur = 0
+        self._tls = threading.local()   # current (handle, stream) slot of each host thread (use_slot)
+        self._lock = threading.Lock()
         self.launches = 0  # libcpb200 calls issued (each launches >= 1 kernel)
         self._pinned = {}   # (key, shape, dtype) -> page-locked host buffer, allocated once (cudaHostAlloc is slow)
         self._staging = {}  # (key, shape) -> device staging buffer for maps that are cheaper to DMA whole
@@ -162,8 +164,9 @@ class Engine:
     def _ring(self):
         """Rotating index for small pinned staging buffers: a buffer is rewritten by the host only 256 calls
         after the asynchronous copy that read it was enqueued (every step synchronises on each layer's search)."""
-        self._seq = (getattr(self, "_seq", -1) + 1) % 256
-        return self._seq
+        with self._lock:
+            self._seq = (getattr(self, "_seq", -1) + 1) % 256
+            return self._seq
 
     def staging(self, key, shape):
         k = (key, tuple(shape))
@@ -178,9 +181,22 @@ class Engine:
         return self._xfer
 
     def use_slot(self, i: int):
-        """Select which (handle, stream) pair subsequent calls use."""
-        self._cur = i % len(self._handles)
-        return self.streams[self._cur]
+        """Select which (handle, stream) pair subsequent calls OF THE CALLING THREAD use (the selection is
+        thread-local: pruner.prune_layers issues the reconstructions of different layers from worker threads)."""
+        self._tls.cur = i % len(self._handles)
+        return self.streams[self._tls.cur]
+
+    def slot_lock(self, i: int):
+        """Lock of slot i's (handle, stream) pair: a handle's scratch is reused by every call in stream order, so two
+        host threads must not interleave their launches on one slot."""
+        with self._lock:
+            if not hasattr(self, "_slot_locks"):
+                self._slot_locks = [threading.Lock() for _ in self._handles]
+        return self._slot_locks[i % len(self._handles)]
+
+    @property
+    def _cur(self):
+        return getattr(self._tls, "cur", 0)
 
     @property
     def h(self):

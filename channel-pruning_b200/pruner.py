@@ -22,6 +22,20 @@ from .engine import Engine, window
 
 
 # ---------------------------------------------------------------------------- assignment
+# host threads that issue the reconstructions of phase 2 (CPB200_PHASE2_THREADS=1: the single-threaded polling loop)
+PHASE2_THREADS = int(os.environ.get("CPB200_PHASE2_THREADS", "6"))
+_POOLS = {}
+
+
+def _phase2_pool(n):
+    import concurrent.futures
+
+    p = _POOLS.get(n)
+    if p is None:
+        p = _POOLS[n] = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cpb200-phase2")
+    return p
+
+
 def assign_layers(costs, world_size):
     """LPT: returns owner[i] for each problem; deterministic (ties by index)."""
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
@@ -229,18 +243,19 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
         phase1.append((X, g_full, res, host, ev))
     out = [None] * len(shapes)
     # phase 2 in COMPLETION order of the searches (which layer finishes first depends on sizes and, with
-    # host-resident inputs, on the transfer order): poll the events, reconstruct whichever is ready
-    pending = list(reversed(range(len(shapes))))
+    # host-resident inputs, on the transfer order): poll the events, reconstruct whichever is ready.
+    # A reconstruction of a wide layer is ~390 kernel launches (~1.3 ms of host time inside libcpb200 calls, which
+    # release the GIL): issued from one thread, the five c = 512 layers of VGG-16 queued behind one another on the
+    # HOST (step timeline, call 23: the last one was not even issued until 7.5 ms after its search had finished).
+    # Worker threads issue them side by side; the engine's current (handle, stream) slot is thread-local.
     checks = []
-    while pending:
-        ready = [i for i in pending if phase1[i][2] is None or phase1[i][4].query()]
-        if not ready:
-            time.sleep(2e-5)
-            continue
-        i = ready[0]
-        pending.remove(i)
+
+    def reconstruct_layer(i):
         s, d = shapes[i], datas[i]
         X, g_full, res, host, ev = phase1[i]
+        if res is not None:
+            ev.synchronize()
+        torch.cuda.set_device(eng.device)
         stream = eng.use_slot(i)
         r = LayerResult()
         if res is None:
@@ -253,7 +268,7 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
             r.idxs = host[1].numpy().astype(bool)
             r.alpha, r.nprobe = float(scal[0]), int(scal[1])
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
-        with ctx:
+        with eng.slot_lock(i), ctx:  # layers that share a slot (more layers than streams) are issued one after the other
             W, b, info, stat = eng.reconstruct_async(g_full, X, d["feats"], d["b2"], r.idxs, s.k * s.k)
             chk = (eng.pinned(("lsinfo", i), (1,), torch.int32), eng.pinned(("lsstat", i), (1,), torch.float64))
             chk[0].copy_(info, non_blocking=True)
@@ -265,7 +280,24 @@ def _prune_layers_ordered(eng, shapes, datas, right0, rank_tol, from_host, to_ho
         r.probes = res
         r.info = {"mode": g_full["mode"], "dual": not (g_full["N"] - 1 >= int(r.idxs.sum()) * s.k * s.k)}
         out[i] = r
-        checks.append((i, chk, ev_ls))
+        return (i, chk, ev_ls)
+
+    nworkers = min(PHASE2_THREADS, len(shapes)) if eng.streams[0] is not None else 1
+    pool = _phase2_pool(nworkers) if nworkers > 1 else None
+    futures = []
+    pending = list(reversed(range(len(shapes))))
+    while pending:
+        ready = [i for i in pending if phase1[i][2] is None or phase1[i][4].query()]
+        if not ready:
+            time.sleep(2e-5)
+            continue
+        i = ready[0]
+        pending.remove(i)
+        if pool is not None:
+            futures.append(pool.submit(reconstruct_layer, i))
+        else:
+            checks.append(reconstruct_layer(i))
+    checks.extend(f.result() for f in futures)
     # ---- every reconstruction is CHECKED before it is handed out: Cholesky status + conditioning signal.
     # Tensor-core statistics are accepted only for well-conditioned systems (engine.LS_RATIO_MIN); otherwise the
     # layer is re-solved from exact-product fp64 statistics; a system that is rank deficient by sklearn's cut-off
