@@ -183,10 +183,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         uint32_t nt = 0;
         for (int w = cid; w < nitems; w += ncl, ++nt) {
             const GtItem it = gt_decode(P, w);
-            mbar_wait(bar(ACC_FULL), nt & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ibase = it.ti * 256 + (int)rank * 128 + quad * 32;   // first row of this warp
             const int jbase = it.tj * 256 + half * 128;                      // first column of this warp
+            // the drain warps idle while the operands load and the MMAs run: pull this warp's 32 x 128 block of C
+            // (32 KB) into L2 meanwhile, so that the read-modify-write below does not start from DRAM latency
+            if (P.beta != 0.0 && ibase + lane < P.M) {
+                const double *crow = P.C + (int64_t)(ibase + lane) * P.ldc + jbase;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (jbase + q * 16 < P.Nn) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + q * 16));
+            }
+            mbar_wait(bar(ACC_FULL), nt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {
                 {

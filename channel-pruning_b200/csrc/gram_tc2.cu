@@ -58,7 +58,7 @@ constexpr int SUB_STAGES = 2;               // stages per accumulator run (128 r
 constexpr int NDRAIN_WARPS = 8;
 constexpr int NTHREADS = 32 * (NDRAIN_WARPS + 2);
 constexpr int W_TMA = NDRAIN_WARPS, W_MMA = NDRAIN_WARPS + 1;  // single-thread roles on the highest warp ids
-constexpr int T_TMA = 32 * W_TMA, T_MMA = 32 * W_MMA;
+constexpr int T_TMA = 32 * W_TMA;
 constexpr int OFF_BAR = STAGES * STAGE_BYTES;
 constexpr int NBAR = 2 * STAGES + 4;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
