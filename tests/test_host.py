@@ -234,3 +234,24 @@ def test_reference_arm_reports_what_it_ran(monkeypatch, capsys):
     st = line["cpu_baseline"]["stack_seconds"]
     assert abs(st["lasso"] + st["ls"] + st["gather"] - len(shapes) / want) <= 1e-9
     assert line["config"] == bench.config_dict(args, shapes, 1)
+
+
+def test_numa_local_context_restores_affinity():
+    """engine.numa_local binds the calling thread to the GPU's NUMA node only for the duration of a pinned allocation;
+    without a GPU (or without NUMA information) it must be a no-op, and the affinity must come back either way."""
+    import cpb200
+
+    before = os.sched_getaffinity(0)
+    with cpb200.engine.numa_local(0) as ctx:
+        inside = os.sched_getaffinity(0)
+        assert inside <= before and len(inside) >= 1
+        assert ctx.cpus is None or (ctx.cpus & before)
+    assert os.sched_getaffinity(0) == before
+
+
+def test_header_documents_the_round2_entry_points():
+    src = open(os.path.join(ROOT, "include", "cpb200.h")).read()
+    for fn in ("cp_gemm_tc_split", "cp_ls_tensor_cores"):
+        head = src[:src.index("int " + fn + "(")]
+        comment = head[head.rindex("/*"):]
+        assert "lib/decompose.py:" in comment, "no reference file:line cited for " + fn
