@@ -40,6 +40,8 @@ LS_RESID = os.environ.get("CPB200_LS_RESID", "tc")
 LS_RESID_TC_MIN_N = 20000
 # Bulk products of the Cholesky solve on the tensor cores when the statistics came from there (cp_ls_tensor_cores)
 LS_TC = os.environ.get("CPB200_LS_TC", "1") == "1"
+# Full Gram of a layer enqueued after its channel search, on a lowest-priority stream (select_channels_async)
+DEFER_FULL_GRAM = os.environ.get("CPB200_DEFER_GRAM", "1") == "1"
 
 _PRIO_HIGHEST = -5  # cudaDeviceGetStreamPriorityRange on B200: [0, -5]; out-of-range values are clamped by the runtime
 _LAYOUTS = {"nchw": 0, "nhwc": 1}
@@ -130,7 +132,7 @@ class Engine:
                 if pol == "graded":
                     prio = min(0, _PRIO_HIGHEST + i)
                 else:
-                    prio = -1 if (i < nstreams // 2 and pol == "1") else 0
+                    prio = -2 if (i < nstreams // 2 and pol == "1") else -1  # 0 is left to the deferred-Gram stream
                 self.streams.append(torch.cuda.Stream(self.device, priority=prio) if nstreams > 1 else None)
         self._tls = threading.local()   # current (handle, stream) slot of each host thread (use_slot)
         self._lock = threading.Lock()
@@ -138,12 +140,16 @@ class Engine:
         self._pinned = {}   # (key, shape, dtype) -> page-locked host buffer, allocated once (cudaHostAlloc is slow)
         self._staging = {}  # (key, shape) -> device staging buffer for maps that are cheaper to DMA whole
         self._xfer = None   # (zero-copy gather stream, DMA stream) of the host-resident input path
+        self._aux = None    # (handle, lowest-priority stream) of the deferred full Grams (select_channels_async)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
         for h in self._handles:
             self.lib.cp_destroy(h)
         self._handles = []
+        if self._aux is not None:
+            self.lib.cp_destroy(self._aux[0])
+            self._aux = None
 
     def __del__(self):  # pragma: no cover
         try:
@@ -200,7 +206,18 @@ class Engine:
 
     @property
     def h(self):
-        return self._handles[self._cur]
+        over = getattr(self._tls, "handle", None)
+        return over if over is not None else self._handles[self._cur]
+
+    def aux_slot(self):
+        """(handle, stream) for work that may run in the shadow of the channel searches: the lowest stream priority, its
+        own handle (scratch), created on first use."""
+        if self._aux is None:
+            with torch.cuda.device(self.device):
+                hp = self.ffi.new("cp_handle_t*")
+                _cabi.check(self.lib.cp_create(hp, self.device.index))
+                self._aux = (hp[0], torch.cuda.Stream(self.device, priority=0))
+        return self._aux
 
     def _s(self):
         return self.ffi.cast("void*", torch.cuda.current_stream(self.device).cuda_stream)
@@ -579,12 +596,39 @@ class Engine:
         without host synchronisation.  Returns (g_full, LassoResult)."""
         n = W2m.shape[0]
         S = samples.numel()
-        g_full = self.gram(X, Y, y_bias=y_bias)
+        # The search needs only the channel-space statistics (Q from the sampled rows and W2); the full Gram feeds the
+        # reconstruction.  In the pipeline (one stream per layer) it is therefore enqueued AFTER the search, on a
+        # lowest-priority stream with its own handle: the ~0.5 ms full-GPU launch no longer delays the start of this
+        # and of every later layer's 8 ms single-SM search, it runs in their shadow.
+        defer = DEFER_FULL_GRAM and self.streams[0] is not None
+        if defer:
+            cur = torch.cuda.current_stream(self.device)
+            ev_x = torch.cuda.Event()
+            ev_x.record(cur)  # X and Y are complete here (recorded BEFORE the search is enqueued on this stream)
+        g_full = None if defer else self.gram(X, Y, y_bias=y_bias)
         g_s = self.gram(X, Y, y_bias=y_bias, rows=samples, want_yy=True, mode=GRAM_FP64)
         g_w = self.gram(W2m, None, want_B=False, mode=GRAM_FP64)
         Q, qv, yn2 = self.lasso_build(g_s, g_w, W2m, c, k2, S)
         lbound, rbound = window(rank, rank_tol)
         res = self.lasso_select(Q, qv, yn2, float(S) * n, rank, lbound, rbound, right0, seeds)
+        if defer:
+            ah, astream = self.aux_slot()
+            self._tls.handle = ah
+            try:
+                with torch.cuda.stream(astream):
+                    astream.wait_event(ev_x)
+                    g_full = self.gram(X, Y, y_bias=y_bias)
+                    ready = torch.cuda.Event()
+                    ready.record(astream)
+            finally:
+                self._tls.handle = None
+            for t in (X, Y, y_bias):
+                if t is not None:
+                    t.record_stream(astream)
+            for key in ("G", "B", "sx", "sy"):
+                if g_full.get(key) is not None:
+                    g_full[key].record_stream(cur)
+            g_full["ready"] = ready
         return g_full, res
 
     def _cols_device(self, idxs_host, k2, K):
@@ -596,6 +640,8 @@ class Engine:
 
     def reconstruct_async(self, g_full, X, Y, y_bias, idxs_host, k2):
         """LS on the surviving channels (device outputs; no host sync).  Returns (W, b, info, stat)."""
+        if g_full.get("ready") is not None:  # full Gram enqueued on the deferred-Gram stream
+            torch.cuda.current_stream(self.device).wait_event(g_full["ready"])
         cols_d = self._cols_device(idxs_host, k2, g_full["K"])
         if g_full["N"] - 1 >= cols_d.numel():
             W, b, info, stat = self.ls_solve(g_full, cols_d)
