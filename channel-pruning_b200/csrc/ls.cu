@@ -475,7 +475,7 @@ int dgemm_big(const double *A, int64_t lda, const double *B, int64_t ldb, double
     using namespace cpgemm;
     // tensor-core handle given and enabled: split-precision product (gemm_tc.cu) for everything wide enough to fill
     // 256 x 256 tiles; one operand buffer per stream of the solver
-    static const int tc_min_nn = [] { const char *e = getenv("CPB200_LS_TC_MIN_NN"); return e ? atoi(e) : 128; }();
+    static const int tc_min_nn = [] { const char *e = getenv("CPB200_LS_TC_MIN_NN"); return e ? atoi(e) : 192; }();
     if (tc && tc->ls_tc && cp_gemm_tc_enabled() && R >= 128 && R <= 1024 && Nn >= tc_min_nn && M >= 256 &&
         (tile_mode == TILES_ALL || tile_mode == TILES_LOWER)) {
         const int slot = stream == tc->side ? 1 : (stream == tc->bulk ? 2 : 0);
