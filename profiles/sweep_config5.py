@@ -27,7 +27,7 @@ def timed(torch, fn, reps=4, skip=1, flush=None):
         torch.cuda.synchronize()
         if it >= skip:
             times.append(a.elapsed_time(b))
-    return statistics.mean(times), out
+    return statistics.median(times), out  # median: the first repetition after a workspace growth is slow
 
 
 def main(args=None):
