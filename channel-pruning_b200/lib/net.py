@@ -13,6 +13,8 @@ the reference).  Methods keep the reference's names, arguments and return conven
   load_frozen(DEBUG=False, feats_dict=None, points_dict=None)            lib/net.py:839-876
   dictionary_kernel(X_name, weights, d_prime, Y_name, Y, DEBUG=0)        lib/net.py:1685-1735
   R3() -> (WPQ, new_pt)    spatial + channel decomposition + pruning     lib/net.py:1292-1471
+  combineHP(WPQ, new_pt), layercomputation(...), computation(...)        lib/net.py:1473-1504, 1049-1081
+      (module-level: they work on the WPQ / topology dictionaries R3 returns -- there is no prototxt here)
 
 The gathers run on the device (cp_point_gather / cp_patch_gather); sampled points come from the
 numpy global RNG with the reference's call sequence, so a seeded run draws the same points.
@@ -415,3 +417,55 @@ class Net:
         checkpoint("final")
         new_pt = {"prefix": prefix, "layers": topology}
         return self.WPQ, new_pt
+
+
+# ---------------------------------------------------------------------------- model surgery on R3's result
+def combineHP(WPQ, new_pt):
+    """lib/net.py:1473-1504: after the 3C walk every conv is a chain V (k x 1) -> H (1 x k, m outputs) -> P (1 x 1,
+    o outputs).  Where the channel decomposition saved little (3 m >= 2 o) the reference folds P back into H:
+        W_H' = P_w . H_w   (o x ...),    b_H' = P_b + P_w . H_b
+    and removes P.  The reference edits the Caffe net and writes a prototxt; here the same rule is applied to the
+    dictionaries ``Net.R3`` returns.  Returns (WPQ', new_pt') -- new objects, the inputs are left alone."""
+    out = dict(WPQ)
+    layers = []
+    for lay in new_pt["layers"]:
+        lay = dict(lay)
+        h, p = lay["H"], lay.get("P")
+        if p is not None and (h, 0) in out and (p, 0) in out:
+            assert h.split('_H')[0] == p.split('_P')[0]  # :1485
+            Hshape = out[(h, 0)].shape
+            m, o = Hshape[0], out[(p, 0)].shape[0]
+            if 3 * m >= 2 * o:  # :1489
+                Hw = np.asarray(out[(h, 0)], dtype=np.float64).reshape((m, -1))
+                Pw = np.asarray(out[(p, 0)], dtype=np.float64).reshape((o, -1))
+                Hb = np.asarray(out[(h, 1)], dtype=np.float64)
+                pb = np.asarray(out[(p, 1)], dtype=np.float64)
+                out[(h, 0)] = Pw.dot(Hw).reshape((o,) + tuple(Hshape[1:]))  # :1495
+                out[(h, 1)] = pb + Pw.dot(Hb)                                # :1496
+                del out[(p, 0)], out[(p, 1)]
+                lay["P"] = None
+                lay["num_output_H"] = int(o)
+        layers.append(lay)
+    return out, dict(new_pt, layers=layers, prefix="cb" + str(new_pt.get("prefix", "")))
+
+
+def layercomputation(blob_shape, param_shape, stride=1, spatial=False, channels=1., outputs=1., innerproduct=False):
+    """lib/net.py:1049-1067: multiply-accumulates of one layer from the shape of its bottom blob (B, C, H, W) and of its
+    weights (n, c, kh, kw); ``spatial`` marks the depth-wise layers of ``Net.spation_convs``."""
+    s, p = blob_shape, param_shape
+    if innerproduct:
+        return int(p[0] * p[1])
+    if spatial:
+        channels = 1
+    else:
+        assert s[1] == p[1]
+        channels *= p[1]
+    outputs *= p[0]
+    return int(s[2] * s[3] * outputs * channels * p[2] * p[3] / stride ** 2)
+
+
+def computation(layers):
+    """lib/net.py:1069-1081: total and per-layer cost; ``layers`` = iterable of (name, blob_shape, param_shape, stride).
+    Returns (total, {name: flops}) instead of printing."""
+    per = {name: layercomputation(bs, ps, st) for name, bs, ps, st in layers}
+    return sum(per.values()), per

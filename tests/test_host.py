@@ -255,3 +255,41 @@ def test_header_documents_the_round2_entry_points():
         head = src[:src.index("int " + fn + "(")]
         comment = head[head.rindex("/*"):]
         assert "lib/decompose.py:" in comment, "no reference file:line cited for " + fn
+
+
+def test_combineHP_folds_P_into_H_like_the_reference_rule():
+    """lib/net.py:1473-1504 on the dictionaries Net.R3 returns: a conv whose channel decomposition kept 3 m >= 2 o is
+    merged (W = P.H, b = P_b + P.H_b): the merged layer must reproduce H followed by P exactly; others stay."""
+    from cpb200.lib import net as N
+
+    r = np.random.RandomState(5)
+    WPQ, layers = {}, []
+    for name, (m, o, c, k) in {"conv2_1": (48, 64, 24, 3), "conv3_1": (40, 128, 32, 3)}.items():
+        WPQ[name + "_V"] = r.standard_normal((c, 16, k, 1))
+        WPQ[(name + "_H", 0)] = r.standard_normal((m, c, 1, k))
+        WPQ[(name + "_H", 1)] = r.standard_normal(m)
+        WPQ[(name + "_P", 0)] = r.standard_normal((o, m, 1, 1))
+        WPQ[(name + "_P", 1)] = r.standard_normal(o)
+        layers.append({"V": name + "_V", "H": name + "_H", "P": name + "_P", "rank": m, "num_output": o})
+    out, pt = N.combineHP(WPQ, {"prefix": "3C5x", "layers": layers})
+    # conv2_1: 3*48 >= 2*64 -> merged; conv3_1: 3*40 < 2*128 -> untouched
+    assert ("conv2_1_P", 0) not in out and out[("conv2_1_H", 0)].shape == (64, 24, 1, 3)
+    assert ("conv3_1_P", 0) in out and out[("conv3_1_H", 0)].shape == (40, 32, 1, 3)
+    x = r.standard_normal(24 * 3)  # one flattened 1 x k patch of the H layer's input
+    h = WPQ[("conv2_1_H", 0)].reshape(48, -1) @ x + WPQ[("conv2_1_H", 1)]
+    y = WPQ[("conv2_1_P", 0)].reshape(64, -1) @ h + WPQ[("conv2_1_P", 1)]
+    y2 = out[("conv2_1_H", 0)].reshape(64, -1) @ x + out[("conv2_1_H", 1)]
+    np.testing.assert_allclose(y2, y, rtol=1e-12, atol=1e-12)
+    assert pt["layers"][0]["P"] is None and pt["layers"][1]["P"] == "conv3_1_P"
+    assert ("conv2_1_P", 0) in WPQ  # the input dictionaries are left alone
+
+
+def test_computation_matches_the_reference_formula():
+    """lib/net.py:1049-1081: VGG-16 conv1_1 (224x224x3 -> 64, 3x3) = 224*224*64*3*9 multiply-accumulates."""
+    from cpb200.lib import net as N
+
+    total, per = N.computation([("conv1_1", (1, 3, 224, 224), (64, 3, 3, 3), 1),
+                                ("conv1_2", (1, 64, 224, 224), (64, 64, 3, 3), 1),
+                                ("down", (1, 64, 112, 112), (128, 64, 3, 3), 2)])
+    assert per["conv1_1"] == 224 * 224 * 64 * 3 * 9 and per["conv1_2"] == 224 * 224 * 64 * 64 * 9
+    assert per["down"] == 112 * 112 * 128 * 64 * 9 // 4 and total == sum(per.values())
