@@ -293,3 +293,27 @@ def test_computation_matches_the_reference_formula():
                                 ("down", (1, 64, 112, 112), (128, 64, 3, 3), 2)])
     assert per["conv1_1"] == 224 * 224 * 64 * 3 * 9 and per["conv1_2"] == 224 * 224 * 64 * 64 * 9
     assert per["down"] == 112 * 112 * 128 * 64 * 9 // 4 and total == sum(per.values())
+
+
+def test_split_fp16_scheme_keeps_22_bits():
+    """The operand split of gram_tc2.cu / gemm_tc.cu, restated in numpy: v = x * 2^e with max|v| in [2^9, 2^10),
+    hi = fp16(v), lo = fp16(v - hi).  hi + lo must reproduce v to 2^-22 relative (2^-25 absolute below 2^-3, where the
+    lo half goes subnormal), and the three products the kernels issue (hi.hi + hi.lo + lo.hi) must reproduce a
+    dot product to ~2^-21 of sum|a||b| -- the bound DESIGN.md and the GPU tests quote."""
+    r = np.random.RandomState(11)
+    x = (r.standard_normal((64, 512)) * np.exp(2.0 * r.standard_normal((64, 1)))).astype(np.float32)
+    mx = np.abs(x).max(1, keepdims=True)
+    e = 9 - np.floor(np.log2(mx)).astype(np.int64)
+    v = (x.astype(np.float64) * np.exp2(e)).astype(np.float32)
+    assert np.all(np.abs(v).max(1) >= 2.0 ** 9) and np.all(np.abs(v).max(1) < 2.0 ** 10)
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float16)
+    rec = hi.astype(np.float64) + lo.astype(np.float64)
+    err = np.abs(rec - v.astype(np.float64))
+    assert np.all(err <= np.maximum(np.abs(v) * 2.0 ** -22, 2.0 ** -25))
+    H, L = hi.astype(np.float64), lo.astype(np.float64)
+    exact = (v.astype(np.float64) @ v.astype(np.float64).T)
+    three = H @ H.T + H @ L.T + L @ H.T          # what the tensor cores accumulate (here without fp32 rounding)
+    bound = np.abs(v.astype(np.float64)) @ np.abs(v.astype(np.float64)).T
+    assert np.abs(three - exact).max() <= 2.0 ** -21 * bound.max()
+    assert (np.abs(three - exact) / bound).max() <= 2.0 ** -20
